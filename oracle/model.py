@@ -1,0 +1,117 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle for the dense half of the path.
+
+Functional, state-dict driven fp32 restatement (torch-CPU ATen ops == the
+reference's own arithmetic) of:
+  * ResNet / ResNeXt forward, eval-mode BN   (mmdet/models/backbones/resnet.py:224-267,
+    507-518; resnext.py:21-56),
+  * FPN forward                               (mmdet/models/necks/fpn.py:97-136),
+  * IoUawareRetinaHead.forward_single         (mmdet/models/anchor_heads/iou_aware_retina_head.py:171-219).
+No nn.Modules are built: the functions walk the reference's state_dict keys
+(SURVEY.md Appendix A), so the same weights can be handed to the CUDA path.
+"""
+import torch
+import torch.nn.functional as F
+
+STAGE_BLOCKS = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3), 152: (3, 8, 36, 3)}
+
+
+def _bn(x, sd, p, eps=1e-5):
+    return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"],
+                        sd[p + ".weight"], sd[p + ".bias"], False, 0.0, eps)
+
+
+def backbone_forward(sd, img, depth=50, groups=1, prefix="backbone."):
+    """resnet.py:507-518.  Returns (C2, C3, C4, C5), NCHW fp32."""
+    x = F.conv2d(img, sd[prefix + "conv1.weight"], None, stride=2, padding=3)
+    x = F.relu(_bn(x, sd, prefix + "bn1"))
+    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    outs = []
+    for s, nblocks in enumerate(STAGE_BLOCKS[depth]):
+        for b in range(nblocks):
+            p = "%slayer%d.%d." % (prefix, s + 1, b)
+            stride = 2 if (b == 0 and s > 0) else 1          # 'pytorch' style: stride in conv2
+            idt = x
+            y = F.relu(_bn(F.conv2d(x, sd[p + "conv1.weight"]), sd, p + "bn1"))
+            y = F.conv2d(y, sd[p + "conv2.weight"], None, stride=stride, padding=1, groups=groups)
+            y = F.relu(_bn(y, sd, p + "bn2"))
+            y = _bn(F.conv2d(y, sd[p + "conv3.weight"]), sd, p + "bn3")
+            if (p + "downsample.0.weight") in sd:
+                idt = _bn(F.conv2d(x, sd[p + "downsample.0.weight"], None, stride=stride),
+                          sd, p + "downsample.1")
+            x = F.relu(y + idt)                               # resnet.py:256,265
+        outs.append(x)
+    return tuple(outs)
+
+
+def fpn_forward(sd, feats, prefix="neck.", start_level=1, num_outs=5):
+    """fpn.py:97-136 with add_extra_convs=True, extra_convs_on_inputs=True,
+    relu_before_extra_convs=False, no norm, no activation."""
+    used = feats[start_level:]
+    lat = [F.conv2d(f, sd["%slateral_convs.%d.conv.weight" % (prefix, i)],
+                    sd["%slateral_convs.%d.conv.bias" % (prefix, i)]) for i, f in enumerate(used)]
+    for i in range(len(lat) - 1, 0, -1):
+        lat[i - 1] = lat[i - 1] + F.interpolate(lat[i], scale_factor=2, mode="nearest")
+    outs = [F.conv2d(l, sd["%sfpn_convs.%d.conv.weight" % (prefix, i)],
+                     sd["%sfpn_convs.%d.conv.bias" % (prefix, i)], padding=1) for i, l in enumerate(lat)]
+    n = len(lat)
+    src = feats[-1]
+    for i in range(n, num_outs):
+        outs.append(F.conv2d(src, sd["%sfpn_convs.%d.conv.weight" % (prefix, i)],
+                             sd["%sfpn_convs.%d.conv.bias" % (prefix, i)], stride=2, padding=1))
+        src = outs[-1]
+    return tuple(outs)
+
+
+def head_forward_single(sd, x, prefix="bbox_head.", stacked=4):
+    """iou_aware_retina_head.py:171-219 with shared_conv=4, no feature alignment."""
+    c = r = x
+    for i in range(stacked):
+        c = F.relu(F.conv2d(c, sd["%scls_convs.%d.conv.weight" % (prefix, i)],
+                            sd["%scls_convs.%d.conv.bias" % (prefix, i)], padding=1))
+        r = F.relu(F.conv2d(r, sd["%sreg_convs.%d.conv.weight" % (prefix, i)],
+                            sd["%sreg_convs.%d.conv.bias" % (prefix, i)], padding=1))
+    cls = F.conv2d(c, sd[prefix + "retina_cls.weight"], sd[prefix + "retina_cls.bias"], padding=1)
+    reg = F.conv2d(r, sd[prefix + "retina_reg.weight"], sd[prefix + "retina_reg.bias"], padding=1)
+    iou = F.conv2d(r, sd[prefix + "retina_iou.weight"], sd[prefix + "retina_iou.bias"], padding=1)
+    return cls, reg, iou
+
+
+def head_forward(sd, feats, prefix="bbox_head."):
+    """anchor_head.py:102-103 (multi_apply over levels) -> (list, list, list)."""
+    outs = [head_forward_single(sd, f, prefix) for f in feats]
+    return tuple(map(list, zip(*outs)))
+
+
+@torch.no_grad()
+def detector_forward(sd, img, depth=50, groups=1):
+    """extract_feat + bbox_head (single_stage.py:39-43, 86-87)."""
+    feats = fpn_forward(sd, backbone_forward(sd, img, depth, groups))
+    return head_forward(sd, feats)
+
+
+def spread_weights_(sd, seed=1, final_std=None):
+    """re-draw BN statistics / affine and widen the final
+    convs so that logits spread (score gaps >> 1e-4) instead of the degenerate
+    reference init.  Operates in place on a state_dict; deterministic in `seed`."""
+    g = torch.Generator().manual_seed(seed)
+    for k in sorted(sd.keys()):
+        v = sd[k]
+        if k.endswith("running_var"):
+            v.copy_(torch.rand(v.shape, generator=g) + 0.5)
+        elif k.endswith("running_mean"):
+            v.copy_(torch.randn(v.shape, generator=g) * 0.1)
+        elif ".bn" in k or "downsample.1" in k or k.startswith("backbone.bn1"):
+            if k.endswith(".weight"):
+                v.copy_(torch.rand(v.shape, generator=g) + 0.5)
+            elif k.endswith(".bias"):
+                v.copy_(torch.randn(v.shape, generator=g) * 0.1)
+    final_std = final_std or {"retina_cls": 0.02, "retina_reg": 0.004, "retina_iou": 0.02}
+    for name, std in final_std.items():
+        k = "bbox_head.%s.weight" % name
+        sd[k].copy_(torch.randn(sd[k].shape, generator=g) * std)
+    for i in range(4):
+        for t in ("cls_convs", "reg_convs"):
+            k = "bbox_head.%s.%d.conv.weight" % (t, i)
+            fan_in = sd[k].shape[1] * 9
+            sd[k].copy_(torch.randn(sd[k].shape, generator=g) * (2.0 / fan_in) ** 0.5)
+    return sd

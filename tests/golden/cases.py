@@ -1,0 +1,135 @@
+"""Deterministic inputs for the golden fixtures (shared by gen_golden.py and the tests).
+
+Inputs are rebuilt from numpy's frozen legacy ``RandomState`` so only the
+reference's OUTPUTS need to be stored in the .npz fixtures.
+"""
+import numpy as np
+import torch
+
+STRIDES = [8, 16, 32, 64, 128]
+TEST_CFG = dict(nms_pre=1000, min_bbox_size=0, score_thr=0.05,
+                nms=dict(type='nms', iou_thr=0.5), max_per_img=100)
+
+
+def level_sizes(pad_h, pad_w):
+    """FPN level sizes for a padded input: /8, /16, /32 then two stride-2 3x3 convs."""
+    sizes = [(pad_h // 8, pad_w // 8), (pad_h // 16, pad_w // 16), (pad_h // 32, pad_w // 32)]
+    for _ in range(2):
+        h, w = sizes[-1]
+        sizes.append(((h + 1) // 2, (w + 1) // 2))
+    return sizes
+
+
+def random_maps(rs, n_img, sizes, cls_mu=-3.0, cls_sd=2.0, iou_sd=1.5, reg_sd=0.5, A=9, C=80):
+    cls, reg, iou = [], [], []
+    for (h, w) in sizes:
+        cls.append(torch.from_numpy((rs.randn(n_img, A * C, h, w) * cls_sd + cls_mu).astype(np.float32)))
+        reg.append(torch.from_numpy((rs.randn(n_img, A * 4, h, w) * reg_sd).astype(np.float32)))
+        iou.append(torch.from_numpy((rs.randn(n_img, A, h, w) * iou_sd).astype(np.float32)))
+    return cls, reg, iou
+
+
+POSTPROC_CASES = ["small", "few", "empty", "full"]
+
+
+def postproc_case(name):
+    cfg = dict(TEST_CFG)
+    if name == "small":
+        rs = np.random.RandomState(1234)
+        sizes = level_sizes(224, 288)
+        cls, reg, iou = random_maps(rs, 2, sizes)
+        cfg["nms_pre"] = 300
+        metas = [dict(ori_shape=(125, 163, 3), img_shape=(200, 261, 3), pad_shape=(224, 288, 3),
+                      scale_factor=1.6, flip=False),
+                 dict(ori_shape=(238, 313, 3), img_shape=(190, 250, 3), pad_shape=(224, 288, 3),
+                      scale_factor=0.8, flip=False)]
+        rescale = True
+    elif name == "few":
+        rs = np.random.RandomState(99)
+        sizes = level_sizes(224, 288)
+        cls, reg, iou = random_maps(rs, 1, sizes, cls_mu=-11.5, cls_sd=1.6)
+        cfg["nms_pre"] = 300
+        metas = [dict(ori_shape=(200, 261, 3), img_shape=(200, 261, 3), pad_shape=(224, 288, 3),
+                      scale_factor=1.0, flip=False)]
+        rescale = False
+    elif name == "empty":
+        rs = np.random.RandomState(7)
+        sizes = level_sizes(224, 288)
+        cls, reg, iou = random_maps(rs, 1, sizes, cls_mu=-14.0, cls_sd=0.5)
+        cfg["nms_pre"] = 300
+        metas = [dict(ori_shape=(200, 261, 3), img_shape=(200, 261, 3), pad_shape=(224, 288, 3),
+                      scale_factor=1.0, flip=False)]
+        rescale = False
+    elif name == "full":
+        rs = np.random.RandomState(2024)
+        sizes = level_sizes(800, 1344)
+        cls, reg, iou = random_maps(rs, 1, sizes)
+        metas = [dict(ori_shape=(800, 1333, 3), img_shape=(800, 1333, 3), pad_shape=(800, 1344, 3),
+                      scale_factor=1.0, flip=False)]
+        rescale = True
+    else:
+        raise KeyError(name)
+    return dict(cls=cls, reg=reg, iou=iou, img_metas=metas, cfg=cfg, rescale=rescale, sizes=sizes)
+
+
+def codec_inputs():
+    rs = np.random.RandomState(5)
+    rois = np.array([[0, 0, 31, 31], [10, 20, 100, 60], [-19, -7, 26, 14], [500, 300, 1400, 900],
+                     [-298, -117, 425, 244]], dtype=np.float32)
+    rois = np.concatenate([rois, (rs.rand(59, 4) * 600).astype(np.float32)])
+    rois[5:, 2:] += rois[5:, :2]
+    deltas = (rs.randn(64, 4) * 0.8).astype(np.float32)
+    deltas[0] = [0.1, -0.2, 0.3, 5.0]       # SURVEY a8 known answer: [0, 0, 39.7977, 799]
+    deltas[1] = [0.0, 0.0, -6.0, 6.0]       # both clamps of dw/dh
+    return rois, deltas
+
+
+def random_dets(rs, n, extent=600.0, size=120.0):
+    xy = rs.rand(n, 2) * extent
+    wh = rs.rand(n, 2) * size + 4.0
+    sc = rs.rand(n, 1)
+    return np.concatenate([xy, xy + wh, sc], axis=1).astype(np.float32)
+
+
+def nms_inputs():
+    rs = np.random.RandomState(11)
+    out = {"n1": random_dets(rs, 1), "n3": np.array([[0, 0, 10, 10, 0.9], [1, 1, 10, 10, 0.8],
+                                                    [20, 20, 30, 30, 0.7]], dtype=np.float32),
+           "n64": random_dets(rs, 64, 200, 80), "n65": random_dets(rs, 65, 200, 80),
+           "n700": random_dets(rs, 700, 500, 150), "n2000": random_dets(rs, 2000),
+           "n4693_dense": random_dets(rs, 4693, 300, 200)}
+    return out
+
+
+def pairwise_iou_f32(b):
+    """IoU matrix with the reference's fp32 operation order (nms_kernel.cu:13-21)."""
+    b = b.astype(np.float32)
+    one = np.float32(1)
+    area = (b[:, 2] - b[:, 0] + one) * (b[:, 3] - b[:, 1] + one)
+    left = np.maximum(b[:, None, 0], b[None, :, 0]); right = np.minimum(b[:, None, 2], b[None, :, 2])
+    top = np.maximum(b[:, None, 1], b[None, :, 1]); bot = np.minimum(b[:, None, 3], b[None, :, 3])
+    w = np.maximum(right - left + one, np.float32(0)); h = np.maximum(bot - top + one, np.float32(0))
+    inter = w * h
+    return inter / (area[:, None] + area[None, :] - inter)
+
+
+def assert_no_threshold_ties(dets, thr):
+    """nms_cpu suppresses at >= thr, nms_cuda at > thr: the golden is only valid for both
+    when no pair sits exactly on the threshold."""
+    n = dets.shape[0]
+    for s in range(0, n, 1024):
+        iou = pairwise_iou_f32(dets[:, :4])[s:s + 1024] if n <= 1024 else \
+            _rows_iou(dets[:, :4], s, min(s + 1024, n))
+        assert not np.any(iou == np.float32(thr)), "IoU == thr tie in golden input"
+
+
+def _rows_iou(b, s, e):
+    b = b.astype(np.float32)
+    one = np.float32(1)
+    area = (b[:, 2] - b[:, 0] + one) * (b[:, 3] - b[:, 1] + one)
+    r = b[s:e]
+    left = np.maximum(r[:, None, 0], b[None, :, 0]); right = np.minimum(r[:, None, 2], b[None, :, 2])
+    top = np.maximum(r[:, None, 1], b[None, :, 1]); bot = np.minimum(r[:, None, 3], b[None, :, 3])
+    w = np.maximum(right - left + one, np.float32(0)); h = np.maximum(bot - top + one, np.float32(0))
+    inter = w * h
+    return inter / (area[s:e, None] + area[None, :] - inter)

@@ -1,0 +1,123 @@
+"""Generates tests/golden/*.npz by running the REAL reference (CPU, shimmed).
+
+Run in the build container only (needs /root/reference):
+    python tests/golden/gen_golden.py
+The fixtures hold OUTPUTS of the reference's own code
+(IoUawareRetinaHead.get_bboxes / get_bboxes_single, multiclass_nms, nms_cpu,
+AnchorGenerator, delta2bbox) for inputs that ``tests/golden/cases.py`` rebuilds
+from a frozen numpy RandomState, so the inputs themselves are not stored.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, HERE)
+
+from oracle import ref_shim  # noqa: E402
+import cases  # noqa: E402
+
+
+def ref_head():
+    ref_shim.load_reference()
+    from mmdet.models.anchor_heads import IoUawareRetinaHead
+    torch.manual_seed(0)
+    return IoUawareRetinaHead(
+        num_classes=81, in_channels=256, stacked_convs=4, feat_channels=256,
+        octave_base_scale=4, scales_per_octave=3, anchor_ratios=[0.5, 1.0, 2.0],
+        anchor_strides=[8, 16, 32, 64, 128], target_means=[.0, .0, .0, .0],
+        target_stds=[1.0, 1.0, 1.0, 1.0],
+        loss_cls=dict(type='FocalLoss', use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0),
+        loss_bbox=dict(type='SmoothL1Loss', beta=0.11, loss_weight=1.0))
+
+
+def run_postproc_case(head, case):
+    """Real reference: candidates that enter multiclass_nms and final detections."""
+    from mmdet.core import multiclass_nms, delta2bbox
+    cfg = ref_shim._to_attr(case["cfg"])
+    cls, reg, iou = case["cls"], case["reg"], case["iou"]     # lists of (N, ch, H, W)
+    n_img = cls[0].shape[0]
+    metas = case["img_metas"]
+    gtb = [torch.zeros(0, 4)] * n_img
+    gtl = [torch.zeros(0, dtype=torch.long)] * n_img
+    out = {}
+    with torch.no_grad():
+        res = head.get_bboxes(cls, reg, iou, gtb, gtl, metas, cfg, rescale=case["rescale"])
+    for i, (d, l) in enumerate(res):
+        out["dets_%d" % i] = d.numpy()
+        out["labels_%d" % i] = l.numpy()
+    # per-level candidate selection, by re-running the reference's own statements
+    # (iou_aware_retina_head.py:502-549) to expose the top-k indices it does not return
+    anchors = [head.anchor_generators[i].grid_anchors(cls[i].shape[-2:], head.anchor_strides[i])
+               for i in range(len(cls))]
+    for i in range(n_img):
+        idxs, boxes, scores = [], [], []
+        for l in range(len(cls)):
+            s = cls[l][i].permute(1, 2, 0).reshape(-1, 80).sigmoid()
+            q = iou[l][i].permute(1, 2, 0).reshape(-1).sigmoid()
+            bp = reg[l][i].permute(1, 2, 0).reshape(-1, 4)
+            s = s.pow(0.5) * q.view(-1, 1).expand(-1, 80).pow(0.5)
+            a = anchors[l]
+            if cfg.nms_pre > 0 and s.shape[0] > cfg.nms_pre:
+                _, ti = s.max(dim=1)[0].topk(cfg.nms_pre)
+            else:
+                ti = torch.arange(s.shape[0])
+            idxs.append(ti)
+            boxes.append(delta2bbox(a[ti], bp[ti], head.target_means, head.target_stds,
+                                    metas[i]["img_shape"]))
+            scores.append(s[ti])
+        b = torch.cat(boxes)
+        if case["rescale"]:
+            b /= b.new_tensor(metas[i]["scale_factor"])
+        sc = torch.cat(scores)
+        out["cand_idx_%d" % i] = torch.cat(idxs).numpy().astype(np.int32)
+        out["cand_boxes_%d" % i] = b.numpy()
+        out["cand_scores_%d" % i] = sc.numpy().astype(np.float32)
+        # cross-check: the exposed candidates reproduce the head's own result
+        pad = torch.cat([sc.new_zeros(sc.shape[0], 1), sc], dim=1)
+        d2, l2 = multiclass_nms(b, pad, cfg.score_thr, cfg.nms, cfg.max_per_img)
+        assert torch.equal(d2, res[i][0]) and torch.equal(l2, res[i][1])
+    return out
+
+
+def main():
+    head = ref_head()
+    nw = sys.modules["mmdet.ops.nms.nms_wrapper"]
+    from mmdet.core import delta2bbox
+    ref_nms_cpu = sys.modules["mmdet.ops.nms.nms_cpu"]
+
+    # ---- anchors / codec known answers ------------------------------------------------
+    kat = {}
+    for i, s in enumerate(head.anchor_strides):
+        kat["base_anchors_%d" % s] = head.anchor_generators[i].base_anchors.numpy()
+    kat["grid_s8_3x5"] = head.anchor_generators[0].grid_anchors((3, 5), 8).numpy()
+    rois, deltas = cases.codec_inputs()
+    kat["delta2bbox"] = delta2bbox(torch.from_numpy(rois), torch.from_numpy(deltas),
+                                   [0., 0., 0., 0.], [1., 1., 1., 1.], (800, 1333, 3)).numpy()
+    kat["delta2bbox_std"] = delta2bbox(torch.from_numpy(rois), torch.from_numpy(deltas),
+                                       [0.1, 0., -0.1, 0.], [0.1, 0.1, 0.2, 0.2], (300, 400, 3)).numpy()
+    np.savez_compressed(os.path.join(HERE, "kat_anchor_codec.npz"), **kat)
+
+    # ---- plain nms --------------------------------------------------------------------
+    nm = {}
+    for name, dets in cases.nms_inputs().items():
+        cases.assert_no_threshold_ties(dets, 0.5)
+        keep = ref_nms_cpu.nms(torch.from_numpy(dets), 0.5)
+        d2, k2 = nw.nms(torch.from_numpy(dets), 0.5)
+        assert torch.equal(keep, k2)
+        nm[name] = keep.numpy()
+    np.savez_compressed(os.path.join(HERE, "nms_keep.npz"), **nm)
+
+    # ---- get_bboxes cases ---------------------------------------------------------------
+    for name in cases.POSTPROC_CASES:
+        case = cases.postproc_case(name)
+        out = run_postproc_case(head, case)
+        np.savez_compressed(os.path.join(HERE, "postproc_%s.npz" % name), **out)
+        print(name, {k: v.shape for k, v in out.items() if k.startswith("dets")})
+
+
+if __name__ == "__main__":
+    main()
