@@ -1,0 +1,195 @@
+/* iou_b200.h -- C ABI of libiou_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the IoU-aware RetinaNet inference hot path of
+ * ShengkaiWu/IoU-aware-single-stage-object-detector (an mmdetection v0.6.0 fork).
+ * Each entry point names the reference interface it replaces (file:line relative
+ * to the reference tree).  Conventions:
+ *   - every pointer is a DEVICE pointer supplied by the caller unless the
+ *     parameter is documented as "host";
+ *   - the library never allocates device memory: scratch comes in through
+ *     `workspace` (size from the matching *_workspace_bytes call);
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises the host;
+ *   - return value 0 = ok, otherwise a negative code; text via iou_last_error();
+ *   - inputs are borrowed and never written.
+ */
+#ifndef IOU_B200_H_
+#define IOU_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IOU_MAX_LEVELS 8
+#define IOU_MAX_ANCHORS 16
+#define IOU_MAX_CANDIDATES 6144   /* per image (sum over levels of min(n_l, nms_pre)) */
+#define IOU_MAX_NMS_BOXES 6144    /* iou_nms: boxes per call */
+
+#define IOU_OK 0
+#define IOU_ERR_INVALID (-1)
+#define IOU_ERR_CUDA (-2)
+#define IOU_ERR_UNSUPPORTED (-3)
+#define IOU_ERR_WORKSPACE (-4)
+
+/* Text of the last error raised on the calling thread ("" if none). */
+const char* iou_last_error(void);
+/* ABI version (bumped on any signature change). */
+int iou_abi_version(void);
+
+/* ------------------------------------------------------------------ get_bboxes
+ * Static description of IoUawareRetinaHead.get_bboxes / get_bboxes_single
+ * (mmdet/models/anchor_heads/iou_aware_retina_head.py:390-564) +
+ * multiclass_nms (mmdet/core/post_processing/bbox_nms.py:6-67).               */
+typedef struct iou_postproc_cfg {
+  int32_t num_levels;                      /* FPN levels, P3..P7 = 5                         */
+  int32_t num_anchors;                     /* A = len(ratios)*len(scales) (anchor_head.py:79) */
+  int32_t num_classes;                     /* C = cls_out_channels (sigmoid: num_classes-1)   */
+  int32_t nms_pre;                         /* test_cfg.nms_pre (<=0: keep all)                */
+  int32_t max_per_img;                     /* test_cfg.max_per_img                            */
+  int32_t feat_h[IOU_MAX_LEVELS];
+  int32_t feat_w[IOU_MAX_LEVELS];
+  int32_t stride[IOU_MAX_LEVELS];          /* anchor_strides                                  */
+  float base_anchors[IOU_MAX_LEVELS][IOU_MAX_ANCHORS][4]; /* AnchorGenerator.base_anchors    */
+  float target_means[4];
+  float target_stds[4];
+  float alpha;                             /* score = cls^alpha * iou^(1-alpha); 0.5 at :510  */
+  float score_thr;                         /* test_cfg.score_thr (strict >)                   */
+  float iou_thr;                           /* test_cfg.nms.iou_thr (strict >, nms_kernel.cu:60)*/
+  float wh_ratio_clip;                     /* delta2bbox wh_ratio_clip, 16/1000               */
+} iou_postproc_cfg;
+
+/* Number of candidate rows per image that enter NMS: sum_l min(H_l*W_l*A, nms_pre). */
+int iou_postproc_num_candidates(const iou_postproc_cfg* cfg);
+size_t iou_postproc_workspace_bytes(const iou_postproc_cfg* cfg, int n_img);
+
+/* Stage 1 -- replaces iou_aware_retina_head.py:499-554 for a whole batch.
+ * cls/reg/iou: host arrays of num_levels device pointers; level l is laid out
+ * NHWC, i.e. [n_img][H_l][W_l][A*C], [..][A*4], [..][A] fp32 (== the reference's
+ * permute(1,2,0).reshape(-1,C) rows).  img_info: [n_img][8] fp32 =
+ * (img_h, img_w, sf_x1, sf_y1, sf_x2, sf_y2, 0, 0); boxes are divided by sf if
+ * rescale != 0.  Outputs: boxes [n_img][M][4]; scores_cm [n_img][C][M]
+ * (class-major); cand_idx [n_img][M] int32 level-local anchor index.          */
+int iou_decode_candidates(const iou_postproc_cfg* cfg, int n_img,
+                          const float* const* cls, const float* const* reg,
+                          const float* const* iou, const float* img_info, int rescale,
+                          float* boxes, float* scores_cm, int32_t* cand_idx,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stage 2 -- replaces multiclass_nms (bbox_nms.py:6-67) incl. the per-class
+ * nms_cuda.nms calls (ops/nms/src/nms_kernel.cu:70-131) for a whole batch.
+ * dets [n_img][max_per_img][5], labels [n_img][max_per_img] int64,
+ * counts [n_img] int32 (rows beyond counts[i] are zero).                      */
+int iou_batched_nms(const iou_postproc_cfg* cfg, int n_img, const float* boxes,
+                    const float* scores_cm, float* dets, int64_t* labels, int32_t* counts,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stage 1 + 2 == IoUawareRetinaHead.get_bboxes (iou_aware_retina_head.py:390-461). */
+int iou_get_bboxes(const iou_postproc_cfg* cfg, int n_img,
+                   const float* const* cls, const float* const* reg, const float* const* iou,
+                   const float* img_info, int rescale,
+                   float* dets, int64_t* labels, int32_t* counts,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ plain NMS
+ * Drop-in for mmdet.ops.nms.nms_cuda.nms (ops/nms/src/nms_cuda.cpp:8-13,
+ * nms_kernel.cu:70-131): dets [n][5] fp32 (x1,y1,x2,y2,score); suppress at
+ * IoU > thr; keep_idx receives the ORIGINAL indices of kept boxes in ascending
+ * order (int64, capacity n), keep_count the number kept.  n <= IOU_MAX_NMS_BOXES. */
+size_t iou_nms_workspace_bytes(int n);
+int iou_nms(const float* dets, int n, float iou_thr, int64_t* keep_idx, int32_t* keep_count,
+            void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ focal loss
+ * Drop-in for sigmoid_focal_loss_cuda.forward / .backward
+ * (ops/sigmoid_focal_loss/src/sigmoid_focal_loss.cpp:17-43,
+ *  sigmoid_focal_loss_cuda.cu:24-105).  logits [n][c] fp32, targets [n] int64
+ * (0 = background, class d <-> d+1).                                          */
+int iou_sigmoid_focal_loss_forward(const float* logits, const int64_t* targets, int n, int c,
+                                   float gamma, float alpha, float* losses, void* stream);
+int iou_sigmoid_focal_loss_backward(const float* logits, const int64_t* targets,
+                                    const float* d_losses, int n, int c, float gamma, float alpha,
+                                    float* d_logits, void* stream);
+
+/* ------------------------------------------------------------------ conv engine
+ * Replaces the F.conv2d (+BatchNorm eval, +bias, +ReLU, +residual add) calls of
+ * ResNet.forward (backbones/resnet.py:224-267,507-518), FPN.forward
+ * (necks/fpn.py:97-136) and IoUawareRetinaHead.forward_single
+ * (anchor_heads/iou_aware_retina_head.py:171-219) with one tcgen05 "tap GEMM".
+ *
+ * Activation layout ("padded rows"): a feature map of n images, H x W, Cch
+ * channels is a bf16 matrix [rows][2*Cch]; row = (img*(H+2) + y+1)*(W+2) + x+1,
+ * columns [0,Cch) hold hi = bf16(v), columns [Cch,2Cch) hold lo = bf16(v - hi);
+ * the one-pixel border rows are zero.  Several maps (FPN levels) may be
+ * concatenated as "segments", each starting at a multiple of 128 rows.
+ * Weight layout: bf16 [taps*cout_pad][2*Cin] (hi | lo), tap-major, K contiguous. */
+#define IOU_CONV_MAX_SEG 8
+#define IOU_CONV_MAX_TAPS 9
+#define IOU_CONV_MAX_SRC 4
+
+typedef struct iou_conv_segment {
+  int32_t row_start;     /* first row of the segment (multiple of 128)           */
+  int32_t n_img, h, w;   /* unpadded output geometry of the segment               */
+} iou_conv_segment;
+
+enum { IOU_OUT_PADDED_BF16X2 = 0,  /* padded-rows bf16 hi|lo, same geometry           */
+       IOU_OUT_DENSE_F32 = 1 };    /* fp32 [n][h][w][cout] per segment (head outputs)  */
+enum { IOU_RES_NONE = 0, IOU_RES_SAME = 1, IOU_RES_UPSAMPLE2 = 2 };
+
+typedef struct iou_conv_desc {
+  int32_t cin, cout, cout_pad, block_n;     /* cin % 64 == 0; cout_pad % block_n == 0    */
+  int32_t num_taps;
+  int32_t tap_src[IOU_CONV_MAX_TAPS];       /* which source matrix a tap reads           */
+  int32_t tap_dy[IOU_CONV_MAX_TAPS];        /* row offset = dy*(w+2) + dx per segment    */
+  int32_t tap_dx[IOU_CONV_MAX_TAPS];
+  int32_t num_src;
+  const void* src[IOU_CONV_MAX_SRC];        /* bf16 [src_rows][2*cin]                    */
+  int64_t src_rows;
+  const void* weight;                       /* bf16 [num_taps*cout_pad][2*cin]           */
+  const float* scale;                       /* [cout_pad] per-channel multiplier (BN fold) or NULL */
+  const float* shift;                       /* [cout_pad] bias / BN shift or NULL        */
+  int32_t relu;
+  int32_t res_mode;
+  const void* residual;                     /* bf16 padded rows [*][2*cout]              */
+  iou_conv_segment res_seg[IOU_CONV_MAX_SEG]; /* geometry of residual (UPSAMPLE2: coarse map) */
+  int32_t out_mode;
+  void* out;                                /* PADDED: bf16 [rows][2*cout]               */
+  void* out_dense[IOU_CONV_MAX_SEG];        /* DENSE: fp32 base pointer per segment      */
+  int32_t dense_split;                      /* DENSE: columns >= split go to out_dense2  */
+  void* out_dense2[IOU_CONV_MAX_SEG];
+  int32_t num_seg;
+  iou_conv_segment seg[IOU_CONV_MAX_SEG];
+  int32_t passes;                           /* 3 = hi*hi+hi*lo+lo*hi (fp32-grade), 1 = bf16 */
+} iou_conv_desc;
+
+typedef struct iou_conv_plan iou_conv_plan;
+/* Validates the descriptor, encodes the TMA tensor maps, sizes the launch. */
+int iou_conv_plan_create(const iou_conv_desc* desc, iou_conv_plan** plan_out);
+int iou_conv_run(const iou_conv_plan* plan, void* stream);
+void iou_conv_plan_destroy(iou_conv_plan* plan);
+/* 2*MAC flops the plan performs on real (non-padding) outputs, for rooflines. */
+double iou_conv_plan_flops(const iou_conv_plan* plan);
+
+/* ------------------------------------------------------------------ layout kernels
+ * (elementwise, HBM-bound helpers around the conv engine)                      */
+/* NCHW fp32 -> padded rows bf16 hi|lo. */
+int iou_pack_nchw(const float* src, int n, int c, int h, int w, void* dst, int64_t dst_row_start,
+                  void* stream);
+/* padded rows bf16 hi|lo -> NCHW fp32 (hi + lo). */
+int iou_unpack_nchw(const void* src, int64_t src_row_start, int n, int c, int h, int w, float* dst,
+                    void* stream);
+/* Stem im2col (resnet.py:454-462, conv 7x7 s2 p3 on 3 channels): NCHW fp32 image
+ * -> padded rows [n][(ho+2)][(wo+2)][2*kpad] with k = (r*7+s)*3 + c, zero padded to kpad. */
+int iou_im2col_stem(const float* img, int n, int h, int w, int kpad, void* dst, void* stream);
+/* 3x3 stride-2 pad-1 max pool (resnet.py:466) on padded rows (inputs >= 0). */
+int iou_maxpool3x3s2(const void* src, int n, int c, int h, int w, void* dst, void* stream);
+/* Splits a padded-rows map into the 4 stride-2 phase maps laid out in the OUTPUT
+ * geometry ((h+1)/2 x (w+1)/2): phase[py][px][u][v] = in_padded[2(u-1)+py][2(v-1)+px]. */
+int iou_phase_split(const void* src, int n, int c, int h, int w, void* const* dst4,
+                    int phase_mask, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* IOU_B200_H_ */

@@ -1,0 +1,47 @@
+"""multiclass_nms with the reference's signature (mmdet/core/post_processing/bbox_nms.py:6-67),
+executed as ONE batched launch pair (class_nms + final_select) instead of an 80-iteration
+Python loop with a device->host sync per class."""
+import torch
+
+from .. import postproc as PP
+
+_ws_cache = {}
+
+
+def multiclass_nms(multi_bboxes, multi_scores, score_thr, nms_cfg, max_num=-1, score_factors=None):
+    """multi_bboxes (n,4); multi_scores (n, 1+C) with background in column 0.  Returns
+    (dets (k,5), labels (k,) int64), class-major / row-minor order, score-sorted if k would
+    exceed max_num."""
+    if not multi_bboxes.is_cuda:
+        raise RuntimeError("multiclass_nms: libiou_b200 handles CUDA tensors only (no CPU fallback)")
+    if multi_bboxes.shape[1] != 4:
+        raise NotImplementedError("per-class boxes (n, C*4) are not on the RetinaNet path")
+    cfg_ = dict(nms_cfg)
+    nms_type = cfg_.pop('type', 'nms')
+    if nms_type != 'nms':
+        raise NotImplementedError("nms type '%s' is outside the accelerated path" % nms_type)
+    iou_thr = cfg_.get('iou_thr', 0.5)
+    n, c1 = multi_scores.shape
+    C = c1 - 1
+    if n == 0 or C == 0:
+        return multi_bboxes.new_zeros((0, 5)), multi_bboxes.new_zeros((0,), dtype=torch.long)
+    scores = multi_scores[:, 1:]
+    if score_factors is not None:
+        scores = scores * score_factors[:, None]
+    if max_num is None or max_num <= 0:
+        raise NotImplementedError("max_num <= 0 (keep everything) is not supported by the batched kernel")
+    Cp = (C + 3) // 4 * 4                      # kernel needs a multiple of 4 classes; pad with zeros
+    scores_cm = multi_bboxes.new_zeros((1, Cp, n))
+    scores_cm[0, :C] = scores.t()
+    key = (n, Cp, float(score_thr), float(iou_thr), int(max_num), multi_bboxes.device)
+    if key not in _ws_cache:
+        # a synthetic single-level description with exactly n candidate rows
+        base = [torch.zeros(1, 4)]
+        cfg = PP.make_cfg([(1, n)], [1], base, Cp, -1, max_num, score_thr, iou_thr)
+        _ws_cache.clear()
+        _ws_cache[key] = PP.PostprocWorkspace(cfg, 1, multi_bboxes.device)
+    wsp = _ws_cache[key]
+    with torch.cuda.device(multi_bboxes.device):
+        dets, labels, counts = PP.batched_nms(wsp, multi_bboxes.float().reshape(1, n, 4), scores_cm)
+    k = int(counts.item())
+    return dets[0, :k].clone(), labels[0, :k].clone()

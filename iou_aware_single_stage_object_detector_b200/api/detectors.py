@@ -1,0 +1,165 @@
+"""Detector shell with the reference's interface (mmdet/models/detectors/{base,single_stage,
+retinanet}.py): BaseDetector.forward -> forward_test -> simple_test = extract_feat + bbox_head +
+get_bboxes + bbox2result.  ``simple_test_batch`` is the batched entry point (the reference asserts
+one image per GPU, base.py:97-98) and runs ONE fused plan: backbone, neck, head and get_bboxes as a
+fixed launch sequence (optionally replayed as a CUDA graph) with a single device->host read at the end.
+"""
+import logging
+
+import torch
+import torch.nn as nn
+
+from .. import engine as E
+from .. import postproc as PP
+from . import builder
+from .engine_cache import PlanCache, cuda_state_dict, param_stamp, require_cuda
+from .registry import DETECTORS
+from .transforms import bbox2result
+
+
+class BaseDetector(nn.Module):
+    def __init__(self):
+        super(BaseDetector, self).__init__()
+
+    @property
+    def with_neck(self):
+        return hasattr(self, 'neck') and self.neck is not None
+
+    @property
+    def with_bbox(self):
+        return hasattr(self, 'bbox_head') and self.bbox_head is not None
+
+    def init_weights(self, pretrained=None):
+        if pretrained is not None:
+            logging.getLogger().info('load model from: {}'.format(pretrained))
+
+    def forward_test(self, imgs, img_metas, gt_bboxes, gt_labels, **kwargs):
+        for var, name in [(imgs, 'imgs'), (img_metas, 'img_metas')]:
+            if not isinstance(var, list):
+                raise TypeError('{} must be a list, but got {}'.format(name, type(var)))
+        num_augs = len(imgs)
+        if num_augs != len(img_metas):
+            raise ValueError('num of augmentations ({}) != num of image meta ({})'.format(
+                len(imgs), len(img_metas)))
+        imgs_per_gpu = imgs[0].size(0)
+        assert imgs_per_gpu == 1
+        if num_augs == 1:
+            return self.simple_test(imgs[0], img_metas[0], gt_bboxes[0], gt_labels[0], **kwargs)
+        return self.aug_test(imgs, img_metas, **kwargs)
+
+    def forward(self, img, img_meta, return_loss=True, **kwargs):
+        if return_loss:
+            return self.forward_train(img, img_meta, **kwargs)
+        return self.forward_test(img, img_meta, **kwargs)
+
+
+class FusedPlan(object):
+    """backbone + neck + head + get_bboxes for one (N,3,H,W) input shape."""
+
+    def __init__(self, det, shape, device, rescale, use_graph=True, passes=3):
+        n, _, h, w = shape
+        self.device = torch.device(device)
+        self.img = torch.empty(shape, dtype=torch.float32, device=self.device)
+        self.img_info = torch.zeros(n, 8, dtype=torch.float32, device=self.device)
+        self.rescale = rescale
+        eng = E.Engine(self.device, passes=passes)
+        sd = cuda_state_dict(det, self.device)
+        feats = det.backbone.plan_into(eng, sd, self.img, prefix="backbone.")
+        F = det.neck.plan_into(eng, sd, feats, prefix="neck.")
+        self.outs = det.bbox_head.plan_into(eng, sd, F, prefix="bbox_head.")
+        self.eng = eng
+        sizes = [tuple(t.shape[-2:]) for t in self.outs[0]]
+        self.wsp = det.bbox_head.postproc_workspace(sizes, n, det.test_cfg, self.device)
+        self.graph = None
+        self.use_graph = use_graph
+        self.conv_flops = eng.flops
+        self.launches = eng.num_launches() + 5
+
+    def _launch(self):
+        self.eng.run()
+        PP.get_bboxes_device(self.wsp, self.outs[0], self.outs[1], self.outs[2], self.img_info, self.rescale)
+
+    def run(self):
+        """Enqueue one pass on the current stream (inputs: self.img, self.img_info)."""
+        with torch.cuda.device(self.device):
+            if not self.use_graph:
+                self._launch()
+            elif self.graph is None:
+                self._launch()                       # warm-up: sets function attributes, loads modules
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch()
+                self.graph = g
+                g.replay()
+            else:
+                self.graph.replay()
+                E.L.launch_count += self.launches
+        return self.wsp.dets, self.wsp.labels, self.wsp.counts
+
+
+@DETECTORS.register_module
+class SingleStageDetector(BaseDetector):
+    def __init__(self, backbone, neck=None, bbox_head=None, train_cfg=None, test_cfg=None, pretrained=None):
+        super(SingleStageDetector, self).__init__()
+        self.backbone = builder.build_backbone(backbone)
+        if neck is not None:
+            self.neck = builder.build_neck(neck)
+        self.bbox_head = builder.build_head(bbox_head)
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self._fused = PlanCache(max_plans=2)
+        self.use_cuda_graph = True
+        self.passes = 3
+        self.init_weights(pretrained=pretrained)
+
+    def init_weights(self, pretrained=None):
+        super(SingleStageDetector, self).init_weights(pretrained)
+        self.backbone.init_weights(pretrained=pretrained)
+        if self.with_neck:
+            if isinstance(self.neck, nn.Sequential):
+                for m in self.neck:
+                    m.init_weights()
+            else:
+                self.neck.init_weights()
+        self.bbox_head.init_weights()
+
+    def extract_feat(self, img):
+        x = self.backbone(img)
+        if self.with_neck:
+            x = self.neck(x)
+        return x
+
+    def forward_train(self, img, img_metas, gt_bboxes, gt_labels, gt_bboxes_ignore=None):
+        raise NotImplementedError("training is outside the accelerated inference path")
+
+    def fused_plan(self, shape, device, rescale):
+        key = (tuple(shape), str(device), bool(rescale), param_stamp(self), self.use_cuda_graph, self.passes)
+        return self._fused.get(key, lambda: FusedPlan(self, shape, device, rescale, self.use_cuda_graph,
+                                                      self.passes))
+
+    def detect_device(self, img, img_metas, rescale=False):
+        """Batched, asynchronous: (dets [n,K,5], labels [n,K] int64, counts [n] int32) on the device."""
+        require_cuda(img, "SingleStageDetector")
+        plan = self.fused_plan(img.shape, img.device, rescale)
+        plan.img.copy_(img, non_blocking=True)
+        plan.img_info.copy_(PP.make_img_info(img_metas, "cpu"), non_blocking=True)
+        return plan.run()
+
+    def simple_test_batch(self, img, img_metas, gt_bboxes=None, gt_labels=None, rescale=False):
+        """Batched simple_test: list (per image) of per-class ndarray lists."""
+        dets, labels, counts = self.detect_device(img, img_metas, rescale)
+        return [bbox2result(d, l, self.bbox_head.num_classes)
+                for d, l in PP.split_results(dets, labels, counts)]
+
+    def simple_test(self, img, img_meta, gt_bboxes, gt_labels, rescale=False):
+        """Reference signature (single_stage.py:64-96): one image in, bbox_results[0] out."""
+        return self.simple_test_batch(img, img_meta, gt_bboxes, gt_labels, rescale)[0]
+
+    def aug_test(self, imgs, img_metas, rescale=False):
+        raise NotImplementedError
+
+
+@DETECTORS.register_module
+class RetinaNet(SingleStageDetector):
+    def __init__(self, backbone, neck, bbox_head, train_cfg=None, test_cfg=None, pretrained=None):
+        super(RetinaNet, self).__init__(backbone, neck, bbox_head, train_cfg, test_cfg, pretrained)

@@ -1,0 +1,143 @@
+"""IoUawareRetinaHead with the reference's constructor, state_dict keys and forward/get_bboxes
+signatures (mmdet/models/anchor_heads/iou_aware_retina_head.py:64-219,390-564).
+
+forward   : one conv-engine plan for ALL levels (weights are shared across levels, so each of the
+            8 tower convs + 2 output GEMMs is a single persistent tcgen05 launch over every level).
+get_bboxes: five kernels for the whole batch (max-score, top-k, gather/decode, class NMS, final
+            select) instead of per-image / per-level / per-class Python loops.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import engine as E
+from .. import postproc as PP
+from .anchor_head import AnchorHead
+from .conv_module import ConvModule
+from .engine_cache import PlanCache, cuda_state_dict, param_stamp, require_cuda
+from .registry import HEADS
+from .weight_init import bias_init_with_prob, normal_init
+
+
+@HEADS.register_module
+class IoUawareRetinaHead(AnchorHead):
+    def __init__(self, num_classes, in_channels, stacked_convs=4, octave_base_scale=4, scales_per_octave=3,
+                 conv_cfg=None, norm_cfg=None,
+                 loss_iou=dict(type='GHMIoU', bins=30, momentum=0.75, use_sigmoid=True, loss_weight=1.0),
+                 **kwargs):
+        self.stacked_convs = stacked_convs
+        self.octave_base_scale, self.scales_per_octave = octave_base_scale, scales_per_octave
+        self.conv_cfg, self.norm_cfg = conv_cfg, norm_cfg
+        octave_scales = np.array([2 ** (i / scales_per_octave) for i in range(scales_per_octave)])
+        super(IoUawareRetinaHead, self).__init__(num_classes, in_channels,
+                                                 anchor_scales=octave_scales * octave_base_scale, **kwargs)
+        self.alpha = 0.5                      # hard-coded at iou_aware_retina_head.py:510
+        self._plans = PlanCache()
+        self._post = {}
+
+    def _init_layers(self):
+        self.cls_convs, self.reg_convs = nn.ModuleList(), nn.ModuleList()
+        for i in range(self.stacked_convs):
+            chn = self.in_channels if i == 0 else self.feat_channels
+            self.cls_convs.append(ConvModule(chn, self.feat_channels, 3, stride=1, padding=1,
+                                             conv_cfg=self.conv_cfg, norm_cfg=self.norm_cfg))
+            self.reg_convs.append(ConvModule(chn, self.feat_channels, 3, stride=1, padding=1,
+                                             conv_cfg=self.conv_cfg, norm_cfg=self.norm_cfg))
+        self.retina_cls = nn.Conv2d(self.feat_channels, self.num_anchors * self.cls_out_channels, 3, padding=1)
+        self.retina_reg = nn.Conv2d(self.feat_channels, self.num_anchors * 4, 3, padding=1)
+        self.shared_conv = 4                  # :122 -- the IoU branch reads the last reg-tower feature
+        self.use_feature_alignment = False    # :139
+        self.retina_iou = nn.Conv2d(self.feat_channels, self.num_anchors, 3, padding=1)
+
+    def init_weights(self):
+        for m in self.cls_convs:
+            normal_init(m.conv, std=0.01)
+        for m in self.reg_convs:
+            normal_init(m.conv, std=0.01)
+        normal_init(self.retina_cls, std=0.01, bias=bias_init_with_prob(0.01))
+        normal_init(self.retina_reg, std=0.01)
+        normal_init(self.retina_iou, std=0.01)
+
+    # ---- forward -----------------------------------------------------------------------------
+    def plan_into(self, eng, sd, F, prefix=""):
+        if self.norm_cfg is not None:
+            raise NotImplementedError("normalised head towers are not planned")
+        if not self.use_sigmoid_cls:
+            raise NotImplementedError("softmax classification is not on the IoU-aware RetinaNet path")
+        return eng.add_head(sd, F, prefix=prefix, stacked=self.stacked_convs, num_anchors=self.num_anchors,
+                            num_classes=self.cls_out_channels)
+
+    def forward(self, feats):
+        """feats: tuple of 5 (N,256,H,W) tensors -> (list5 cls, list5 reg, list5 iou) with logical shapes
+        (N, A*C, H, W), (N, A*4, H, W), (N, A, H, W) (anchor_head.py:102-103); storage is NHWC."""
+        for t in feats:
+            require_cuda(t, "IoUawareRetinaHead.forward")
+        feats = [t.float().contiguous() for t in feats]
+        dev = feats[0].device
+        key = (tuple(tuple(t.shape) for t in feats), dev, param_stamp(self))
+
+        def build():
+            eng = E.Engine(dev)
+            ins = [torch.empty_like(t) for t in feats]
+            F = E.FlatMap([(t.shape[0], t.shape[2], t.shape[3]) for t in ins], ins[0].shape[1], dev)
+            for s, t in enumerate(ins):
+                n, c, h, w = t.shape
+                rs = F.segs[s][0]
+                lib, tp, fp = eng.lib, t.data_ptr(), F.ptr
+                eng.ops.append(("pack", lambda st, tp=tp, n=n, c=c, h=h, w=w, rs=rs, fp=fp, lib=lib:
+                                E.L.check(lib.iou_pack_nchw(tp, n, c, h, w, fp, rs, st))))
+            outs = self.plan_into(eng, cuda_state_dict(self, dev), F)
+            return eng, ins, outs
+        eng, ins, outs = self._plans.get(key, build)
+        for a, b in zip(ins, feats):
+            a.copy_(b)
+        with torch.cuda.device(dev):
+            eng.run()
+        return outs
+
+    def forward_single(self, x):
+        c, r, q = self.forward((x,))
+        return c[0], r[0], q[0]
+
+    # ---- get_bboxes --------------------------------------------------------------------------
+    def postproc_workspace(self, featmap_sizes, n_img, cfg, device):
+        key = (tuple(featmap_sizes), n_img, cfg.get('nms_pre', -1), cfg['score_thr'],
+               cfg['nms'].get('iou_thr', 0.5), cfg['max_per_img'], str(device))
+        if key not in self._post:
+            nms_cfg = dict(cfg['nms'])
+            if nms_cfg.pop('type', 'nms') != 'nms':
+                raise NotImplementedError("only nms type 'nms' is on the accelerated path")
+            pcfg = PP.make_cfg(featmap_sizes, self.anchor_strides,
+                               [g.base_anchors for g in self.anchor_generators], self.cls_out_channels,
+                               cfg.get('nms_pre', -1), cfg['max_per_img'], cfg['score_thr'],
+                               nms_cfg.get('iou_thr', 0.5), self.target_means, self.target_stds, self.alpha)
+            self._post.clear()
+            self._post[key] = PP.PostprocWorkspace(pcfg, n_img, device)
+        return self._post[key]
+
+    def get_bboxes_device(self, cls_scores, bbox_preds, iou_preds, img_metas, cfg, rescale=False,
+                          img_info=None):
+        """Asynchronous form: returns padded device tensors (dets [n,K,5], labels [n,K], counts [n])."""
+        assert len(cls_scores) == len(bbox_preds) == len(iou_preds)
+        n_img = len(img_metas)
+        assert cls_scores[0].shape[0] == n_img
+        sizes = [tuple(t.shape[-2:]) for t in cls_scores]
+        dev = cls_scores[0].device
+        wsp = self.postproc_workspace(sizes, n_img, cfg, dev)
+        if img_info is None:
+            img_info = PP.make_img_info(img_metas, dev)
+        with torch.cuda.device(dev):
+            return PP.get_bboxes_device(wsp, cls_scores, bbox_preds, iou_preds, img_info, rescale)
+
+    def get_bboxes(self, cls_scores, bbox_preds, iou_preds, gt_bboxes, gt_labels, img_metas, cfg,
+                   rescale=False):
+        """Same signature/return as the reference (:390-461).  gt_* are accepted and ignored (the
+        reference only feeds them to a discarded diagnostic, :517-524)."""
+        for t in cls_scores:
+            require_cuda(t, "IoUawareRetinaHead.get_bboxes")
+        dets, labels, counts = self.get_bboxes_device(cls_scores, bbox_preds, iou_preds, img_metas, cfg,
+                                                      rescale)
+        return [(d.clone(), l.clone()) for d, l in PP.split_results(dets, labels, counts)]
+
+
+HEADS.register_module(IoUawareRetinaHead, name='IoUAwareRetinaHead')   # BASELINE.json spelling

@@ -1,0 +1,130 @@
+"""``mmdet.ops`` surface backed by libiou_b200 (mmdet/ops/__init__.py:1-19).
+
+nms                -> iou_nms                (ops/nms/nms_wrapper.py:8-49, nms_kernel.cu:70-131)
+sigmoid_focal_loss -> iou_sigmoid_focal_loss_* (ops/sigmoid_focal_loss/functions/sigmoid_focal_loss.py:8-42)
+soft_nms           -> not on the north-star path: importable, raises when called.
+There is no CPU implementation here: CPU tensors raise (the CPU path is the oracle's job).
+"""
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from .. import lib as L
+from .. import postproc as PP
+
+
+def _nms_cpu_unavailable(dets, iou_thr):
+    raise RuntimeError("libiou_b200 implements nms for CUDA tensors only (no CPU fallback); "
+                       "pass a CUDA tensor or a device_id")
+
+
+nms_cuda = types.SimpleNamespace(nms=PP.nms_cuda)
+nms_cpu = types.SimpleNamespace(nms=_nms_cpu_unavailable)
+
+
+def nms(dets, iou_thr, device_id=None):
+    """Same contract as nms_wrapper.nms: returns (dets[inds, :], inds), inds ascending."""
+    if isinstance(dets, torch.Tensor):
+        is_numpy, dets_th = False, dets
+    elif isinstance(dets, np.ndarray):
+        is_numpy = True
+        device = 'cpu' if device_id is None else 'cuda:{}'.format(device_id)
+        dets_th = torch.from_numpy(dets).to(device)
+    else:
+        raise TypeError('dets must be either a Tensor or numpy array, but got {}'.format(type(dets)))
+    if dets_th.shape[0] == 0:
+        inds = dets_th.new_zeros(0, dtype=torch.long)
+    elif dets_th.is_cuda:
+        inds = nms_cuda.nms(dets_th, iou_thr)
+    else:
+        inds = nms_cpu.nms(dets_th, iou_thr)
+    if is_numpy:
+        inds = inds.cpu().numpy()
+    return dets[inds, :], inds
+
+
+def soft_nms(dets, iou_thr, method='linear', sigma=0.5, min_score=1e-3):
+    if method not in ('linear', 'gaussian'):
+        raise ValueError('Invalid method for SoftNMS: {}'.format(method))
+    raise NotImplementedError("soft_nms is outside the accelerated path (SURVEY.md 8(f) rank 3)")
+
+
+class _FocalLossCuda(object):
+    """Stands where the reference's pybind module sigmoid_focal_loss_cuda stood."""
+
+    @staticmethod
+    def forward(logits, targets, num_classes, gamma, alpha):
+        if not logits.is_cuda:
+            raise RuntimeError("sigmoid_focal_loss_cuda: logits must be a CUDA tensor")
+        x = logits.detach().float().contiguous()
+        t = targets.detach().long().contiguous()
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            L.check(L.load().iou_sigmoid_focal_loss_forward(x.data_ptr(), t.data_ptr(), x.shape[0],
+                                                            num_classes, gamma, alpha, out.data_ptr(),
+                                                            L.stream_ptr()))
+        L.launch_count += 1
+        return out
+
+    @staticmethod
+    def backward(logits, targets, d_losses, num_classes, gamma, alpha):
+        x = logits.detach().float().contiguous()
+        t = targets.detach().long().contiguous()
+        g = d_losses.detach().float().contiguous()
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            L.check(L.load().iou_sigmoid_focal_loss_backward(x.data_ptr(), t.data_ptr(), g.data_ptr(),
+                                                             x.shape[0], num_classes, gamma, alpha,
+                                                             out.data_ptr(), L.stream_ptr()))
+        L.launch_count += 1
+        return out
+
+
+sigmoid_focal_loss_cuda = _FocalLossCuda
+
+
+class SigmoidFocalLossFunction(Function):
+    @staticmethod
+    def forward(ctx, input, target, gamma=2.0, alpha=0.25, reduction='mean'):
+        ctx.save_for_backward(input, target)
+        ctx.num_classes, ctx.gamma, ctx.alpha, ctx.reduction = input.shape[1], gamma, alpha, reduction
+        loss = sigmoid_focal_loss_cuda.forward(input, target, input.shape[1], gamma, alpha)
+        if reduction == 'none':
+            return loss
+        if reduction == 'mean':
+            return loss.mean()
+        if reduction == 'sum':
+            return loss.sum()
+        raise ValueError(reduction)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_loss):
+        input, target = ctx.saved_tensors
+        if ctx.reduction == 'none':
+            d = d_loss.contiguous()
+        else:
+            scale = 1.0 / input.numel() if ctx.reduction == 'mean' else 1.0
+            d = (d_loss * scale).expand_as(input).contiguous()
+        d_input = sigmoid_focal_loss_cuda.backward(input, target, d, ctx.num_classes, ctx.gamma, ctx.alpha)
+        return d_input, None, None, None, None
+
+
+sigmoid_focal_loss = SigmoidFocalLossFunction.apply
+
+
+class SigmoidFocalLoss(nn.Module):
+    def __init__(self, gamma, alpha):
+        super(SigmoidFocalLoss, self).__init__()
+        self.gamma, self.alpha = gamma, alpha
+
+    def forward(self, logits, targets):
+        assert logits.is_cuda
+        return sigmoid_focal_loss(logits, targets, self.gamma, self.alpha, 'none').sum()
+
+    def __repr__(self):
+        return "{}(gamma={}, alpha={})".format(self.__class__.__name__, self.gamma, self.alpha)

@@ -1,0 +1,502 @@
+// tcgen05 "tap GEMM" convolution for sm_100a.
+//
+// One persistent, warp-specialised kernel computes, for every 128-row tile of a padded-rows
+// output map and every BLOCK_N-wide slice of output channels,
+//     acc[m, n] = sum_taps sum_k  A_tap[m + off_tap, k] * W_tap[n, k]
+// where A_tap is a 2-D view [rows][2*Cin] (bf16 hi | lo) of an activation map in the
+// padded-rows layout (include/iou_b200.h) and off_tap = dy*(W+2)+dx is a constant row offset:
+// a 3x3 convolution is nine shifted TMA box loads of the SAME matrix, no im2col buffer exists.
+// Stride-2 convolutions read the four phase maps written by iou_phase_split, which turns
+// them into the same constant-offset form.  Out-of-range rows are zero-filled by TMA.
+//
+//   warp 0      : TMA producer (cp.async.bulk.tensor.2d, 128B swizzle, mbarrier complete_tx)
+//   warp 1      : TMEM allocator + tcgen05.mma issuer (kind::f16, bf16 x bf16 -> fp32 in TMEM)
+//   warps 2..5  : epilogue (tcgen05.ld -> scale/shift (BN fold or bias) -> +residual -> ReLU
+//                 -> bf16 hi|lo padded rows, or dense fp32 NHWC for the head outputs)
+// fp32-grade accuracy comes from three bf16 MMAs per K step (hi*hi + hi*lo + lo*hi) into the
+// same fp32 accumulator; `passes = 1` runs plain bf16.  Two TMEM accumulator stages let the
+// epilogue of tile i overlap the MMAs of tile i+1.
+//
+// Replaces the F.conv2d / cuDNN calls of mmdet/models/backbones/resnet.py:224-267,
+// mmdet/models/necks/fpn.py:97-136, mmdet/models/anchor_heads/iou_aware_retina_head.py:171-219.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <new>
+#include "common.cuh"
+
+namespace iou {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                  // bf16 elements = one 128-byte swizzle row
+constexpr int kATileBytes = kBlockM * kBlockK * 2;   // 16 KiB
+constexpr int kNumThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr int kAccStride = 256;              // TMEM columns between the two accumulator stages
+constexpr int kTmemCols = 512;
+constexpr int kSmemBudget = 227 * 1024;
+constexpr int kCtrlBytes = 1024;
+
+struct SegDev { int row_start, n_img, h, w; };
+
+struct ConvParams {
+  CUtensorMap tmap_src[IOU_CONV_MAX_SRC];
+  CUtensorMap tmap_w;
+  int cin, cout, cout_pad, block_n, num_taps, k_slabs, passes;
+  int tap_src[IOU_CONV_MAX_TAPS], tap_dy[IOU_CONV_MAX_TAPS], tap_dx[IOU_CONV_MAX_TAPS];
+  int num_seg;
+  SegDev seg[IOU_CONV_MAX_SEG];
+  int seg_tile_off[IOU_CONV_MAX_SEG + 1];
+  int num_m_tiles, num_n_tiles, total_tiles;
+  int num_stages, stage_bytes, b_tile_bytes;
+  const float* scale;
+  const float* shift;
+  int relu, res_mode;
+  const __nv_bfloat16* residual;
+  SegDev res_seg[IOU_CONV_MAX_SEG];
+  int out_mode;
+  __nv_bfloat16* out;
+  float* out_dense[IOU_CONV_MAX_SEG];
+  float* out_dense2[IOU_CONV_MAX_SEG];
+  int dense_split;
+  unsigned int idesc;
+};
+
+// ------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug must surface as a trapped launch (an error the host sees), never
+// as a hung GPU.  The bound (~4 s of wall clock) is far above any legitimate wait in this kernel.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3ffu) == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 4000000000ull) {
+        printf("conv_tap_gemm_kernel: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n",
+               (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tmap, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 | LBO(16B)>>4 <<16 | SBO(1024B: 8 rows x 128B)>>4 <<32 | version=1 <<46 | SWIZZLE_128B(2) <<61
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// ------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __grid_constant__ ConvParams P) {
+  extern __shared__ unsigned char smem_dyn[];
+  // 1024-byte alignment is required by the 128B swizzle atoms
+  const uint32_t raw = smem_u32(smem_dyn);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  unsigned char* ctrl = smem_dyn + (base - raw);
+  const uint32_t ctrl_addr = base;
+  const uint32_t tiles_addr = base + kCtrlBytes;
+  // control block: full[8] @0, empty[8] @64, tfull[2] @128, tempty[2] @144, tmem ptr @160
+  const uint32_t bar_full = ctrl_addr, bar_empty = ctrl_addr + 64, bar_tfull = ctrl_addr + 128,
+                 bar_tempty = ctrl_addr + 144;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(ctrl + 160);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < P.num_stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int i = 0; i < IOU_CONV_MAX_SRC; ++i)
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tmap_src[i]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tmap_w) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(ctrl_addr + 160), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int k_iters = P.num_taps * P.k_slabs;
+  const uint32_t a_lo_off = kATileBytes;
+  const uint32_t b_hi_off = (P.passes == 3) ? 2 * kATileBytes : kATileBytes;
+  const uint32_t b_lo_off = b_hi_off + P.b_tile_bytes;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / P.num_n_tiles, n_tile = tile - m_tile * P.num_n_tiles;
+        int s = 0;
+        while (m_tile >= P.seg_tile_off[s + 1]) ++s;
+        const int row0 = P.seg[s].row_start + (m_tile - P.seg_tile_off[s]) * kBlockM;
+        const int wp = P.seg[s].w + 2;
+        for (int t = 0; t < P.num_taps; ++t) {
+          const int arow = row0 + P.tap_dy[t] * wp + P.tap_dx[t];
+          const int wrow = t * P.cout_pad + n_tile * P.block_n;
+          const CUtensorMap* tm = &P.tmap_src[P.tap_src[t]];
+          for (int ks = 0; ks < P.k_slabs; ++ks) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+            const uint32_t fb = bar_full + 8 * stage;
+            const uint32_t sa = tiles_addr + stage * P.stage_bytes;
+            mbar_expect_tx(fb, (uint32_t)P.stage_bytes);
+            tma_load_2d(tm, fb, sa, ks * kBlockK, arow);
+            tma_load_2d(&P.tmap_w, fb, sa + b_hi_off, ks * kBlockK, wrow);
+            if (P.passes == 3) {
+              tma_load_2d(tm, fb, sa + a_lo_off, P.cin + ks * kBlockK, arow);
+              tma_load_2d(&P.tmap_w, fb, sa + b_lo_off, P.cin + ks * kBlockK, wrow);
+            }
+            if (++stage == P.num_stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
+      for (int ki = 0; ki < k_iters; ++ki) {
+        mbar_wait(bar_full + 8 * stage, phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = tiles_addr + stage * P.stage_bytes;
+#pragma unroll
+          for (int kk = 0; kk < kBlockK / 16; ++kk) {
+            const uint64_t a_hi = umma_desc_sw128(sa + kk * 32);
+            const uint64_t b_hi = umma_desc_sw128(sa + b_hi_off + kk * 32);
+            tc_mma_bf16(d_tmem, a_hi, b_hi, P.idesc, (ki > 0 || kk > 0) ? 1u : 0u);
+            if (P.passes == 3) {
+              const uint64_t a_lo = umma_desc_sw128(sa + a_lo_off + kk * 32);
+              const uint64_t b_lo = umma_desc_sw128(sa + b_lo_off + kk * 32);
+              tc_mma_bf16(d_tmem, a_hi, b_lo, P.idesc, 1u);
+              tc_mma_bf16(d_tmem, a_lo, b_hi, P.idesc, 1u);
+            }
+          }
+          tc_commit(bar_empty + 8 * stage);            // frees the smem stage when the MMAs retire
+          if (ki == k_iters - 1) tc_commit(bar_tfull + 8 * acc);   // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == P.num_stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    // =============================== epilogue ===============================
+    const int lane_group = warp & 3;                      // TMEM lanes 32*lane_group .. +31
+    const int m_local = lane_group * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int m_tile = tile / P.num_n_tiles, n_tile = tile - m_tile * P.num_n_tiles;
+      int s = 0;
+      while (m_tile >= P.seg_tile_off[s + 1]) ++s;
+      const SegDev sg = P.seg[s];
+      const int grow = sg.row_start + (m_tile - P.seg_tile_off[s]) * kBlockM + m_local;
+      const int wp = sg.w + 2, plane = (sg.h + 2) * wp;
+      const int rel = grow - sg.row_start;
+      const int img = rel / plane, rem = rel - img * plane;
+      const int yp = rem / wp, xp = rem - yp * wp;
+      const bool interior = (img < sg.n_img) && (yp >= 1) && (yp <= sg.h) && (xp >= 1) && (xp <= sg.w);
+      const __nv_bfloat16* res_row = nullptr;
+      if (P.res_mode == IOU_RES_SAME) {
+        res_row = P.residual + (size_t)grow * (2 * P.cout);
+      } else if (P.res_mode == IOU_RES_UPSAMPLE2 && interior) {
+        const SegDev rs = P.res_seg[s];
+        const int ry = ((yp - 1) >> 1) + 1, rx = ((xp - 1) >> 1) + 1;
+        const size_t rrow = (size_t)rs.row_start + ((size_t)img * (rs.h + 2) + ry) * (rs.w + 2) + rx;
+        res_row = P.residual + rrow * (2 * P.cout);
+      }
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(acc * kAccStride);
+      const int n_chunks = P.block_n >> 4;
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        uint32_t v[16];
+        tc_ld16(t_row + ch * 16, v);
+        tc_wait_ld();
+        const int c0 = n_tile * P.block_n + ch * 16;      // first output channel of this chunk
+        float f[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          float x = __uint_as_float(v[q]);
+          if (P.scale) x *= __ldg(P.scale + c0 + q);
+          if (P.shift) x += __ldg(P.shift + c0 + q);
+          f[q] = x;
+        }
+        if (res_row != nullptr && interior) {
+          const uint4* rh = reinterpret_cast<const uint4*>(res_row + c0);
+          const uint4* rl = reinterpret_cast<const uint4*>(res_row + P.cout + c0);
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const uint4 hv = __ldg(rh + h2), lv = __ldg(rl + h2);
+            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              f[h2 * 8 + q * 2 + 0] += __uint_as_float(hw[q] << 16) + __uint_as_float(lw[q] << 16);
+              f[h2 * 8 + q * 2 + 1] += __uint_as_float(hw[q] & 0xffff0000u) + __uint_as_float(lw[q] & 0xffff0000u);
+            }
+          }
+        }
+        if (P.relu) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) f[q] = fmaxf(f[q], 0.f);
+        }
+        if (P.out_mode == IOU_OUT_PADDED_BF16X2) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float x0 = interior ? f[2 * q] : 0.f, x1 = interior ? f[2 * q + 1] : 0.f;
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+            hi[q] = pack_bf16x2(h0, h1);
+            lo[q] = pack_bf16x2(l0, l1);
+          }
+          __nv_bfloat16* orow = P.out + (size_t)grow * (2 * P.cout) + c0;
+          uint4* oh = reinterpret_cast<uint4*>(orow);
+          uint4* ol = reinterpret_cast<uint4*>(orow + P.cout);
+          oh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          oh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          ol[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          ol[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        } else if (interior) {
+          const size_t pix = ((size_t)img * sg.h + (yp - 1)) * sg.w + (xp - 1);
+          const int split = P.dense_split > 0 ? P.dense_split : P.cout;
+          if (c0 + 16 <= split && (split & 3) == 0) {
+            float4* o = reinterpret_cast<float4*>(P.out_dense[s] + pix * split + c0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+          } else {
+            const int w2 = P.cout - split;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const int c = c0 + q;
+              if (c < split) P.out_dense[s][pix * split + c] = f[q];
+              else if (c < P.cout) P.out_dense2[s][pix * w2 + (c - split)] = f[q];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * acc);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 matrix [rows][cols] (row-major), box = 64 cols x box_rows rows, 128B swizzle, zero OOB fill.
+static int encode_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(IOU_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(IOU_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return IOU_OK;
+}
+
+}  // namespace iou
+
+struct iou_conv_plan {
+  iou::ConvParams params;
+  int grid;
+  size_t smem_bytes;
+  double flops;
+};
+
+using namespace iou;
+
+extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan_out) {
+  IOU_REQUIRE(d && plan_out, "NULL argument");
+  IOU_REQUIRE(d->cin > 0 && d->cin % kBlockK == 0, "cin must be a positive multiple of %d (got %d)", kBlockK, d->cin);
+  IOU_REQUIRE(d->block_n >= 16 && d->block_n <= 256 && d->block_n % 16 == 0, "block_n must be in 16..256, multiple of 16");
+  IOU_REQUIRE(d->cout >= 1 && d->cout_pad >= d->cout && d->cout_pad % d->block_n == 0, "cout_pad must be a multiple of block_n >= cout");
+  IOU_REQUIRE(d->num_taps >= 1 && d->num_taps <= IOU_CONV_MAX_TAPS, "num_taps out of range");
+  IOU_REQUIRE(d->num_src >= 1 && d->num_src <= IOU_CONV_MAX_SRC, "num_src out of range");
+  IOU_REQUIRE(d->num_seg >= 1 && d->num_seg <= IOU_CONV_MAX_SEG, "num_seg out of range");
+  IOU_REQUIRE(d->passes == 1 || d->passes == 3, "passes must be 1 or 3");
+  IOU_REQUIRE(d->weight != nullptr, "weight is NULL");
+  IOU_REQUIRE(d->src_rows > 0 && d->src_rows < (1ll << 31), "src_rows out of range");
+  if (d->out_mode == IOU_OUT_PADDED_BF16X2) {
+    IOU_REQUIRE(d->out != nullptr, "out is NULL");
+    IOU_REQUIRE(d->cout == d->cout_pad, "padded output needs cout == cout_pad");
+    IOU_REQUIRE(((uintptr_t)d->out & 15) == 0, "out must be 16-byte aligned");
+  } else {
+    IOU_REQUIRE(d->out_mode == IOU_OUT_DENSE_F32, "bad out_mode");
+    IOU_REQUIRE(d->dense_split >= 0 && d->dense_split < d->cout, "dense_split out of range");
+  }
+  if (d->res_mode != IOU_RES_NONE) {
+    IOU_REQUIRE(d->residual != nullptr, "residual is NULL");
+    IOU_REQUIRE(d->cout == d->cout_pad && d->cout % 16 == 0, "residual needs cout == cout_pad, multiple of 16");
+  }
+  iou_conv_plan* plan = new (std::nothrow) iou_conv_plan();
+  if (!plan) return fail(IOU_ERR_INVALID, "out of host memory");
+  ConvParams& P = plan->params;
+  memset(&P, 0, sizeof(P));
+  P.cin = d->cin; P.cout = d->cout; P.cout_pad = d->cout_pad; P.block_n = d->block_n;
+  P.num_taps = d->num_taps; P.k_slabs = d->cin / kBlockK; P.passes = d->passes;
+  for (int t = 0; t < d->num_taps; ++t) {
+    if (d->tap_src[t] < 0 || d->tap_src[t] >= d->num_src) { delete plan; return fail(IOU_ERR_INVALID, "tap_src out of range"); }
+    P.tap_src[t] = d->tap_src[t]; P.tap_dy[t] = d->tap_dy[t]; P.tap_dx[t] = d->tap_dx[t];
+  }
+  P.num_seg = d->num_seg;
+  int toff = 0;
+  double real_rows = 0;
+  for (int s = 0; s < d->num_seg; ++s) {
+    const iou_conv_segment& g = d->seg[s];
+    if (g.row_start % kBlockM != 0 || g.n_img < 1 || g.h < 1 || g.w < 1) {
+      delete plan;
+      return fail(IOU_ERR_INVALID, "segment %d: row_start must be a multiple of %d and dims positive", s, kBlockM);
+    }
+    P.seg[s] = SegDev{g.row_start, g.n_img, g.h, g.w};
+    P.res_seg[s] = SegDev{d->res_seg[s].row_start, d->res_seg[s].n_img, d->res_seg[s].h, d->res_seg[s].w};
+    P.seg_tile_off[s] = toff;
+    const long long rows = (long long)g.n_img * (g.h + 2) * (g.w + 2);
+    toff += (int)((rows + kBlockM - 1) / kBlockM);
+    real_rows += (double)g.n_img * g.h * g.w;
+    P.out_dense[s] = (float*)d->out_dense[s];
+    P.out_dense2[s] = (float*)d->out_dense2[s];
+    if (d->out_mode == IOU_OUT_DENSE_F32 && !d->out_dense[s]) { delete plan; return fail(IOU_ERR_INVALID, "out_dense[%d] is NULL", s); }
+    if (d->out_mode == IOU_OUT_DENSE_F32 && d->dense_split > 0 && !d->out_dense2[s]) { delete plan; return fail(IOU_ERR_INVALID, "out_dense2[%d] is NULL", s); }
+  }
+  for (int s = d->num_seg; s <= IOU_CONV_MAX_SEG; ++s) P.seg_tile_off[s] = toff;
+  P.num_m_tiles = toff;
+  P.num_n_tiles = d->cout_pad / d->block_n;
+  P.total_tiles = P.num_m_tiles * P.num_n_tiles;
+  P.b_tile_bytes = d->block_n * kBlockK * 2;
+  P.stage_bytes = (d->passes == 3 ? 2 : 1) * (kATileBytes + P.b_tile_bytes);
+  int stages = (kSmemBudget - kCtrlBytes - 1024) / P.stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) { delete plan; return fail(IOU_ERR_INVALID, "tile does not fit shared memory"); }
+  P.num_stages = stages;
+  P.scale = d->scale; P.shift = d->shift; P.relu = d->relu; P.res_mode = d->res_mode;
+  P.residual = (const __nv_bfloat16*)d->residual;
+  P.out_mode = d->out_mode; P.out = (__nv_bfloat16*)d->out; P.dense_split = d->dense_split;
+  // cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=BF16 (1<<7, 1<<10), K-major both, N>>3 @17, M>>4 @24
+  P.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d->block_n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+  for (int i = 0; i < d->num_src; ++i) {
+    if (!d->src[i] || ((uintptr_t)d->src[i] & 15)) { delete plan; return fail(IOU_ERR_INVALID, "src[%d] NULL or misaligned", i); }
+    if (int e = encode_2d(&P.tmap_src[i], d->src[i], (uint64_t)d->src_rows, (uint64_t)2 * d->cin, kBlockM)) { delete plan; return e; }
+  }
+  for (int i = d->num_src; i < IOU_CONV_MAX_SRC; ++i) P.tmap_src[i] = P.tmap_src[0];
+  if (int e = encode_2d(&P.tmap_w, d->weight, (uint64_t)d->num_taps * d->cout_pad, (uint64_t)2 * d->cin, (uint32_t)d->block_n)) { delete plan; return e; }
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  plan->grid = P.total_tiles < sms ? P.total_tiles : sms;
+  plan->smem_bytes = (size_t)kCtrlBytes + 1024 + (size_t)stages * P.stage_bytes;
+  plan->flops = 2.0 * real_rows * d->cout * d->cin * d->num_taps;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tap_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e != cudaSuccess) { delete plan; return fail(IOU_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
+    attr_set = true;
+  }
+  *plan_out = plan;
+  return IOU_OK;
+}
+
+extern "C" int iou_conv_run(const iou_conv_plan* plan, void* stream) {
+  IOU_REQUIRE(plan != nullptr, "plan is NULL");
+  conv_tap_gemm_kernel<<<plan->grid, kNumThreads, plan->smem_bytes, (cudaStream_t)stream>>>(plan->params);
+  return launch_status("conv_tap_gemm_kernel");
+}
+
+extern "C" void iou_conv_plan_destroy(iou_conv_plan* plan) { delete plan; }
+
+extern "C" double iou_conv_plan_flops(const iou_conv_plan* plan) { return plan ? plan->flops : 0.0; }

@@ -1,0 +1,749 @@
+// Post-processing half of IoUawareRetinaHead.get_bboxes on the device:
+//   K1 max_score   : streaming pass over the class logits, one fused score per anchor
+//   K2 topk        : per (image, level) radix-select + bitonic sort of nms_pre anchors
+//   K3 gather      : decode (delta2bbox) + full class scores of the selected candidates
+//   K4 class_nms   : one CTA per (class, image): threshold, sort, blocked greedy NMS
+//   K5 final_select: per image top max_per_img over all classes
+// Reference semantics: mmdet/models/anchor_heads/iou_aware_retina_head.py:463-564,
+// mmdet/core/bbox/transforms.py:44-78, mmdet/core/post_processing/bbox_nms.py:6-67,
+// mmdet/ops/nms/src/nms_kernel.cu:13-131.  Arithmetic that feeds a comparison
+// (IoU, decode) uses explicit round-to-nearest intrinsics so no FMA contraction
+// can move a threshold decision away from the reference's unfused fp32 result.
+#include <math.h>
+#include "common.cuh"
+
+namespace iou {
+
+// ----------------------------------------------------------------------------------------
+struct PostParams {
+  int num_levels, A, C, nms_pre, n_img, M, A_total, max_per_img, kcap;
+  int feat_h[IOU_MAX_LEVELS], feat_w[IOU_MAX_LEVELS], stride[IOU_MAX_LEVELS];
+  int n_anchor[IOU_MAX_LEVELS];      // H*W*A
+  int anchor_off[IOU_MAX_LEVELS];    // prefix of n_anchor
+  int keep[IOU_MAX_LEVELS];          // min(n_anchor, nms_pre)
+  int cand_off[IOU_MAX_LEVELS + 1];  // prefix of keep
+  int is_topk[IOU_MAX_LEVELS];
+  long long group_off[IOU_MAX_LEVELS + 1];  // K1 work prefix (only top-k levels have width)
+  int num_topk_levels;
+  int topk_level[IOU_MAX_LEVELS];
+  const float* cls[IOU_MAX_LEVELS];
+  const float* reg[IOU_MAX_LEVELS];
+  const float* iou[IOU_MAX_LEVELS];
+  float base[IOU_MAX_LEVELS][IOU_MAX_ANCHORS][4];
+  float mean[4], stdv[4];
+  float alpha, score_thr, iou_thr, max_ratio;
+  int rescale;
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+// score = sigmoid(cls)^alpha * sigmoid(iou)^(1-alpha)   (iou_aware_retina_head.py:510,531)
+__device__ __forceinline__ float fuse_score(float cls_logit, float iou_logit, float alpha) {
+  float s = sigmoidf_(cls_logit), q = sigmoidf_(iou_logit);
+  if (alpha == 0.5f) return __fmul_rn(__fsqrt_rn(s), __fsqrt_rn(q));
+  return __fmul_rn(powf(s, alpha), powf(q, 1.0f - alpha));
+}
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------- K1
+// One warp per group of 32 consecutive anchors (32*C contiguous floats): coalesced 16-byte
+// streaming loads, per-slot max staged in shared memory, then lane a reduces anchor a.
+__global__ void __launch_bounds__(256) max_score_kernel(const __grid_constant__ PostParams P,
+                                                        float* __restrict__ maxscore) {
+  extern __shared__ float smem_f[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Q = P.C >> 2;
+  float* sm = smem_f + warp * 32 * Q;
+  const long long total = P.group_off[P.num_levels];
+  for (long long g = (long long)blockIdx.x * 8 + warp; g < total; g += (long long)gridDim.x * 8) {
+    int l = 0;
+    while (g >= P.group_off[l + 1]) ++l;
+    const int n_l = P.n_anchor[l];
+    const int gpi = (n_l + 31) >> 5;
+    const int gl = (int)(g - P.group_off[l]);
+    const int img = gl / gpi, gi = gl - img * gpi;
+    const int a0 = gi * 32;
+    const int v = min(32, n_l - a0);
+    const float4* src = reinterpret_cast<const float4*>(P.cls[l] + ((size_t)img * n_l + a0) * P.C);
+    const int nslots = v * Q;
+#pragma unroll 4
+    for (int f = lane; f < nslots; f += 32) {
+      float4 x = ldg_stream(src + f);
+      sm[f] = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
+    }
+    __syncwarp();
+    if (lane < v) {
+      float m = -INFINITY;
+      for (int t = 0; t < Q; ++t) m = fmaxf(m, sm[lane * Q + t]);
+      float q = __ldg(P.iou[l] + (size_t)img * n_l + a0 + lane);
+      maxscore[(size_t)img * P.A_total + P.anchor_off[l] + a0 + lane] = fuse_score(m, q, P.alpha);
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------- sort
+// In-place descending bitonic sort of P (power of two) u64 keys in shared memory.
+__device__ void bitonic_sort_desc(unsigned long long* a, int P) {
+  __syncthreads();
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        int l = i ^ j;
+        if (l > i) {
+          unsigned long long x = a[i], y = a[l];
+          bool desc = ((i & k) == 0);
+          if (desc ? (x < y) : (x > y)) { a[i] = y; a[l] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ int next_pow2(int x) {
+  int p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+// ---------------------------------------------------------------------------------------- K2
+// torch.topk(max_scores, nms_pre) (iou_aware_retina_head.py:544): exact k-th key by 4x8-bit
+// radix select, then the selected set is ordered by (score desc, index asc).
+#define TOPK_MAX 2048
+__global__ void __launch_bounds__(1024) topk_kernel(const __grid_constant__ PostParams P,
+                                                    const float* __restrict__ maxscore,
+                                                    int32_t* __restrict__ cand_idx) {
+  __shared__ unsigned long long sortbuf[TOPK_MAX];
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int s_prefix, s_mask, s_kleft, s_cnt, s_eq_total, s_eq_run;
+  __shared__ unsigned int warp_eq[32];
+  const int l = P.topk_level[blockIdx.x], img = blockIdx.y;
+  const int n = P.n_anchor[l], k = P.keep[l];
+  const float* keys = maxscore + (size_t)img * P.A_total + P.anchor_off[l];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { s_prefix = 0; s_mask = 0; s_kleft = k; s_cnt = 0; s_eq_run = 0; }
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    const unsigned int prefix = s_prefix, mask = s_mask;
+    for (int base = 0; base < n; base += 1024) {
+      int i = base + tid;
+      unsigned int u = (i < n) ? float_to_ordered(keys[i]) : 0u;
+      bool valid = (i < n) && ((u & mask) == prefix);
+      unsigned int d = valid ? ((u >> shift) & 255u) : (256u + lane);
+      unsigned int peers = __match_any_sync(0xffffffffu, d);
+      if (valid && (__ffs(peers) - 1) == lane) atomicAdd(&hist[d], __popc(peers));
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int c = 0, kl = s_kleft;
+      int d = 255;
+      for (; d > 0; --d) {
+        if (c + hist[d] >= kl) break;
+        c += hist[d];
+      }
+      s_kleft = kl - c;
+      s_prefix = prefix | ((unsigned int)d << shift);
+      s_mask = mask | (255u << shift);
+      s_eq_total = hist[d];
+    }
+    __syncthreads();
+  }
+  const unsigned int T = s_prefix, need_eq = s_kleft;
+  const bool ties = (s_eq_total != need_eq);   // more keys equal to T than we may take
+  for (int base = 0; base < n; base += 1024) {
+    int i = base + tid;
+    unsigned int u = (i < n) ? float_to_ordered(keys[i]) : 0u;
+    bool gt = (i < n) && (u > T);
+    bool eq = (i < n) && (u == T);
+    bool take = gt;
+    if (!ties) {
+      take = gt || eq;
+    } else {  // lowest indices first among the ties (block-wide ordered rank)
+      unsigned int be = __ballot_sync(0xffffffffu, eq);
+      if (lane == 0) warp_eq[warp] = __popc(be);
+      __syncthreads();
+      unsigned int before = s_eq_run;
+      for (int w = 0; w < warp; ++w) before += warp_eq[w];
+      unsigned int rank = before + __popc(be & ((1u << lane) - 1u));
+      if (eq && rank < need_eq) take = true;
+      __syncthreads();
+      if (tid == 0) {
+        unsigned int t = 0;
+        for (int w = 0; w < 32; ++w) t += warp_eq[w];
+        s_eq_run += t;
+      }
+      __syncthreads();
+    }
+    unsigned int bt = __ballot_sync(0xffffffffu, take);
+    unsigned int slot0 = 0;
+    if (lane == 0 && bt) slot0 = atomicAdd(&s_cnt, __popc(bt));
+    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+    if (take) {
+      unsigned int slot = slot0 + __popc(bt & ((1u << lane) - 1u));
+      if (slot < TOPK_MAX)
+        sortbuf[slot] = ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (unsigned int)i);
+    }
+  }
+  __syncthreads();
+  const int Psort = next_pow2(k);
+  for (int i = k + tid; i < Psort; i += 1024) sortbuf[i] = 0ull;
+  bitonic_sort_desc(sortbuf, Psort);
+  int32_t* out = cand_idx + (size_t)img * P.M + P.cand_off[l];
+  for (int r = tid; r < k; r += 1024)
+    out[r] = (int32_t)(0xffffffffu - (unsigned int)(sortbuf[r] & 0xffffffffull));
+}
+
+// ---------------------------------------------------------------------------------------- K3
+// 32 candidates per CTA: every warp computes the C class scores of 4 candidates (coalesced
+// row reads), lane 0 decodes the box; the score tile is transposed through shared memory so
+// the class-major output rows are written 128 B at a time.
+__device__ __forceinline__ float clampf_(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+__global__ void __launch_bounds__(256) gather_decode_kernel(const __grid_constant__ PostParams P,
+                                                            const float* __restrict__ img_info,
+                                                            int32_t* __restrict__ cand_idx,
+                                                            float* __restrict__ boxes,
+                                                            float* __restrict__ scores_cm) {
+  extern __shared__ float tile[];   // [C][33]
+  const int img = blockIdx.y, j0 = blockIdx.x * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* info = img_info + img * 8;
+  for (int t = warp * 4; t < warp * 4 + 4; ++t) {
+    const int j = j0 + t;
+    if (j >= P.M) {
+      for (int c = lane; c < P.C; c += 32) tile[c * 33 + t] = 0.f;
+      continue;
+    }
+    int l = 0;
+    while (j >= P.cand_off[l + 1]) ++l;
+    int i;
+    if (P.is_topk[l]) {
+      i = cand_idx[(size_t)img * P.M + j];
+    } else {
+      i = j - P.cand_off[l];     // natural order when the level has <= nms_pre anchors (:536)
+      if (lane == 0) cand_idx[(size_t)img * P.M + j] = i;
+    }
+    const int n_l = P.n_anchor[l];
+    const size_t row = (size_t)img * n_l + i;
+    const float ql = __ldg(P.iou[l] + row);
+    const float* crow = P.cls[l] + row * P.C;
+    for (int c = lane; c < P.C; c += 32) tile[c * 33 + t] = fuse_score(__ldg(crow + c), ql, P.alpha);
+    if (lane == 0) {
+      // anchor (anchor_generator.py:57-67): base[a] + (x*s, y*s, x*s, y*s)
+      const int a = i % P.A, pos = i / P.A;
+      const int x = pos % P.feat_w[l], y = pos / P.feat_w[l];
+      const float sx = (float)(x * P.stride[l]), sy = (float)(y * P.stride[l]);
+      const float ax1 = __fadd_rn(P.base[l][a][0], sx), ay1 = __fadd_rn(P.base[l][a][1], sy);
+      const float ax2 = __fadd_rn(P.base[l][a][2], sx), ay2 = __fadd_rn(P.base[l][a][3], sy);
+      const float4 d = __ldg(reinterpret_cast<const float4*>(P.reg[l]) + row);
+      // delta2bbox (transforms.py:44-78)
+      const float dx = __fadd_rn(__fmul_rn(d.x, P.stdv[0]), P.mean[0]);
+      const float dy = __fadd_rn(__fmul_rn(d.y, P.stdv[1]), P.mean[1]);
+      float dw = __fadd_rn(__fmul_rn(d.z, P.stdv[2]), P.mean[2]);
+      float dh = __fadd_rn(__fmul_rn(d.w, P.stdv[3]), P.mean[3]);
+      dw = clampf_(dw, -P.max_ratio, P.max_ratio);
+      dh = clampf_(dh, -P.max_ratio, P.max_ratio);
+      const float px = __fmul_rn(__fadd_rn(ax1, ax2), 0.5f), py = __fmul_rn(__fadd_rn(ay1, ay2), 0.5f);
+      const float pw = __fadd_rn(__fsub_rn(ax2, ax1), 1.0f), ph = __fadd_rn(__fsub_rn(ay2, ay1), 1.0f);
+      const float gw = __fmul_rn(pw, expf(dw)), gh = __fmul_rn(ph, expf(dh));
+      const float gx = __fadd_rn(px, __fmul_rn(pw, dx)), gy = __fadd_rn(py, __fmul_rn(ph, dy));
+      const float hw = __fmul_rn(gw, 0.5f), hh = __fmul_rn(gh, 0.5f);
+      float x1 = __fadd_rn(__fsub_rn(gx, hw), 0.5f), y1 = __fadd_rn(__fsub_rn(gy, hh), 0.5f);
+      float x2 = __fsub_rn(__fadd_rn(gx, hw), 0.5f), y2 = __fsub_rn(__fadd_rn(gy, hh), 0.5f);
+      const float xmax = __fsub_rn(info[1], 1.0f), ymax = __fsub_rn(info[0], 1.0f);
+      x1 = clampf_(x1, 0.f, xmax); y1 = clampf_(y1, 0.f, ymax);
+      x2 = clampf_(x2, 0.f, xmax); y2 = clampf_(y2, 0.f, ymax);
+      if (P.rescale) {   // mlvl_bboxes /= scale_factor, after the clamp (:553-554)
+        x1 = __fdiv_rn(x1, info[2]); y1 = __fdiv_rn(y1, info[3]);
+        x2 = __fdiv_rn(x2, info[4]); y2 = __fdiv_rn(y2, info[5]);
+      }
+      reinterpret_cast<float4*>(boxes)[(size_t)img * P.M + j] = make_float4(x1, y1, x2, y2);
+    }
+  }
+  __syncthreads();
+  const int jj = j0 + lane;
+  if (jj < P.M)
+    for (int c = warp; c < P.C; c += 8)
+      scores_cm[((size_t)img * P.C + c) * P.M + jj] = tile[c * 33 + lane];
+}
+
+// ---------------------------------------------------------------------------------------- NMS core
+// IoU > thr with the reference's operation order (nms_kernel.cu:13-21,60).
+__device__ __forceinline__ bool iou_gt(const float4 a, const float sa, const float4 b, const float sb,
+                                       const float thr) {
+  const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
+  const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+  const float w = fmaxf(__fadd_rn(__fsub_rn(right, left), 1.0f), 0.0f);
+  const float h = fmaxf(__fadd_rn(__fsub_rn(bottom, top), 1.0f), 0.0f);
+  const float inter = __fmul_rn(w, h);
+  if (inter == 0.0f) return 0.0f > thr;
+  const float uni = __fsub_rn(__fadd_rn(sa, sb), inter);
+  return __fdiv_rn(inter, uni) > thr;
+}
+__device__ __forceinline__ float box_area(const float4 a) {
+  return __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.0f), __fadd_rn(__fsub_rn(a.w, a.y), 1.0f));
+}
+
+struct NmsSmem {
+  unsigned long long* sortbuf;   // [P]
+  float4* sbox;                  // [n]
+  float* sarea;                  // [n]
+  unsigned int* removed;         // [ceil(n/32)]
+};
+
+// Greedy NMS over n boxes already ordered by (score desc, index asc) in shared memory.
+// Calls emit(r) from thread 0 for every kept sorted position r, in order; stops once
+// `stop_after` boxes are kept (0 = never).  Returns the number kept (block-uniform).
+// 64-box chunks: the chunk's own 64x64 suppression mask is built with warp ballots, one
+// thread resolves it serially, then all threads propagate the newly kept boxes to the tail.
+template <typename Emit>
+__device__ int greedy_nms_sorted(const NmsSmem& S, const int n, const float thr, const int stop_after,
+                                 Emit emit) {
+  __shared__ unsigned long long cmask[64];
+  __shared__ unsigned long long s_keptmask;
+  __shared__ int s_total;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  for (int i = tid; i < (n + 31) / 32; i += blockDim.x) S.removed[i] = 0u;
+  if (tid == 0) s_total = 0;
+  __syncthreads();
+  for (int cs = 0; cs < n; cs += 64) {
+    const int cnt = min(64, n - cs);
+    // (a) intra-chunk mask rows
+    for (int r = warp; r < cnt; r += nwarps) {
+      const float4 a = S.sbox[cs + r];
+      const float sa = S.sarea[cs + r];
+      bool h0 = false, h1 = false;
+      int c0 = lane, c1 = lane + 32;
+      if (c0 > r && c0 < cnt) h0 = iou_gt(a, sa, S.sbox[cs + c0], S.sarea[cs + c0], thr);
+      if (c1 > r && c1 < cnt) h1 = iou_gt(a, sa, S.sbox[cs + c1], S.sarea[cs + c1], thr);
+      unsigned int b0 = __ballot_sync(0xffffffffu, h0), b1 = __ballot_sync(0xffffffffu, h1);
+      if (lane == 0) cmask[r] = ((unsigned long long)b1 << 32) | b0;
+    }
+    __syncthreads();
+    // (b) serial resolve of the chunk
+    if (tid == 0) {
+      unsigned long long R = (unsigned long long)S.removed[cs >> 5];
+      if (cs + 32 < n) R |= (unsigned long long)S.removed[(cs >> 5) + 1] << 32;
+      unsigned long long kept = 0ull;
+      int total = s_total;
+      for (int i = 0; i < cnt; ++i) {
+        if (!((R >> i) & 1ull)) {
+          kept |= 1ull << i;
+          R |= cmask[i];
+          emit(cs + i, total);
+          ++total;
+          if (stop_after && total >= stop_after) break;
+        }
+      }
+      s_keptmask = kept;
+      s_total = total;
+    }
+    __syncthreads();
+    const unsigned long long kept = s_keptmask;
+    const int total = s_total;
+    if (stop_after && total >= stop_after) break;
+    // (c) propagate to the tail
+    if (kept) {
+      for (int kpos = cs + cnt + tid; kpos < n; kpos += blockDim.x) {
+        if ((S.removed[kpos >> 5] >> (kpos & 31)) & 1u) continue;
+        const float4 b = S.sbox[kpos];
+        const float sb = S.sarea[kpos];
+        unsigned long long m = kept;
+        bool dead = false;
+        while (m) {
+          int i = __ffsll((long long)m) - 1;
+          m &= m - 1;
+          if (iou_gt(S.sbox[cs + i], S.sarea[cs + i], b, sb, thr)) { dead = true; break; }
+        }
+        if (dead) atomicOr(&S.removed[kpos >> 5], 1u << (kpos & 31));
+      }
+    }
+    __syncthreads();
+  }
+  return s_total;
+}
+
+// ---------------------------------------------------------------------------------------- K4
+__global__ void __launch_bounds__(512) class_nms_kernel(const __grid_constant__ PostParams P,
+                                                        const float* __restrict__ boxes,
+                                                        const float* __restrict__ scores_cm,
+                                                        unsigned long long* __restrict__ kept_keys,
+                                                        int32_t* __restrict__ kept_cnt, const int Pmax) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  NmsSmem S;
+  S.sortbuf = reinterpret_cast<unsigned long long*>(smem_raw);
+  S.sbox = reinterpret_cast<float4*>(smem_raw + (size_t)Pmax * 8);
+  S.sarea = reinterpret_cast<float*>(smem_raw + (size_t)Pmax * 8 + (size_t)P.M * 16);
+  S.removed = reinterpret_cast<unsigned int*>(smem_raw + (size_t)Pmax * 8 + (size_t)P.M * 20);
+  __shared__ unsigned int s_n, warp_cnt[16];
+  const int c = blockIdx.x, img = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* sc = scores_cm + ((size_t)img * P.C + c) * P.M;
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  // compaction of rows with score > score_thr (bbox_nms.py:37), ascending row index
+  for (int base = 0; base < P.M; base += 512) {
+    const int j = base + tid;
+    const float s = (j < P.M) ? __ldg(sc + j) : 0.f;
+    const bool pass = (j < P.M) && (s > P.score_thr);
+    const unsigned int b = __ballot_sync(0xffffffffu, pass);
+    if (lane == 0) warp_cnt[warp] = __popc(b);
+    __syncthreads();
+    unsigned int off = s_n;
+    for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+    if (pass) {
+      const unsigned int slot = off + __popc(b & ((1u << lane) - 1u));
+      S.sortbuf[slot] = ((unsigned long long)float_to_ordered(s) << 32) |
+                        (unsigned long long)(0xffffffffu - (unsigned int)j);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int t = 0;
+      for (int w = 0; w < 16; ++w) t += warp_cnt[w];
+      s_n += t;
+    }
+    __syncthreads();
+  }
+  const int n = (int)s_n;
+  int32_t* cnt_out = kept_cnt + (size_t)img * P.C + c;
+  if (n == 0) {
+    if (tid == 0) *cnt_out = 0;
+    return;
+  }
+  const int Ps = next_pow2(n);
+  for (int i = n + tid; i < Ps; i += 512) S.sortbuf[i] = 0ull;
+  bitonic_sort_desc(S.sortbuf, Ps);
+  const float4* bx = reinterpret_cast<const float4*>(boxes) + (size_t)img * P.M;
+  for (int r = tid; r < n; r += 512) {
+    const unsigned int j = 0xffffffffu - (unsigned int)(S.sortbuf[r] & 0xffffffffull);
+    const float4 b = __ldg(bx + j);
+    S.sbox[r] = b;
+    S.sarea[r] = box_area(b);
+  }
+  __syncthreads();
+  unsigned long long* keys_out = kept_keys + ((size_t)img * P.C + c) * P.kcap;
+  const unsigned long long* sb = S.sortbuf;
+  const int total = greedy_nms_sorted(S, n, P.iou_thr, P.kcap,
+                                      [&](int r, int pos) { keys_out[pos] = sb[r]; });
+  if (tid == 0) *cnt_out = total;
+}
+
+// ---------------------------------------------------------------------------------------- K5
+// bbox_nms.py:55-62: concat classes; if more than max_per_img remain, order by score desc.
+__global__ void __launch_bounds__(1024) final_select_kernel(const __grid_constant__ PostParams P,
+                                                            const float* __restrict__ boxes,
+                                                            const unsigned long long* __restrict__ kept_keys,
+                                                            const int32_t* __restrict__ kept_cnt,
+                                                            float* __restrict__ dets,
+                                                            long long* __restrict__ labels,
+                                                            int32_t* __restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(smem_raw);   // [Pcap]
+  __shared__ int s_off[257];
+  const int img = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) {
+    int t = 0;
+    for (int c = 0; c < P.C; ++c) { s_off[c] = t; t += kept_cnt[(size_t)img * P.C + c]; }
+    s_off[P.C] = t;
+  }
+  __syncthreads();
+  const int total = s_off[P.C];
+  const bool by_score = total > P.max_per_img;
+  const int Ps = next_pow2(max(total, 1));
+  for (int i = total + tid; i < Ps; i += 1024) sortbuf[i] = 0ull;
+  for (int c = 0; c < P.C; ++c) {
+    const int n_c = s_off[c + 1] - s_off[c];
+    const unsigned long long* kk = kept_keys + ((size_t)img * P.C + c) * P.kcap;
+    for (int r = tid; r < n_c; r += 1024) {
+      const unsigned long long key = kk[r];
+      const unsigned int sbits = (unsigned int)(key >> 32);
+      const unsigned int j = 0xffffffffu - (unsigned int)(key & 0xffffffffull);
+      const unsigned int pos = (unsigned int)c * (unsigned int)P.M + j;   // class-major, row-minor
+      const int e = s_off[c] + r;
+      // payload (pos) must survive the sort: by_score -> key = (score, ~pos); else key = (~pos, score)
+      sortbuf[e] = by_score ? (((unsigned long long)sbits << 32) | (0xffffffffu - pos))
+                            : (((unsigned long long)(0xffffffffu - pos) << 32) | sbits);
+    }
+  }
+  bitonic_sort_desc(sortbuf, Ps);
+  const int k = min(total, P.max_per_img);
+  float* d_out = dets + (size_t)img * P.max_per_img * 5;
+  long long* l_out = labels + (size_t)img * P.max_per_img;
+  const float4* bx = reinterpret_cast<const float4*>(boxes) + (size_t)img * P.M;
+  for (int r = tid; r < P.max_per_img; r += 1024) {
+    if (r < k) {
+      const unsigned long long key = sortbuf[r];
+      const unsigned int hi = (unsigned int)(key >> 32), lo = (unsigned int)(key & 0xffffffffull);
+      const unsigned int sbits = by_score ? hi : lo;
+      const unsigned int pos = 0xffffffffu - (by_score ? lo : hi);
+      const unsigned int c = pos / (unsigned int)P.M, j = pos - c * (unsigned int)P.M;
+      const float4 b = __ldg(bx + j);
+      d_out[r * 5 + 0] = b.x; d_out[r * 5 + 1] = b.y; d_out[r * 5 + 2] = b.z; d_out[r * 5 + 3] = b.w;
+      d_out[r * 5 + 4] = ordered_to_float(sbits);
+      l_out[r] = (long long)c;
+    } else {
+      for (int q = 0; q < 5; ++q) d_out[r * 5 + q] = 0.f;
+      l_out[r] = 0;
+    }
+  }
+  if (tid == 0) counts[img] = k;
+}
+
+// ---------------------------------------------------------------------------------------- single NMS
+// Drop-in for nms_cuda.nms: all n boxes take part; output = ascending original indices.
+__global__ void __launch_bounds__(512) single_nms_kernel(const float* __restrict__ dets, const int n,
+                                                         const float thr, long long* __restrict__ keep_idx,
+                                                         int32_t* __restrict__ keep_count, const int Pmax) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  NmsSmem S;
+  S.sortbuf = reinterpret_cast<unsigned long long*>(smem_raw);
+  S.sbox = reinterpret_cast<float4*>(smem_raw + (size_t)Pmax * 8);
+  S.sarea = reinterpret_cast<float*>(smem_raw + (size_t)Pmax * 8 + (size_t)n * 16);
+  S.removed = reinterpret_cast<unsigned int*>(smem_raw + (size_t)Pmax * 8 + (size_t)n * 20);
+  unsigned int* keepbits = S.removed + (n + 31) / 32;
+  __shared__ unsigned int s_run, warp_cnt[16];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Ps = next_pow2(n);
+  for (int i = tid; i < Ps; i += 512)
+    S.sortbuf[i] = (i < n) ? (((unsigned long long)float_to_ordered(dets[(size_t)i * 5 + 4]) << 32) |
+                              (unsigned long long)(0xffffffffu - (unsigned int)i))
+                           : 0ull;
+  for (int i = tid; i < (n + 31) / 32; i += 512) keepbits[i] = 0u;
+  bitonic_sort_desc(S.sortbuf, Ps);
+  for (int r = tid; r < n; r += 512) {
+    const unsigned int j = 0xffffffffu - (unsigned int)(S.sortbuf[r] & 0xffffffffull);
+    const float4 b = make_float4(dets[(size_t)j * 5], dets[(size_t)j * 5 + 1], dets[(size_t)j * 5 + 2],
+                                 dets[(size_t)j * 5 + 3]);
+    S.sbox[r] = b;
+    S.sarea[r] = box_area(b);
+  }
+  __syncthreads();
+  const unsigned long long* sb = S.sortbuf;
+  greedy_nms_sorted(S, n, thr, 0, [&](int r, int) {
+    const unsigned int j = 0xffffffffu - (unsigned int)(sb[r] & 0xffffffffull);
+    keepbits[j >> 5] |= 1u << (j & 31);     // only thread 0 emits
+  });
+  __syncthreads();
+  if (tid == 0) s_run = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 512) {
+    const int j = base + tid;
+    const bool kp = (j < n) && ((keepbits[j >> 5] >> (j & 31)) & 1u);
+    const unsigned int b = __ballot_sync(0xffffffffu, kp);
+    if (lane == 0) warp_cnt[warp] = __popc(b);
+    __syncthreads();
+    unsigned int off = s_run;
+    for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+    if (kp) keep_idx[off + __popc(b & ((1u << lane) - 1u))] = (long long)j;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int t = 0;
+      for (int w = 0; w < 16; ++w) t += warp_cnt[w];
+      s_run += t;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) *keep_count = (int32_t)s_run;
+}
+
+// ---------------------------------------------------------------------------------------- host
+static int fill_params(const iou_postproc_cfg* cfg, int n_img, PostParams& P) {
+  IOU_REQUIRE(cfg != nullptr, "cfg is NULL");
+  IOU_REQUIRE(cfg->num_levels >= 1 && cfg->num_levels <= IOU_MAX_LEVELS, "num_levels out of range");
+  IOU_REQUIRE(cfg->num_anchors >= 1 && cfg->num_anchors <= IOU_MAX_ANCHORS, "num_anchors out of range");
+  IOU_REQUIRE(cfg->num_classes >= 1 && cfg->num_classes <= 256, "num_classes out of range");
+  IOU_REQUIRE(n_img >= 1, "n_img must be >= 1");
+  IOU_REQUIRE(cfg->max_per_img >= 1, "max_per_img must be >= 1");
+  if (cfg->num_classes % 4 != 0)
+    return fail(IOU_ERR_UNSUPPORTED, "num_classes %% 4 != 0 is not supported (got %d)", cfg->num_classes);
+  if (cfg->nms_pre > TOPK_MAX)
+    return fail(IOU_ERR_UNSUPPORTED, "nms_pre > %d is not supported (got %d)", TOPK_MAX, cfg->nms_pre);
+  memset(&P, 0, sizeof(P));
+  P.num_levels = cfg->num_levels; P.A = cfg->num_anchors; P.C = cfg->num_classes;
+  P.nms_pre = cfg->nms_pre; P.n_img = n_img; P.max_per_img = cfg->max_per_img;
+  P.kcap = cfg->max_per_img + 1;
+  if (next_pow2_host(P.C * P.kcap) > 8192)
+    return fail(IOU_ERR_UNSUPPORTED, "num_classes*(max_per_img+1) > 8192 is not supported");
+  int aoff = 0, coff = 0;
+  long long goff = 0;
+  for (int l = 0; l < P.num_levels; ++l) {
+    IOU_REQUIRE(cfg->feat_h[l] > 0 && cfg->feat_w[l] > 0, "empty feature map at level %d", l);
+    P.feat_h[l] = cfg->feat_h[l]; P.feat_w[l] = cfg->feat_w[l]; P.stride[l] = cfg->stride[l];
+    P.n_anchor[l] = cfg->feat_h[l] * cfg->feat_w[l] * P.A;
+    P.anchor_off[l] = aoff; aoff += P.n_anchor[l];
+    P.is_topk[l] = (P.nms_pre > 0 && P.n_anchor[l] > P.nms_pre);
+    P.keep[l] = P.is_topk[l] ? P.nms_pre : P.n_anchor[l];
+    P.cand_off[l] = coff; coff += P.keep[l];
+    P.group_off[l] = goff;
+    if (P.is_topk[l]) {
+      goff += (long long)n_img * ((P.n_anchor[l] + 31) / 32);
+      P.topk_level[P.num_topk_levels++] = l;
+    }
+    for (int a = 0; a < P.A; ++a)
+      for (int q = 0; q < 4; ++q) P.base[l][a][q] = cfg->base_anchors[l][a][q];
+  }
+  P.cand_off[P.num_levels] = coff;
+  P.group_off[P.num_levels] = goff;
+  for (int l = P.num_levels + 1; l <= IOU_MAX_LEVELS; ++l) { P.cand_off[l] = coff; P.group_off[l] = goff; }
+  P.A_total = aoff; P.M = coff;
+  if (P.M > IOU_MAX_CANDIDATES)
+    return fail(IOU_ERR_UNSUPPORTED, "%d candidates per image exceed IOU_MAX_CANDIDATES=%d", P.M,
+                IOU_MAX_CANDIDATES);
+  for (int q = 0; q < 4; ++q) { P.mean[q] = cfg->target_means[q]; P.stdv[q] = cfg->target_stds[q]; }
+  P.alpha = cfg->alpha; P.score_thr = cfg->score_thr; P.iou_thr = cfg->iou_thr;
+  P.max_ratio = (float)fabs(log((double)cfg->wh_ratio_clip));
+  return IOU_OK;
+}
+
+struct PostWorkspace {
+  float* maxscore; unsigned long long* kept_keys; int32_t* kept_cnt;
+  float* boxes; float* scores_cm; int32_t* cand_idx;
+  size_t total;
+};
+static PostWorkspace carve(const PostParams& P, void* base) {
+  PostWorkspace W;
+  size_t off = 0;
+  unsigned char* b = static_cast<unsigned char*>(base);
+  auto take = [&](size_t bytes) { void* p = b ? b + off : nullptr; off += align_up(bytes, 256); return p; };
+  W.maxscore = (float*)take((size_t)P.n_img * P.A_total * 4);
+  W.kept_keys = (unsigned long long*)take((size_t)P.n_img * P.C * P.kcap * 8);
+  W.kept_cnt = (int32_t*)take((size_t)P.n_img * P.C * 4);
+  W.boxes = (float*)take((size_t)P.n_img * P.M * 16);
+  W.scores_cm = (float*)take((size_t)P.n_img * P.C * P.M * 4);
+  W.cand_idx = (int32_t*)take((size_t)P.n_img * P.M * 4);
+  W.total = off;
+  return W;
+}
+
+static int run_decode(PostParams& P, const float* const* cls, const float* const* reg,
+                      const float* const* iou, const float* img_info, int rescale, float* boxes,
+                      float* scores_cm, int32_t* cand_idx, float* maxscore, cudaStream_t st) {
+  for (int l = 0; l < P.num_levels; ++l) {
+    IOU_REQUIRE(cls[l] && reg[l] && iou[l], "NULL level pointer at level %d", l);
+    IOU_REQUIRE(((uintptr_t)cls[l] & 15) == 0 && ((uintptr_t)reg[l] & 15) == 0,
+                "cls/reg pointers must be 16-byte aligned (level %d)", l);
+    P.cls[l] = cls[l]; P.reg[l] = reg[l]; P.iou[l] = iou[l];
+  }
+  P.rescale = rescale;
+  const long long groups = P.group_off[P.num_levels];
+  if (groups > 0) {
+    const int blocks = (int)((groups + 7) / 8 < 148 * 8 ? (groups + 7) / 8 : 148 * 8);
+    const size_t sm = (size_t)8 * 32 * (P.C / 4) * sizeof(float);
+    max_score_kernel<<<blocks, 256, sm, st>>>(P, maxscore);
+    if (int e = launch_status("max_score_kernel")) return e;
+    topk_kernel<<<dim3(P.num_topk_levels, P.n_img), 1024, 0, st>>>(P, maxscore, cand_idx);
+    if (int e = launch_status("topk_kernel")) return e;
+  }
+  const size_t sm3 = (size_t)P.C * 33 * sizeof(float);
+  gather_decode_kernel<<<dim3((P.M + 31) / 32, P.n_img), 256, sm3, st>>>(P, img_info, cand_idx, boxes,
+                                                                        scores_cm);
+  return launch_status("gather_decode_kernel");
+}
+
+static int run_nms(const PostParams& P, const float* boxes, const float* scores_cm, float* dets,
+                   int64_t* labels, int32_t* counts, unsigned long long* kept_keys, int32_t* kept_cnt,
+                   cudaStream_t st) {
+  const int Pmax = next_pow2_host(P.M);
+  const size_t sm4 = (size_t)Pmax * 8 + (size_t)P.M * 20 + (size_t)((P.M + 31) / 32) * 4 + 16;
+  IOU_CHECK_CUDA(cudaFuncSetAttribute(class_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4));
+  class_nms_kernel<<<dim3(P.C, P.n_img), 512, sm4, st>>>(P, boxes, scores_cm, kept_keys, kept_cnt, Pmax);
+  if (int e = launch_status("class_nms_kernel")) return e;
+  const size_t sm5 = (size_t)next_pow2_host(P.C * P.kcap) * 8 + 64;
+  IOU_CHECK_CUDA(cudaFuncSetAttribute(final_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm5));
+  final_select_kernel<<<P.n_img, 1024, sm5, st>>>(P, boxes, kept_keys, kept_cnt, dets,
+                                                   reinterpret_cast<long long*>(labels), counts);
+  return launch_status("final_select_kernel");
+}
+
+}  // namespace iou
+
+using namespace iou;
+
+extern "C" int iou_postproc_num_candidates(const iou_postproc_cfg* cfg) {
+  PostParams P;
+  int e = fill_params(cfg, 1, P);
+  return e ? e : P.M;
+}
+
+extern "C" size_t iou_postproc_workspace_bytes(const iou_postproc_cfg* cfg, int n_img) {
+  PostParams P;
+  if (fill_params(cfg, n_img, P)) return 0;
+  return carve(P, nullptr).total;
+}
+
+extern "C" int iou_decode_candidates(const iou_postproc_cfg* cfg, int n_img, const float* const* cls,
+                                     const float* const* reg, const float* const* iou,
+                                     const float* img_info, int rescale, float* boxes, float* scores_cm,
+                                     int32_t* cand_idx, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+  PostParams P;
+  if (int e = fill_params(cfg, n_img, P)) return e;
+  IOU_REQUIRE(cls && reg && iou && img_info && boxes && scores_cm && cand_idx, "NULL argument");
+  PostWorkspace W = carve(P, workspace);
+  if (!workspace || workspace_bytes < W.total)
+    return fail(IOU_ERR_WORKSPACE, "workspace too small: need %zu bytes", W.total);
+  return run_decode(P, cls, reg, iou, img_info, rescale, boxes, scores_cm, cand_idx, W.maxscore,
+                    (cudaStream_t)stream);
+}
+
+extern "C" int iou_batched_nms(const iou_postproc_cfg* cfg, int n_img, const float* boxes,
+                               const float* scores_cm, float* dets, int64_t* labels, int32_t* counts,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  PostParams P;
+  if (int e = fill_params(cfg, n_img, P)) return e;
+  IOU_REQUIRE(boxes && scores_cm && dets && labels && counts, "NULL argument");
+  PostWorkspace W = carve(P, workspace);
+  if (!workspace || workspace_bytes < W.total)
+    return fail(IOU_ERR_WORKSPACE, "workspace too small: need %zu bytes", W.total);
+  return run_nms(P, boxes, scores_cm, dets, labels, counts, W.kept_keys, W.kept_cnt, (cudaStream_t)stream);
+}
+
+extern "C" int iou_get_bboxes(const iou_postproc_cfg* cfg, int n_img, const float* const* cls,
+                              const float* const* reg, const float* const* iou, const float* img_info,
+                              int rescale, float* dets, int64_t* labels, int32_t* counts,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  PostParams P;
+  if (int e = fill_params(cfg, n_img, P)) return e;
+  IOU_REQUIRE(cls && reg && iou && img_info && dets && labels && counts, "NULL argument");
+  PostWorkspace W = carve(P, workspace);
+  if (!workspace || workspace_bytes < W.total)
+    return fail(IOU_ERR_WORKSPACE, "workspace too small: need %zu bytes", W.total);
+  if (int e = run_decode(P, cls, reg, iou, img_info, rescale, W.boxes, W.scores_cm, W.cand_idx,
+                         W.maxscore, (cudaStream_t)stream))
+    return e;
+  return run_nms(P, W.boxes, W.scores_cm, dets, labels, counts, W.kept_keys, W.kept_cnt,
+                 (cudaStream_t)stream);
+}
+
+extern "C" size_t iou_nms_workspace_bytes(int n) { (void)n; return 256; }
+
+extern "C" int iou_nms(const float* dets, int n, float iou_thr, int64_t* keep_idx, int32_t* keep_count,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  IOU_REQUIRE(n >= 0, "n must be >= 0");
+  IOU_REQUIRE(keep_count != nullptr, "keep_count is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    IOU_CHECK_CUDA(cudaMemsetAsync(keep_count, 0, sizeof(int32_t), st));
+    return IOU_OK;
+  }
+  IOU_REQUIRE(dets && keep_idx, "NULL argument");
+  if (n > IOU_MAX_NMS_BOXES)
+    return fail(IOU_ERR_UNSUPPORTED, "iou_nms supports at most %d boxes per call (got %d)",
+                IOU_MAX_NMS_BOXES, n);
+  const int Pmax = next_pow2_host(n);
+  const size_t sm = (size_t)Pmax * 8 + (size_t)n * 20 + (size_t)((n + 31) / 32) * 8 + 16;
+  IOU_CHECK_CUDA(cudaFuncSetAttribute(single_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  single_nms_kernel<<<1, 512, sm, st>>>(dets, n, iou_thr, reinterpret_cast<long long*>(keep_idx),
+                                        keep_count, Pmax);
+  return launch_status("single_nms_kernel");
+}

@@ -1,0 +1,341 @@
+"""Execution plans over the padded-rows activation layout (see include/iou_b200.h).
+
+An ``Engine`` turns a state_dict of the reference's modules into a flat list of
+C-ABI launches: every convolution becomes one ``iou_conv_run`` of the tcgen05
+tap-GEMM kernel with BatchNorm / bias / ReLU / residual folded into its
+epilogue; layout kernels (stem im2col, max pool, stride-2 phase split) sit
+between them.  Buffers and TMA plans are created once per input shape, so a whole
+forward is a fixed launch sequence that can be captured in a CUDA graph.
+
+What each builder mirrors in the reference:
+  add_backbone : ResNet.forward            mmdet/models/backbones/resnet.py:224-267,507-518
+  add_fpn      : FPN.forward               mmdet/models/necks/fpn.py:97-136
+  add_head     : IoUawareRetinaHead.forward_single (all levels at once)
+                                           mmdet/models/anchor_heads/iou_aware_retina_head.py:171-219
+"""
+import ctypes
+
+import torch
+
+from . import lib as L
+
+TILE_M = 128
+STAGE_BLOCKS = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3), 152: (3, 8, 36, 3)}
+TAPS_1X1 = [(0, 0, 0)]
+TAPS_3X3 = [(0, r - 1, s - 1) for r in range(3) for s in range(3)]                    # stride 1, pad 1
+TAPS_3X3_S2 = [((r & 1) * 2 + (s & 1), r >> 1, s >> 1) for r in range(3) for s in range(3)]  # on phase maps
+TAPS_1X1_S2 = [(3, 0, 0)]                                                             # phase (1,1)
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class FlatMap(object):
+    """A bf16 [rows][2*c] padded-rows buffer holding one or more (n, h, w) segments."""
+
+    def __init__(self, segs, c, device, tensor=None, ptr=None, rows=None):
+        self.c = c
+        self.segs = []          # (row_start, n, h, w)
+        off = 0
+        for (n, h, w) in segs:
+            self.segs.append((off, n, h, w))
+            off += _round_up(n * (h + 2) * (w + 2), TILE_M)
+        if tensor is None and ptr is None:
+            tensor = torch.empty(off, 2 * c, dtype=torch.bfloat16, device=device)
+        self.tensor = tensor
+        self.ptr = tensor.data_ptr() if ptr is None else ptr
+        self.rows = off if rows is None else rows
+
+    def view(self, s):
+        """Single-segment view starting at segment s (rows run to the end of the parent)."""
+        rs, n, h, w = self.segs[s]
+        m = FlatMap([(n, h, w)], self.c, None, tensor=self.tensor, ptr=self.ptr + rs * 2 * self.c * 2,
+                    rows=self.rows - rs)
+        return m
+
+
+def split_hi_lo(x):
+    """fp32 -> (bf16 hi, bf16 lo) with hi + lo == x to ~2^-17 relative."""
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+def pack_weight(w, cout_pad, kpad=None):
+    """(Cout, Cin, kh, kw) fp32 -> bf16 [kh*kw*cout_pad][2*Cin'] (hi | lo), tap-major, K contiguous."""
+    cout, cin, kh, kw = w.shape
+    t = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin).float()
+    if kpad is not None and kpad != cin:
+        t = torch.nn.functional.pad(t, (0, kpad - cin))
+        cin = kpad
+    if cout_pad != cout:
+        t = torch.nn.functional.pad(t, (0, 0, 0, cout_pad - cout))
+    hi, lo = split_hi_lo(t)
+    return torch.cat([hi, lo], dim=2).reshape(kh * kw * cout_pad, 2 * cin).contiguous()
+
+
+def bn_fold(sd, prefix, eps=1e-5):
+    """Eval-mode BN as per-channel (scale, shift): y = conv*scale + shift."""
+    scale = sd[prefix + ".weight"].float() / torch.sqrt(sd[prefix + ".running_var"].float() + eps)
+    shift = sd[prefix + ".bias"].float() - sd[prefix + ".running_mean"].float() * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+def pick_block_n(cout):
+    if cout % 256 == 0:
+        return 256, cout
+    if cout in (64, 128):
+        return cout, cout
+    if cout % 240 == 0:
+        return 240, cout
+    pad = _round_up(cout, 16)
+    if pad <= 256:
+        return pad, pad
+    return 256, _round_up(cout, 256)
+
+
+class Engine(object):
+    def __init__(self, device, passes=3):
+        self.device = torch.device(device)
+        self.passes = passes
+        self.ops = []            # (name, callable(stream_ptr))
+        self.plans = []
+        self.keep = []           # tensors that must outlive the plan
+        self.flops = 0.0
+        self.lib = L.load()
+
+    # ------------------------------------------------------------------ primitive ops
+    def _dev(self, t):
+        t = t.detach().to(self.device, torch.float32).contiguous()
+        self.keep.append(t)
+        return t
+
+    def conv(self, name, srcs, taps, weight, cin, cout, out=None, scale=None, shift=None, relu=False,
+             residual=None, res_mode=L.RES_NONE, dense_out=None, dense_out2=None, dense_split=0,
+             segs_from=None):
+        """srcs: list[FlatMap] (same geometry); out: FlatMap or None (dense).  Returns out."""
+        block_n, cout_pad = pick_block_n(cout)
+        geo = segs_from or srcs[0]
+        d = L.ConvDesc()
+        d.cin, d.cout, d.cout_pad, d.block_n = cin, cout, cout_pad, block_n
+        d.num_taps = len(taps)
+        for i, (s, dy, dx) in enumerate(taps):
+            d.tap_src[i], d.tap_dy[i], d.tap_dx[i] = s, dy, dx
+        d.num_src = len(srcs)
+        for i, m in enumerate(srcs):
+            assert m.c == cin, (name, m.c, cin)
+            d.src[i] = m.ptr
+        d.src_rows = min(m.rows for m in srcs)
+        wp = weight.to(self.device)
+        self.keep.append(wp)
+        assert wp.shape == (len(taps) * cout_pad, 2 * cin), (name, wp.shape, len(taps), cout_pad, cin)
+        d.weight = wp.data_ptr()
+
+        def padc(v):
+            v = self._dev(v)
+            if v.numel() != cout_pad:
+                v = torch.nn.functional.pad(v, (0, cout_pad - v.numel())).contiguous()
+                self.keep.append(v)
+            return v
+        if scale is not None:
+            d.scale = padc(scale).data_ptr()
+        if shift is not None:
+            d.shift = padc(shift).data_ptr()
+        d.relu = int(relu)
+        d.res_mode = res_mode
+        if residual is not None:
+            d.residual = residual.ptr
+            for i, (rs, n, h, w) in enumerate(residual.segs):
+                d.res_seg[i] = L.ConvSegment(rs, n, h, w)
+        d.num_seg = len(geo.segs)
+        for i, (rs, n, h, w) in enumerate(geo.segs):
+            d.seg[i] = L.ConvSegment(rs, n, h, w)
+        if dense_out is None:
+            if out is None:
+                out = FlatMap([(n, h, w) for (_, n, h, w) in geo.segs], cout, self.device)
+            assert out.c == cout
+            d.out_mode, d.out = L.OUT_PADDED, out.ptr
+        else:
+            d.out_mode = L.OUT_DENSE
+            d.dense_split = dense_split
+            for i, t in enumerate(dense_out):
+                d.out_dense[i] = t.data_ptr()
+            if dense_out2 is not None:
+                for i, t in enumerate(dense_out2):
+                    d.out_dense2[i] = t.data_ptr()
+        d.passes = self.passes
+        plan = ctypes.c_void_p()
+        L.check(self.lib.iou_conv_plan_create(ctypes.byref(d), ctypes.byref(plan)))
+        self.plans.append(plan)
+        self.flops += self.lib.iou_conv_plan_flops(plan)
+        lib = self.lib
+        self.ops.append((name, lambda st, p=plan: L.check(lib.iou_conv_run(p, st))))
+        return out
+
+    def phase_split(self, name, src, mask=15):
+        """-> list of 4 FlatMaps (None where masked out) in the stride-2 output geometry."""
+        assert len(src.segs) == 1
+        _, n, h, w = src.segs[0]
+        ho, wo = (h + 1) // 2, (w + 1) // 2
+        outs = [FlatMap([(n, ho, wo)], src.c, self.device) if (mask >> i) & 1 else None for i in range(4)]
+        arr = (ctypes.c_void_p * 4)(*[(o.ptr if o is not None else None) for o in outs])
+        self.keep.append(arr)
+        lib, c, sp = self.lib, src.c, src.ptr
+        self.ops.append((name, lambda st: L.check(lib.iou_phase_split(sp, n, c, h, w, arr, mask, st))))
+        return outs
+
+    # ------------------------------------------------------------------ network builders
+    def add_stem(self, sd, img, prefix="backbone."):
+        """conv1 7x7/s2 + bn1 + relu + maxpool (resnet.py:508-511).  img: (N,3,H,W) fp32 cuda tensor."""
+        n, _, h, w = img.shape
+        ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        kpad = 192
+        cols = FlatMap([(n, ho, wo)], kpad, self.device)
+        lib, ip, cp = self.lib, img.data_ptr(), cols.ptr
+        self.keep.append(img)
+        self.ops.append(("stem.im2col", lambda st: L.check(lib.iou_im2col_stem(ip, n, h, w, kpad, cp, st))))
+        wt = sd[prefix + "conv1.weight"].float().permute(0, 2, 3, 1).reshape(64, 147, 1, 1)
+        scale, shift = bn_fold(sd, prefix + "bn1")
+        s1 = self.conv("stem.conv1", [cols], TAPS_1X1, pack_weight(wt, 64, kpad), kpad, 64,
+                       scale=scale, shift=shift, relu=True)
+        self.flops -= 2.0 * n * ho * wo * 64 * (kpad - 147)      # K padding is not algorithmic work
+        hp, wq = (ho - 1) // 2 + 1, (wo - 1) // 2 + 1
+        x = FlatMap([(n, hp, wq)], 64, self.device)
+        sp, xp = s1.ptr, x.ptr
+        self.ops.append(("stem.maxpool", lambda st: L.check(lib.iou_maxpool3x3s2(sp, n, 64, ho, wo, xp, st))))
+        return x
+
+    def add_backbone(self, sd, img, depth=50, groups=1, prefix="backbone."):
+        if groups != 1:
+            raise NotImplementedError("grouped (ResNeXt) 3x3 convolutions are not built yet")
+        x = self.add_stem(sd, img, prefix)
+        outs = []
+        for s, nblocks in enumerate(STAGE_BLOCKS[depth]):
+            planes = 64 * 2 ** s
+            for b in range(nblocks):
+                p = "%slayer%d.%d." % (prefix, s + 1, b)
+                stride = 2 if (b == 0 and s > 0) else 1
+                cin = x.c
+                sc1, sh1 = bn_fold(sd, p + "bn1")
+                t1 = self.conv(p + "conv1", [x], TAPS_1X1, pack_weight(sd[p + "conv1.weight"], planes),
+                               cin, planes, scale=sc1, shift=sh1, relu=True)
+                sc2, sh2 = bn_fold(sd, p + "bn2")
+                w2 = pack_weight(sd[p + "conv2.weight"], planes)
+                if stride == 2:
+                    ph = self.phase_split(p + "conv2.phase", t1)
+                    t2 = self.conv(p + "conv2", ph, TAPS_3X3_S2, w2, planes, planes, scale=sc2, shift=sh2,
+                                   relu=True)
+                else:
+                    t2 = self.conv(p + "conv2", [t1], TAPS_3X3, w2, planes, planes, scale=sc2, shift=sh2,
+                                   relu=True)
+                idt = x
+                if (p + "downsample.0.weight") in sd:
+                    scd, shd = bn_fold(sd, p + "downsample.1")
+                    wd = pack_weight(sd[p + "downsample.0.weight"], planes * 4)
+                    if stride == 2:
+                        xs = self.phase_split(p + "downsample.phase", x, mask=8)
+                        srcs = [xs[3], xs[3], xs[3], xs[3]]
+                        idt = self.conv(p + "downsample", srcs, TAPS_1X1_S2, wd, cin, planes * 4,
+                                        scale=scd, shift=shd)
+                    else:
+                        idt = self.conv(p + "downsample", [x], TAPS_1X1, wd, cin, planes * 4,
+                                        scale=scd, shift=shd)
+                sc3, sh3 = bn_fold(sd, p + "bn3")
+                x = self.conv(p + "conv3", [t2], TAPS_1X1, pack_weight(sd[p + "conv3.weight"], planes * 4),
+                              planes, planes * 4, scale=sc3, shift=sh3, relu=True, residual=idt,
+                              res_mode=L.RES_SAME)
+            outs.append(x)
+        return outs
+
+    def add_fpn(self, sd, feats, prefix="neck.", start_level=1, num_outs=5, out_channels=256):
+        """feats: list of FlatMaps C2..C5.  Returns one multi-segment FlatMap (P3..P7)."""
+        used = feats[start_level:]
+        nl = len(used)
+        lat = [None] * nl
+        for i in range(nl - 1, -1, -1):
+            kp = "%slateral_convs.%d.conv." % (prefix, i)
+            res = lat[i + 1] if i + 1 < nl else None
+            lat[i] = self.conv(kp[:-1], [used[i]], TAPS_1X1, pack_weight(sd[kp + "weight"], out_channels),
+                               used[i].c, out_channels, shift=sd[kp + "bias"], residual=res,
+                               res_mode=L.RES_UPSAMPLE2 if res is not None else L.RES_NONE)
+        geos = [m.segs[0][1:] for m in lat]
+        n, h, w = geos[-1]
+        for _ in range(nl, num_outs):
+            h, w = (h + 1) // 2, (w + 1) // 2
+            geos.append((n, h, w))
+        F = FlatMap(geos, out_channels, self.device)
+        for i in range(nl):
+            kp = "%sfpn_convs.%d.conv." % (prefix, i)
+            self.conv(kp[:-1], [lat[i]], TAPS_3X3, pack_weight(sd[kp + "weight"], out_channels),
+                      out_channels, out_channels, out=F.view(i), shift=sd[kp + "bias"])
+        src = feats[-1]                                   # extra_convs_on_inputs=True: P6 from C5
+        for i in range(nl, num_outs):
+            kp = "%sfpn_convs.%d.conv." % (prefix, i)
+            ph = self.phase_split(kp + "phase", src)
+            self.conv(kp[:-1], ph, TAPS_3X3_S2, pack_weight(sd[kp + "weight"], out_channels), src.c,
+                      out_channels, out=F.view(i), shift=sd[kp + "bias"])
+            src = F.view(i)                               # relu_before_extra_convs=False
+        return F
+
+    def add_head(self, sd, F, prefix="bbox_head.", stacked=4, num_anchors=9, num_classes=80):
+        """All levels in one launch per conv.  Returns (cls, reg, iou) lists of NHWC fp32 tensors
+        exposed with the reference's logical shape (N, A*C, H, W)."""
+        c = r = F
+        fc = sd[prefix + "cls_convs.0.conv.weight"].shape[0]
+        for i in range(stacked):
+            kc, kr = "%scls_convs.%d.conv." % (prefix, i), "%sreg_convs.%d.conv." % (prefix, i)
+            c = self.conv(kc[:-1], [c], TAPS_3X3, pack_weight(sd[kc + "weight"], fc), c.c, fc,
+                          shift=sd[kc + "bias"], relu=True)
+            r = self.conv(kr[:-1], [r], TAPS_3X3, pack_weight(sd[kr + "weight"], fc), r.c, fc,
+                          shift=sd[kr + "bias"], relu=True)
+        ncls, nreg, niou = num_anchors * num_classes, num_anchors * 4, num_anchors
+        cls_out = [torch.empty(n, h, w, ncls, dtype=torch.float32, device=self.device) for (_, n, h, w) in F.segs]
+        reg_out = [torch.empty(n, h, w, nreg, dtype=torch.float32, device=self.device) for (_, n, h, w) in F.segs]
+        iou_out = [torch.empty(n, h, w, niou, dtype=torch.float32, device=self.device) for (_, n, h, w) in F.segs]
+        bn_c, pad_c = pick_block_n(ncls)
+        self.conv(prefix + "retina_cls", [c], TAPS_3X3, pack_weight(sd[prefix + "retina_cls.weight"], pad_c),
+                  fc, ncls, shift=sd[prefix + "retina_cls.bias"], dense_out=cls_out)
+        # retina_reg and retina_iou read the same feature (shared_conv=4, :198-204): one GEMM, split store
+        w_ri = torch.cat([sd[prefix + "retina_reg.weight"], sd[prefix + "retina_iou.weight"]], dim=0)
+        b_ri = torch.cat([sd[prefix + "retina_reg.bias"], sd[prefix + "retina_iou.bias"]], dim=0)
+        _, pad_ri = pick_block_n(nreg + niou)
+        self.conv(prefix + "retina_reg+iou", [r], TAPS_3X3, pack_weight(w_ri, pad_ri), fc, nreg + niou,
+                  shift=b_ri, dense_out=reg_out, dense_out2=iou_out, dense_split=nreg)
+        self.keep += cls_out + reg_out + iou_out
+        as_nchw = lambda ts: [t.permute(0, 3, 1, 2) for t in ts]
+        return as_nchw(cls_out), as_nchw(reg_out), as_nchw(iou_out)
+
+    # ------------------------------------------------------------------ layout I/O
+    def pack_input(self, x):
+        """(N,C,H,W) fp32 cuda tensor -> FlatMap (op appended)."""
+        n, c, h, w = x.shape
+        m = FlatMap([(n, h, w)], c, self.device)
+        lib, xp, mp = self.lib, x.data_ptr(), m.ptr
+        self.keep.append(x)
+        self.ops.append(("pack", lambda st: L.check(lib.iou_pack_nchw(xp, n, c, h, w, mp, 0, st))))
+        return m
+
+    def unpack_output(self, m, s=0):
+        rs, n, h, w = m.segs[s]
+        out = torch.empty(n, m.c, h, w, dtype=torch.float32, device=self.device)
+        lib, mp, op, c = self.lib, m.ptr, out.data_ptr(), m.c
+        self.ops.append(("unpack", lambda st: L.check(lib.iou_unpack_nchw(mp, rs, n, c, h, w, op, st))))
+        return out
+
+    # ------------------------------------------------------------------ execution
+    def run(self):
+        st = L.stream_ptr()
+        for _, fn in self.ops:
+            fn(st)
+        L.launch_count += len(self.ops)
+
+    def num_launches(self):
+        return len(self.ops)
+
+    def __del__(self):
+        try:
+            for p in self.plans:
+                self.lib.iou_conv_plan_destroy(p)
+        except Exception:
+            pass

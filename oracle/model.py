@@ -89,29 +89,40 @@ def detector_forward(sd, img, depth=50, groups=1):
     return head_forward(sd, feats)
 
 
-def spread_weights_(sd, seed=1, final_std=None):
-    """re-draw BN statistics / affine and widen the final
-    convs so that logits spread (score gaps >> 1e-4) instead of the degenerate
-    reference init.  Operates in place on a state_dict; deterministic in `seed`."""
+def spread_weights_(sd, seed=1, depth=50, groups=1, targets=(2.0, 0.5, 1.5), cls_bias=-3.0):
+    """re-draw BN statistics / affine (un-zeroing bn3) and the head so that
+    logits SPREAD (score gaps >> 1e-4) instead of the degenerate reference init, then calibrate the
+    three output convs on a fixed probe image so that cls / reg / iou logits have std `targets`
+    (a trained-net-like regime).  Operates in place on a state_dict; deterministic in `seed`."""
     g = torch.Generator().manual_seed(seed)
     for k in sorted(sd.keys()):
         v = sd[k]
+        is_bn = (".bn" in k) or ("downsample.1" in k) or k.startswith("backbone.bn1")
         if k.endswith("running_var"):
             v.copy_(torch.rand(v.shape, generator=g) + 0.5)
         elif k.endswith("running_mean"):
             v.copy_(torch.randn(v.shape, generator=g) * 0.1)
-        elif ".bn" in k or "downsample.1" in k or k.startswith("backbone.bn1"):
-            if k.endswith(".weight"):
+        elif is_bn and k.endswith(".weight"):
+            if ".bn3." in k:      # keep the residual branch modest so depth does not blow the scale up
+                v.copy_(torch.rand(v.shape, generator=g) * 0.3 + 0.1)
+            else:
                 v.copy_(torch.rand(v.shape, generator=g) + 0.5)
-            elif k.endswith(".bias"):
-                v.copy_(torch.randn(v.shape, generator=g) * 0.1)
-    final_std = final_std or {"retina_cls": 0.02, "retina_reg": 0.004, "retina_iou": 0.02}
-    for name, std in final_std.items():
-        k = "bbox_head.%s.weight" % name
-        sd[k].copy_(torch.randn(sd[k].shape, generator=g) * std)
+        elif is_bn and k.endswith(".bias"):
+            v.copy_(torch.randn(v.shape, generator=g) * 0.1)
     for i in range(4):
         for t in ("cls_convs", "reg_convs"):
             k = "bbox_head.%s.%d.conv.weight" % (t, i)
             fan_in = sd[k].shape[1] * 9
             sd[k].copy_(torch.randn(sd[k].shape, generator=g) * (2.0 / fan_in) ** 0.5)
+    for name in ("retina_cls", "retina_reg", "retina_iou"):
+        k = "bbox_head.%s.weight" % name
+        sd[k].copy_(torch.randn(sd[k].shape, generator=g) * 0.01)
+        sd["bbox_head.%s.bias" % name].zero_()
+    probe = torch.randn(1, 3, 128, 160, generator=g)
+    cls, reg, iou = detector_forward(sd, probe, depth, groups)
+    for name, maps, tgt in (("retina_cls", cls, targets[0]), ("retina_reg", reg, targets[1]),
+                            ("retina_iou", iou, targets[2])):
+        std = torch.cat([m.reshape(-1) for m in maps]).std().item()
+        sd["bbox_head.%s.weight" % name].mul_(tgt / max(std, 1e-12))
+    sd["bbox_head.retina_cls.bias"].fill_(cls_bias)
     return sd

@@ -1,0 +1,210 @@
+"""Shared parity checkers (used by the -m gpu tests and by __graft_entry__.smoke()).
+
+Everything here compares the CUDA path (called through the package == through the C ABI) with the
+CPU oracle and with the golden fixtures generated from the real reference.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import cases  # noqa: E402
+from oracle import model as om  # noqa: E402
+from oracle import postproc as op  # noqa: E402
+
+import iou_aware_single_stage_object_detector_b200 as P  # noqa: E402
+from iou_aware_single_stage_object_detector_b200 import postproc as PP  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+CFG_DIR = os.path.join(ROOT, "configs", "iou_aware_single_stage_detector")
+# parity bar of BASELINE.json north_star: scores / boxes within 1e-4 (fp32), indices exact
+RTOL = ATOL = 1e-4
+
+
+def head_cfg():
+    return dict(type='IoUawareRetinaHead', num_classes=81, in_channels=256, stacked_convs=4,
+                feat_channels=256, octave_base_scale=4, scales_per_octave=3,
+                anchor_ratios=[0.5, 1.0, 2.0], anchor_strides=[8, 16, 32, 64, 128],
+                target_means=[.0, .0, .0, .0], target_stds=[1.0, 1.0, 1.0, 1.0],
+                loss_cls=dict(type='FocalLoss', use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0),
+                loss_bbox=dict(type='SmoothL1Loss', beta=0.11, loss_weight=1.0))
+
+
+_head = None
+
+
+def get_head():
+    global _head
+    if _head is None:
+        torch.manual_seed(0)
+        _head = P.build_head(head_cfg())
+    return _head
+
+
+def oracle_bases():
+    sc = op.retina_anchor_scales(4, 3)
+    return [op.base_anchors(s, sc, [0.5, 1.0, 2.0]) for s in cases.STRIDES]
+
+
+def near_tie_explained(scores_sorted_desc, tol=2e-6):
+    """True if some adjacent pair of the sorted key list is closer than tol (order then undefined)."""
+    d = np.diff(scores_sorted_desc.astype(np.float64))
+    return bool(np.any(np.abs(d) < tol))
+
+
+def check_postproc_case(name, verbose=True):
+    """get_bboxes on the GPU vs golden fixtures made from the real reference."""
+    gold = np.load(os.path.join(GOLD, "postproc_%s.npz" % name))
+    case = cases.postproc_case(name)
+    head = get_head()
+    dev = torch.device("cuda:0")
+    cfg = P.ConfigDict(case["cfg"])
+    cls = [t.to(dev) for t in case["cls"]]
+    reg = [t.to(dev) for t in case["reg"]]
+    iou = [t.to(dev) for t in case["iou"]]
+    n_img = cls[0].shape[0]
+    metas = case["img_metas"]
+    sizes = [tuple(t.shape[-2:]) for t in cls]
+    wsp = head.postproc_workspace(sizes, n_img, cfg, dev)
+    info = PP.make_img_info(metas, dev)
+    # ---- stage 1: candidates
+    boxes, scores_cm, idx = PP.decode_candidates(wsp, cls, reg, iou, info, case["rescale"])
+    torch.cuda.synchronize()
+    idx_exact = True
+    for i in range(n_img):
+        g_idx = gold["cand_idx_%d" % i]
+        g_box = gold["cand_boxes_%d" % i]
+        g_sc = gold["cand_scores_%d" % i]
+        my_idx = idx[i].cpu().numpy()
+        my_box = boxes[i].cpu().numpy()
+        my_sc = scores_cm[i].t().contiguous().cpu().numpy()
+        same = np.array_equal(my_idx, g_idx)
+        if not same:
+            idx_exact = False
+            # order may only differ where two keys are closer than fp32 noise
+            assert sorted(my_idx.tolist()) == sorted(g_idx.tolist()) or \
+                near_tie_explained(np.sort(g_sc.max(1))[::-1]), "candidate set differs (%s, img %d)" % (name, i)
+            bad = int((my_idx != g_idx).sum())
+            assert bad <= 8, "%d candidate order mismatches (%s, img %d)" % (bad, name, i)
+            if verbose:
+                print("[%s] img %d: %d candidate order differences (near-ties)" % (name, i, bad))
+        else:
+            assert np.allclose(my_box, g_box, rtol=RTOL, atol=ATOL), \
+                "boxes differ: max %g" % np.abs(my_box - g_box).max()
+            assert np.allclose(my_sc, g_sc, rtol=RTOL, atol=ATOL), \
+                "scores differ: max %g" % np.abs(my_sc - g_sc).max()
+            if verbose:
+                print("[%s] img %d: candidates exact order; max |dbox| %.3g, max |dscore| %.3g" % (
+                    name, i, np.abs(my_box - g_box).max(), np.abs(my_sc - g_sc).max()))
+    # ---- stage 2 on the GOLDEN candidates: bit-exact indices/labels/values
+    M = wsp.M
+    gb = torch.stack([torch.from_numpy(gold["cand_boxes_%d" % i]) for i in range(n_img)]).to(dev)
+    gs = torch.stack([torch.from_numpy(gold["cand_scores_%d" % i]).t().contiguous() for i in range(n_img)]).to(dev)
+    assert gb.shape[1] == M
+    dets, labels, counts = PP.batched_nms(wsp, gb, gs)
+    for i, (d, l) in enumerate(PP.split_results(dets, labels, counts)):
+        gd, gl = gold["dets_%d" % i], gold["labels_%d" % i]
+        assert d.shape[0] == gd.shape[0], "det count %d != %d (%s img %d)" % (d.shape[0], gd.shape[0], name, i)
+        assert np.array_equal(l.cpu().numpy(), gl), "labels differ (%s img %d)" % (name, i)
+        assert np.array_equal(d.cpu().numpy(), gd), "dets differ (%s img %d)" % (name, i)
+    # ---- end to end through the reference-signature API
+    res = head.get_bboxes(cls, reg, iou, [None] * n_img, [None] * n_img, metas, cfg, rescale=case["rescale"])
+    for i, (d, l) in enumerate(res):
+        gd, gl = gold["dets_%d" % i], gold["labels_%d" % i]
+        assert d.shape[0] == gd.shape[0]
+        if idx_exact:
+            assert np.array_equal(l.cpu().numpy(), gl), "e2e labels differ (%s img %d)" % (name, i)
+            assert np.allclose(d.cpu().numpy(), gd, rtol=RTOL, atol=ATOL), \
+                "e2e dets differ: %g" % np.abs(d.cpu().numpy() - gd).max()
+        else:
+            match_as_sets(d.cpu().numpy(), l.cpu().numpy(), gd, gl)
+    return True
+
+
+def match_as_sets(d, l, gd, gl, min_frac=0.97):
+    """Order-free comparison keyed by label + box."""
+    used = np.zeros(len(gd), bool)
+    hit = 0
+    for k in range(len(d)):
+        cand = np.where((gl == l[k]) & ~used)[0]
+        if cand.size == 0:
+            continue
+        err = np.abs(gd[cand] - d[k]).max(1)
+        j = cand[err.argmin()]
+        if np.allclose(d[k], gd[j], rtol=RTOL, atol=ATOL):
+            used[j] = True
+            hit += 1
+    frac = hit / max(len(gd), 1)
+    assert frac >= min_frac, "only %.3f of detections matched" % frac
+    return frac
+
+
+def small_detector(seed=0, spread=True, cfg_name="iou_aware_retinanet_r50_fpn_1x_4gpu.py"):
+    cfg = P.Config.fromfile(os.path.join(CFG_DIR, cfg_name))
+    cfg.model.pretrained = None
+    torch.manual_seed(seed)
+    det = P.build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg)
+    det.eval()
+    if spread:
+        sd = det.state_dict()
+        om.spread_weights_(sd, seed=seed + 1)
+        det.load_state_dict(sd)
+    return det, cfg
+
+
+def results_to_arrays(per_class):
+    n = sum(len(m) for m in per_class)
+    if n == 0:
+        return np.zeros((0, 5), np.float32), np.zeros((0,), np.int64)
+    d = np.concatenate(list(per_class), 0)
+    l = np.concatenate([np.full(len(m), c) for c, m in enumerate(per_class)]).astype(np.int64)
+    return d, l
+
+
+def check_detector_small(h=128, w=160, n=2, verbose=True, use_graph=False):
+    """Whole path on a small image: CUDA head maps vs oracle (torch-CPU fp32) maps, then detections."""
+    det, cfg = small_detector()
+    sd = {k: v.clone() for k, v in det.state_dict().items()}
+    dev = torch.device("cuda:0")
+    det = det.to(dev)
+    g = torch.Generator().manual_seed(3)
+    img = torch.randn(n, 3, h, w, generator=g)
+    metas = [dict(ori_shape=(h, w - 3, 3), img_shape=(h, w - 3, 3), pad_shape=(h, w, 3), scale_factor=1.0,
+                  flip=False) for _ in range(n)]
+    det.use_cuda_graph = use_graph
+    results = det.simple_test_batch(img.to(dev), metas, rescale=False)
+    if use_graph:   # second call replays the captured graph
+        results = det.simple_test_batch(img.to(dev), metas, rescale=False)
+    plan = det.fused_plan(img.shape, dev, False)
+    torch.cuda.synchronize()
+    ref_cls, ref_reg, ref_iou = om.detector_forward(sd, img)
+    worst = 0.0
+    for name, mine, ref in (("cls", plan.outs[0], ref_cls), ("reg", plan.outs[1], ref_reg),
+                            ("iou", plan.outs[2], ref_iou)):
+        for l, (a, b) in enumerate(zip(mine, ref)):
+            a = a.cpu().contiguous()
+            err = (a - b).abs().max().item()
+            scale = b.abs().max().item()
+            worst = max(worst, err / max(scale, 1e-6))
+            if verbose:
+                print("head %s level %d: max|d| %.3g (ref max %.3g)" % (name, l, err, scale))
+            assert torch.allclose(a, b, rtol=1e-3, atol=1e-3 * max(scale, 1.0)), \
+                "head %s level %d differs: %g" % (name, l, err)
+    bases = oracle_bases()
+    for i in range(n):
+        d_ref, l_ref = op.get_bboxes_single([c[i] for c in ref_cls], [r[i] for r in ref_reg],
+                                            [q[i] for q in ref_iou], cases.STRIDES, bases,
+                                            metas[i]["img_shape"], 1.0, dict(cfg.test_cfg), rescale=False)
+        d_my, l_my = results_to_arrays(results[i])
+        if verbose:
+            print("image %d: %d dets (oracle %d)" % (i, len(d_my), d_ref.shape[0]))
+        assert abs(len(d_my) - d_ref.shape[0]) <= 3
+        if d_ref.shape[0]:
+            match_as_sets(d_my, l_my, d_ref.numpy(), l_ref.numpy(), min_frac=0.9)
+    return worst

@@ -1,0 +1,217 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol declared in include/iou_b200.h,
+the host-side mirror of the reference interface behaves, and the N>1 plumbing works over gloo."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+import iou_aware_single_stage_object_detector_b200 as P
+from iou_aware_single_stage_object_detector_b200 import dist as D
+from iou_aware_single_stage_object_detector_b200 import engine as E
+from iou_aware_single_stage_object_detector_b200 import lib as L
+
+CFG_DIR = os.path.join(ROOT, "configs", "iou_aware_single_stage_detector")
+
+
+def header_functions():
+    txt = open(os.path.join(ROOT, "include", "iou_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(iou_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    path = L.build()
+    assert os.path.isfile(path)
+    lib = ctypes.CDLL(path)
+    names = header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "symbol %s declared in the header is not exported" % n
+    assert set(names) == set(L.EXPORTED_SYMBOLS)
+    lib.iou_abi_version.restype = ctypes.c_int
+    assert lib.iou_abi_version() == 1
+
+
+def test_sass_is_blackwell_native():
+    """tcgen05 / TMA show up in SASS as UTCHMMA / UTMALDG / LDTM (B200_PROFILING.md)."""
+    out = subprocess.run(["cuobjdump", "-sass", L.build()], capture_output=True, text=True).stdout
+    for mnem in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnem in out, mnem
+    assert "HMMA.16816" not in out       # no legacy mma.sync path
+
+
+def test_struct_layouts_match_header():
+    # sizes the C side computes for the same structs (plain-C layout rules)
+    assert ctypes.sizeof(L.ConvSegment) == 16
+    assert ctypes.sizeof(L.PostprocCfg) == 5 * 4 + 3 * 8 * 4 + 8 * 16 * 4 * 4 + 8 * 4 + 4 * 4
+    assert L.ConvDesc.src.offset % 8 == 0 and L.ConvDesc.weight.offset % 8 == 0
+
+
+def test_errors_are_loud_without_gpu():
+    lib = L.load()
+    cfg = L.PostprocCfg()
+    assert lib.iou_postproc_num_candidates(ctypes.byref(cfg)) < 0
+    assert b"num_levels" in lib.iou_last_error()
+    with pytest.raises(RuntimeError):
+        P.nms(torch.zeros(4, 5), 0.5)                 # CPU tensor -> no fallback
+    with pytest.raises(RuntimeError):
+        P.multiclass_nms(torch.zeros(4, 4), torch.zeros(4, 81), 0.05, dict(type='nms', iou_thr=0.5), 100)
+    cfg = P.Config.fromfile(os.path.join(CFG_DIR, "iou_aware_retinanet_r50_fpn_1x_4gpu.py"))
+    with pytest.raises(RuntimeError):          # model-zoo URLs need a network: loud, not silent
+        P.build_detector(cfg.model)
+    cfg.model.pretrained = None
+    det = P.build_detector(cfg.model)
+    with pytest.raises(RuntimeError):
+        det.backbone(torch.zeros(1, 3, 64, 64))
+
+
+@pytest.mark.parametrize("name,params_m", [("iou_aware_retinanet_r50_fpn_1x_4gpu.py", 37.99),
+                                           ("iou_aware_retinanet_r50_fpn_1x_2gpu.py", 37.99),
+                                           ("iou_aware_retinanet_r101_fpn_1x_4gpu.py", 56.98),
+                                           ("iou_aware_retinanet_x101_32x4d_fpn_1x_4gpu.py", None),
+                                           ("iou_aware_retinanet_x101_64x4d_fpn_1x.py", None)])
+def test_configs_build(name, params_m):
+    cfg = P.Config.fromfile(os.path.join(CFG_DIR, name))
+    cfg.model.pretrained = None
+    det = P.build_detector(cfg.model, train_cfg=cfg.train_cfg, test_cfg=cfg.test_cfg)
+    assert type(det).__name__ == "RetinaNet" and type(det.bbox_head).__name__ == "IoUawareRetinaHead"
+    if params_m:
+        assert abs(sum(p.numel() for p in det.parameters()) / 1e6 - params_m) < 0.01
+    assert det.test_cfg.nms.iou_thr == 0.5 and det.test_cfg.get('nms_pre', -1) == 1000
+    h = det.bbox_head
+    assert h.num_anchors == 9 and h.cls_out_channels == 80
+    assert h.retina_cls.weight.shape == (720, 256, 3, 3) and h.retina_iou.weight.shape == (9, 256, 3, 3)
+    # reference init of the head (iou_aware_retina_head.py:153-165)
+    assert float(h.retina_cls.bias[0]) == pytest.approx(-4.59512, abs=1e-4)
+    assert float(h.retina_cls.weight.std()) == pytest.approx(0.01, rel=0.05)
+
+
+@pytest.mark.reference
+def test_reference_config_files_load_unchanged_and_keys_match():
+    ref_dir = "/root/reference/configs/iou_aware_single_stage_detector"
+    for f in sorted(os.listdir(ref_dir)):
+        cfg = P.Config.fromfile(os.path.join(ref_dir, f))
+        cfg.model.pretrained = None
+        det = P.build_detector(cfg.model, train_cfg=cfg.train_cfg, test_cfg=cfg.test_cfg)
+        assert cfg.test_cfg.max_per_img == 100 and cfg.dist_params.backend == 'nccl'
+        mine = os.path.join(CFG_DIR, f)
+        if os.path.isfile(mine):
+            c2 = P.Config.fromfile(mine)
+            assert dict(c2.test_cfg) == dict(cfg.test_cfg)
+            c2.model.pretrained = None
+            assert c2.model == cfg.model
+    # state_dict schema == the reference's, checked in a subprocess so that the
+    # reference's `mmdet` package never shares a process with this repo's modules
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from oracle import ref_shim\n"
+            "m, cfg = ref_shim.build_reference_detector()\n"
+            "print('\\n'.join('%%s %%s' %% (k, tuple(v.shape)) for k, v in m.state_dict().items()))\n") % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    ref_keys = [l for l in out.stdout.strip().splitlines() if l.startswith(("backbone", "neck", "bbox_head"))]
+    cfg = P.Config.fromfile(os.path.join(ref_dir, "iou_aware_retinanet_r50_fpn_1x_4gpu.py"))
+    cfg.model.pretrained = None
+    det = P.build_detector(cfg.model, test_cfg=cfg.test_cfg)
+    my_keys = ['%s %s' % (k, tuple(v.shape)) for k, v in det.state_dict().items()]
+    assert sorted(my_keys) == sorted(ref_keys)
+    assert len(my_keys) == 356
+
+
+def test_registry_and_builder_semantics():
+    assert 'IoUawareRetinaHead' in P.HEADS.module_dict and 'RetinaNet' in P.DETECTORS.module_dict
+    assert 'ResNet' in P.BACKBONES.module_dict and 'ResNeXt' in P.BACKBONES.module_dict
+    assert 'FPN' in P.NECKS.module_dict and 'FocalLoss' in P.LOSSES.module_dict
+    with pytest.raises(KeyError):
+        P.build_head(dict(type='NoSuchHead'))
+    with pytest.raises(KeyError):
+        P.HEADS.register_module(P.IoUawareRetinaHead)
+    with pytest.raises(TypeError):
+        P.HEADS.register_module(int)
+    seq = P.build([dict(type='FocalLoss', use_sigmoid=True), dict(type='SmoothL1Loss')], P.LOSSES)
+    assert isinstance(seq, torch.nn.Sequential) and len(seq) == 2
+
+
+def test_anchor_generator_matches_oracle():
+    from oracle import postproc as op
+    for s in (8, 16, 32, 64, 128):
+        g = P.AnchorGenerator(s, op.retina_anchor_scales(4, 3), [0.5, 1.0, 2.0])
+        assert torch.equal(g.base_anchors, op.base_anchors(s, op.retina_anchor_scales(4, 3), [0.5, 1.0, 2.0]))
+        assert torch.equal(g.grid_anchors((3, 5), s), op.grid_anchors(g.base_anchors, 3, 5, s))
+    rois = torch.tensor([[0., 0., 31., 31.]])
+    out = P.delta2bbox(rois, torch.tensor([[0.1, -0.2, 0.3, 5.0]]), max_shape=(800, 1333, 3))
+    assert np.allclose(out.numpy(), [[0, 0, 39.7977, 799]], atol=1e-3)
+
+
+def test_bbox2result_formats():
+    d = torch.tensor([[1., 2., 3., 4., .9], [5., 6., 7., 8., .8]])
+    l = torch.tensor([3, 0])
+    r = P.bbox2result(d, l, 81)
+    assert len(r) == 80 and r[3].shape == (1, 5) and r[0][0, 4] == np.float32(.8) and r[1].shape == (0, 5)
+    e = P.bbox2result(torch.zeros(0, 5), torch.zeros(0, dtype=torch.long), 81)
+    assert len(e) == 80 and all(a.shape == (0, 5) and a.dtype == np.float32 for a in e)
+
+
+def test_weight_packing_and_layout_helpers():
+    w = torch.randn(7, 64, 3, 3)
+    p = E.pack_weight(w, 16)
+    assert p.shape == (9 * 16, 128) and p.dtype == torch.bfloat16
+    hi, lo = p[:, :64].float(), p[:, 64:].float()
+    tap = (hi + lo).reshape(9, 16, 64)
+    assert torch.allclose(tap[4, :7], w[:, :, 1, 1], rtol=2e-5, atol=1e-30)
+    assert float(tap[:, 7:].abs().max()) == 0
+    assert E.pick_block_n(720) == (240, 720) and E.pick_block_n(45) == (48, 48)
+    assert E.pick_block_n(256) == (256, 256) and E.pick_block_n(2048) == (256, 2048)
+    assert E.pick_block_n(64) == (64, 64)
+    m = E.FlatMap([(8, 100, 168), (8, 50, 84), (8, 25, 42), (8, 13, 21), (8, 7, 11)], 256, "meta",
+                  tensor=torch.empty(0), ptr=0, rows=0)
+    starts = [s[0] for s in m.segs]
+    assert all(s % 128 == 0 for s in starts) and starts[1] == 138752
+    # stride-2 taps: tap (r,s) reads phase (r&1, s&1) at offset (r>>1, s>>1)
+    assert E.TAPS_3X3_S2[0] == (0, 0, 0) and E.TAPS_3X3_S2[4] == (3, 0, 0) and E.TAPS_3X3_S2[8] == (0, 1, 1)
+
+
+def test_shard_ranges_cover_batch():
+    for world in (1, 2, 3, 4, 8):
+        for B in (8, 13, 64):
+            r = [D.shard_range(k, world, B) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == B and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    r, w, _ = D.init_dist("gloo")
+    b, k = 3, 100
+    g = torch.Generator().manual_seed(100 + rank)
+    dets = torch.rand(b, k, 5, generator=g)
+    labels = torch.randint(0, 80, (b, k), generator=g)
+    counts = torch.tensor([rank, 50 + rank, 100], dtype=torch.int32)
+    gd, gl, gc = D.gather_detections(dets, labels, counts)
+    q.put((rank, gd, gl, gc, dets, labels, counts))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_all_gather_of_detections_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29641
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, gd, gl, gc, *_ in got:
+        assert gd.shape == (6, 100, 5) and gl.shape == (6, 100) and gl.dtype == torch.int64
+        for src in range(2):
+            assert torch.equal(gd[src * 3:(src + 1) * 3], got[src][4])
+            assert torch.equal(gl[src * 3:(src + 1) * 3], got[src][5])
+            assert torch.equal(gc[src * 3:(src + 1) * 3], got[src][6])

@@ -1,0 +1,192 @@
+"""-m gpu numerics tests of the tcgen05 conv engine and the layout kernels against plain
+PyTorch fp32 (CPU) references of the same ops."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import parity_util as U  # noqa: F401  (sets sys.path)
+from iou_aware_single_stage_object_detector_b200 import engine as E
+from iou_aware_single_stage_object_detector_b200 import lib as L
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+# 3-pass bf16 split accumulates in fp32: expected relative error ~1e-5 of the output scale
+TOL = 2e-4
+
+
+def rel_err(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-6)).item()
+
+
+def run_conv(x, w, bias=None, stride=1, relu=False, scale=None, shift=None, residual=None, passes=3):
+    """x (N,C,H,W) cpu, w (Co,Ci,k,k) cpu -> engine output (N,Co,Ho,Wo) cpu."""
+    eng = E.Engine(DEV, passes=passes)
+    xin = x.to(DEV).contiguous()
+    m = eng.pack_input(xin)
+    k = w.shape[-1]
+    co = w.shape[0]
+    wp = E.pack_weight(w, E.pick_block_n(co)[1])
+    res = eng.pack_input(residual.to(DEV).contiguous()) if residual is not None else None
+    sh = shift if shift is not None else bias
+    if stride == 1:
+        taps = E.TAPS_1X1 if k == 1 else E.TAPS_3X3
+        out = eng.conv("t", [m], taps, wp, x.shape[1], co, scale=scale, shift=sh, relu=relu, residual=res,
+                       res_mode=L.RES_SAME if res is not None else L.RES_NONE)
+    else:
+        if k == 1:
+            ph = eng.phase_split("p", m, mask=8)
+            out = eng.conv("t", [ph[3]] * 4, E.TAPS_1X1_S2, wp, x.shape[1], co, scale=scale, shift=sh, relu=relu)
+        else:
+            ph = eng.phase_split("p", m)
+            out = eng.conv("t", ph, E.TAPS_3X3_S2, wp, x.shape[1], co, scale=scale, shift=sh, relu=relu)
+    y = eng.unpack_output(out)
+    eng.run()
+    torch.cuda.synchronize()
+    return y.cpu()
+
+
+def test_pack_unpack_roundtrip():
+    g = torch.Generator().manual_seed(0)
+    for shape in ((2, 64, 7, 11), (1, 256, 13, 21), (3, 8, 5, 4)):
+        x = torch.randn(*shape, generator=g)
+        eng = E.Engine(DEV)
+        xin = x.to(DEV)
+        m = eng.pack_input(xin)
+        y = eng.unpack_output(m)
+        eng.run()
+        torch.cuda.synchronize()
+        # hi + lo carries 16 mantissa bits
+        assert torch.allclose(y.cpu(), x, rtol=2e-5, atol=1e-30), rel_err(y.cpu(), x)
+        # border rows of the padded layout are zero
+        n, c, h, w = shape
+        t = m.tensor[: n * (h + 2) * (w + 2)].view(n, h + 2, w + 2, 2 * c).float()
+        assert float(t[:, 0].abs().max()) == 0 and float(t[:, -1].abs().max()) == 0
+        assert float(t[:, :, 0].abs().max()) == 0 and float(t[:, :, -1].abs().max()) == 0
+
+
+@pytest.mark.parametrize("cin,cout,k,hw", [(64, 64, 1, (9, 13)), (64, 256, 1, (17, 23)), (256, 64, 1, (8, 8)),
+                                           (64, 64, 3, (12, 20)), (128, 128, 3, (25, 42)),
+                                           (256, 256, 3, (13, 21)), (512, 128, 1, (7, 11)),
+                                           (256, 512, 1, (10, 10)), (2048, 256, 1, (5, 6))])
+def test_conv_stride1_vs_torch(cin, cout, k, hw):
+    g = torch.Generator().manual_seed(cin + cout + k)
+    x = torch.randn(2, cin, *hw, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = F.conv2d(x, w, b, padding=k // 2)
+    y = run_conv(x, w, bias=b)
+    assert y.shape == ref.shape
+    assert rel_err(y, ref) < TOL, rel_err(y, ref)
+
+
+def test_conv_bn_relu_residual_epilogue():
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 64, 14, 18, generator=g)
+    w = torch.randn(256, 64, 1, 1, generator=g) * 0.2
+    scale = torch.rand(256, generator=g) + 0.5
+    shift = torch.randn(256, generator=g) * 0.3
+    res = torch.randn(2, 256, 14, 18, generator=g)
+    ref = F.relu(F.conv2d(x, w) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) + res)
+    y = run_conv(x, w, scale=scale, shift=shift, relu=True, residual=res)
+    assert rel_err(y, ref) < TOL, rel_err(y, ref)
+
+
+@pytest.mark.parametrize("cin,cout,k,hw", [(64, 64, 3, (12, 20)), (128, 128, 3, (25, 42)), (256, 256, 3, (13, 21)),
+                                           (256, 512, 1, (20, 28)), (512, 1024, 1, (25, 42)),
+                                           (2048, 256, 3, (25, 42)), (256, 256, 3, (7, 11))])
+def test_conv_stride2_vs_torch(cin, cout, k, hw):
+    g = torch.Generator().manual_seed(cin * 3 + cout + k)
+    x = torch.randn(2, cin, *hw, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = F.conv2d(x, w, b, stride=2, padding=k // 2)
+    y = run_conv(x, w, bias=b, stride=2)
+    assert y.shape == ref.shape, (y.shape, ref.shape)
+    assert rel_err(y, ref) < TOL, rel_err(y, ref)
+
+
+def test_conv_single_pass_bf16_is_coarser_but_close():
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 128, 10, 10, generator=g)
+    w = torch.randn(128, 128, 3, 3, generator=g) * 0.03
+    ref = F.conv2d(x, w, padding=1)
+    e1 = rel_err(run_conv(x, w, passes=1), ref)
+    e3 = rel_err(run_conv(x, w, passes=3), ref)
+    assert e3 < TOL and e1 < 3e-2 and e3 < e1 / 10, (e1, e3)
+
+
+def test_multi_segment_head_style_dense_outputs():
+    """Shared weights over several levels in ONE launch, dense fp32 NHWC outputs with a split."""
+    g = torch.Generator().manual_seed(21)
+    sizes = [(2, 12, 20), (2, 6, 10), (2, 3, 5), (2, 2, 3), (2, 1, 2)]
+    xs = [torch.randn(n, 256, h, w, generator=g) for (n, h, w) in sizes]
+    w_cls = torch.randn(720, 256, 3, 3, generator=g) * 0.02
+    b_cls = torch.randn(720, generator=g)
+    w_ri = torch.randn(45, 256, 3, 3, generator=g) * 0.02
+    b_ri = torch.randn(45, generator=g)
+    eng = E.Engine(DEV)
+    Fm = E.FlatMap(sizes, 256, DEV)
+    xin = [x.to(DEV) for x in xs]
+    for s, x in enumerate(xin):
+        n, c, h, w = x.shape
+        L.check(eng.lib.iou_pack_nchw(x.data_ptr(), n, c, h, w, Fm.ptr, Fm.segs[s][0], L.stream_ptr()))
+    cls_out = [torch.zeros(n, h, w, 720, device=DEV) for (n, h, w) in sizes]
+    reg_out = [torch.zeros(n, h, w, 36, device=DEV) for (n, h, w) in sizes]
+    iou_out = [torch.zeros(n, h, w, 9, device=DEV) for (n, h, w) in sizes]
+    eng.conv("cls", [Fm], E.TAPS_3X3, E.pack_weight(w_cls, 720), 256, 720, shift=b_cls, dense_out=cls_out)
+    eng.conv("ri", [Fm], E.TAPS_3X3, E.pack_weight(w_ri, 48), 256, 45, shift=b_ri, dense_out=reg_out,
+             dense_out2=iou_out, dense_split=36)
+    eng.run()
+    torch.cuda.synchronize()
+    for s, x in enumerate(xs):
+        ref_c = F.conv2d(x, w_cls, b_cls, padding=1).permute(0, 2, 3, 1)
+        ref_ri = F.conv2d(x, w_ri, b_ri, padding=1).permute(0, 2, 3, 1)
+        assert rel_err(cls_out[s].cpu(), ref_c) < TOL
+        assert rel_err(reg_out[s].cpu(), ref_ri[..., :36]) < TOL
+        assert rel_err(iou_out[s].cpu(), ref_ri[..., 36:]) < TOL
+
+
+def test_lateral_upsample_add_epilogue():
+    g = torch.Generator().manual_seed(31)
+    fine = torch.randn(2, 512, 12, 20, generator=g)
+    coarse = torch.randn(2, 256, 6, 10, generator=g)
+    w = torch.randn(256, 512, 1, 1, generator=g) * 0.05
+    b = torch.randn(256, generator=g)
+    ref = F.conv2d(fine, w, b) + F.interpolate(coarse, scale_factor=2, mode="nearest")
+    eng = E.Engine(DEV)
+    mf = eng.pack_input(fine.to(DEV))
+    mc = eng.pack_input(coarse.to(DEV))
+    out = eng.conv("lat", [mf], E.TAPS_1X1, E.pack_weight(w, 256), 512, 256, shift=b, residual=mc,
+                   res_mode=L.RES_UPSAMPLE2)
+    y = eng.unpack_output(out)
+    eng.run()
+    torch.cuda.synchronize()
+    assert rel_err(y.cpu(), ref) < TOL
+
+
+def test_stem_im2col_conv_maxpool_vs_torch():
+    g = torch.Generator().manual_seed(41)
+    img = torch.randn(2, 3, 64, 96, generator=g)
+    sd = {"backbone.conv1.weight": torch.randn(64, 3, 7, 7, generator=g) * 0.1,
+          "backbone.bn1.weight": torch.rand(64, generator=g) + 0.5,
+          "backbone.bn1.bias": torch.randn(64, generator=g) * 0.1,
+          "backbone.bn1.running_mean": torch.randn(64, generator=g) * 0.1,
+          "backbone.bn1.running_var": torch.rand(64, generator=g) + 0.5}
+    x = F.conv2d(img, sd["backbone.conv1.weight"], stride=2, padding=3)
+    x = F.batch_norm(x, sd["backbone.bn1.running_mean"], sd["backbone.bn1.running_var"],
+                     sd["backbone.bn1.weight"], sd["backbone.bn1.bias"], False, 0.0, 1e-5)
+    ref = F.max_pool2d(F.relu(x), 3, 2, 1)
+    eng = E.Engine(DEV)
+    out = eng.add_stem(sd, img.to(DEV))
+    y = eng.unpack_output(out)
+    eng.run()
+    torch.cuda.synchronize()
+    assert y.shape == ref.shape
+    assert rel_err(y.cpu(), ref) < TOL, rel_err(y.cpu(), ref)
+
+
+def test_conv_rejects_bad_descriptors_loudly():
+    eng = E.Engine(DEV)
+    m = E.FlatMap([(1, 4, 4)], 48, DEV)       # cin not a multiple of 64
+    with pytest.raises(RuntimeError):
+        eng.conv("bad", [m], E.TAPS_1X1, torch.zeros(64, 96, dtype=torch.bfloat16), 48, 64)

@@ -1,0 +1,160 @@
+"""-m gpu parity tests of the post-processing kernels (through the C ABI) against the golden
+fixtures generated from the real reference and against the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import parity_util as U
+from oracle import postproc as op
+
+pytestmark = pytest.mark.gpu
+P = U.P
+PP = U.PP
+
+
+@pytest.mark.parametrize("name", cases.POSTPROC_CASES)
+def test_get_bboxes_vs_reference_golden(name):
+    assert U.check_postproc_case(name)
+
+
+@pytest.mark.parametrize("name", list(cases.nms_inputs().keys()))
+def test_nms_indices_bit_exact(name):
+    """iou_nms == mmdet.ops.nms (reference nms_cpu golden; no IoU==thr ties in these inputs)."""
+    gold = np.load(os.path.join(U.GOLD, "nms_keep.npz"))[name]
+    dets = torch.from_numpy(cases.nms_inputs()[name]).cuda()
+    kept, inds = P.nms(dets, 0.5)
+    assert inds.dtype == torch.int64 and inds.is_cuda
+    assert np.array_equal(inds.cpu().numpy(), gold)
+    assert torch.equal(kept, dets[inds])
+    # numpy in / numpy out with device_id (nms_wrapper.py:27-31,47-48)
+    k2, i2 = P.nms(cases.nms_inputs()[name], 0.5, device_id=0)
+    assert isinstance(i2, np.ndarray) and np.array_equal(i2, gold)
+
+
+def test_nms_edge_cases():
+    empty = torch.zeros(0, 5, device="cuda")
+    kept, inds = P.nms(empty, 0.5)
+    assert kept.shape == (0, 5) and inds.numel() == 0 and inds.dtype == torch.int64
+    # IoU exactly == thr is NOT suppressed by the CUDA op (nms_kernel.cu:60, strict >)
+    d = torch.tensor([[0, 0, 9, 9, 0.9], [0, 0, 9, 19, 0.8]], device="cuda")
+    assert P.nms(d, 0.5)[1].tolist() == [0, 1]
+    assert P.nms(d, 0.49)[1].tolist() == [0]
+    with pytest.raises(TypeError):
+        P.nms([1, 2, 3], 0.5)
+    with pytest.raises(RuntimeError):
+        P.nms(torch.zeros(7000, 5, device="cuda"), 0.5)     # > IOU_MAX_NMS_BOXES: loud, not silent
+    with pytest.raises(RuntimeError):
+        P.nms(torch.zeros(3, 5), 0.5)                        # CPU tensor: no fallback
+
+
+def test_nms_random_vs_oracle_many_sizes():
+    rs = np.random.RandomState(3)
+    for n in (2, 31, 32, 33, 63, 64, 65, 127, 128, 129, 500, 1025, 3000, 6144):
+        dets = cases.random_dets(rs, n, 400, 150)
+        want = op.nms(dets, 0.45, "cuda").numpy()
+        got = P.nms(torch.from_numpy(dets).cuda(), 0.45)[1].cpu().numpy()
+        assert np.array_equal(got, want), n
+
+
+def test_nms_duplicate_scores_tie_rule():
+    """Equal scores: visiting order = ascending index (documented tie rule, same as the oracle)."""
+    rs = np.random.RandomState(5)
+    dets = cases.random_dets(rs, 300, 200, 90)
+    dets[:, 4] = np.round(dets[:, 4] * 4) / 4
+    want = op.nms(dets, 0.5, "cuda").numpy()
+    got = P.nms(torch.from_numpy(dets).cuda(), 0.5)[1].cpu().numpy()
+    assert np.array_equal(got, want)
+
+
+def test_multiclass_nms_api_vs_oracle():
+    rs = np.random.RandomState(8)
+    n, C = 900, 80
+    boxes = cases.random_dets(rs, n, 500, 160)[:, :4]
+    scores = (rs.rand(n, C + 1) ** 6).astype(np.float32)
+    scores[:, 0] = 0
+    for max_num in (100, 3000):
+        d_ref, l_ref = op.multiclass_nms(torch.from_numpy(boxes), torch.from_numpy(scores), 0.05, 0.5, max_num)
+        if max_num * 80 > 8000:
+            with pytest.raises(RuntimeError):
+                P.multiclass_nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), 0.05,
+                                 dict(type='nms', iou_thr=0.5), max_num)
+            continue
+        d, l = P.multiclass_nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), 0.05,
+                                dict(type='nms', iou_thr=0.5), max_num)
+        assert np.array_equal(l.cpu().numpy(), l_ref.numpy())
+        assert np.array_equal(d.cpu().numpy(), d_ref.numpy())
+    # nothing above the threshold -> empty (0,5) / (0,) (bbox_nms.py:63-65)
+    d, l = P.multiclass_nms(torch.from_numpy(boxes).cuda(), torch.zeros(n, C + 1).cuda(), 0.05,
+                            dict(type='nms', iou_thr=0.5), 100)
+    assert d.shape == (0, 5) and l.shape == (0,) and l.dtype == torch.int64
+
+
+def test_topk_with_exact_ties_is_deterministic():
+    """Many identical max scores at the top-k boundary: lowest anchor indices win (documented rule)."""
+    case = cases.postproc_case("small")
+    head = U.get_head()
+    dev = torch.device("cuda:0")
+    cls = [torch.full_like(t[:1], -2.0).to(dev) for t in case["cls"]]
+    iou = [torch.zeros_like(t[:1]).to(dev) for t in case["iou"]]
+    reg = [t[:1].to(dev) for t in case["reg"]]
+    cfg = P.ConfigDict(case["cfg"])
+    wsp = head.postproc_workspace([tuple(t.shape[-2:]) for t in cls], 1, cfg, dev)
+    info = PP.make_img_info(case["img_metas"][:1], dev)
+    _, _, idx = PP.decode_candidates(wsp, cls, reg, iou, info, False)
+    idx = idx[0].cpu().numpy()
+    off = 0
+    for t in cls:
+        n_l = t.shape[-1] * t.shape[-2] * 9
+        k = min(n_l, cfg.nms_pre)
+        assert np.array_equal(idx[off:off + k], np.arange(k)), "level with %d anchors" % n_l
+        off += k
+
+
+def test_full_size_properties():
+    """BASELINE-size invariants that need no oracle run: counts, ordering, clamping, idempotence."""
+    case = cases.postproc_case("full")
+    head = U.get_head()
+    dev = torch.device("cuda:0")
+    cfg = P.ConfigDict(case["cfg"])
+    n = 4
+    rs = np.random.RandomState(77)
+    cls, reg, iou = cases.random_maps(rs, n, case["sizes"])
+    cls, reg, iou = [t.to(dev) for t in cls], [t.to(dev) for t in reg], [t.to(dev) for t in iou]
+    metas = case["img_metas"] * n
+    r1 = head.get_bboxes(cls, reg, iou, None, None, metas, cfg, rescale=False)
+    r2 = head.get_bboxes(cls, reg, iou, None, None, metas, cfg, rescale=False)
+    for (d, l), (d2, l2) in zip(r1, r2):
+        assert torch.equal(d, d2) and torch.equal(l, l2)                  # deterministic
+        assert d.shape == (100, 5) and l.dtype == torch.int64
+        s = d[:, 4]
+        assert bool((s[:-1] >= s[1:]).all()) and bool((s > 0.05).all())  # sorted, thresholded
+        assert bool((d[:, 0] >= 0).all()) and bool((d[:, 2] <= 1332).all()) and bool((d[:, 3] <= 799).all())
+        assert bool((l >= 0).all()) and bool((l < 80).all())
+    # batch independence: image i alone gives the same detections as inside the batch
+    solo = head.get_bboxes([t[1:2] for t in cls], [t[1:2] for t in reg], [t[1:2] for t in iou], None, None,
+                           metas[:1], cfg, rescale=False)
+    assert torch.equal(solo[0][0], r1[1][0]) and torch.equal(solo[0][1], r1[1][1])
+
+
+def test_focal_loss_forward_backward_vs_oracle():
+    torch.manual_seed(0)
+    x = (torch.randn(513, 80) * 3)
+    t = torch.randint(0, 81, (513,))
+    for gamma, alpha in ((2.0, 0.25), (1.5, 0.4)):
+        ref_f = op.sigmoid_focal_loss_forward(x, t, gamma, alpha)
+        ref_b = op.sigmoid_focal_loss_backward(x, t, torch.ones_like(x), gamma, alpha)
+        f = P.sigmoid_focal_loss_cuda.forward(x.cuda(), t.cuda(), 80, gamma, alpha)
+        b = P.sigmoid_focal_loss_cuda.backward(x.cuda(), t.cuda(), torch.ones_like(x).cuda(), 80, gamma, alpha)
+        assert torch.allclose(f.cpu(), ref_f, rtol=1e-4, atol=1e-6)
+        assert torch.allclose(b.cpu(), ref_b, rtol=1e-4, atol=1e-6)
+    xg = x.cuda().requires_grad_(True)
+    loss = P.sigmoid_focal_loss(xg, t.cuda(), 2.0, 0.25, 'mean')
+    loss.backward()
+    assert torch.allclose(loss.detach().cpu(), op.sigmoid_focal_loss_forward(x, t, 2.0, 0.25).mean(), rtol=1e-4)
+    assert torch.allclose(xg.grad.cpu(), op.sigmoid_focal_loss_backward(
+        x, t, torch.full_like(x, 1.0 / x.numel()), 2.0, 0.25), rtol=1e-4, atol=1e-9)
+    assert P.SigmoidFocalLoss(2.0, 0.25)(x.cuda(), t.cuda()).item() == pytest.approx(
+        op.sigmoid_focal_loss_forward(x, t, 2.0, 0.25).sum().item(), rel=1e-4)

@@ -1,0 +1,51 @@
+"""Pins oracle/model.py (the torch-CPU restatement of backbone+FPN+head) to the REAL reference's
+modules on identical weights.  Needs /root/reference, so it runs in the build container only; it
+executes in a subprocess because the reference's package is also called `mmdet`."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CODE = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from oracle import ref_shim, model as om
+torch.manual_seed(0)
+m, cfg = ref_shim.build_reference_detector()
+sd = {k: v.clone() for k, v in m.state_dict().items()}
+om.spread_weights_(sd, seed=1)
+m.load_state_dict(sd)
+img = torch.randn(1, 3, 128, 160)
+with torch.no_grad():
+    feats = m.extract_feat(img)
+    outs = m.bbox_head(feats)
+mine = om.detector_forward(sd, img)
+worst = 0.0
+for a_list, b_list in zip(outs, mine):
+    for a, b in zip(a_list, b_list):
+        assert a.shape == b.shape
+        worst = max(worst, (a - b).abs().max().item())
+print("WORST", worst)
+assert worst == 0.0, worst
+# end to end: reference get_bboxes == oracle get_bboxes on the reference's own maps
+from oracle import postproc as op
+meta = dict(ori_shape=(128,157,3), img_shape=(128,157,3), pad_shape=(128,160,3), scale_factor=1.0, flip=False)
+with torch.no_grad():
+    res = m.bbox_head.get_bboxes(*outs, [torch.zeros(0,4)], [torch.zeros(0,dtype=torch.long)], [meta], cfg.test_cfg, rescale=True)
+sc = op.retina_anchor_scales(4, 3)
+bases = [op.base_anchors(s, sc, [0.5, 1.0, 2.0]) for s in (8, 16, 32, 64, 128)]
+d, l = op.get_bboxes_single([c[0] for c in outs[0]], [r[0] for r in outs[1]], [q[0] for q in outs[2]],
+                            [8, 16, 32, 64, 128], bases, meta["img_shape"], 1.0, dict(cfg.test_cfg), rescale=True, nms_mode="cpu")
+assert torch.equal(d, res[0][0]) and torch.equal(l, res[0][1]), (d.shape, res[0][0].shape)
+print("DETS", d.shape[0])
+'''
+
+
+@pytest.mark.reference
+def test_oracle_model_equals_reference_modules():
+    out = subprocess.run([sys.executable, "-c", CODE % ROOT], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-3000:]
+    assert "WORST 0.0" in out.stdout
