@@ -160,7 +160,7 @@ typedef struct iou_conv_desc {
   void* out_dense2[IOU_CONV_MAX_SEG];
   int32_t num_seg;
   iou_conv_segment seg[IOU_CONV_MAX_SEG];
-  int32_t passes;                           /* 3 = hi*hi+hi*lo+lo*hi (fp32-grade), 1 = bf16 */
+  int32_t passes;                           /* 3 = hi*hi+hi*lo+lo*hi (fp32-grade), 4 = +lo*lo, 1 = bf16 */
 } iou_conv_desc;
 
 typedef struct iou_conv_plan iou_conv_plan;

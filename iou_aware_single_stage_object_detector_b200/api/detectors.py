@@ -137,12 +137,20 @@ class SingleStageDetector(BaseDetector):
         return self._fused.get(key, lambda: FusedPlan(self, shape, device, rescale, self.use_cuda_graph,
                                                       self.passes))
 
-    def detect_device(self, img, img_metas, rescale=False):
-        """Batched, asynchronous: (dets [n,K,5], labels [n,K] int64, counts [n] int32) on the device."""
-        require_cuda(img, "SingleStageDetector")
-        plan = self.fused_plan(img.shape, img.device, rescale)
-        plan.img.copy_(img, non_blocking=True)
-        plan.img_info.copy_(PP.make_img_info(img_metas, "cpu"), non_blocking=True)
+    def detect_device(self, img, img_metas, rescale=False, device=None):
+        """Batched, asynchronous: (dets [n,K,5], labels [n,K] int64, counts [n] int32) on the device.
+        `img` may live on the GPU or in (pinned) host memory; a host batch is copied to `device`
+        (default: the parameters' device) inside this call -- all arithmetic runs on the GPU."""
+        if device is None:
+            device = img.device if img.is_cuda else next(self.parameters()).device
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("SingleStageDetector: move the model to a CUDA device first -- this path "
+                               "has no CPU fallback")
+        plan = self.fused_plan(img.shape, device, rescale)
+        with torch.cuda.device(device):
+            plan.img.copy_(img, non_blocking=True)
+            plan.img_info.copy_(PP.make_img_info(img_metas, "cpu"), non_blocking=True)
         return plan.run()
 
     def simple_test_batch(self, img, img_metas, gt_bboxes=None, gt_labels=None, rescale=False):

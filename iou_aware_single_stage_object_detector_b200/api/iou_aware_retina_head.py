@@ -79,7 +79,7 @@ class IoUawareRetinaHead(AnchorHead):
         def build():
             eng = E.Engine(dev)
             ins = [torch.empty_like(t) for t in feats]
-            F = E.FlatMap([(t.shape[0], t.shape[2], t.shape[3]) for t in ins], ins[0].shape[1], dev)
+            F = eng.new_map([(t.shape[0], t.shape[2], t.shape[3]) for t in ins], ins[0].shape[1])
             for s, t in enumerate(ins):
                 n, c, h, w = t.shape
                 rs = F.segs[s][0]

@@ -41,7 +41,7 @@ struct SegDev { int row_start, n_img, h, w; };
 struct ConvParams {
   CUtensorMap tmap_src[IOU_CONV_MAX_SRC];
   CUtensorMap tmap_w;
-  int cin, cout, cout_pad, block_n, num_taps, k_slabs, passes;
+  int cin, cout, cout_pad, block_n, num_taps, k_slabs, passes, lolo;
   int tap_src[IOU_CONV_MAX_TAPS], tap_dy[IOU_CONV_MAX_TAPS], tap_dx[IOU_CONV_MAX_TAPS];
   int num_seg;
   SegDev seg[IOU_CONV_MAX_SEG];
@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
               const uint64_t b_lo = umma_desc_sw128(sa + b_lo_off + kk * 32);
               tc_mma_bf16(d_tmem, a_hi, b_lo, P.idesc, 1u);
               tc_mma_bf16(d_tmem, a_lo, b_hi, P.idesc, 1u);
+              if (P.lolo) tc_mma_bf16(d_tmem, a_lo, b_lo, P.idesc, 1u);
             }
           }
           tc_commit(bar_empty + 8 * stage);            // frees the smem stage when the MMAs retire
@@ -410,7 +411,7 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   IOU_REQUIRE(d->num_taps >= 1 && d->num_taps <= IOU_CONV_MAX_TAPS, "num_taps out of range");
   IOU_REQUIRE(d->num_src >= 1 && d->num_src <= IOU_CONV_MAX_SRC, "num_src out of range");
   IOU_REQUIRE(d->num_seg >= 1 && d->num_seg <= IOU_CONV_MAX_SEG, "num_seg out of range");
-  IOU_REQUIRE(d->passes == 1 || d->passes == 3, "passes must be 1 or 3");
+  IOU_REQUIRE(d->passes == 1 || d->passes == 3 || d->passes == 4, "passes must be 1, 3 or 4");
   IOU_REQUIRE(d->weight != nullptr, "weight is NULL");
   IOU_REQUIRE(d->src_rows > 0 && d->src_rows < (1ll << 31), "src_rows out of range");
   if (d->out_mode == IOU_OUT_PADDED_BF16X2) {
@@ -430,7 +431,9 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   ConvParams& P = plan->params;
   memset(&P, 0, sizeof(P));
   P.cin = d->cin; P.cout = d->cout; P.cout_pad = d->cout_pad; P.block_n = d->block_n;
-  P.num_taps = d->num_taps; P.k_slabs = d->cin / kBlockK; P.passes = d->passes;
+  P.num_taps = d->num_taps; P.k_slabs = d->cin / kBlockK;
+  P.passes = d->passes == 1 ? 1 : 3;   // 3 = hi/lo operands staged; lolo adds the fourth product
+  P.lolo = d->passes == 4;
   for (int t = 0; t < d->num_taps; ++t) {
     if (d->tap_src[t] < 0 || d->tap_src[t] >= d->num_src) { delete plan; return fail(IOU_ERR_INVALID, "tap_src out of range"); }
     P.tap_src[t] = d->tap_src[t]; P.tap_dy[t] = d->tap_dy[t]; P.tap_dx[t] = d->tap_dx[t];
@@ -460,7 +463,7 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   P.num_n_tiles = d->cout_pad / d->block_n;
   P.total_tiles = P.num_m_tiles * P.num_n_tiles;
   P.b_tile_bytes = d->block_n * kBlockK * 2;
-  P.stage_bytes = (d->passes == 3 ? 2 : 1) * (kATileBytes + P.b_tile_bytes);
+  P.stage_bytes = (d->passes >= 3 ? 2 : 1) * (kATileBytes + P.b_tile_bytes);
   int stages = (kSmemBudget - kCtrlBytes - 1024) / P.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) { delete plan; return fail(IOU_ERR_INVALID, "tile does not fit shared memory"); }

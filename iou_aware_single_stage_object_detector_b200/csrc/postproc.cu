@@ -652,7 +652,7 @@ static int run_decode(PostParams& P, const float* const* cls, const float* const
 static int run_nms(const PostParams& P, const float* boxes, const float* scores_cm, float* dets,
                    int64_t* labels, int32_t* counts, unsigned long long* kept_keys, int32_t* kept_cnt,
                    cudaStream_t st) {
-  const int Pmax = next_pow2_host(P.M);
+  const int Pmax = next_pow2_host(P.M) < 2 ? 2 : next_pow2_host(P.M);   // keeps the float4 region 16-byte aligned
   const size_t sm4 = (size_t)Pmax * 8 + (size_t)P.M * 20 + (size_t)((P.M + 31) / 32) * 4 + 16;
   IOU_CHECK_CUDA(cudaFuncSetAttribute(class_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4));
   class_nms_kernel<<<dim3(P.C, P.n_img), 512, sm4, st>>>(P, boxes, scores_cm, kept_keys, kept_cnt, Pmax);
@@ -740,7 +740,7 @@ extern "C" int iou_nms(const float* dets, int n, float iou_thr, int64_t* keep_id
   if (n > IOU_MAX_NMS_BOXES)
     return fail(IOU_ERR_UNSUPPORTED, "iou_nms supports at most %d boxes per call (got %d)",
                 IOU_MAX_NMS_BOXES, n);
-  const int Pmax = next_pow2_host(n);
+  const int Pmax = next_pow2_host(n) < 2 ? 2 : next_pow2_host(n);
   const size_t sm = (size_t)Pmax * 8 + (size_t)n * 20 + (size_t)((n + 31) / 32) * 8 + 16;
   IOU_CHECK_CUDA(cudaFuncSetAttribute(single_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   single_nms_kernel<<<1, 512, sm, st>>>(dets, n, iou_thr, reinterpret_cast<long long*>(keep_idx),

@@ -103,9 +103,16 @@ class Engine(object):
         self.plans = []
         self.keep = []           # tensors that must outlive the plan
         self.flops = 0.0
+        self.op_flops = {}
         self.lib = L.load()
 
     # ------------------------------------------------------------------ primitive ops
+    def new_map(self, segs, c):
+        """Allocates a padded-rows buffer owned by this engine (plans only hold raw pointers)."""
+        m = FlatMap(segs, c, self.device)
+        self.keep.append(m.tensor)
+        return m
+
     def _dev(self, t):
         t = t.detach().to(self.device, torch.float32).contiguous()
         self.keep.append(t)
@@ -153,7 +160,7 @@ class Engine(object):
             d.seg[i] = L.ConvSegment(rs, n, h, w)
         if dense_out is None:
             if out is None:
-                out = FlatMap([(n, h, w) for (_, n, h, w) in geo.segs], cout, self.device)
+                out = self.new_map([(n, h, w) for (_, n, h, w) in geo.segs], cout)
             assert out.c == cout
             d.out_mode, d.out = L.OUT_PADDED, out.ptr
         else:
@@ -168,7 +175,9 @@ class Engine(object):
         plan = ctypes.c_void_p()
         L.check(self.lib.iou_conv_plan_create(ctypes.byref(d), ctypes.byref(plan)))
         self.plans.append(plan)
-        self.flops += self.lib.iou_conv_plan_flops(plan)
+        f = self.lib.iou_conv_plan_flops(plan)
+        self.flops += f
+        self.op_flops[name] = self.op_flops.get(name, 0.0) + f
         lib = self.lib
         self.ops.append((name, lambda st, p=plan: L.check(lib.iou_conv_run(p, st))))
         return out
@@ -178,7 +187,7 @@ class Engine(object):
         assert len(src.segs) == 1
         _, n, h, w = src.segs[0]
         ho, wo = (h + 1) // 2, (w + 1) // 2
-        outs = [FlatMap([(n, ho, wo)], src.c, self.device) if (mask >> i) & 1 else None for i in range(4)]
+        outs = [self.new_map([(n, ho, wo)], src.c) if (mask >> i) & 1 else None for i in range(4)]
         arr = (ctypes.c_void_p * 4)(*[(o.ptr if o is not None else None) for o in outs])
         self.keep.append(arr)
         lib, c, sp = self.lib, src.c, src.ptr
@@ -191,7 +200,7 @@ class Engine(object):
         n, _, h, w = img.shape
         ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
         kpad = 192
-        cols = FlatMap([(n, ho, wo)], kpad, self.device)
+        cols = self.new_map([(n, ho, wo)], kpad)
         lib, ip, cp = self.lib, img.data_ptr(), cols.ptr
         self.keep.append(img)
         self.ops.append(("stem.im2col", lambda st: L.check(lib.iou_im2col_stem(ip, n, h, w, kpad, cp, st))))
@@ -199,9 +208,11 @@ class Engine(object):
         scale, shift = bn_fold(sd, prefix + "bn1")
         s1 = self.conv("stem.conv1", [cols], TAPS_1X1, pack_weight(wt, 64, kpad), kpad, 64,
                        scale=scale, shift=shift, relu=True)
-        self.flops -= 2.0 * n * ho * wo * 64 * (kpad - 147)      # K padding is not algorithmic work
+        pad_f = 2.0 * n * ho * wo * 64 * (kpad - 147)             # K padding is not algorithmic work
+        self.flops -= pad_f
+        self.op_flops["stem.conv1"] -= pad_f
         hp, wq = (ho - 1) // 2 + 1, (wo - 1) // 2 + 1
-        x = FlatMap([(n, hp, wq)], 64, self.device)
+        x = self.new_map([(n, hp, wq)], 64)
         sp, xp = s1.ptr, x.ptr
         self.ops.append(("stem.maxpool", lambda st: L.check(lib.iou_maxpool3x3s2(sp, n, 64, ho, wo, xp, st))))
         return x
@@ -264,7 +275,7 @@ class Engine(object):
         for _ in range(nl, num_outs):
             h, w = (h + 1) // 2, (w + 1) // 2
             geos.append((n, h, w))
-        F = FlatMap(geos, out_channels, self.device)
+        F = self.new_map(geos, out_channels)
         for i in range(nl):
             kp = "%sfpn_convs.%d.conv." % (prefix, i)
             self.conv(kp[:-1], [lat[i]], TAPS_3X3, pack_weight(sd[kp + "weight"], out_channels),
@@ -310,7 +321,7 @@ class Engine(object):
     def pack_input(self, x):
         """(N,C,H,W) fp32 cuda tensor -> FlatMap (op appended)."""
         n, c, h, w = x.shape
-        m = FlatMap([(n, h, w)], c, self.device)
+        m = self.new_map([(n, h, w)], c)
         lib, xp, mp = self.lib, x.data_ptr(), m.ptr
         self.keep.append(x)
         self.ops.append(("pack", lambda st: L.check(lib.iou_pack_nchw(xp, n, c, h, w, mp, 0, st))))
@@ -319,6 +330,7 @@ class Engine(object):
     def unpack_output(self, m, s=0):
         rs, n, h, w = m.segs[s]
         out = torch.empty(n, m.c, h, w, dtype=torch.float32, device=self.device)
+        self.keep.append(out)
         lib, mp, op, c = self.lib, m.ptr, out.data_ptr(), m.c
         self.ops.append(("unpack", lambda st: L.check(lib.iou_unpack_nchw(mp, rs, n, c, h, w, op, st))))
         return out
@@ -329,6 +341,26 @@ class Engine(object):
         for _, fn in self.ops:
             fn(st)
         L.launch_count += len(self.ops)
+
+    def profile(self, iters=3):
+        """Eager pass with a CUDA event pair around every launch (on the launching stream).
+        Returns [(name, avg_ms)] in launch order; used by bench.py for the live roofline."""
+        st_t = torch.cuda.current_stream()
+        st = L.stream_ptr()
+        acc = [0.0] * len(self.ops)
+        for _ in range(iters):
+            evs = []
+            for _, fn in self.ops:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(st_t)
+                fn(st)
+                b.record(st_t)
+                evs.append((a, b))
+            torch.cuda.synchronize()
+            for i, (a, b) in enumerate(evs):
+                acc[i] += a.elapsed_time(b)
+        L.launch_count += iters * len(self.ops)
+        return [(name, t / iters) for (name, _), t in zip(self.ops, acc)]
 
     def num_launches(self):
         return len(self.ops)

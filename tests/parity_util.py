@@ -127,22 +127,27 @@ def check_postproc_case(name, verbose=True):
     return True
 
 
-def match_as_sets(d, l, gd, gl, min_frac=0.97):
-    """Order-free comparison keyed by label + box."""
+def match_as_sets(d, l, gd, gl, min_frac=0.97, score_tol=ATOL, box_tol=None):
+    """Order-free comparison keyed by label + nearest box.  A detection matches
+    when |dscore| <= score_tol and every coordinate is within box_tol pixels (default: allclose with
+    rtol = atol = 1e-4).  Returns (matched fraction, max |dscore|, max |dbox| px) over the matches."""
     used = np.zeros(len(gd), bool)
-    hit = 0
+    hit, ms, mb = 0, 0.0, 0.0
     for k in range(len(d)):
         cand = np.where((gl == l[k]) & ~used)[0]
         if cand.size == 0:
             continue
-        err = np.abs(gd[cand] - d[k]).max(1)
+        err = np.abs(gd[cand, :4] - d[k, :4]).max(1)
         j = cand[err.argmin()]
-        if np.allclose(d[k], gd[j], rtol=RTOL, atol=ATOL):
+        ok_box = err.min() <= box_tol if box_tol is not None else \
+            np.allclose(d[k, :4], gd[j, :4], rtol=RTOL, atol=ATOL)
+        if ok_box and abs(d[k, 4] - gd[j, 4]) <= score_tol:
             used[j] = True
             hit += 1
+            ms, mb = max(ms, float(abs(d[k, 4] - gd[j, 4]))), max(mb, float(err.min()))
     frac = hit / max(len(gd), 1)
     assert frac >= min_frac, "only %.3f of detections matched" % frac
-    return frac
+    return frac, ms, mb
 
 
 def small_detector(seed=0, spread=True, cfg_name="iou_aware_retinanet_r50_fpn_1x_4gpu.py"):
@@ -194,8 +199,8 @@ def check_detector_small(h=128, w=160, n=2, verbose=True, use_graph=False):
             worst = max(worst, err / max(scale, 1e-6))
             if verbose:
                 print("head %s level %d: max|d| %.3g (ref max %.3g)" % (name, l, err, scale))
-            assert torch.allclose(a, b, rtol=1e-3, atol=1e-3 * max(scale, 1.0)), \
-                "head %s level %d differs: %g" % (name, l, err)
+            # budget of the 3-pass split-bf16 path over ~60 stacked convs: <= 2e-4 of the map's range
+            assert err <= 2e-4 * max(scale, 1.0), "head %s level %d differs: %g" % (name, l, err)
     bases = oracle_bases()
     for i in range(n):
         d_ref, l_ref = op.get_bboxes_single([c[i] for c in ref_cls], [r[i] for r in ref_reg],
@@ -206,5 +211,9 @@ def check_detector_small(h=128, w=160, n=2, verbose=True, use_graph=False):
             print("image %d: %d dets (oracle %d)" % (i, len(d_my), d_ref.shape[0]))
         assert abs(len(d_my) - d_ref.shape[0]) <= 3
         if d_ref.shape[0]:
-            match_as_sets(d_my, l_my, d_ref.numpy(), l_ref.numpy(), min_frac=0.9)
+            # bar: scores within 1e-4; boxes within 1e-4 of the coordinate range (max(h, w) pixels)
+            frac, ms, mb = match_as_sets(d_my, l_my, d_ref.numpy(), l_ref.numpy(), min_frac=0.97,
+                                         score_tol=1e-4, box_tol=1e-4 * max(h, w))
+            if verbose:
+                print("image %d: matched %.3f, max|dscore| %.3g, max|dbox| %.3g px" % (i, frac, ms, mb))
     return worst
