@@ -146,10 +146,15 @@ def run_ours(args):
         time.sleep(0.3)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.ncu_range:
+        torch.cuda.profiler.start()
     e0.record()
     for _ in range(args.steps):
         out = step_device()
     e1.record()
+    if args.ncu_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
@@ -333,6 +338,8 @@ def main():
     ap.add_argument("--passes", type=int, default=3, choices=[1, 3, 4])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu launch lists)")
+    ap.add_argument("--ncu-range", action="store_true",
+                    help="bracket the timed steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     ap.add_argument("--dump-ops", default=None, help="write the per-launch CUDA-event table to this JSON file")
     ap.add_argument("--cpu-images", type=int, default=3)
     ap.add_argument("--reference-budget-s", type=int, default=150)
