@@ -161,6 +161,8 @@ typedef struct iou_conv_desc {
   int32_t num_seg;
   iou_conv_segment seg[IOU_CONV_MAX_SEG];
   int32_t passes;                           /* 3 = hi*hi+hi*lo+lo*hi (fp32-grade), 4 = +lo*lo, 1 = bf16 */
+  int64_t out_rows;                         /* PADDED: rows allocated behind `out` (TMA store clips there) */
+  int64_t res_rows;                         /* rows allocated behind `residual`                             */
 } iou_conv_desc;
 
 typedef struct iou_conv_plan iou_conv_plan;

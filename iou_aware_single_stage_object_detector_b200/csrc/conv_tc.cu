@@ -41,6 +41,8 @@ struct SegDev { int row_start, n_img, h, w; };
 struct ConvParams {
   CUtensorMap tmap_src[IOU_CONV_MAX_SRC];
   CUtensorMap tmap_w;
+  CUtensorMap tmap_out;     // padded-rows output, box 64 cols x 32 rows (TMA store)
+  CUtensorMap tmap_res;     // residual (same geometry), box 64 cols x 32 rows (TMA load)
   int cin, cout, cout_pad, block_n, num_taps, k_slabs, passes, lolo;
   int tap_src[IOU_CONV_MAX_TAPS], tap_dy[IOU_CONV_MAX_TAPS], tap_dx[IOU_CONV_MAX_TAPS];
   int num_seg;
@@ -48,6 +50,7 @@ struct ConvParams {
   int seg_tile_off[IOU_CONV_MAX_SEG + 1];
   int num_m_tiles, num_n_tiles, total_tiles;
   int num_stages, stage_bytes, b_tile_bytes;
+  int staged, res_staged, staging_per_warp;
   const float* scale;
   const float* shift;
   int relu, res_mode;
@@ -129,6 +132,32 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(tmap), "r"(c0), "r"(c1), "r"(src) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
@@ -160,11 +189,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < P.num_stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 128); }
+    for (int r = 0; r < 8; ++r) mbar_init(ctrl_addr + 192 + 8 * r, 1);     // residual ring: 4 warps x 2
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     for (int i = 0; i < IOU_CONV_MAX_SRC; ++i)
       asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tmap_src[i]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tmap_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tmap_out) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tmap_res) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -252,6 +284,23 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
     // =============================== epilogue ===============================
     const int lane_group = warp & 3;                      // TMEM lanes 32*lane_group .. +31
     const int m_local = lane_group * 32 + lane;
+    const int ew = warp - 2;
+    const uint32_t st_out = tiles_addr + P.num_stages * P.stage_bytes + ew * P.staging_per_warp;
+    const uint32_t st_res = st_out + 8192;
+    const uint32_t bar_res = ctrl_addr + 192 + ew * 16;
+    auto issue_res = [&](int tile_, int g_, int q_) {      // lane 0 only
+      const int mt = tile_ / P.num_n_tiles, nt = tile_ - mt * P.num_n_tiles;
+      int s_ = 0;
+      while (mt >= P.seg_tile_off[s_ + 1]) ++s_;
+      const int row = P.seg[s_].row_start + (mt - P.seg_tile_off[s_]) * kBlockM + lane_group * 32;
+      const int col = nt * P.block_n + g_ * 64;
+      const uint32_t bar = bar_res + 8 * (q_ & 1), dst = st_res + (q_ & 1) * 8192;
+      mbar_expect_tx(bar, 8192u);
+      tma_load_2d(&P.tmap_res, bar, dst, col, row);
+      tma_load_2d(&P.tmap_res, bar, dst + 4096, P.cout + col, row);
+    };
+    int rq = 0;                                            // running slab counter of the residual ring
+    if (P.res_staged && lane == 0) issue_res(blockIdx.x, 0, 0);
     int it = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -267,7 +316,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
       const int yp = rem / wp, xp = rem - yp * wp;
       const bool interior = (img < sg.n_img) && (yp >= 1) && (yp <= sg.h) && (xp >= 1) && (xp <= sg.w);
       const __nv_bfloat16* res_row = nullptr;
-      if (P.res_mode == IOU_RES_SAME) {
+      if (P.res_mode == IOU_RES_SAME && !P.res_staged) {
         res_row = P.residual + (size_t)grow * (2 * P.cout);
       } else if (P.res_mode == IOU_RES_UPSAMPLE2 && interior) {
         const SegDev rs = P.res_seg[s];
@@ -279,6 +328,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(acc * kAccStride);
       const int n_chunks = P.block_n >> 4;
+      if (!P.staged) {
       for (int ch = 0; ch < n_chunks; ++ch) {
         uint32_t v[16];
         tc_ld16(t_row + ch * 16, v);
@@ -310,25 +360,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
 #pragma unroll
           for (int q = 0; q < 16; ++q) f[q] = fmaxf(f[q], 0.f);
         }
-        if (P.out_mode == IOU_OUT_PADDED_BF16X2) {
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float x0 = interior ? f[2 * q] : 0.f, x1 = interior ? f[2 * q + 1] : 0.f;
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-            const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
-            const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-            hi[q] = pack_bf16x2(h0, h1);
-            lo[q] = pack_bf16x2(l0, l1);
-          }
-          __nv_bfloat16* orow = P.out + (size_t)grow * (2 * P.cout) + c0;
-          uint4* oh = reinterpret_cast<uint4*>(orow);
-          uint4* ol = reinterpret_cast<uint4*>(orow + P.cout);
-          oh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          oh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-          ol[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          ol[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-        } else if (interior) {
+        if (interior) {
           const size_t pix = ((size_t)img * sg.h + (yp - 1)) * sg.w + (xp - 1);
           const int split = P.dense_split > 0 ? P.dense_split : P.cout;
           if (c0 + 16 <= split && (split & 3) == 0) {
@@ -346,9 +378,96 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
           }
         }
       }
+      } else {
+        // ---- staged path (padded-rows output): 64 output channels per step.  Results go to a
+        // 128B-swizzled shared-memory tile and leave through TMA stores (fully coalesced, clipped at
+        // the end of the buffer); a same-geometry residual arrives through a 2-deep TMA-load ring.
+        const int row_tile0 = grow - lane;                 // first row of this warp's 32-row slab
+        const int n_groups = P.block_n >> 6;
+        for (int g = 0; g < n_groups; ++g, ++rq) {
+          const int c0 = n_tile * P.block_n + g * 64;
+          if (P.res_staged) {
+            if (lane == 0) {                               // prefetch the next slab of the ring
+              int nt = tile, ng = g + 1;
+              if (ng == n_groups) { nt = tile + gridDim.x; ng = 0; }
+              if (nt < P.total_tiles) issue_res(nt, ng, rq + 1);
+            }
+            mbar_wait(bar_res + 8 * (rq & 1), (uint32_t)(rq >> 1) & 1u);
+          }
+          uint32_t v[64];
+          tc_ld32(t_row + g * 64, v);
+          tc_ld32(t_row + g * 64 + 32, v + 32);
+          const float sc0 = P.scale ? __ldg(P.scale + c0 + lane) : 1.f, sc1 = P.scale ? __ldg(P.scale + c0 + 32 + lane) : 1.f;
+          const float sh0 = P.shift ? __ldg(P.shift + c0 + lane) : 0.f, sh1 = P.shift ? __ldg(P.shift + c0 + 32 + lane) : 0.f;
+          tc_wait_ld();
+          float f[64];
+#pragma unroll
+          for (int q = 0; q < 64; ++q) {
+            const float sc = __shfl_sync(0xffffffffu, q < 32 ? sc0 : sc1, q & 31);
+            const float sh = __shfl_sync(0xffffffffu, q < 32 ? sh0 : sh1, q & 31);
+            f[q] = fmaf(__uint_as_float(v[q]), sc, sh);
+          }
+          if (P.res_staged) {
+            const uint32_t rb = st_res + (rq & 1) * 8192 + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t sw = (uint32_t)((j ^ (lane & 7)) << 4);
+              const uint4 hv = lds128(rb + sw), lv = lds128(rb + 4096 + sw);
+              const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                f[j * 8 + q * 2 + 0] += __uint_as_float(hw[q] << 16) + __uint_as_float(lw[q] << 16);
+                f[j * 8 + q * 2 + 1] += __uint_as_float(hw[q] & 0xffff0000u) + __uint_as_float(lw[q] & 0xffff0000u);
+              }
+            }
+          } else if (res_row != nullptr && interior) {     // nearest-2x upsampled residual (FPN laterals)
+            const uint4* rh = reinterpret_cast<const uint4*>(res_row + c0);
+            const uint4* rl = reinterpret_cast<const uint4*>(res_row + P.cout + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint4 hv = __ldg(rh + j), lv = __ldg(rl + j);
+              const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                f[j * 8 + q * 2 + 0] += __uint_as_float(hw[q] << 16) + __uint_as_float(lw[q] << 16);
+                f[j * 8 + q * 2 + 1] += __uint_as_float(hw[q] & 0xffff0000u) + __uint_as_float(lw[q] & 0xffff0000u);
+              }
+            }
+          }
+          if (lane == 0) tma_store_wait_read();            // previous slab has left the staging tile
+          __syncwarp();
+          const uint32_t ob = st_out + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float x0 = f[j * 8 + 2 * q], x1 = f[j * 8 + 2 * q + 1];
+              if (P.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+              if (!interior) { x0 = 0.f; x1 = 0.f; }
+              const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+              const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+              const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+              hi[q] = pack_bf16x2(h0, h1);
+              lo[q] = pack_bf16x2(l0, l1);
+            }
+            const uint32_t sw = (uint32_t)((j ^ (lane & 7)) << 4);
+            sts128(ob + sw, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+            sts128(ob + 4096 + sw, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&P.tmap_out, st_out, c0, row_tile0);
+            tma_store_2d(&P.tmap_out, st_out + 4096, P.cout + c0, row_tile0);
+            tma_store_commit();
+          }
+        }
+      }
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * acc);
     }
+    if (P.staged && lane == 0) tma_store_wait_read();      // staging must outlive the last TMA store
   }
 
   tc_fence_before();
@@ -464,9 +583,14 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   P.total_tiles = P.num_m_tiles * P.num_n_tiles;
   P.b_tile_bytes = d->block_n * kBlockK * 2;
   P.stage_bytes = (d->passes >= 3 ? 2 : 1) * (kATileBytes + P.b_tile_bytes);
-  int stages = (kSmemBudget - kCtrlBytes - 1024) / P.stage_bytes;
+  // padded-rows outputs leave through a per-warp 128B-swizzled staging tile (32 rows x 64 ch, hi + lo)
+  // and TMA stores; a same-geometry residual arrives through a 2-deep TMA-load ring per warp
+  P.staged = (d->out_mode == IOU_OUT_PADDED_BF16X2) && (d->block_n % 64 == 0);
+  P.res_staged = P.staged && d->res_mode == IOU_RES_SAME;
+  P.staging_per_warp = P.staged ? (8192 + (P.res_staged ? 16384 : 0)) : 0;
+  int stages = (kSmemBudget - kCtrlBytes - 1024 - 4 * P.staging_per_warp) / P.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) { delete plan; return fail(IOU_ERR_INVALID, "tile does not fit shared memory"); }
+  if (stages < 2) { delete plan; return fail(IOU_ERR_INVALID, "tile does not fit shared memory (block_n %d, residual %d): use a smaller block_n", d->block_n, d->res_mode); }
   P.num_stages = stages;
   P.scale = d->scale; P.shift = d->shift; P.relu = d->relu; P.res_mode = d->res_mode;
   P.residual = (const __nv_bfloat16*)d->residual;
@@ -478,11 +602,21 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
     if (int e = encode_2d(&P.tmap_src[i], d->src[i], (uint64_t)d->src_rows, (uint64_t)2 * d->cin, kBlockM)) { delete plan; return e; }
   }
   for (int i = d->num_src; i < IOU_CONV_MAX_SRC; ++i) P.tmap_src[i] = P.tmap_src[0];
+  P.tmap_out = P.tmap_w; P.tmap_res = P.tmap_w;
+  if (P.staged) {
+    const uint64_t orow = d->out_rows > 0 ? (uint64_t)d->out_rows : (uint64_t)d->src_rows;
+    if (int e = encode_2d(&P.tmap_out, d->out, orow, (uint64_t)2 * d->cout, 32)) { delete plan; return e; }
+  }
+  if (P.res_staged) {
+    const uint64_t rrow = d->res_rows > 0 ? (uint64_t)d->res_rows : (uint64_t)d->src_rows;
+    if (((uintptr_t)d->residual & 15) != 0) { delete plan; return fail(IOU_ERR_INVALID, "residual must be 16-byte aligned"); }
+    if (int e = encode_2d(&P.tmap_res, d->residual, rrow, (uint64_t)2 * d->cout, 32)) { delete plan; return e; }
+  }
   if (int e = encode_2d(&P.tmap_w, d->weight, (uint64_t)d->num_taps * d->cout_pad, (uint64_t)2 * d->cin, (uint32_t)d->block_n)) { delete plan; return e; }
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   plan->grid = P.total_tiles < sms ? P.total_tiles : sms;
-  plan->smem_bytes = (size_t)kCtrlBytes + 1024 + (size_t)stages * P.stage_bytes;
+  plan->smem_bytes = (size_t)kCtrlBytes + 1024 + (size_t)stages * P.stage_bytes + (size_t)4 * P.staging_per_warp;
   plan->flops = 2.0 * real_rows * d->cout * d->cin * d->num_taps;
   static bool attr_set = false;
   if (!attr_set) {

@@ -72,55 +72,88 @@ __global__ void __launch_bounds__(256) unpack_nchw_kernel(const __nv_bfloat16* _
 }
 
 // ---- stem im2col: conv 7x7 stride 2 pad 3 on 3 channels (resnet.py:454-462).
-// One CTA per (output row yo in padded coords, image).  k = (r*7+s)*3 + ch, zero-padded to kpad.
+// One CTA per (output row yo in padded coords, image): the 7 input rows are staged once in shared
+// memory; every thread then emits 16-byte vectors (8 consecutive k) of the hi and lo planes, so the
+// 768-byte output rows are written fully coalesced.  k = (r*7+s)*3 + ch, zero-padded to kpad.
+__device__ __forceinline__ uint32_t pack2_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
 __global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restrict__ img, int n, int h, int w,
                                                           int ho, int wo, int kpad, __nv_bfloat16* __restrict__ dst) {
   extern __shared__ float rows[];                 // [3 ch][7 rows][w + 6] zero-padded input rows
+  __shared__ int koff[256];                       // smem offset of tap k (or -1 for the K padding)
   const int yp = blockIdx.x, im = blockIdx.y;
   const int wop = wo + 2, wpad = w + 6;
-  __nv_bfloat16* drow = dst + ((size_t)im * (ho + 2) + yp) * wop * (2 * kpad);
-  const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
+  const int vec_per_px = kpad >> 3;               // 16-byte vectors per plane per pixel
+  uint4* drow = reinterpret_cast<uint4*>(dst + ((size_t)im * (ho + 2) + yp) * wop * (2 * kpad));
   if (yp == 0 || yp == ho + 1) {
-    for (size_t i = threadIdx.x; i < (size_t)wop * 2 * kpad; i += blockDim.x) drow[i] = z;
+    for (int i = threadIdx.x; i < wop * 2 * vec_per_px; i += blockDim.x) drow[i] = make_uint4(0, 0, 0, 0);
     return;
   }
   const int yo = yp - 1;
+  for (int k = threadIdx.x; k < kpad; k += blockDim.x) {
+    int off = -1;
+    if (k < 147) {
+      const int tap = k / 3, ch = k - tap * 3;
+      const int r = tap / 7, s = tap - r * 7;
+      off = (ch * 7 + r) * wpad + s;
+    }
+    koff[k] = off;
+  }
   for (int i = threadIdx.x; i < 3 * 7 * wpad; i += blockDim.x) {
     const int ch = i / (7 * wpad), rem = i - ch * 7 * wpad;
     const int r = rem / wpad, xx = rem - r * wpad;
     const int y = yo * 2 - 3 + r, x = xx - 3;
-    rows[i] = (y >= 0 && y < h && x >= 0 && x < w) ? img[(((size_t)im * 3 + ch) * h + y) * w + x] : 0.f;
+    rows[i] = (y >= 0 && y < h && x >= 0 && x < w) ? __ldg(img + (((size_t)im * 3 + ch) * h + y) * w + x) : 0.f;
   }
   __syncthreads();
-  for (size_t i = threadIdx.x; i < (size_t)wop * kpad; i += blockDim.x) {
-    const int xp = (int)(i / kpad), k = (int)(i - (size_t)xp * kpad);
-    float v = 0.f;
-    if (xp >= 1 && xp <= wo && k < 147) {
-      const int tap = k / 3, ch = k - tap * 3;
-      const int r = tap / 7, s = tap - r * 7;
-      v = rows[(ch * 7 + r) * wpad + (xp - 1) * 2 + s];
+  for (int i = threadIdx.x; i < wop * vec_per_px; i += blockDim.x) {
+    const int xp = i / vec_per_px, ck = i - xp * vec_per_px;
+    uint32_t hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
+    if (xp >= 1 && xp <= wo) {
+      const int xbase = (xp - 1) * 2;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int o0 = koff[ck * 8 + 2 * e], o1 = koff[ck * 8 + 2 * e + 1];
+        const float v0 = o0 >= 0 ? rows[o0 + xbase] : 0.f, v1 = o1 >= 0 ? rows[o1 + xbase] : 0.f;
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(v0, h0, l0);
+        split_bf16(v1, h1, l1);
+        hi[e] = pack2_bf16(h0, h1);
+        lo[e] = pack2_bf16(l0, l1);
+      }
     }
-    __nv_bfloat16 hi, lo;
-    split_bf16(v, hi, lo);
-    drow[(size_t)xp * 2 * kpad + k] = hi;
-    drow[(size_t)xp * 2 * kpad + kpad + k] = lo;
+    uint4* px = drow + (size_t)xp * 2 * vec_per_px;
+    px[ck] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    px[vec_per_px + ck] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 
 // ---- 3x3 stride-2 pad-1 max pool on padded rows (inputs are post-ReLU, so the zero border
-// is equivalent to -inf padding).  One thread per (output pixel, channel pair).
+// is equivalent to -inf padding).  One thread per (output pixel, 8-channel group): 16-byte loads
+// of the hi and lo planes, max on the reconstructed fp32 values, 16-byte stores.
+__device__ __forceinline__ void max8(float (&m)[8], const uint4 hv, const uint4 lv) {
+  const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    m[2 * q] = fmaxf(m[2 * q], __uint_as_float(hw[q] << 16) + __uint_as_float(lw[q] << 16));
+    m[2 * q + 1] = fmaxf(m[2 * q + 1], __uint_as_float(hw[q] & 0xffff0000u) + __uint_as_float(lw[q] & 0xffff0000u));
+  }
+}
+
 __global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* __restrict__ src, int n, int c, int h,
                                                       int w, int ho, int wo, __nv_bfloat16* __restrict__ dst) {
-  const int c2 = c >> 1;
-  const size_t total = (size_t)n * (ho + 2) * (wo + 2) * c2;
+  const int c8 = c >> 3;
+  const size_t total = (size_t)n * (ho + 2) * (wo + 2) * c8;
   const int wp = w + 2, wop = wo + 2;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int cp = (int)(i % c2);
-    size_t t = i / c2;
+    const int cg = (int)(i % c8);
+    size_t t = i / c8;
     const int xp = (int)(t % wop); t /= wop;
     const int yp = (int)(t % (ho + 2));
     const int img = (int)(t / (ho + 2));
-    float m0 = 0.f, m1 = 0.f;
+    float m[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (xp >= 1 && xp <= wo && yp >= 1 && yp <= ho) {
       // window rows 2*yo-1 .. 2*yo+1 (unpadded) == padded rows 2*yo .. 2*yo+2
       const int py0 = 2 * (yp - 1), px0 = 2 * (xp - 1);
@@ -131,19 +164,22 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* __res
           const int py = py0 + r, px = px0 + s;
           if (py <= h + 1 && px <= w + 1) {
             const __nv_bfloat16* p = src + (((size_t)img * (h + 2) + py) * wp + px) * (2 * c);
-            const __nv_bfloat162 hv = *reinterpret_cast<const __nv_bfloat162*>(p + 2 * cp);
-            const __nv_bfloat162 lv = *reinterpret_cast<const __nv_bfloat162*>(p + c + 2 * cp);
-            m0 = fmaxf(m0, __bfloat162float(hv.x) + __bfloat162float(lv.x));
-            m1 = fmaxf(m1, __bfloat162float(hv.y) + __bfloat162float(lv.y));
+            max8(m, __ldg(reinterpret_cast<const uint4*>(p) + cg), __ldg(reinterpret_cast<const uint4*>(p + c) + cg));
           }
         }
     }
-    __nv_bfloat162 ho2, lo2;
-    split_bf16(m0, ho2.x, lo2.x);
-    split_bf16(m1, ho2.y, lo2.y);
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(m[2 * q], h0, l0);
+      split_bf16(m[2 * q + 1], h1, l1);
+      hi[q] = pack2_bf16(h0, h1);
+      lo[q] = pack2_bf16(l0, l1);
+    }
     __nv_bfloat16* o = dst + (((size_t)img * (ho + 2) + yp) * wop + xp) * (2 * c);
-    *reinterpret_cast<__nv_bfloat162*>(o + 2 * cp) = ho2;
-    *reinterpret_cast<__nv_bfloat162*>(o + c + 2 * cp) = lo2;
+    reinterpret_cast<uint4*>(o)[cg] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    reinterpret_cast<uint4*>(o + c)[cg] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 
@@ -195,7 +231,7 @@ extern "C" int iou_unpack_nchw(const void* src, int64_t src_row_start, int n, in
 
 extern "C" int iou_im2col_stem(const float* img, int n, int h, int w, int kpad, void* dst, void* stream) {
   IOU_REQUIRE(img && dst && n > 0 && h > 0 && w > 0, "bad argument");
-  IOU_REQUIRE(kpad >= 147 && kpad % 64 == 0, "kpad must be a multiple of 64 >= 147");
+  IOU_REQUIRE(kpad >= 147 && kpad % 64 == 0 && kpad <= 256, "kpad must be a multiple of 64 in [147, 256]");
   const int ho = (h + 6 - 7) / 2 + 1, wo = (w + 6 - 7) / 2 + 1;
   const size_t sm = (size_t)3 * 7 * (w + 6) * 4;
   IOU_REQUIRE(sm <= 200 * 1024, "image too wide for the stem im2col kernel");
@@ -209,9 +245,9 @@ extern "C" int iou_im2col_stem(const float* img, int n, int h, int w, int kpad, 
 }
 
 extern "C" int iou_maxpool3x3s2(const void* src, int n, int c, int h, int w, void* dst, void* stream) {
-  IOU_REQUIRE(src && dst && n > 0 && c > 0 && (c & 1) == 0 && h > 0 && w > 0, "bad argument");
+  IOU_REQUIRE(src && dst && n > 0 && c > 0 && (c & 7) == 0 && h > 0 && w > 0, "bad argument (c % 8)");
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
-  const size_t total = (size_t)n * (ho + 2) * (wo + 2) * (c / 2);
+  const size_t total = (size_t)n * (ho + 2) * (wo + 2) * (c / 8);
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   maxpool_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, n, c, h, w, ho, wo,
                                                            (__nv_bfloat16*)dst);

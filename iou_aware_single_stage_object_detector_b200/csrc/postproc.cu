@@ -134,13 +134,22 @@ __global__ void __launch_bounds__(1024) topk_kernel(const __grid_constant__ Post
     if (tid < 256) hist[tid] = 0;
     __syncthreads();
     const unsigned int prefix = s_prefix, mask = s_mask;
-    for (int base = 0; base < n; base += 1024) {
-      int i = base + tid;
-      unsigned int u = (i < n) ? float_to_ordered(keys[i]) : 0u;
-      bool valid = (i < n) && ((u & mask) == prefix);
-      unsigned int d = valid ? ((u >> shift) & 255u) : (256u + lane);
-      unsigned int peers = __match_any_sync(0xffffffffu, d);
-      if (valid && (__ffs(peers) - 1) == lane) atomicAdd(&hist[d], __popc(peers));
+    for (int base = 0; base < n; base += 4096) {
+      unsigned int u4[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {                  // four independent loads in flight per thread
+        const int i = base + q * 1024 + tid;
+        u4[q] = (i < n) ? float_to_ordered(__ldg(keys + i)) : 0u;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = base + q * 1024 + tid;
+        const unsigned int u = u4[q];
+        const bool valid = (i < n) && ((u & mask) == prefix);
+        const unsigned int d = valid ? ((u >> shift) & 255u) : (256u + lane);
+        const unsigned int peers = __match_any_sync(0xffffffffu, d);
+        if (valid && (__ffs(peers) - 1) == lane) atomicAdd(&hist[d], __popc(peers));
+      }
     }
     __syncthreads();
     if (tid == 0) {
@@ -297,77 +306,76 @@ struct NmsSmem {
   unsigned long long* sortbuf;   // [P]
   float4* sbox;                  // [n]
   float* sarea;                  // [n]
-  unsigned int* removed;         // [ceil(n/32)]
+  int* kept;                     // [n] sorted positions of the boxes kept so far
 };
 
 // Greedy NMS over n boxes already ordered by (score desc, index asc) in shared memory.
-// Calls emit(r) from thread 0 for every kept sorted position r, in order; stops once
+// Calls emit(r, pos) from thread 0 for every kept sorted position r, in order; stops once
 // `stop_after` boxes are kept (0 = never).  Returns the number kept (block-uniform).
-// 64-box chunks: the chunk's own 64x64 suppression mask is built with warp ballots, one
-// thread resolves it serially, then all threads propagate the newly kept boxes to the tail.
+// The scan is LAZY: a 64-box chunk is only tested when the scan reaches it --
+//   (a) every (chunk box, previously kept box) pair is tested in parallel,
+//   (b) the chunk's own 64x64 suppression mask is built with warp ballots,
+//   (c) one thread resolves the chunk serially and appends to the kept list --
+// so with the max_per_img+1 early stop only the first few chunks are ever touched.
 template <typename Emit>
 __device__ int greedy_nms_sorted(const NmsSmem& S, const int n, const float thr, const int stop_after,
                                  Emit emit) {
   __shared__ unsigned long long cmask[64];
-  __shared__ unsigned long long s_keptmask;
+  __shared__ unsigned int dead[2];
   __shared__ int s_total;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  for (int i = tid; i < (n + 31) / 32; i += blockDim.x) S.removed[i] = 0u;
   if (tid == 0) s_total = 0;
   __syncthreads();
   for (int cs = 0; cs < n; cs += 64) {
     const int cnt = min(64, n - cs);
-    // (a) intra-chunk mask rows
+    const int total0 = s_total;
+    if (tid < 2) dead[tid] = 0u;
+    __syncthreads();
+    // (a) chunk boxes vs everything kept so far: thread -> (box b, kept slots k0, k0+stride, ...)
+    {
+      const int b = tid & 63, k0 = tid >> 6, kstride = blockDim.x >> 6;
+      if (b < cnt && total0 > 0) {
+        const float4 bb = S.sbox[cs + b];
+        const float sb = S.sarea[cs + b];
+        for (int k = k0; k < total0; k += kstride) {
+          if ((((volatile unsigned int*)dead)[b >> 5] >> (b & 31)) & 1u) break;
+          const int kp = S.kept[k];
+          if (iou_gt(S.sbox[kp], S.sarea[kp], bb, sb, thr)) {
+            atomicOr(&dead[b >> 5], 1u << (b & 31));
+            break;
+          }
+        }
+      }
+    }
+    // (b) intra-chunk mask rows (bits > row only)
     for (int r = warp; r < cnt; r += nwarps) {
       const float4 a = S.sbox[cs + r];
       const float sa = S.sarea[cs + r];
       bool h0 = false, h1 = false;
-      int c0 = lane, c1 = lane + 32;
+      const int c0 = lane, c1 = lane + 32;
       if (c0 > r && c0 < cnt) h0 = iou_gt(a, sa, S.sbox[cs + c0], S.sarea[cs + c0], thr);
       if (c1 > r && c1 < cnt) h1 = iou_gt(a, sa, S.sbox[cs + c1], S.sarea[cs + c1], thr);
-      unsigned int b0 = __ballot_sync(0xffffffffu, h0), b1 = __ballot_sync(0xffffffffu, h1);
+      const unsigned int b0 = __ballot_sync(0xffffffffu, h0), b1 = __ballot_sync(0xffffffffu, h1);
       if (lane == 0) cmask[r] = ((unsigned long long)b1 << 32) | b0;
     }
     __syncthreads();
-    // (b) serial resolve of the chunk
+    // (c) serial resolve of the chunk
     if (tid == 0) {
-      unsigned long long R = (unsigned long long)S.removed[cs >> 5];
-      if (cs + 32 < n) R |= (unsigned long long)S.removed[(cs >> 5) + 1] << 32;
-      unsigned long long kept = 0ull;
-      int total = s_total;
+      unsigned long long R = (unsigned long long)dead[0] | ((unsigned long long)dead[1] << 32);
+      int total = total0;
       for (int i = 0; i < cnt; ++i) {
         if (!((R >> i) & 1ull)) {
-          kept |= 1ull << i;
           R |= cmask[i];
+          S.kept[total] = cs + i;
           emit(cs + i, total);
           ++total;
           if (stop_after && total >= stop_after) break;
         }
       }
-      s_keptmask = kept;
       s_total = total;
     }
     __syncthreads();
-    const unsigned long long kept = s_keptmask;
-    const int total = s_total;
-    if (stop_after && total >= stop_after) break;
-    // (c) propagate to the tail
-    if (kept) {
-      for (int kpos = cs + cnt + tid; kpos < n; kpos += blockDim.x) {
-        if ((S.removed[kpos >> 5] >> (kpos & 31)) & 1u) continue;
-        const float4 b = S.sbox[kpos];
-        const float sb = S.sarea[kpos];
-        unsigned long long m = kept;
-        bool dead = false;
-        while (m) {
-          int i = __ffsll((long long)m) - 1;
-          m &= m - 1;
-          if (iou_gt(S.sbox[cs + i], S.sarea[cs + i], b, sb, thr)) { dead = true; break; }
-        }
-        if (dead) atomicOr(&S.removed[kpos >> 5], 1u << (kpos & 31));
-      }
-    }
-    __syncthreads();
+    if (stop_after && s_total >= stop_after) break;
   }
   return s_total;
 }
@@ -383,7 +391,7 @@ __global__ void __launch_bounds__(512) class_nms_kernel(const __grid_constant__ 
   S.sortbuf = reinterpret_cast<unsigned long long*>(smem_raw);
   S.sbox = reinterpret_cast<float4*>(smem_raw + (size_t)Pmax * 8);
   S.sarea = reinterpret_cast<float*>(smem_raw + (size_t)Pmax * 8 + (size_t)P.M * 16);
-  S.removed = reinterpret_cast<unsigned int*>(smem_raw + (size_t)Pmax * 8 + (size_t)P.M * 20);
+  S.kept = reinterpret_cast<int*>(smem_raw + (size_t)Pmax * 8 + (size_t)P.M * 20);
   __shared__ unsigned int s_n, warp_cnt[16];
   const int c = blockIdx.x, img = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -508,8 +516,8 @@ __global__ void __launch_bounds__(512) single_nms_kernel(const float* __restrict
   S.sortbuf = reinterpret_cast<unsigned long long*>(smem_raw);
   S.sbox = reinterpret_cast<float4*>(smem_raw + (size_t)Pmax * 8);
   S.sarea = reinterpret_cast<float*>(smem_raw + (size_t)Pmax * 8 + (size_t)n * 16);
-  S.removed = reinterpret_cast<unsigned int*>(smem_raw + (size_t)Pmax * 8 + (size_t)n * 20);
-  unsigned int* keepbits = S.removed + (n + 31) / 32;
+  S.kept = reinterpret_cast<int*>(smem_raw + (size_t)Pmax * 8 + (size_t)n * 20);
+  unsigned int* keepbits = reinterpret_cast<unsigned int*>(S.kept + n);
   __shared__ unsigned int s_run, warp_cnt[16];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Ps = next_pow2(n);
@@ -653,7 +661,7 @@ static int run_nms(const PostParams& P, const float* boxes, const float* scores_
                    int64_t* labels, int32_t* counts, unsigned long long* kept_keys, int32_t* kept_cnt,
                    cudaStream_t st) {
   const int Pmax = next_pow2_host(P.M) < 2 ? 2 : next_pow2_host(P.M);   // keeps the float4 region 16-byte aligned
-  const size_t sm4 = (size_t)Pmax * 8 + (size_t)P.M * 20 + (size_t)((P.M + 31) / 32) * 4 + 16;
+  const size_t sm4 = (size_t)Pmax * 8 + (size_t)P.M * 24 + 16;
   IOU_CHECK_CUDA(cudaFuncSetAttribute(class_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4));
   class_nms_kernel<<<dim3(P.C, P.n_img), 512, sm4, st>>>(P, boxes, scores_cm, kept_keys, kept_cnt, Pmax);
   if (int e = launch_status("class_nms_kernel")) return e;
@@ -741,7 +749,7 @@ extern "C" int iou_nms(const float* dets, int n, float iou_thr, int64_t* keep_id
     return fail(IOU_ERR_UNSUPPORTED, "iou_nms supports at most %d boxes per call (got %d)",
                 IOU_MAX_NMS_BOXES, n);
   const int Pmax = next_pow2_host(n) < 2 ? 2 : next_pow2_host(n);
-  const size_t sm = (size_t)Pmax * 8 + (size_t)n * 20 + (size_t)((n + 31) / 32) * 8 + 16;
+  const size_t sm = (size_t)Pmax * 8 + (size_t)n * 24 + (size_t)((n + 31) / 32) * 4 + 16;
   IOU_CHECK_CUDA(cudaFuncSetAttribute(single_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   single_nms_kernel<<<1, 512, sm, st>>>(dets, n, iou_thr, reinterpret_cast<long long*>(keep_idx),
                                         keep_count, Pmax);

@@ -82,17 +82,23 @@ def bn_fold(sd, prefix, eps=1e-5):
     return scale.contiguous(), shift.contiguous()
 
 
-def pick_block_n(cout):
-    if cout % 256 == 0:
-        return 256, cout
-    if cout in (64, 128):
-        return cout, cout
-    if cout % 240 == 0:
-        return 240, cout
-    pad = _round_up(cout, 16)
-    if pad <= 256:
-        return pad, pad
-    return 256, _round_up(cout, 256)
+NUM_SMS = 148
+
+
+def pick_block_n(cout, m_tiles=None, max_bn=256):
+    """(block_n, cout_pad) for the tap-GEMM.  With the number of 128-row tiles known, the N tile is
+    chosen to minimise waves x per-tile cost on 148 SMs (small maps get narrower tiles so that more
+    CTAs share the K loop; big maps keep N=256 so the A tile is loaded once)."""
+    if cout % 64 != 0:                       # head outputs: 720 -> 3 x 240, 45 -> 48
+        if cout % 240 == 0:
+            return 240, cout
+        pad = _round_up(cout, 16)
+        return (pad, pad) if pad <= 256 else (256, _round_up(cout, 256))
+    cands = [bn for bn in (256, 128, 64) if cout % bn == 0 and bn <= max_bn]
+    if m_tiles is None:
+        return cands[0], cout
+    best = min(cands, key=lambda bn: (-(-(m_tiles * (cout // bn)) // NUM_SMS)) * (bn + 64))
+    return best, cout
 
 
 class Engine(object):
@@ -122,8 +128,10 @@ class Engine(object):
              residual=None, res_mode=L.RES_NONE, dense_out=None, dense_out2=None, dense_split=0,
              segs_from=None):
         """srcs: list[FlatMap] (same geometry); out: FlatMap or None (dense).  Returns out."""
-        block_n, cout_pad = pick_block_n(cout)
         geo = segs_from or srcs[0]
+        m_tiles = sum(_round_up(n * (h + 2) * (w + 2), TILE_M) // TILE_M for (_, n, h, w) in geo.segs)
+        # a same-geometry residual needs its TMA staging ring in shared memory: N tile <= 128
+        block_n, cout_pad = pick_block_n(cout, m_tiles, max_bn=128 if res_mode == L.RES_SAME else 256)
         d = L.ConvDesc()
         d.cin, d.cout, d.cout_pad, d.block_n = cin, cout, cout_pad, block_n
         d.num_taps = len(taps)
@@ -153,6 +161,7 @@ class Engine(object):
         d.res_mode = res_mode
         if residual is not None:
             d.residual = residual.ptr
+            d.res_rows = residual.rows
             for i, (rs, n, h, w) in enumerate(residual.segs):
                 d.res_seg[i] = L.ConvSegment(rs, n, h, w)
         d.num_seg = len(geo.segs)
@@ -163,6 +172,7 @@ class Engine(object):
                 out = self.new_map([(n, h, w) for (_, n, h, w) in geo.segs], cout)
             assert out.c == cout
             d.out_mode, d.out = L.OUT_PADDED, out.ptr
+            d.out_rows = out.rows
         else:
             d.out_mode = L.OUT_DENSE
             d.dense_split = dense_split

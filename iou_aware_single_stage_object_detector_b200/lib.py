@@ -90,7 +90,7 @@ class ConvDesc(ctypes.Structure):
                 ("out", ctypes.c_void_p), ("out_dense", ctypes.c_void_p * CONV_MAX_SEG),
                 ("dense_split", ctypes.c_int32), ("out_dense2", ctypes.c_void_p * CONV_MAX_SEG),
                 ("num_seg", ctypes.c_int32), ("seg", ConvSegment * CONV_MAX_SEG),
-                ("passes", ctypes.c_int32)]
+                ("passes", ctypes.c_int32), ("out_rows", ctypes.c_int64), ("res_rows", ctypes.c_int64)]
 
 
 _SIGS = {
