@@ -37,6 +37,9 @@ extern "C" {
 const char* iou_last_error(void);
 /* ABI version (bumped on any signature change). */
 int iou_abi_version(void);
+/* sizeof of the ABI structs as compiled (0: iou_postproc_cfg, 1: iou_conv_desc, 2: iou_conv_segment),
+ * so that a foreign-language binding can verify its own struct layout. */
+size_t iou_sizeof(int what);
 
 /* ------------------------------------------------------------------ get_bboxes
  * Static description of IoUawareRetinaHead.get_bboxes / get_bboxes_single
@@ -163,6 +166,8 @@ typedef struct iou_conv_desc {
   int32_t passes;                           /* 3 = hi*hi+hi*lo+lo*hi (fp32-grade), 4 = +lo*lo, 1 = bf16 */
   int64_t out_rows;                         /* PADDED: rows allocated behind `out` (TMA store clips there) */
   int64_t res_rows;                         /* rows allocated behind `residual`                             */
+  int32_t diag_k;                           /* grouped conv (cin == cout, block_n == 64): output tile j contracts
+                                               only input channels [64j, 64j+64); weight is [taps*cout][2*64]   */
 } iou_conv_desc;
 
 typedef struct iou_conv_plan iou_conv_plan;

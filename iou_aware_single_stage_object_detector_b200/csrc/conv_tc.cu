@@ -44,6 +44,7 @@ struct ConvParams {
   CUtensorMap tmap_out;     // padded-rows output, box 64 cols x 32 rows (TMA store)
   CUtensorMap tmap_res;     // residual (same geometry), box 64 cols x 32 rows (TMA load)
   int cin, cout, cout_pad, block_n, num_taps, k_slabs, passes, lolo;
+  int diag_k, b_cin;        // grouped conv: N tile j contracts only input channels [64j, 64j+64)
   int tap_src[IOU_CONV_MAX_TAPS], tap_dy[IOU_CONV_MAX_TAPS], tap_dx[IOU_CONV_MAX_TAPS];
   int num_seg;
   SegDev seg[IOU_CONV_MAX_SEG];
@@ -233,11 +234,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
             const uint32_t fb = bar_full + 8 * stage;
             const uint32_t sa = tiles_addr + stage * P.stage_bytes;
             mbar_expect_tx(fb, (uint32_t)P.stage_bytes);
-            tma_load_2d(tm, fb, sa, ks * kBlockK, arow);
+            const int a_col = P.diag_k ? n_tile * kBlockK : ks * kBlockK;
+            tma_load_2d(tm, fb, sa, a_col, arow);
             tma_load_2d(&P.tmap_w, fb, sa + b_hi_off, ks * kBlockK, wrow);
             if (P.passes == 3) {
-              tma_load_2d(tm, fb, sa + a_lo_off, P.cin + ks * kBlockK, arow);
-              tma_load_2d(&P.tmap_w, fb, sa + b_lo_off, P.cin + ks * kBlockK, wrow);
+              tma_load_2d(tm, fb, sa + a_lo_off, P.cin + a_col, arow);
+              tma_load_2d(&P.tmap_w, fb, sa + b_lo_off, P.b_cin + ks * kBlockK, wrow);
             }
             if (++stage == P.num_stages) { stage = 0; phase ^= 1u; }
           }
@@ -532,6 +534,7 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   IOU_REQUIRE(d->num_seg >= 1 && d->num_seg <= IOU_CONV_MAX_SEG, "num_seg out of range");
   IOU_REQUIRE(d->passes == 1 || d->passes == 3 || d->passes == 4, "passes must be 1, 3 or 4");
   IOU_REQUIRE(d->weight != nullptr, "weight is NULL");
+  IOU_REQUIRE(!d->diag_k || (d->block_n == 64 && d->cin == d->cout), "diag_k (grouped conv) needs block_n == 64 and cin == cout");
   IOU_REQUIRE(d->src_rows > 0 && d->src_rows < (1ll << 31), "src_rows out of range");
   if (d->out_mode == IOU_OUT_PADDED_BF16X2) {
     IOU_REQUIRE(d->out != nullptr, "out is NULL");
@@ -550,7 +553,10 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   ConvParams& P = plan->params;
   memset(&P, 0, sizeof(P));
   P.cin = d->cin; P.cout = d->cout; P.cout_pad = d->cout_pad; P.block_n = d->block_n;
-  P.num_taps = d->num_taps; P.k_slabs = d->cin / kBlockK;
+  P.num_taps = d->num_taps;
+  P.diag_k = d->diag_k ? 1 : 0;
+  P.b_cin = P.diag_k ? kBlockK : d->cin;
+  P.k_slabs = P.diag_k ? 1 : d->cin / kBlockK;
   P.passes = d->passes == 1 ? 1 : 3;   // 3 = hi/lo operands staged; lolo adds the fourth product
   P.lolo = d->passes == 4;
   for (int t = 0; t < d->num_taps; ++t) {
@@ -612,12 +618,12 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
     if (((uintptr_t)d->residual & 15) != 0) { delete plan; return fail(IOU_ERR_INVALID, "residual must be 16-byte aligned"); }
     if (int e = encode_2d(&P.tmap_res, d->residual, rrow, (uint64_t)2 * d->cout, 32)) { delete plan; return e; }
   }
-  if (int e = encode_2d(&P.tmap_w, d->weight, (uint64_t)d->num_taps * d->cout_pad, (uint64_t)2 * d->cin, (uint32_t)d->block_n)) { delete plan; return e; }
+  if (int e = encode_2d(&P.tmap_w, d->weight, (uint64_t)d->num_taps * d->cout_pad, (uint64_t)2 * P.b_cin, (uint32_t)d->block_n)) { delete plan; return e; }
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   plan->grid = P.total_tiles < sms ? P.total_tiles : sms;
   plan->smem_bytes = (size_t)kCtrlBytes + 1024 + (size_t)stages * P.stage_bytes + (size_t)4 * P.staging_per_warp;
-  plan->flops = 2.0 * real_rows * d->cout * d->cin * d->num_taps;
+  plan->flops = 2.0 * real_rows * d->cout * (double)(P.diag_k ? kBlockK : d->cin) * d->num_taps;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tap_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);

@@ -17,3 +17,11 @@ int fail(int code, const char* fmt, ...) {
 
 extern "C" const char* iou_last_error(void) { return iou::g_last_error.c_str(); }
 extern "C" int iou_abi_version(void) { return 1; }
+extern "C" size_t iou_sizeof(int what) {
+  switch (what) {
+    case 0: return sizeof(iou_postproc_cfg);
+    case 1: return sizeof(iou_conv_desc);
+    case 2: return sizeof(iou_conv_segment);
+    default: return 0;
+  }
+}

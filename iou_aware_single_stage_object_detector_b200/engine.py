@@ -75,6 +75,21 @@ def pack_weight(w, cout_pad, kpad=None):
     return torch.cat([hi, lo], dim=2).reshape(kh * kw * cout_pad, 2 * cin).contiguous()
 
 
+def pack_weight_grouped(w, groups):
+    """Grouped (Cout, Cout/groups, kh, kw) fp32 -> block-diagonal bf16 [kh*kw*Cout][2*64]: row o holds the
+    64 input channels of its own 64-channel block (zeros outside o's group), hi | lo."""
+    cout, cg, kh, kw = w.shape
+    assert cout % 64 == 0 and 64 % cg == 0 and cout // groups == cg, (w.shape, groups)
+    t = torch.zeros(kh * kw, cout, 64, dtype=torch.float32, device=w.device)
+    wt = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, cg).float()
+    o = torch.arange(cout, device=w.device)
+    base = (o // cg) * cg - (o // 64) * 64                     # first local input channel of o's group
+    idx = (base[:, None] + torch.arange(cg, device=w.device)[None, :])          # (cout, cg)
+    t.scatter_(2, idx[None].expand(kh * kw, cout, cg), wt)
+    hi, lo = split_hi_lo(t)
+    return torch.cat([hi, lo], dim=2).reshape(kh * kw * cout, 128).contiguous()
+
+
 def bn_fold(sd, prefix, eps=1e-5):
     """Eval-mode BN as per-channel (scale, shift): y = conv*scale + shift."""
     scale = sd[prefix + ".weight"].float() / torch.sqrt(sd[prefix + ".running_var"].float() + eps)
@@ -126,12 +141,14 @@ class Engine(object):
 
     def conv(self, name, srcs, taps, weight, cin, cout, out=None, scale=None, shift=None, relu=False,
              residual=None, res_mode=L.RES_NONE, dense_out=None, dense_out2=None, dense_split=0,
-             segs_from=None):
+             segs_from=None, diag_k=False, true_flops_scale=1.0):
         """srcs: list[FlatMap] (same geometry); out: FlatMap or None (dense).  Returns out."""
         geo = segs_from or srcs[0]
         m_tiles = sum(_round_up(n * (h + 2) * (w + 2), TILE_M) // TILE_M for (_, n, h, w) in geo.segs)
         # a same-geometry residual needs its TMA staging ring in shared memory: N tile <= 128
         block_n, cout_pad = pick_block_n(cout, m_tiles, max_bn=128 if res_mode == L.RES_SAME else 256)
+        if diag_k:
+            block_n, cout_pad = 64, cout
         d = L.ConvDesc()
         d.cin, d.cout, d.cout_pad, d.block_n = cin, cout, cout_pad, block_n
         d.num_taps = len(taps)
@@ -144,7 +161,8 @@ class Engine(object):
         d.src_rows = min(m.rows for m in srcs)
         wp = weight.to(self.device)
         self.keep.append(wp)
-        assert wp.shape == (len(taps) * cout_pad, 2 * cin), (name, wp.shape, len(taps), cout_pad, cin)
+        assert wp.shape == (len(taps) * cout_pad, 2 * (64 if diag_k else cin)), (name, wp.shape, len(taps), cout_pad, cin)
+        d.diag_k = int(diag_k)
         d.weight = wp.data_ptr()
 
         def padc(v):
@@ -185,7 +203,7 @@ class Engine(object):
         plan = ctypes.c_void_p()
         L.check(self.lib.iou_conv_plan_create(ctypes.byref(d), ctypes.byref(plan)))
         self.plans.append(plan)
-        f = self.lib.iou_conv_plan_flops(plan)
+        f = self.lib.iou_conv_plan_flops(plan) * true_flops_scale
         self.flops += f
         self.op_flops[name] = self.op_flops.get(name, 0.0) + f
         lib = self.lib
@@ -228,8 +246,7 @@ class Engine(object):
         return x
 
     def add_backbone(self, sd, img, depth=50, groups=1, prefix="backbone."):
-        if groups != 1:
-            raise NotImplementedError("grouped (ResNeXt) 3x3 convolutions are not built yet")
+        """ResNet (groups == 1) or ResNeXt (grouped 3x3 run as a block-diagonal tap-GEMM)."""
         x = self.add_stem(sd, img, prefix)
         outs = []
         for s, nblocks in enumerate(STAGE_BLOCKS[depth]):
@@ -238,18 +255,24 @@ class Engine(object):
                 p = "%slayer%d.%d." % (prefix, s + 1, b)
                 stride = 2 if (b == 0 and s > 0) else 1
                 cin = x.c
+                width = sd[p + "conv1.weight"].shape[0]          # == planes for ResNet (resnext.py:21-24)
                 sc1, sh1 = bn_fold(sd, p + "bn1")
-                t1 = self.conv(p + "conv1", [x], TAPS_1X1, pack_weight(sd[p + "conv1.weight"], planes),
-                               cin, planes, scale=sc1, shift=sh1, relu=True)
+                t1 = self.conv(p + "conv1", [x], TAPS_1X1, pack_weight(sd[p + "conv1.weight"], width),
+                               cin, width, scale=sc1, shift=sh1, relu=True)
                 sc2, sh2 = bn_fold(sd, p + "bn2")
-                w2 = pack_weight(sd[p + "conv2.weight"], planes)
+                if groups == 1:
+                    w2, kw = pack_weight(sd[p + "conv2.weight"], width), {}
+                else:
+                    cg = sd[p + "conv2.weight"].shape[1]
+                    w2 = pack_weight_grouped(sd[p + "conv2.weight"], groups)
+                    kw = dict(diag_k=True, true_flops_scale=cg / 64.0)
                 if stride == 2:
                     ph = self.phase_split(p + "conv2.phase", t1)
-                    t2 = self.conv(p + "conv2", ph, TAPS_3X3_S2, w2, planes, planes, scale=sc2, shift=sh2,
-                                   relu=True)
+                    t2 = self.conv(p + "conv2", ph, TAPS_3X3_S2, w2, width, width, scale=sc2, shift=sh2,
+                                   relu=True, **kw)
                 else:
-                    t2 = self.conv(p + "conv2", [t1], TAPS_3X3, w2, planes, planes, scale=sc2, shift=sh2,
-                                   relu=True)
+                    t2 = self.conv(p + "conv2", [t1], TAPS_3X3, w2, width, width, scale=sc2, shift=sh2,
+                                   relu=True, **kw)
                 idt = x
                 if (p + "downsample.0.weight") in sd:
                     scd, shd = bn_fold(sd, p + "downsample.1")
@@ -264,7 +287,7 @@ class Engine(object):
                                         scale=scd, shift=shd)
                 sc3, sh3 = bn_fold(sd, p + "bn3")
                 x = self.conv(p + "conv3", [t2], TAPS_1X1, pack_weight(sd[p + "conv3.weight"], planes * 4),
-                              planes, planes * 4, scale=sc3, shift=sh3, relu=True, residual=idt,
+                              width, planes * 4, scale=sc3, shift=sh3, relu=True, residual=idt,
                               res_mode=L.RES_SAME)
             outs.append(x)
         return outs

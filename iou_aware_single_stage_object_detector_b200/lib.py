@@ -90,12 +90,14 @@ class ConvDesc(ctypes.Structure):
                 ("out", ctypes.c_void_p), ("out_dense", ctypes.c_void_p * CONV_MAX_SEG),
                 ("dense_split", ctypes.c_int32), ("out_dense2", ctypes.c_void_p * CONV_MAX_SEG),
                 ("num_seg", ctypes.c_int32), ("seg", ConvSegment * CONV_MAX_SEG),
-                ("passes", ctypes.c_int32), ("out_rows", ctypes.c_int64), ("res_rows", ctypes.c_int64)]
+                ("passes", ctypes.c_int32), ("out_rows", ctypes.c_int64), ("res_rows", ctypes.c_int64),
+                ("diag_k", ctypes.c_int32)]
 
 
 _SIGS = {
     "iou_last_error": (ctypes.c_char_p, []),
     "iou_abi_version": (ctypes.c_int, []),
+    "iou_sizeof": (ctypes.c_size_t, [ctypes.c_int]),
     "iou_postproc_num_candidates": (ctypes.c_int, [ctypes.POINTER(PostprocCfg)]),
     "iou_postproc_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(PostprocCfg), ctypes.c_int]),
     "iou_decode_candidates": (ctypes.c_int, [ctypes.POINTER(PostprocCfg), ctypes.c_int, ctypes.c_void_p,

@@ -51,6 +51,10 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(L.ConvSegment) == 16
     assert ctypes.sizeof(L.PostprocCfg) == 5 * 4 + 3 * 8 * 4 + 8 * 16 * 4 * 4 + 8 * 4 + 4 * 4
     assert L.ConvDesc.src.offset % 8 == 0 and L.ConvDesc.weight.offset % 8 == 0
+    lib = L.load()                                   # the compiled C structs agree with the ctypes mirror
+    assert lib.iou_sizeof(0) == ctypes.sizeof(L.PostprocCfg)
+    assert lib.iou_sizeof(1) == ctypes.sizeof(L.ConvDesc)
+    assert lib.iou_sizeof(2) == ctypes.sizeof(L.ConvSegment)
 
 
 def test_errors_are_loud_without_gpu():
@@ -174,6 +178,15 @@ def test_weight_packing_and_layout_helpers():
     assert all(s % 128 == 0 for s in starts) and starts[1] == 138752
     # stride-2 taps: tap (r,s) reads phase (r&1, s&1) at offset (r>>1, s>>1)
     assert E.TAPS_3X3_S2[0] == (0, 0, 0) and E.TAPS_3X3_S2[4] == (3, 0, 0) and E.TAPS_3X3_S2[8] == (0, 1, 1)
+    # tile-count-aware N tile: small maps get narrow tiles, big maps keep N=256
+    assert E.pick_block_n(256, 22)[0] == 64 and E.pick_block_n(256, 1469)[0] == 256
+    assert E.pick_block_n(256, 4266, max_bn=128)[0] == 128
+    # ResNeXt grouped weights -> block-diagonal 64-channel blocks
+    wg = torch.randn(256, 4, 3, 3)
+    pg = E.pack_weight_grouped(wg, 64)
+    tg = (pg[:, :64].float() + pg[:, 64:].float()).reshape(9, 256, 64)
+    assert torch.allclose(tg[4, 70, 4:8], wg[70, :, 1, 1], rtol=2e-5, atol=1e-30)
+    assert float(tg[4, 70, :4].abs().max()) == 0 and float(tg[4, 70, 8:].abs().max()) == 0
 
 
 def test_shard_ranges_cover_batch():

@@ -190,3 +190,28 @@ def test_conv_rejects_bad_descriptors_loudly():
     m = E.FlatMap([(1, 4, 4)], 48, DEV)       # cin not a multiple of 64
     with pytest.raises(RuntimeError):
         eng.conv("bad", [m], E.TAPS_1X1, torch.zeros(64, 96, dtype=torch.bfloat16), 48, 64)
+
+
+@pytest.mark.parametrize("width,groups,stride,hw", [(128, 32, 1, (14, 18)), (256, 64, 1, (9, 13)),
+                                                    (256, 32, 2, (20, 28)), (512, 64, 2, (13, 21)),
+                                                    (1024, 32, 1, (7, 11))])
+def test_grouped_conv_block_diagonal_vs_torch(width, groups, stride, hw):
+    """ResNeXt 3x3 grouped conv (resnext.py:47-56) as a block-diagonal tap-GEMM."""
+    g = torch.Generator().manual_seed(width + groups + stride)
+    cg = width // groups
+    x = torch.randn(2, width, *hw, generator=g)
+    w = torch.randn(width, cg, 3, 3, generator=g) * (2.0 / (cg * 9)) ** 0.5
+    b = torch.randn(width, generator=g)
+    ref = F.conv2d(x, w, b, stride=stride, padding=1, groups=groups)
+    eng = E.Engine(DEV)
+    m = eng.pack_input(x.to(DEV).contiguous())
+    wp = E.pack_weight_grouped(w, groups)
+    if stride == 1:
+        out = eng.conv("g", [m], E.TAPS_3X3, wp, width, width, shift=b, diag_k=True)
+    else:
+        out = eng.conv("g", eng.phase_split("p", m), E.TAPS_3X3_S2, wp, width, width, shift=b, diag_k=True)
+    y = eng.unpack_output(out)
+    eng.run()
+    torch.cuda.synchronize()
+    assert y.shape == ref.shape
+    assert rel_err(y.cpu(), ref) < TOL, rel_err(y.cpu(), ref)

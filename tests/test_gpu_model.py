@@ -1,4 +1,6 @@
 """-m gpu: module-level and whole-detector parity against the oracle's torch-CPU fp32 forward."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -88,3 +90,31 @@ def test_reference_init_degenerate_scores():
     assert counts.tolist() == [100, 100]
     s = dets[..., 4]
     assert bool(torch.isfinite(dets).all()) and float((s - 0.07098).abs().max()) < 2e-3
+
+
+@pytest.mark.parametrize("cfg_name,depth,groups", [("iou_aware_retinanet_r101_fpn_1x_4gpu.py", 101, 1),
+                                                    ("iou_aware_retinanet_x101_32x4d_fpn_1x_4gpu.py", 101, 32),
+                                                    ("iou_aware_retinanet_x101_64x4d_fpn_1x.py", 101, 64)])
+def test_other_backbones_head_maps_vs_oracle(cfg_name, depth, groups):
+    """BASELINE configs 2-4: R101 / X101-32x4d / X101-64x4d through the same engine."""
+    cfg = P.Config.fromfile(os.path.join(U.CFG_DIR, cfg_name))
+    cfg.model.pretrained = None
+    torch.manual_seed(5)
+    det = P.build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg).eval()
+    sd = det.state_dict()
+    om.spread_weights_(sd, seed=6, depth=depth, groups=groups)
+    det.load_state_dict(sd)
+    sd = {k: v.clone() for k, v in det.state_dict().items()}
+    det = det.to(DEV)
+    det.use_cuda_graph = False
+    h, w = 96, 128
+    img = torch.randn(1, 3, h, w, generator=torch.Generator().manual_seed(2))
+    meta = dict(ori_shape=(h, w, 3), img_shape=(h, w, 3), pad_shape=(h, w, 3), scale_factor=1.0, flip=False)
+    det.simple_test_batch(img.to(DEV), [meta])
+    plan = det.fused_plan(img.shape, torch.device(DEV), False)
+    torch.cuda.synchronize()
+    ref = om.detector_forward(sd, img, depth, groups)
+    for mine, r in zip(plan.outs, ref):
+        for a, b in zip(mine, r):
+            err = (a.cpu().contiguous() - b).abs().max().item()
+            assert err <= 3e-4 * max(b.abs().max().item(), 1.0), (cfg_name, err)
