@@ -189,6 +189,11 @@ int iou_unpack_nchw(const void* src, int64_t src_row_start, int n, int c, int h,
 /* Stem im2col (resnet.py:454-462, conv 7x7 s2 p3 on 3 channels): NCHW fp32 image
  * -> padded rows [n][(ho+2)][(wo+2)][2*kpad] with k = (r*7+s)*3 + c, zero padded to kpad. */
 int iou_im2col_stem(const float* img, int n, int h, int w, int kpad, void* dst, void* stream);
+/* Stem without an im2col buffer (resnet.py:454-462): NCHW fp32 image -> padded rows
+ * [n][(ho+2)][(wo+2)][2*64] where the 64 "channels" of output pixel x' are the four horizontally
+ * neighbouring pixels x'-2..x'+1 of the 2x2 space-to-depth image (16 channels each, 12 real):
+ * kk = j*16 + (py*2+px)*3 + ch.  The 7x7/s2 conv is then 4 taps (dy=-2..1) of K=64 on iou_conv_run. */
+int iou_stem_pack(const float* img, int n, int h, int w, void* dst, void* stream);
 /* 3x3 stride-2 pad-1 max pool (resnet.py:466) on padded rows (inputs >= 0). */
 int iou_maxpool3x3s2(const void* src, int n, int c, int h, int w, void* dst, void* stream);
 /* Splits a padded-rows map into the 4 stride-2 phase maps laid out in the OUTPUT

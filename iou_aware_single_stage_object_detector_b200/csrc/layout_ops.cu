@@ -130,6 +130,60 @@ __global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restric
   }
 }
 
+// ---- stem pack (replaces the stem's im2col): the 7x7 stride-2 conv on 3 channels equals a
+// 4-row x 4-pixel window over the 2x2 space-to-depth image (12 channels).  Every output pixel row
+// of the padded-rows map stores the 4 horizontally neighbouring s2d pixels x'-2..x'+1, 16 channels
+// each (12 real + 4 zero): K index kk = j*16 + (py*2+px)*3 + ch.  The conv is then FOUR taps
+// (dy = -2..1) of K = 64 on the ordinary tap-GEMM -- one third of the im2col bytes, no K padding.
+__global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict__ img, int n, int h, int w,
+                                                        int ho, int wo, __nv_bfloat16* __restrict__ dst) {
+  extern __shared__ float rows[];                 // [3 ch][2 rows][w + 8]: input cols -4 .. w+3
+  const int yp = blockIdx.x, im = blockIdx.y;
+  const int wop = wo + 2, wpad = w + 8;
+  uint4* drow = reinterpret_cast<uint4*>(dst + ((size_t)im * (ho + 2) + yp) * wop * 128);
+  if (yp == 0 || yp == ho + 1) {
+    for (int i = threadIdx.x; i < wop * 16; i += blockDim.x) drow[i] = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  const int ys = yp - 1;                          // s2d row y'
+  for (int i = threadIdx.x; i < 3 * 2 * wpad; i += blockDim.x) {
+    const int ch = i / (2 * wpad), rem = i - ch * 2 * wpad;
+    const int py = rem / wpad, xx = rem - py * wpad;
+    const int y = 2 * ys + py, x = xx - 4;
+    rows[i] = (y < h && x >= 0 && x < w) ? __ldg(img + (((size_t)im * 3 + ch) * h + y) * w + x) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < wop * 8; i += blockDim.x) {
+    const int xp = i >> 3, v = i & 7;             // vector v holds kk = 8v .. 8v+7
+    uint32_t hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
+    if (xp >= 1 && xp <= wo) {
+      const int j = v >> 1, q0 = (v & 1) * 8;
+      const int xs = xp - 1 + j - 2;              // s2d column x' of window pixel j
+      float val[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int q = q0 + e;
+        float t = 0.f;
+        if (q < 12 && xs >= 0) {
+          const int pp = q / 3, ch = q - pp * 3, py = pp >> 1, px = pp & 1;
+          t = rows[(ch * 2 + py) * wpad + 2 * xs + px + 4];
+        }
+        val[e] = t;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(val[2 * e], h0, l0);
+        split_bf16(val[2 * e + 1], h1, l1);
+        hi[e] = pack2_bf16(h0, h1);
+        lo[e] = pack2_bf16(l0, l1);
+      }
+    }
+    drow[(size_t)xp * 16 + v] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    drow[(size_t)xp * 16 + 8 + v] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
 // ---- 3x3 stride-2 pad-1 max pool on padded rows (inputs are post-ReLU, so the zero border
 // is equivalent to -inf padding).  One thread per (output pixel, 8-channel group): 16-byte loads
 // of the hi and lo planes, max on the reconstructed fp32 values, 16-byte stores.
@@ -242,6 +296,20 @@ extern "C" int iou_im2col_stem(const float* img, int n, int h, int w, int kpad, 
   }
   im2col_stem_kernel<<<dim3(ho + 2, n), 256, sm, (cudaStream_t)stream>>>(img, n, h, w, ho, wo, kpad, (__nv_bfloat16*)dst);
   return launch_status("im2col_stem_kernel");
+}
+
+extern "C" int iou_stem_pack(const float* img, int n, int h, int w, void* dst, void* stream) {
+  IOU_REQUIRE(img && dst && n > 0 && h > 0 && w > 0, "bad argument");
+  const int ho = (h + 6 - 7) / 2 + 1, wo = (w + 6 - 7) / 2 + 1;
+  const size_t sm = (size_t)3 * 2 * (w + 8) * 4;
+  IOU_REQUIRE(sm <= 200 * 1024, "image too wide for the stem pack kernel");
+  static bool attr = false;
+  if (!attr) {
+    IOU_CHECK_CUDA(cudaFuncSetAttribute(stem_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  stem_pack_kernel<<<dim3(ho + 2, n), 256, sm, (cudaStream_t)stream>>>(img, n, h, w, ho, wo, (__nv_bfloat16*)dst);
+  return launch_status("stem_pack_kernel");
 }
 
 extern "C" int iou_maxpool3x3s2(const void* src, int n, int c, int h, int w, void* dst, void* stream) {

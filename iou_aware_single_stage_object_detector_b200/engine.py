@@ -24,7 +24,8 @@ STAGE_BLOCKS = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3), 152: (3, 8, 36, 3)}
 TAPS_1X1 = [(0, 0, 0)]
 TAPS_3X3 = [(0, r - 1, s - 1) for r in range(3) for s in range(3)]                    # stride 1, pad 1
 TAPS_3X3_S2 = [((r & 1) * 2 + (s & 1), r >> 1, s >> 1) for r in range(3) for s in range(3)]  # on phase maps
-TAPS_1X1_S2 = [(3, 0, 0)]                                                             # phase (1,1)
+TAPS_1X1_S2 = [(3, 0, 0)]
+TAPS_STEM = [(0, r - 2, 0) for r in range(4)]                                          # stem: dy = -2..1                                                             # phase (1,1)
 
 
 def _round_up(x, m):
@@ -73,6 +74,23 @@ def pack_weight(w, cout_pad, kpad=None):
         t = torch.nn.functional.pad(t, (0, 0, 0, cout_pad - cout))
     hi, lo = split_hi_lo(t)
     return torch.cat([hi, lo], dim=2).reshape(kh * kw * cout_pad, 2 * cin).contiguous()
+
+
+def pack_weight_stem(w):
+    """(64, 3, 7, 7) stem weight -> [4 taps * 64][2*64] for the packed space-to-depth layout of
+    iou_stem_pack: tap r (dy = r-2), K index kk = j*16 + (py*2+px)*3 + ch  <->  w[o, ch, 2r+py-1, 2j+px-1]."""
+    cout = w.shape[0]
+    t = torch.zeros(4, cout, 64, dtype=torch.float32, device=w.device)
+    for r in range(4):
+        for j in range(4):
+            for py in range(2):
+                for px in range(2):
+                    ky, kx = 2 * r + py - 1, 2 * j + px - 1
+                    if 0 <= ky <= 6 and 0 <= kx <= 6:
+                        k0 = j * 16 + (py * 2 + px) * 3
+                        t[r, :, k0:k0 + 3] = w[:, :, ky, kx].float()
+    hi, lo = split_hi_lo(t)
+    return torch.cat([hi, lo], dim=2).reshape(4 * cout, 128).contiguous()
 
 
 def pack_weight_grouped(w, groups):
@@ -224,21 +242,17 @@ class Engine(object):
 
     # ------------------------------------------------------------------ network builders
     def add_stem(self, sd, img, prefix="backbone."):
-        """conv1 7x7/s2 + bn1 + relu + maxpool (resnet.py:508-511).  img: (N,3,H,W) fp32 cuda tensor."""
+        """conv1 7x7/s2 + bn1 + relu + maxpool (resnet.py:508-511).  img: (N,3,H,W) fp32 cuda tensor.
+        The 7x7/s2 conv runs as 4 taps of K=64 over the packed space-to-depth map (iou_stem_pack)."""
         n, _, h, w = img.shape
         ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
-        kpad = 192
-        cols = self.new_map([(n, ho, wo)], kpad)
-        lib, ip, cp = self.lib, img.data_ptr(), cols.ptr
+        packed = self.new_map([(n, ho, wo)], 64)
+        lib, ip, pp = self.lib, img.data_ptr(), packed.ptr
         self.keep.append(img)
-        self.ops.append(("stem.im2col", lambda st: L.check(lib.iou_im2col_stem(ip, n, h, w, kpad, cp, st))))
-        wt = sd[prefix + "conv1.weight"].float().permute(0, 2, 3, 1).reshape(64, 147, 1, 1)
+        self.ops.append(("stem.pack", lambda st: L.check(lib.iou_stem_pack(ip, n, h, w, pp, st))))
         scale, shift = bn_fold(sd, prefix + "bn1")
-        s1 = self.conv("stem.conv1", [cols], TAPS_1X1, pack_weight(wt, 64, kpad), kpad, 64,
-                       scale=scale, shift=shift, relu=True)
-        pad_f = 2.0 * n * ho * wo * 64 * (kpad - 147)             # K padding is not algorithmic work
-        self.flops -= pad_f
-        self.op_flops["stem.conv1"] -= pad_f
+        s1 = self.conv("stem.conv1", [packed], TAPS_STEM, pack_weight_stem(sd[prefix + "conv1.weight"]), 64, 64,
+                       scale=scale, shift=shift, relu=True, true_flops_scale=147.0 / 256.0)
         hp, wq = (ho - 1) // 2 + 1, (wo - 1) // 2 + 1
         x = self.new_map([(n, hp, wq)], 64)
         sp, xp = s1.ptr, x.ptr
