@@ -302,6 +302,7 @@ __device__ __forceinline__ float box_area(const float4 a) {
   return __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.0f), __fadd_rn(__fsub_rn(a.w, a.y), 1.0f));
 }
 
+#define NMS_ROUND 1024
 struct NmsSmem {
   unsigned long long* sortbuf;   // [P]
   float4* sbox;                  // [n]
@@ -310,23 +311,23 @@ struct NmsSmem {
 };
 
 // Greedy NMS over n boxes already ordered by (score desc, index asc) in shared memory.
-// Calls emit(r, pos) from thread 0 for every kept sorted position r, in order; stops once
-// `stop_after` boxes are kept (0 = never).  Returns the number kept (block-uniform).
+// Scans sorted positions [begin, n).  Calls emit(r, pos) from thread 0 for every kept position r, in
+// order; stops once `stop_after` boxes are kept in total (0 = never).  *s_total_p (shared memory) holds
+// the kept count and persists across calls, so the scan can proceed in rounds.
 // The scan is LAZY: a 64-box chunk is only tested when the scan reaches it --
 //   (a) every (chunk box, previously kept box) pair is tested in parallel,
 //   (b) the chunk's own 64x64 suppression mask is built with warp ballots,
 //   (c) one thread resolves the chunk serially and appends to the kept list --
 // so with the max_per_img+1 early stop only the first few chunks are ever touched.
 template <typename Emit>
-__device__ int greedy_nms_sorted(const NmsSmem& S, const int n, const float thr, const int stop_after,
-                                 Emit emit) {
+__device__ int greedy_nms_range(const NmsSmem& S, const int begin, const int n, const float thr,
+                                const int stop_after, int* s_total_p, Emit emit) {
   __shared__ unsigned long long cmask[64];
   __shared__ unsigned int dead[2];
-  __shared__ int s_total;
+  int& s_total = *s_total_p;                   // kept count so far (shared memory, persists across ranges)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  if (tid == 0) s_total = 0;
   __syncthreads();
-  for (int cs = 0; cs < n; cs += 64) {
+  for (int cs = begin; cs < n; cs += 64) {
     const int cnt = min(64, n - cs);
     const int total0 = s_total;
     if (tid < 2) dead[tid] = 0u;
@@ -427,22 +428,96 @@ __global__ void __launch_bounds__(512) class_nms_kernel(const __grid_constant__ 
     if (tid == 0) *cnt_out = 0;
     return;
   }
-  const int Ps = next_pow2(n);
-  for (int i = n + tid; i < Ps; i += 512) S.sortbuf[i] = 0ull;
-  bitonic_sort_desc(S.sortbuf, Ps);
   const float4* bx = reinterpret_cast<const float4*>(boxes) + (size_t)img * P.M;
-  for (int r = tid; r < n; r += 512) {
-    const unsigned int j = 0xffffffffu - (unsigned int)(S.sortbuf[r] & 0xffffffffull);
-    const float4 b = __ldg(bx + j);
-    S.sbox[r] = b;
-    S.sarea[r] = box_area(b);
+  unsigned long long* keys_out = kept_keys + ((size_t)img * P.C + c) * P.kcap;
+  __shared__ int s_total;
+  if (tid == 0) s_total = 0;
+  if (n <= NMS_ROUND) {
+    // small class: sort everything once
+    const int Ps = next_pow2(n);
+    for (int i = n + tid; i < Ps; i += 512) S.sortbuf[i] = 0ull;
+    bitonic_sort_desc(S.sortbuf, Ps);
+    for (int r = tid; r < n; r += 512) {
+      const unsigned int j = 0xffffffffu - (unsigned int)(S.sortbuf[r] & 0xffffffffull);
+      const float4 b = __ldg(bx + j);
+      S.sbox[r] = b;
+      S.sarea[r] = box_area(b);
+    }
+    const unsigned long long* sb = S.sortbuf;
+    greedy_nms_range(S, 0, n, P.iou_thr, P.kcap, &s_total, [&](int r, int pos) { keys_out[pos] = sb[r]; });
+  } else {
+    // big class: the scan stops after max_per_img+1 kept boxes, so only the head of the score order is
+    // ever needed.  Rounds of NMS_ROUND boxes: exact radix select of the round's lowest composite key
+    // (keys are unique: score bits | ~index), compaction, a 1024-wide sort, then the lazy greedy scan.
+    __shared__ unsigned long long rb[NMS_ROUND];
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned int s_kleft, s_slot;
+    unsigned long long bound = ~0ull;           // keys of this round are < bound
+    int processed = 0;
+    while (processed < n) {
+      const int teff = min(NMS_ROUND, n - processed);
+      if (tid == 0) { s_prefix = 0ull; s_kleft = teff; s_slot = 0; }
+      unsigned long long mask = 0ull;
+      for (int pass = 0; pass < 8; ++pass) {
+        const int shift = 56 - 8 * pass;
+        if (tid < 256) hist[tid] = 0;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        for (int base = 0; base < n; base += 512) {
+          const int i = base + tid;
+          const unsigned long long u = (i < n) ? S.sortbuf[i] : 0ull;
+          const bool valid = (i < n) && (u < bound) && ((u & mask) == prefix);
+          const unsigned int d = valid ? (unsigned int)((u >> shift) & 255ull) : (256u + lane);
+          const unsigned int peers = __match_any_sync(0xffffffffu, d);
+          if (valid && (__ffs(peers) - 1) == lane) atomicAdd(&hist[d], __popc(peers));
+        }
+        __syncthreads();
+        if (tid == 0) {
+          unsigned int cacc = 0, kl = s_kleft;
+          int d = 255;
+          for (; d > 0; --d) {
+            if (cacc + hist[d] >= kl) break;
+            cacc += hist[d];
+          }
+          s_kleft = kl - cacc;
+          s_prefix = prefix | ((unsigned long long)d << shift);
+        }
+        mask |= 255ull << shift;
+        __syncthreads();
+      }
+      const unsigned long long kt = s_prefix;   // the teff-th largest key below `bound`
+      for (int base = 0; base < n; base += 512) {
+        const int i = base + tid;
+        const unsigned long long u = (i < n) ? S.sortbuf[i] : 0ull;
+        const bool take = (i < n) && (u < bound) && (u >= kt);
+        const unsigned int bt = __ballot_sync(0xffffffffu, take);
+        unsigned int slot0 = 0;
+        if (lane == 0 && bt) slot0 = atomicAdd(&s_slot, __popc(bt));
+        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+        if (take) rb[slot0 + __popc(bt & ((1u << lane) - 1u))] = u;
+      }
+      __syncthreads();
+      const int Ps = next_pow2(teff);
+      for (int i = teff + tid; i < Ps; i += 512) rb[i] = 0ull;
+      bitonic_sort_desc(rb, Ps);
+      for (int r = tid; r < teff; r += 512) {
+        const unsigned int j = 0xffffffffu - (unsigned int)(rb[r] & 0xffffffffull);
+        const float4 b = __ldg(bx + j);
+        S.sbox[processed + r] = b;
+        S.sarea[processed + r] = box_area(b);
+      }
+      const int p0 = processed;
+      const int total = greedy_nms_range(S, p0, p0 + teff, P.iou_thr, P.kcap, &s_total,
+                                         [&](int r, int pos) { keys_out[pos] = rb[r - p0]; });
+      processed += teff;
+      bound = kt;
+      if (total >= P.kcap) break;
+      __syncthreads();
+    }
   }
   __syncthreads();
-  unsigned long long* keys_out = kept_keys + ((size_t)img * P.C + c) * P.kcap;
-  const unsigned long long* sb = S.sortbuf;
-  const int total = greedy_nms_sorted(S, n, P.iou_thr, P.kcap,
-                                      [&](int r, int pos) { keys_out[pos] = sb[r]; });
-  if (tid == 0) *cnt_out = total;
+  if (tid == 0) *cnt_out = s_total;
 }
 
 // ---------------------------------------------------------------------------------------- K5
@@ -536,7 +611,9 @@ __global__ void __launch_bounds__(512) single_nms_kernel(const float* __restrict
   }
   __syncthreads();
   const unsigned long long* sb = S.sortbuf;
-  greedy_nms_sorted(S, n, thr, 0, [&](int r, int) {
+  __shared__ int s_total;
+  if (tid == 0) s_total = 0;
+  greedy_nms_range(S, 0, n, thr, 0, &s_total, [&](int r, int) {
     const unsigned int j = 0xffffffffu - (unsigned int)(sb[r] & 0xffffffffull);
     keepbits[j >> 5] |= 1u << (j & 31);     // only thread 0 emits
   });
