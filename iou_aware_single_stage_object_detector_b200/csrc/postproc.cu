@@ -9,8 +9,11 @@
 // mmdet/ops/nms/src/nms_kernel.cu:13-131.  Arithmetic that feeds a comparison
 // (IoU, decode) uses explicit round-to-nearest intrinsics so no FMA contraction
 // can move a threshold decision away from the reference's unfused fp32 result.
+#include <cooperative_groups.h>
 #include <math.h>
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace iou {
 
@@ -209,6 +212,137 @@ __global__ void __launch_bounds__(1024) topk_kernel(const __grid_constant__ Post
   int32_t* out = cand_idx + (size_t)img * P.M + P.cand_off[l];
   for (int r = tid; r < k; r += 1024)
     out[r] = (int32_t)(0xffffffffu - (unsigned int)(sortbuf[r] & 0xffffffffull));
+}
+
+// ---------------------------------------------------------------------------------------- K2'
+// Cluster version of the top-k: 8 CTAs (one thread-block cluster) per (image, level).  Every CTA
+// loads its eighth of the keys into shared memory ONCE; the four radix-select passes then run out
+// of shared memory, with the 256-bin histograms merged across the cluster through distributed
+// shared memory.  Same result as topk_kernel (exact k-th key, ties by lowest index, output ordered
+// by score desc / index asc); topk_kernel stays as the fallback for slices that do not fit.
+#define TOPK_CLUSTER 8
+__global__ void __cluster_dims__(TOPK_CLUSTER, 1, 1) __launch_bounds__(1024)
+topk_cluster_kernel(const __grid_constant__ PostParams P, const float* __restrict__ maxscore,
+                    int32_t* __restrict__ cand_idx, unsigned long long* __restrict__ scratch) {
+  extern __shared__ __align__(16) unsigned char tk_smem[];
+  unsigned int* skeys = reinterpret_cast<unsigned int*>(tk_smem);
+  __shared__ unsigned int hist[256], tot[256];
+  __shared__ unsigned int s_prefix, s_kleft, s_eq_total, s_cnt[2], s_slot, s_eq_run, warp_eq[32];
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned int rank = cluster.block_rank();
+  const int lslot = blockIdx.x / TOPK_CLUSTER, l = P.topk_level[lslot], img = blockIdx.y;
+  const int n = P.n_anchor[l], k = P.keep[l];
+  const float* keys = maxscore + (size_t)img * P.A_total + P.anchor_off[l];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slice = (n + TOPK_CLUSTER - 1) / TOPK_CLUSTER;
+  const int lo = min(n, (int)rank * slice), m = min(n, lo + slice) - lo;
+  for (int i = tid; i < m; i += 1024) skeys[i] = float_to_ordered(__ldg(keys + lo + i));
+  if (tid == 0) { s_prefix = 0; s_kleft = k; s_slot = 0; s_eq_run = 0; }
+  unsigned int mask = 0;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    const unsigned int prefix = s_prefix;
+    for (int base = 0; base < m; base += 1024) {
+      const int i = base + tid;
+      const unsigned int u = (i < m) ? skeys[i] : 0u;
+      const bool valid = (i < m) && ((u & mask) == prefix);
+      const unsigned int d = valid ? ((u >> shift) & 255u) : (256u + lane);
+      const unsigned int peers = __match_any_sync(0xffffffffu, d);
+      if (valid && (__ffs(peers) - 1) == lane) atomicAdd(&hist[d], __popc(peers));
+    }
+    cluster.sync();
+    if (tid < 256) {
+      unsigned int t = 0;
+      for (unsigned int r = 0; r < TOPK_CLUSTER; ++r) t += cluster.map_shared_rank(hist, r)[tid];
+      tot[tid] = t;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int c = 0, kl = s_kleft;
+      int d = 255;
+      for (; d > 0; --d) {
+        if (c + tot[d] >= kl) break;
+        c += tot[d];
+      }
+      s_kleft = kl - c;
+      s_prefix = prefix | ((unsigned int)d << shift);
+      s_eq_total = tot[d];
+    }
+    mask |= 255u << shift;
+    cluster.sync();                       // nobody still reads my histogram when the next pass clears it
+  }
+  const unsigned int T = s_prefix, need_eq = s_kleft;
+  const bool ties = (s_eq_total != need_eq);
+  // counts of (> T) and (== T) in my slice
+  if (tid < 2) s_cnt[tid] = 0;
+  __syncthreads();
+  {
+    unsigned int g = 0, e = 0;
+    for (int i = tid; i < m; i += 1024) { const unsigned int u = skeys[i]; g += (u > T); e += (u == T); }
+    for (int o = 16; o > 0; o >>= 1) { g += __shfl_xor_sync(0xffffffffu, g, o); e += __shfl_xor_sync(0xffffffffu, e, o); }
+    if (lane == 0) { atomicAdd(&s_cnt[0], g); atomicAdd(&s_cnt[1], e); }
+  }
+  cluster.sync();
+  unsigned int base_slot = 0, eq_before = 0;
+  {
+    unsigned int eqb = 0;
+    for (unsigned int r = 0; r < TOPK_CLUSTER; ++r) {
+      const unsigned int* rc = cluster.map_shared_rank(s_cnt, r);
+      const unsigned int gr = rc[0], er = rc[1];
+      const unsigned int left = need_eq > eqb ? need_eq - eqb : 0u;
+      const unsigned int take = gr + (er < left ? er : left);
+      if (r < rank) base_slot += take;
+      if (r == rank) eq_before = eqb;
+      eqb += er;
+    }
+  }
+  const unsigned int my_eq_quota = need_eq > eq_before ? need_eq - eq_before : 0u;   // ties: lowest index first
+  unsigned long long* out = scratch + ((size_t)img * IOU_MAX_LEVELS + lslot) * TOPK_MAX;
+  for (int base = 0; base < m; base += 1024) {
+    const int i = base + tid;
+    const unsigned int u = (i < m) ? skeys[i] : 0u;
+    const bool gt = (i < m) && (u > T), eq = (i < m) && (u == T);
+    bool take = gt;
+    if (!ties) {
+      take = gt || eq;
+    } else {
+      const unsigned int be = __ballot_sync(0xffffffffu, eq);
+      if (lane == 0) warp_eq[warp] = __popc(be);
+      __syncthreads();
+      unsigned int before = s_eq_run;
+      for (int w = 0; w < warp; ++w) before += warp_eq[w];
+      if (eq && before + __popc(be & ((1u << lane) - 1u)) < my_eq_quota) take = true;
+      __syncthreads();
+      if (tid == 0) {
+        unsigned int t = 0;
+        for (int w = 0; w < 32; ++w) t += warp_eq[w];
+        s_eq_run += t;
+      }
+      __syncthreads();
+    }
+    const unsigned int bt = __ballot_sync(0xffffffffu, take);
+    unsigned int slot0 = 0;
+    if (lane == 0 && bt) slot0 = atomicAdd(&s_slot, __popc(bt));
+    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+    if (take) {
+      const unsigned int slot = base_slot + slot0 + __popc(bt & ((1u << lane) - 1u));
+      if (slot < TOPK_MAX)
+        out[slot] = ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (unsigned int)(lo + i));
+    }
+  }
+  __threadfence();
+  cluster.sync();
+  if (rank == 0) {
+    unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(tk_smem);
+    const int Psort = next_pow2(k);
+    for (int i = tid; i < Psort; i += 1024) sortbuf[i] = (i < k) ? __ldcg(out + i) : 0ull;
+    bitonic_sort_desc(sortbuf, Psort);
+    int32_t* dst = cand_idx + (size_t)img * P.M + P.cand_off[l];
+    for (int r = tid; r < k; r += 1024)
+      dst[r] = (int32_t)(0xffffffffu - (unsigned int)(sortbuf[r] & 0xffffffffull));
+  }
 }
 
 // ---------------------------------------------------------------------------------------- K3
@@ -692,6 +826,7 @@ static int fill_params(const iou_postproc_cfg* cfg, int n_img, PostParams& P) {
 struct PostWorkspace {
   float* maxscore; unsigned long long* kept_keys; int32_t* kept_cnt;
   float* boxes; float* scores_cm; int32_t* cand_idx;
+  unsigned long long* topk_scratch;
   size_t total;
 };
 static PostWorkspace carve(const PostParams& P, void* base) {
@@ -705,13 +840,15 @@ static PostWorkspace carve(const PostParams& P, void* base) {
   W.boxes = (float*)take((size_t)P.n_img * P.M * 16);
   W.scores_cm = (float*)take((size_t)P.n_img * P.C * P.M * 4);
   W.cand_idx = (int32_t*)take((size_t)P.n_img * P.M * 4);
+  W.topk_scratch = (unsigned long long*)take((size_t)P.n_img * IOU_MAX_LEVELS * TOPK_MAX * 8);
   W.total = off;
   return W;
 }
 
 static int run_decode(PostParams& P, const float* const* cls, const float* const* reg,
                       const float* const* iou, const float* img_info, int rescale, float* boxes,
-                      float* scores_cm, int32_t* cand_idx, float* maxscore, cudaStream_t st) {
+                      float* scores_cm, int32_t* cand_idx, float* maxscore, unsigned long long* topk_scratch,
+                      cudaStream_t st) {
   for (int l = 0; l < P.num_levels; ++l) {
     IOU_REQUIRE(cls[l] && reg[l] && iou[l], "NULL level pointer at level %d", l);
     IOU_REQUIRE(((uintptr_t)cls[l] & 15) == 0 && ((uintptr_t)reg[l] & 15) == 0,
@@ -725,8 +862,19 @@ static int run_decode(PostParams& P, const float* const* cls, const float* const
     const size_t sm = (size_t)8 * 32 * (P.C / 4) * sizeof(float);
     max_score_kernel<<<blocks, 256, sm, st>>>(P, maxscore);
     if (int e = launch_status("max_score_kernel")) return e;
-    topk_kernel<<<dim3(P.num_topk_levels, P.n_img), 1024, 0, st>>>(P, maxscore, cand_idx);
-    if (int e = launch_status("topk_kernel")) return e;
+    int max_n = 0;
+    for (int t = 0; t < P.num_topk_levels; ++t) max_n = max_n > P.n_anchor[P.topk_level[t]] ? max_n : P.n_anchor[P.topk_level[t]];
+    size_t tk_sm = (size_t)((max_n + TOPK_CLUSTER - 1) / TOPK_CLUSTER) * 4;
+    if (tk_sm < (size_t)TOPK_MAX * 8) tk_sm = (size_t)TOPK_MAX * 8;
+    if (tk_sm <= 200 * 1024) {
+      IOU_CHECK_CUDA(cudaFuncSetAttribute(topk_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      topk_cluster_kernel<<<dim3(P.num_topk_levels * TOPK_CLUSTER, P.n_img), 1024, tk_sm, st>>>(P, maxscore, cand_idx,
+                                                                                              topk_scratch);
+      if (int e = launch_status("topk_cluster_kernel")) return e;
+    } else {
+      topk_kernel<<<dim3(P.num_topk_levels, P.n_img), 1024, 0, st>>>(P, maxscore, cand_idx);
+      if (int e = launch_status("topk_kernel")) return e;
+    }
   }
   const size_t sm3 = (size_t)P.C * 33 * sizeof(float);
   gather_decode_kernel<<<dim3((P.M + 31) / 32, P.n_img), 256, sm3, st>>>(P, img_info, cand_idx, boxes,
@@ -777,7 +925,7 @@ extern "C" int iou_decode_candidates(const iou_postproc_cfg* cfg, int n_img, con
   if (!workspace || workspace_bytes < W.total)
     return fail(IOU_ERR_WORKSPACE, "workspace too small: need %zu bytes", W.total);
   return run_decode(P, cls, reg, iou, img_info, rescale, boxes, scores_cm, cand_idx, W.maxscore,
-                    (cudaStream_t)stream);
+                    W.topk_scratch, (cudaStream_t)stream);
 }
 
 extern "C" int iou_batched_nms(const iou_postproc_cfg* cfg, int n_img, const float* boxes,
@@ -803,7 +951,7 @@ extern "C" int iou_get_bboxes(const iou_postproc_cfg* cfg, int n_img, const floa
   if (!workspace || workspace_bytes < W.total)
     return fail(IOU_ERR_WORKSPACE, "workspace too small: need %zu bytes", W.total);
   if (int e = run_decode(P, cls, reg, iou, img_info, rescale, W.boxes, W.scores_cm, W.cand_idx,
-                         W.maxscore, (cudaStream_t)stream))
+                         W.maxscore, W.topk_scratch, (cudaStream_t)stream))
     return e;
   return run_nms(P, W.boxes, W.scores_cm, dets, labels, counts, W.kept_keys, W.kept_cnt,
                  (cudaStream_t)stream);
