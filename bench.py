@@ -25,8 +25,16 @@ sys.path.insert(0, ROOT)
 
 METRIC = "images/sec (1333x800, bs=8/GPU) IoU-aware RetinaNet-R50 inference"
 UNIT = "images/sec"
-CFG = os.path.join(ROOT, "configs", "iou_aware_single_stage_detector", "iou_aware_retinanet_r50_fpn_1x_4gpu.py")
+CFG_DIR = os.path.join(ROOT, "configs", "iou_aware_single_stage_detector")
+MODELS = {   # name -> (config file, depth, groups, default per-GPU batch)   (BASELINE.json configs 1-3)
+    "r50": ("iou_aware_retinanet_r50_fpn_1x_4gpu.py", 50, 1, 8),
+    "r101": ("iou_aware_retinanet_r101_fpn_1x_4gpu.py", 101, 1, 8),
+    "x101_32x4d": ("iou_aware_retinanet_x101_32x4d_fpn_1x_4gpu.py", 101, 32, 8),
+    "x101_64x4d": ("iou_aware_retinanet_x101_64x4d_fpn_1x.py", 101, 64, 4),
+}
+CFG = os.path.join(CFG_DIR, MODELS["r50"][0])
 H, W, BATCH = 800, 1344, 8
+DEPTH, GROUPS, MODEL = 50, 1, "r50"
 GFLOP_PER_IMG = {"head": 290.36, "fpn": 36.39, "backbone": 175.16}
 
 
@@ -219,7 +227,7 @@ def run_ours(args):
         pe1.record()
         torch.cuda.synchronize()
         post_ms = pe0.elapsed_time(pe1) / 5
-        logits_bytes = BATCH * 201600 * 85 * 4
+        logits_bytes = BATCH * 201600 * 85 * 4      # cls + reg + iou logits read by the decode stage
         extra["postproc_ms_per_step"] = round(post_ms, 3)
         extra["decode_read_gbs_lower_bound"] = round(logits_bytes / (post_ms / 1e3) / 1e9, 1)
     line = None
@@ -229,8 +237,8 @@ def run_ours(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "fp32 (bf16x3 split on tcgen05, fp32 accumulate)" if args.passes == 3 else "bf16",
                 "data": "synthetic",
-                "config": {"workload": "IoU-aware RetinaNet R50-FPN inference bs=8/GPU, synthetic 800x1344 "
-                                       "(img_shape 800x1333), backbone+FPN+head+get_bboxes",
+                "config": {"workload": "IoU-aware RetinaNet %s-FPN inference bs=%d/GPU, synthetic 800x1344 "
+                                       "(img_shape 800x1333), backbone+FPN+head+get_bboxes" % (MODEL.upper(), BATCH),
                            "global_batch": world * BATCH, "weights": args.weights + " (seeded random)",
                            "parallelism": "dp%d (image batch sharded, one all-gather of detections)" % world,
                            "l2": "per-step working set (~10 GB of activations) exceeds the 126 MB L2; no flush",
@@ -261,7 +269,7 @@ def oracle_setup(weights, seed=0):
     det = P.build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg)   # parameter container only
     sd = {k: v.clone() for k, v in det.state_dict().items()}
     if weights == "spread":
-        om.spread_weights_(sd, seed=seed + 1)
+        om.spread_weights_(sd, seed=seed + 1, depth=DEPTH, groups=GROUPS)
     sc = op.retina_anchor_scales(4, 3)
     bases = [op.base_anchors(s, sc, [0.5, 1.0, 2.0]) for s in (8, 16, 32, 64, 128)]
     return sd, dict(cfg.test_cfg), bases, om, op
@@ -269,7 +277,7 @@ def oracle_setup(weights, seed=0):
 
 def oracle_image(sd, test_cfg, bases, om, op, img, meta):
     """One image exactly like tools/test.py:single_gpu_test drives the reference (1 image / iteration)."""
-    cls, reg, iou = om.detector_forward(sd, img)
+    cls, reg, iou = om.detector_forward(sd, img, DEPTH, GROUPS)
     d, l = op.get_bboxes_single([c[0] for c in cls], [r[0] for r in reg], [q[0] for q in iou],
                                 [8, 16, 32, 64, 128], bases, meta["img_shape"], meta["scale_factor"],
                                 test_cfg, rescale=True, nms_mode="cpu")
@@ -319,8 +327,8 @@ def run_reference(args):
                       "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                       "ms_per_step": round(dt / done * 1e3, 1), "higher_is_better": True, "scaling": "weak",
                       "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-                      "config": {"workload": "IoU-aware RetinaNet R50-FPN inference, synthetic 800x1344, CPU "
-                                             "reference path (oracle port), 1 image per step",
+                      "config": {"workload": "IoU-aware RetinaNet %s-FPN inference, synthetic 800x1344, CPU "
+                                             "reference path (oracle port), 1 image per step" % MODEL.upper(),
                                  "weights": args.weights + " (seeded random)"},
                       "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port",
                                        "sample": sample},
@@ -343,7 +351,16 @@ def main():
     ap.add_argument("--dump-ops", default=None, help="write the per-launch CUDA-event table to this JSON file")
     ap.add_argument("--cpu-images", type=int, default=3)
     ap.add_argument("--reference-budget-s", type=int, default=150)
+    ap.add_argument("--model", default="r50", choices=sorted(MODELS),
+                    help="r50 = the headline workload; the others are BASELINE configs 2-3 (extra lines)")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: 8, 4 for x101_64x4d)")
     args = ap.parse_args()
+    global CFG, BATCH, DEPTH, GROUPS, MODEL, METRIC
+    cfg_file, DEPTH, GROUPS, default_bs = MODELS[args.model]
+    CFG, MODEL = os.path.join(CFG_DIR, cfg_file), args.model
+    BATCH = args.batch or default_bs
+    if args.model != "r50" or BATCH != 8:
+        METRIC = "images/sec (1333x800, bs=%d/GPU) IoU-aware RetinaNet-%s inference" % (BATCH, args.model.upper())
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -127,6 +127,8 @@ def pick_block_n(cout, m_tiles=None, max_bn=256):
             return 240, cout
         pad = _round_up(cout, 16)
         return (pad, pad) if pad <= 256 else (256, _round_up(cout, 256))
+    import os
+    max_bn = min(max_bn, int(os.environ.get("IOU_MAX_BN", "256")))     # tuning knob for experiments
     cands = [bn for bn in (256, 128, 64) if cout % bn == 0 and bn <= max_bn]
     if m_tiles is None:
         return cands[0], cout
