@@ -168,6 +168,7 @@ typedef struct iou_conv_desc {
   int64_t res_rows;                         /* rows allocated behind `residual`                             */
   int32_t diag_k;                           /* grouped conv (cin == cout, block_n == 64): output tile j contracts
                                                only input channels [64j, 64j+64); weight is [taps*cout][2*64]   */
+  int32_t two_cta;                          /* 1: run as CTA pairs (tcgen05 cta_group::2, cluster of 2)      */
 } iou_conv_desc;
 
 typedef struct iou_conv_plan iou_conv_plan;

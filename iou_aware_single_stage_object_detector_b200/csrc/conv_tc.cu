@@ -50,6 +50,7 @@ struct ConvParams {
   SegDev seg[IOU_CONV_MAX_SEG];
   int seg_tile_off[IOU_CONV_MAX_SEG + 1];
   int num_m_tiles, num_n_tiles, total_tiles;
+  int two_cta, total_pair_tiles;   // cta_group::2: a CTA pair owns two consecutive 128-row tiles x BLOCK_N
   int num_stages, stage_bytes, b_tile_bytes;
   int staged, res_staged, staging_per_warp;
   const float* scale;
@@ -110,6 +111,40 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tmap, uint32_t ba
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+// ---- CTA-pair (cta_group::2) variants.  kPeerMask clears the pair bit of a shared::cluster address, so a
+// barrier operand built from a local address names the EVEN (leader) CTA's barrier (CUTLASS Sm100MmaPeerBitMask).
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* tmap, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar & kPeerMask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerMask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -172,6 +207,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
 }
 
 // ------------------------------------------------------------------------------------ kernel
+template <bool kTwoCta>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __grid_constant__ ConvParams P) {
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte alignment is required by the 128B swizzle atoms
@@ -186,10 +222,22 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(ctrl + 160);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // work distribution: one item = (128-row tile, N tile) per CTA, or (two 128-row tiles, N tile) per CTA pair
+  const int rank = kTwoCta ? (int)cluster_ctarank() : 0;
+  const int w_first = kTwoCta ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int w_stride = kTwoCta ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int w_total = kTwoCta ? P.total_pair_tiles : P.total_tiles;
+  auto decode_tile = [&](int wi, int& m_tile, int& n_tile, int& sidx) {
+    const int q = wi / P.num_n_tiles;
+    n_tile = wi - q * P.num_n_tiles;
+    m_tile = kTwoCta ? 2 * q + rank : q;
+    sidx = 0;
+    while (sidx + 1 < P.num_seg && m_tile >= P.seg_tile_off[sidx + 1]) ++sidx;
+  };
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < P.num_stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, kTwoCta ? 256 : 128); }
     for (int r = 0; r < 8; ++r) mbar_init(ctrl_addr + 192 + 8 * r, 1);     // residual ring: 4 warps x 2
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -200,12 +248,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tmap_res) : "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(ctrl_addr + 160), "r"(kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (kTwoCta) {       // the same warp of both CTAs allocates collectively
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(ctrl_addr + 160), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(ctrl_addr + 160), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kTwoCta) cluster_sync_all();   // the peer's barriers must be initialised before any remote signal
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -219,27 +274,38 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const int m_tile = tile / P.num_n_tiles, n_tile = tile - m_tile * P.num_n_tiles;
-        int s = 0;
-        while (m_tile >= P.seg_tile_off[s + 1]) ++s;
+      for (int tile = w_first; tile < w_total; tile += w_stride) {
+        int m_tile, n_tile, s;
+        decode_tile(tile, m_tile, n_tile, s);
         const int row0 = P.seg[s].row_start + (m_tile - P.seg_tile_off[s]) * kBlockM;
         const int wp = P.seg[s].w + 2;
+        const int b_rows = kTwoCta ? (P.block_n >> 1) : P.block_n;     // a pair splits the B tile by rows
         for (int t = 0; t < P.num_taps; ++t) {
           const int arow = row0 + P.tap_dy[t] * wp + P.tap_dx[t];
-          const int wrow = t * P.cout_pad + n_tile * P.block_n;
+          const int wrow = t * P.cout_pad + n_tile * P.block_n + rank * b_rows;
           const CUtensorMap* tm = &P.tmap_src[P.tap_src[t]];
           for (int ks = 0; ks < P.k_slabs; ++ks) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
             const uint32_t fb = bar_full + 8 * stage;
             const uint32_t sa = tiles_addr + stage * P.stage_bytes;
-            mbar_expect_tx(fb, (uint32_t)P.stage_bytes);
             const int a_col = P.diag_k ? n_tile * kBlockK : ks * kBlockK;
-            tma_load_2d(tm, fb, sa, a_col, arow);
-            tma_load_2d(&P.tmap_w, fb, sa + b_hi_off, ks * kBlockK, wrow);
-            if (P.passes == 3) {
-              tma_load_2d(tm, fb, sa + a_lo_off, P.cin + a_col, arow);
-              tma_load_2d(&P.tmap_w, fb, sa + b_lo_off, P.b_cin + ks * kBlockK, wrow);
+            if constexpr (kTwoCta) {
+              // both CTAs' loads complete on the LEADER's full barrier; only the leader posts the byte count
+              if (rank == 0) mbar_expect_tx(fb, 2u * (uint32_t)P.stage_bytes);
+              tma_load_2d_pair(tm, fb, sa, a_col, arow);
+              tma_load_2d_pair(&P.tmap_w, fb, sa + b_hi_off, ks * kBlockK, wrow);
+              if (P.passes == 3) {
+                tma_load_2d_pair(tm, fb, sa + a_lo_off, P.cin + a_col, arow);
+                tma_load_2d_pair(&P.tmap_w, fb, sa + b_lo_off, P.b_cin + ks * kBlockK, wrow);
+              }
+            } else {
+              mbar_expect_tx(fb, (uint32_t)P.stage_bytes);
+              tma_load_2d(tm, fb, sa, a_col, arow);
+              tma_load_2d(&P.tmap_w, fb, sa + b_hi_off, ks * kBlockK, wrow);
+              if (P.passes == 3) {
+                tma_load_2d(tm, fb, sa + a_lo_off, P.cin + a_col, arow);
+                tma_load_2d(&P.tmap_w, fb, sa + b_lo_off, P.b_cin + ks * kBlockK, wrow);
+              }
             }
             if (++stage == P.num_stages) { stage = 0; phase ^= 1u; }
           }
@@ -247,11 +313,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
       }
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
+    // =============================== MMA issuer (pair mode: leader CTA only) ===============================
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = w_first; tile < w_total && rank == 0; tile += w_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);
@@ -266,17 +332,26 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
           for (int kk = 0; kk < kBlockK / 16; ++kk) {
             const uint64_t a_hi = umma_desc_sw128(sa + kk * 32);
             const uint64_t b_hi = umma_desc_sw128(sa + b_hi_off + kk * 32);
-            tc_mma_bf16(d_tmem, a_hi, b_hi, P.idesc, (ki > 0 || kk > 0) ? 1u : 0u);
+            auto mma = [&](uint64_t ad, uint64_t bd, uint32_t accum) {
+              if constexpr (kTwoCta) tc_mma_bf16_pair(d_tmem, ad, bd, P.idesc, accum);
+              else tc_mma_bf16(d_tmem, ad, bd, P.idesc, accum);
+            };
+            mma(a_hi, b_hi, (ki > 0 || kk > 0) ? 1u : 0u);
             if (P.passes == 3) {
               const uint64_t a_lo = umma_desc_sw128(sa + a_lo_off + kk * 32);
               const uint64_t b_lo = umma_desc_sw128(sa + b_lo_off + kk * 32);
-              tc_mma_bf16(d_tmem, a_hi, b_lo, P.idesc, 1u);
-              tc_mma_bf16(d_tmem, a_lo, b_hi, P.idesc, 1u);
-              if (P.lolo) tc_mma_bf16(d_tmem, a_lo, b_lo, P.idesc, 1u);
+              mma(a_hi, b_lo, 1u);
+              mma(a_lo, b_hi, 1u);
+              if (P.lolo) mma(a_lo, b_lo, 1u);
             }
           }
-          tc_commit(bar_empty + 8 * stage);            // frees the smem stage when the MMAs retire
-          if (ki == k_iters - 1) tc_commit(bar_tfull + 8 * acc);   // accumulator complete
+          if constexpr (kTwoCta) {                     // multicast: frees the stage / publishes the accumulator in BOTH CTAs
+            tc_commit_pair(bar_empty + 8 * stage);
+            if (ki == k_iters - 1) tc_commit_pair(bar_tfull + 8 * acc);
+          } else {
+            tc_commit(bar_empty + 8 * stage);            // frees the smem stage when the MMAs retire
+            if (ki == k_iters - 1) tc_commit(bar_tfull + 8 * acc);   // accumulator complete
+          }
         }
         __syncwarp();
         if (++stage == P.num_stages) { stage = 0; phase ^= 1u; }
@@ -291,9 +366,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
     const uint32_t st_res = st_out + 8192;
     const uint32_t bar_res = ctrl_addr + 192 + ew * 16;
     auto issue_res = [&](int tile_, int g_, int q_) {      // lane 0 only
-      const int mt = tile_ / P.num_n_tiles, nt = tile_ - mt * P.num_n_tiles;
-      int s_ = 0;
-      while (mt >= P.seg_tile_off[s_ + 1]) ++s_;
+      int mt, nt, s_;
+      decode_tile(tile_, mt, nt, s_);
       const int row = P.seg[s_].row_start + (mt - P.seg_tile_off[s_]) * kBlockM + lane_group * 32;
       const int col = nt * P.block_n + g_ * 64;
       const uint32_t bar = bar_res + 8 * (q_ & 1), dst = st_res + (q_ & 1) * 8192;
@@ -302,21 +376,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
       tma_load_2d(&P.tmap_res, bar, dst + 4096, P.cout + col, row);
     };
     int rq = 0;                                            // running slab counter of the residual ring
-    if (P.res_staged && lane == 0) issue_res(blockIdx.x, 0, 0);
+    if (P.res_staged && lane == 0 && w_first < w_total) issue_res(w_first, 0, 0);
     int it = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = w_first; tile < w_total; tile += w_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      const int m_tile = tile / P.num_n_tiles, n_tile = tile - m_tile * P.num_n_tiles;
-      int s = 0;
-      while (m_tile >= P.seg_tile_off[s + 1]) ++s;
+      int m_tile, n_tile, s;
+      decode_tile(tile, m_tile, n_tile, s);
+      const bool tile_valid = m_tile < P.num_m_tiles;        // pair mode: the odd CTA of the last pair may idle
       const SegDev sg = P.seg[s];
       const int grow = sg.row_start + (m_tile - P.seg_tile_off[s]) * kBlockM + m_local;
       const int wp = sg.w + 2, plane = (sg.h + 2) * wp;
       const int rel = grow - sg.row_start;
       const int img = rel / plane, rem = rel - img * plane;
       const int yp = rem / wp, xp = rem - yp * wp;
-      const bool interior = (img < sg.n_img) && (yp >= 1) && (yp <= sg.h) && (xp >= 1) && (xp <= sg.w);
+      const bool interior = tile_valid && (img < sg.n_img) && (yp >= 1) && (yp <= sg.h) && (xp >= 1) && (xp <= sg.w);
       const __nv_bfloat16* res_row = nullptr;
       if (P.res_mode == IOU_RES_SAME && !P.res_staged) {
         res_row = P.residual + (size_t)grow * (2 * P.cout);
@@ -391,8 +465,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
           if (P.res_staged) {
             if (lane == 0) {                               // prefetch the next slab of the ring
               int nt = tile, ng = g + 1;
-              if (ng == n_groups) { nt = tile + gridDim.x; ng = 0; }
-              if (nt < P.total_tiles) issue_res(nt, ng, rq + 1);
+              if (ng == n_groups) { nt = tile + w_stride; ng = 0; }
+              if (nt < w_total) issue_res(nt, ng, rq + 1);
             }
             mbar_wait(bar_res + 8 * (rq & 1), (uint32_t)(rq >> 1) & 1u);
           }
@@ -459,7 +533,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
           }
           fence_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && tile_valid) {
             tma_store_2d(&P.tmap_out, st_out, c0, row_tile0);
             tma_store_2d(&P.tmap_out, st_out + 4096, P.cout + c0, row_tile0);
             tma_store_commit();
@@ -467,16 +541,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
         }
       }
       tc_fence_before();
-      mbar_arrive(bar_tempty + 8 * acc);
+      if constexpr (kTwoCta) mbar_arrive_leader(bar_tempty + 8 * acc);   // only the leader's MMA warp waits on it
+      else mbar_arrive(bar_tempty + 8 * acc);
     }
     if (P.staged && lane == 0) tma_store_wait_read();      // staging must outlive the last TMA store
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kTwoCta) cluster_sync_all();   // neither CTA may release TMEM / exit while the pair is still in flight
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    if constexpr (kTwoCta)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -587,7 +666,11 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   P.num_m_tiles = toff;
   P.num_n_tiles = d->cout_pad / d->block_n;
   P.total_tiles = P.num_m_tiles * P.num_n_tiles;
-  P.b_tile_bytes = d->block_n * kBlockK * 2;
+  // CTA-pair mode (tcgen05 cta_group::2): two CTAs of a cluster own two consecutive 128-row tiles and share
+  // one BLOCK_N-wide B tile, each staging half of its rows -> half the B traffic per CTA and a deeper pipeline
+  P.two_cta = (d->two_cta && d->block_n % 32 == 0 && !d->diag_k) ? 1 : 0;
+  P.total_pair_tiles = ((P.num_m_tiles + 1) / 2) * P.num_n_tiles;
+  P.b_tile_bytes = (P.two_cta ? d->block_n / 2 : d->block_n) * kBlockK * 2;
   P.stage_bytes = (d->passes >= 3 ? 2 : 1) * (kATileBytes + P.b_tile_bytes);
   // padded-rows outputs leave through a per-warp 128B-swizzled staging tile (32 rows x 64 ch, hi + lo)
   // and TMA stores; a same-geometry residual arrives through a 2-deep TMA-load ring per warp
@@ -602,7 +685,8 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   P.residual = (const __nv_bfloat16*)d->residual;
   P.out_mode = d->out_mode; P.out = (__nv_bfloat16*)d->out; P.dense_split = d->dense_split;
   // cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=BF16 (1<<7, 1<<10), K-major both, N>>3 @17, M>>4 @24
-  P.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d->block_n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+  P.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d->block_n >> 3) << 17) |
+            ((uint32_t)((P.two_cta ? 2 * kBlockM : kBlockM) >> 4) << 24);
   for (int i = 0; i < d->num_src; ++i) {
     if (!d->src[i] || ((uintptr_t)d->src[i] & 15)) { delete plan; return fail(IOU_ERR_INVALID, "src[%d] NULL or misaligned", i); }
     if (int e = encode_2d(&P.tmap_src[i], d->src[i], (uint64_t)d->src_rows, (uint64_t)2 * d->cin, kBlockM)) { delete plan; return e; }
@@ -618,15 +702,22 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
     if (((uintptr_t)d->residual & 15) != 0) { delete plan; return fail(IOU_ERR_INVALID, "residual must be 16-byte aligned"); }
     if (int e = encode_2d(&P.tmap_res, d->residual, rrow, (uint64_t)2 * d->cout, 32)) { delete plan; return e; }
   }
-  if (int e = encode_2d(&P.tmap_w, d->weight, (uint64_t)d->num_taps * d->cout_pad, (uint64_t)2 * P.b_cin, (uint32_t)d->block_n)) { delete plan; return e; }
+  if (int e = encode_2d(&P.tmap_w, d->weight, (uint64_t)d->num_taps * d->cout_pad, (uint64_t)2 * P.b_cin, (uint32_t)(P.two_cta ? d->block_n / 2 : d->block_n))) { delete plan; return e; }
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  plan->grid = P.total_tiles < sms ? P.total_tiles : sms;
+  if (P.two_cta) {
+    const int pairs = sms / 2;
+    plan->grid = 2 * (P.total_pair_tiles < pairs ? P.total_pair_tiles : pairs);
+  } else {
+    plan->grid = P.total_tiles < sms ? P.total_tiles : sms;
+  }
   plan->smem_bytes = (size_t)kCtrlBytes + 1024 + (size_t)stages * P.stage_bytes + (size_t)4 * P.staging_per_warp;
   plan->flops = 2.0 * real_rows * d->cout * (double)(P.diag_k ? kBlockK : d->cin) * d->num_taps;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tap_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    cudaError_t e = cudaFuncSetAttribute(conv_tap_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_tap_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     if (e != cudaSuccess) { delete plan; return fail(IOU_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
     attr_set = true;
   }
@@ -636,7 +727,21 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
 
 extern "C" int iou_conv_run(const iou_conv_plan* plan, void* stream) {
   IOU_REQUIRE(plan != nullptr, "plan is NULL");
-  conv_tap_gemm_kernel<<<plan->grid, kNumThreads, plan->smem_bytes, (cudaStream_t)stream>>>(plan->params);
+  if (plan->params.two_cta) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(plan->grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = plan->smem_bytes;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tap_gemm_kernel<true>, plan->params);
+    if (e != cudaSuccess) return fail(IOU_ERR_CUDA, "conv_tap_gemm_kernel<pair> launch failed: %s", cudaGetErrorString(e));
+    return IOU_OK;
+  }
+  conv_tap_gemm_kernel<false><<<plan->grid, kNumThreads, plan->smem_bytes, (cudaStream_t)stream>>>(plan->params);
   return launch_status("conv_tap_gemm_kernel");
 }
 

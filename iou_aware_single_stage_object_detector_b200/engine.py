@@ -145,6 +145,8 @@ class Engine(object):
         self.keep = []           # tensors that must outlive the plan
         self.flops = 0.0
         self.op_flops = {}
+        import os
+        self.two_cta = os.environ.get("IOU_TWO_CTA", "1") != "0"
         self.lib = L.load()
 
     # ------------------------------------------------------------------ primitive ops
@@ -161,7 +163,7 @@ class Engine(object):
 
     def conv(self, name, srcs, taps, weight, cin, cout, out=None, scale=None, shift=None, relu=False,
              residual=None, res_mode=L.RES_NONE, dense_out=None, dense_out2=None, dense_split=0,
-             segs_from=None, diag_k=False, true_flops_scale=1.0):
+             segs_from=None, diag_k=False, true_flops_scale=1.0, two_cta=None):
         """srcs: list[FlatMap] (same geometry); out: FlatMap or None (dense).  Returns out."""
         geo = segs_from or srcs[0]
         m_tiles = sum(_round_up(n * (h + 2) * (w + 2), TILE_M) // TILE_M for (_, n, h, w) in geo.segs)
@@ -183,6 +185,9 @@ class Engine(object):
         self.keep.append(wp)
         assert wp.shape == (len(taps) * cout_pad, 2 * (64 if diag_k else cin)), (name, wp.shape, len(taps), cout_pad, cin)
         d.diag_k = int(diag_k)
+        # big maps with a wide N tile run as CTA pairs (cta_group::2): half the B traffic, deeper pipeline
+        d.two_cta = int(self.two_cta and not diag_k and block_n in (256, 240) and m_tiles >= 2 * NUM_SMS) \
+            if two_cta is None else int(two_cta)
         d.weight = wp.data_ptr()
 
         def padc(v):

@@ -215,3 +215,53 @@ def test_grouped_conv_block_diagonal_vs_torch(width, groups, stride, hw):
     torch.cuda.synchronize()
     assert y.shape == ref.shape
     assert rel_err(y.cpu(), ref) < TOL, rel_err(y.cpu(), ref)
+
+
+@pytest.mark.parametrize("cin,cout,k,shape,res", [(256, 256, 3, (2, 60, 80), False),     # even tile count
+                                                  (256, 256, 3, (1, 41, 59), False),     # odd: last pair half idle
+                                                  (128, 512, 1, (2, 33, 47), False),     # two N tiles
+                                                  (64, 128, 1, (2, 50, 70), True),       # residual ring, N tile 128
+                                                  (512, 256, 1, (3, 25, 42), False)])
+def test_cta_pair_mode_matches_torch(cin, cout, k, shape, res):
+    """tcgen05 cta_group::2 path (a cluster of two CTAs shares the B tile) forced on small maps."""
+    n, h, w = shape
+    g = torch.Generator().manual_seed(cin + cout + h)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    b = torch.randn(cout, generator=g)
+    r = torch.randn(n, cout, h, w, generator=g) if res else None
+    ref = F.conv2d(x, wt, b, padding=k // 2)
+    if res:
+        ref = F.relu(ref + r)
+    eng = E.Engine(DEV)
+    m = eng.pack_input(x.to(DEV).contiguous())
+    rm = eng.pack_input(r.to(DEV).contiguous()) if res else None
+    out = eng.conv("pair", [m], E.TAPS_1X1 if k == 1 else E.TAPS_3X3, E.pack_weight(wt, cout), cin, cout, shift=b,
+                   relu=res, residual=rm, res_mode=L.RES_SAME if res else L.RES_NONE, two_cta=True)
+    y = eng.unpack_output(out)
+    eng.run()
+    torch.cuda.synchronize()
+    assert rel_err(y.cpu(), ref) < TOL, rel_err(y.cpu(), ref)
+
+
+def test_cta_pair_mode_dense_head_outputs():
+    g = torch.Generator().manual_seed(77)
+    sizes = [(2, 30, 44), (2, 15, 22), (2, 8, 11)]
+    xs = [torch.randn(n, 256, h, w, generator=g) for (n, h, w) in sizes]
+    w_cls = torch.randn(720, 256, 3, 3, generator=g) * 0.02
+    b_cls = torch.randn(720, generator=g)
+    eng = E.Engine(DEV)
+    Fm = eng.new_map(sizes, 256)
+    for s, x in enumerate(xs):
+        n, c, h, w = x.shape
+        xd = x.to(DEV)
+        eng.keep.append(xd)
+        L.check(eng.lib.iou_pack_nchw(xd.data_ptr(), n, c, h, w, Fm.ptr, Fm.segs[s][0], L.stream_ptr()))
+    cls_out = [torch.zeros(n, h, w, 720, device=DEV) for (n, h, w) in sizes]
+    eng.conv("cls", [Fm], E.TAPS_3X3, E.pack_weight(w_cls, 720), 256, 720, shift=b_cls, dense_out=cls_out,
+             two_cta=True)
+    eng.run()
+    torch.cuda.synchronize()
+    for s, x in enumerate(xs):
+        ref = F.conv2d(x, w_cls, b_cls, padding=1).permute(0, 2, 3, 1)
+        assert rel_err(cls_out[s].cpu(), ref) < TOL
