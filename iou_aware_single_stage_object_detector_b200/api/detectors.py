@@ -153,6 +153,58 @@ class SingleStageDetector(BaseDetector):
             plan.img_info.copy_(PP.make_img_info(img_metas, "cpu"), non_blocking=True)
         return plan.run()
 
+    def detect_stream(self, batches, rescale=False, device=None, gather=None):
+        """Pipelined batched inference over an iterable of (img, img_metas) with HOST (ideally pinned)
+        images: the host->device copy of batch i+1 runs on a copy stream while batch i computes, then
+        yields (dets, labels, counts) as CPU tensors per batch (one device->host read per batch).
+        `gather(dets, labels, counts)` (e.g. dist.gather_detections) is applied on the device first."""
+        device = torch.device(device) if device is not None else next(self.parameters()).device
+        if device.type != "cuda":
+            raise RuntimeError("SingleStageDetector: move the model to a CUDA device first -- this path "
+                               "has no CPU fallback")
+        it = iter(batches)
+        with torch.cuda.device(device):
+            copy_stream = torch.cuda.Stream(device)
+            main = torch.cuda.current_stream(device)
+            stage, ready, consumed = [None, None], [None, None], [None, None]
+
+            def prefetch(slot, item):
+                img, metas = item
+                if stage[slot] is None or stage[slot].shape != img.shape:
+                    stage[slot] = torch.empty(img.shape, dtype=torch.float32, device=device)
+                with torch.cuda.stream(copy_stream):
+                    if consumed[slot] is not None:
+                        copy_stream.wait_event(consumed[slot])      # the previous use of this slot is over
+                    stage[slot].copy_(img, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                ready[slot] = (ev, metas)
+
+            nxt = next(it, None)
+            if nxt is None:
+                return
+            prefetch(0, nxt)
+            slot = 0
+            while True:
+                ev, metas = ready[slot]
+                nxt = next(it, None)
+                if nxt is not None:
+                    prefetch(slot ^ 1, nxt)                          # overlaps with this batch's compute
+                plan = self.fused_plan(stage[slot].shape, device, rescale)
+                main.wait_event(ev)
+                plan.img.copy_(stage[slot], non_blocking=True)       # device->device, ~70 us for 103 MB
+                done = torch.cuda.Event()
+                done.record(main)
+                consumed[slot] = done
+                plan.img_info.copy_(PP.make_img_info(metas, "cpu"), non_blocking=True)
+                dets, labels, counts = plan.run()
+                if gather is not None:
+                    dets, labels, counts = gather(dets, labels, counts)
+                yield dets.cpu(), labels.cpu(), counts.cpu()
+                if nxt is None:
+                    return
+                slot ^= 1
+
     def simple_test_batch(self, img, img_metas, gt_bboxes=None, gt_labels=None, rescale=False):
         """Batched simple_test: list (per image) of per-class ndarray lists."""
         dets, labels, counts = self.detect_device(img, img_metas, rescale)

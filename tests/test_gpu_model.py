@@ -118,3 +118,20 @@ def test_other_backbones_head_maps_vs_oracle(cfg_name, depth, groups):
         for a, b in zip(mine, r):
             err = (a.cpu().contiguous() - b).abs().max().item()
             assert err <= 3e-4 * max(b.abs().max().item(), 1.0), (cfg_name, err)
+
+
+def test_detect_stream_matches_detect_device():
+    """The pipelined host-batch API returns exactly what the one-shot API returns, batch by batch."""
+    det, cfg = U.small_detector(seed=7)
+    det = det.to(DEV)
+    h, w = 96, 128
+    meta = dict(ori_shape=(h, w, 3), img_shape=(h, w, 3), pad_shape=(h, w, 3), scale_factor=1.0, flip=False)
+    imgs = [torch.randn(2, 3, h, w, generator=torch.Generator().manual_seed(s)).pin_memory() for s in range(4)]
+    want = []
+    for im in imgs:
+        d, l, c = det.detect_device(im, [meta, meta], rescale=True)
+        want.append((d.cpu().clone(), l.cpu().clone(), c.cpu().clone()))
+    got = list(det.detect_stream(((im, [meta, meta]) for im in imgs), rescale=True))
+    assert len(got) == 4
+    for (d, l, c), (d2, l2, c2) in zip(want, got):
+        assert torch.equal(c, c2) and torch.equal(d, d2) and torch.equal(l, l2)
