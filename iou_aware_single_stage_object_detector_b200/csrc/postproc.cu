@@ -515,6 +515,78 @@ __device__ int greedy_nms_range(const NmsSmem& S, const int begin, const int n, 
   return s_total;
 }
 
+// Bounded variant for the per-class kernel, where the scan always stops after `stop_after` kept boxes:
+// only the kept boxes (<= stop_after) and the current 64-box chunk live in shared memory, the rest is
+// fetched from global memory by candidate index, so several CTAs fit on one SM.
+// keys: the range's composite keys sorted descending (shared memory); bx: the image's boxes (global).
+template <typename Emit>
+__device__ int greedy_nms_bounded(const unsigned long long* keys, const int n, const float4* __restrict__ bx,
+                                  const float thr, const int stop_after, int* s_total_p, float4* kbox,
+                                  float* karea, Emit emit) {
+  __shared__ unsigned long long cmask[64];
+  __shared__ float4 cbox[64];
+  __shared__ float carea[64];
+  __shared__ unsigned int dead[2];
+  int& s_total = *s_total_p;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  __syncthreads();
+  for (int cs = 0; cs < n; cs += 64) {
+    const int cnt = min(64, n - cs);
+    const int total0 = s_total;
+    if (tid < cnt) {
+      const unsigned int j = 0xffffffffu - (unsigned int)(keys[cs + tid] & 0xffffffffull);
+      const float4 b = __ldg(bx + j);
+      cbox[tid] = b;
+      carea[tid] = box_area(b);
+    }
+    if (tid < 2) dead[tid] = 0u;
+    __syncthreads();
+    {
+      const int b = tid & 63, k0 = tid >> 6, kstride = blockDim.x >> 6;
+      if (b < cnt && total0 > 0) {
+        const float4 bb = cbox[b];
+        const float sb = carea[b];
+        for (int k = k0; k < total0; k += kstride) {
+          if ((((volatile unsigned int*)dead)[b >> 5] >> (b & 31)) & 1u) break;
+          if (iou_gt(kbox[k], karea[k], bb, sb, thr)) {
+            atomicOr(&dead[b >> 5], 1u << (b & 31));
+            break;
+          }
+        }
+      }
+    }
+    for (int r = warp; r < cnt; r += nwarps) {
+      const float4 a = cbox[r];
+      const float sa = carea[r];
+      bool h0 = false, h1 = false;
+      const int c0 = lane, c1 = lane + 32;
+      if (c0 > r && c0 < cnt) h0 = iou_gt(a, sa, cbox[c0], carea[c0], thr);
+      if (c1 > r && c1 < cnt) h1 = iou_gt(a, sa, cbox[c1], carea[c1], thr);
+      const unsigned int b0 = __ballot_sync(0xffffffffu, h0), b1 = __ballot_sync(0xffffffffu, h1);
+      if (lane == 0) cmask[r] = ((unsigned long long)b1 << 32) | b0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long R = (unsigned long long)dead[0] | ((unsigned long long)dead[1] << 32);
+      int total = total0;
+      for (int i = 0; i < cnt; ++i) {
+        if (!((R >> i) & 1ull)) {
+          R |= cmask[i];
+          kbox[total] = cbox[i];
+          karea[total] = carea[i];
+          emit(cs + i, total);
+          ++total;
+          if (total >= stop_after) break;
+        }
+      }
+      s_total = total;
+    }
+    __syncthreads();
+    if (s_total >= stop_after) break;
+  }
+  return s_total;
+}
+
 // ---------------------------------------------------------------------------------------- K4
 __global__ void __launch_bounds__(512) class_nms_kernel(const __grid_constant__ PostParams P,
                                                         const float* __restrict__ boxes,
@@ -523,10 +595,9 @@ __global__ void __launch_bounds__(512) class_nms_kernel(const __grid_constant__ 
                                                         int32_t* __restrict__ kept_cnt, const int Pmax) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   NmsSmem S;
-  S.sortbuf = reinterpret_cast<unsigned long long*>(smem_raw);
-  S.sbox = reinterpret_cast<float4*>(smem_raw + (size_t)Pmax * 8);
-  S.sarea = reinterpret_cast<float*>(smem_raw + (size_t)Pmax * 8 + (size_t)P.M * 16);
-  S.kept = reinterpret_cast<int*>(smem_raw + (size_t)Pmax * 8 + (size_t)P.M * 20);
+  S.sortbuf = reinterpret_cast<unsigned long long*>(smem_raw);                 // [Pmax] composite keys
+  float4* kbox = reinterpret_cast<float4*>(smem_raw + (size_t)Pmax * 8);       // [kcap] kept boxes
+  float* karea = reinterpret_cast<float*>(smem_raw + (size_t)Pmax * 8 + (size_t)P.kcap * 16);
   __shared__ unsigned int s_n, warp_cnt[16];
   const int c = blockIdx.x, img = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -571,14 +642,9 @@ __global__ void __launch_bounds__(512) class_nms_kernel(const __grid_constant__ 
     const int Ps = next_pow2(n);
     for (int i = n + tid; i < Ps; i += 512) S.sortbuf[i] = 0ull;
     bitonic_sort_desc(S.sortbuf, Ps);
-    for (int r = tid; r < n; r += 512) {
-      const unsigned int j = 0xffffffffu - (unsigned int)(S.sortbuf[r] & 0xffffffffull);
-      const float4 b = __ldg(bx + j);
-      S.sbox[r] = b;
-      S.sarea[r] = box_area(b);
-    }
     const unsigned long long* sb = S.sortbuf;
-    greedy_nms_range(S, 0, n, P.iou_thr, P.kcap, &s_total, [&](int r, int pos) { keys_out[pos] = sb[r]; });
+    greedy_nms_bounded(sb, n, bx, P.iou_thr, P.kcap, &s_total, kbox, karea,
+                       [&](int r, int pos) { keys_out[pos] = sb[r]; });
   } else {
     // big class: the scan stops after max_per_img+1 kept boxes, so only the head of the score order is
     // ever needed.  Rounds of NMS_ROUND boxes: exact radix select of the round's lowest composite key
@@ -635,15 +701,8 @@ __global__ void __launch_bounds__(512) class_nms_kernel(const __grid_constant__ 
       const int Ps = next_pow2(teff);
       for (int i = teff + tid; i < Ps; i += 512) rb[i] = 0ull;
       bitonic_sort_desc(rb, Ps);
-      for (int r = tid; r < teff; r += 512) {
-        const unsigned int j = 0xffffffffu - (unsigned int)(rb[r] & 0xffffffffull);
-        const float4 b = __ldg(bx + j);
-        S.sbox[processed + r] = b;
-        S.sarea[processed + r] = box_area(b);
-      }
-      const int p0 = processed;
-      const int total = greedy_nms_range(S, p0, p0 + teff, P.iou_thr, P.kcap, &s_total,
-                                         [&](int r, int pos) { keys_out[pos] = rb[r - p0]; });
+      const int total = greedy_nms_bounded(rb, teff, bx, P.iou_thr, P.kcap, &s_total, kbox, karea,
+                                           [&](int r, int pos) { keys_out[pos] = rb[r]; });
       processed += teff;
       bound = kt;
       if (total >= P.kcap) break;
@@ -885,8 +944,9 @@ static int run_decode(PostParams& P, const float* const* cls, const float* const
 static int run_nms(const PostParams& P, const float* boxes, const float* scores_cm, float* dets,
                    int64_t* labels, int32_t* counts, unsigned long long* kept_keys, int32_t* kept_cnt,
                    cudaStream_t st) {
-  const int Pmax = next_pow2_host(P.M) < 2 ? 2 : next_pow2_host(P.M);   // keeps the float4 region 16-byte aligned
-  const size_t sm4 = (size_t)Pmax * 8 + (size_t)P.M * 24 + 16;
+  // key buffer: all M candidates (unsorted) or a <= NMS_ROUND-wide full sort; even length keeps kbox 16B-aligned
+  const int Pmax = ((P.M > NMS_ROUND ? P.M : NMS_ROUND) + 1) & ~1;
+  const size_t sm4 = (size_t)Pmax * 8 + (size_t)P.kcap * 20 + 16;
   IOU_CHECK_CUDA(cudaFuncSetAttribute(class_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4));
   class_nms_kernel<<<dim3(P.C, P.n_img), 512, sm4, st>>>(P, boxes, scores_cm, kept_keys, kept_cnt, Pmax);
   if (int e = launch_status("class_nms_kernel")) return e;
