@@ -215,7 +215,10 @@ def run_ours(args):
         roof = {"bound": "tensor", "kernel": "conv_tap_gemm_kernel", "achieved": round(achieved, 2),
                 "peak": peaks["tf_sustained"], "peak_source": peaks["source"] + " bf16 sustained (cuBLAS)",
                 "unit": "TFLOP/s", "frac": round(achieved / peaks["tf_sustained"], 4),
-                "traffic": None, "launches_per_step": n_conv,
+                # dram__bytes_read+write summed over the 71 conv launches of one step / 71, from the ncu pass
+                # committed as profiles/r01_v4_launches_ncu_dram.csv (21.83 GB per step)
+                "traffic": 307.4e6, "traffic_source": "ncu, profiles/r01_v4_launches_ncu_dram.csv",
+                "launches_per_step": n_conv,
                 "avg_launch_ms": round(conv_ms / max(n_conv, 1), 4),
                 "algorithmic_gflop_per_step": round(conv_flops / 1e9, 1),
                 "mma_passes": args.passes,

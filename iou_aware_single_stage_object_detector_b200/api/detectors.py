@@ -67,6 +67,9 @@ class FusedPlan(object):
         feats = det.backbone.plan_into(eng, sd, self.img, prefix="backbone.")
         F = det.neck.plan_into(eng, sd, feats, prefix="neck.")
         self.outs = det.bbox_head.plan_into(eng, sd, F, prefix="bbox_head.")
+        if det.test_cfg is None:
+            raise RuntimeError("SingleStageDetector was built without test_cfg (nms_pre, score_thr, nms, "
+                               "max_per_img): pass test_cfg=cfg.test_cfg to build_detector")
         self.eng = eng
         sizes = [tuple(t.shape[-2:]) for t in self.outs[0]]
         self.wsp = det.bbox_head.postproc_workspace(sizes, n, det.test_cfg, self.device)

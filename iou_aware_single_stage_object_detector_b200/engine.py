@@ -321,6 +321,13 @@ class Engine(object):
         for i in range(nl - 1, -1, -1):
             kp = "%slateral_convs.%d.conv." % (prefix, i)
             res = lat[i + 1] if i + 1 < nl else None
+            if res is not None:
+                # F.interpolate(scale_factor=2) + in-place add (fpn.py:108-110) needs exact 2x sizes; the
+                # reference raises on a mismatch (e.g. an input not padded to a multiple of 32), so do we
+                (_, _, hf, wf), (_, _, hc, wc) = used[i].segs[0], res.segs[0]
+                if (hf, wf) != (2 * hc, 2 * wc):
+                    raise RuntimeError("FPN top-down add: level sizes %dx%d and %dx%d are not 2x apart "
+                                       "(pad the input to a multiple of 32)" % (hf, wf, hc, wc))
             lat[i] = self.conv(kp[:-1], [used[i]], TAPS_1X1, pack_weight(sd[kp + "weight"], out_channels),
                                used[i].c, out_channels, shift=sd[kp + "bias"], residual=res,
                                res_mode=L.RES_UPSAMPLE2 if res is not None else L.RES_NONE)

@@ -135,3 +135,14 @@ def test_detect_stream_matches_detect_device():
     assert len(got) == 4
     for (d, l, c), (d2, l2, c2) in zip(want, got):
         assert torch.equal(c, c2) and torch.equal(d, d2) and torch.equal(l, l2)
+
+
+def test_unpadded_input_raises_like_the_reference():
+    """An input whose FPN levels are not exactly 2x apart makes the reference fail in the top-down add
+    (fpn.py:108-110); the engine raises as well instead of silently producing something."""
+    det, cfg = U.small_detector(seed=0, spread=False)
+    det = det.to(DEV)
+    img = torch.randn(1, 3, 100, 136).to(DEV)            # 100/8 = 13 (ceil) vs 2*7 = 14
+    meta = dict(ori_shape=(100, 136, 3), img_shape=(100, 136, 3), pad_shape=(100, 136, 3), scale_factor=1.0, flip=False)
+    with pytest.raises(RuntimeError):
+        det.simple_test_batch(img, [meta])
