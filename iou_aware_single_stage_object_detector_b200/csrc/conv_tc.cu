@@ -29,7 +29,8 @@ namespace iou {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                  // bf16 elements = one 128-byte swizzle row
 constexpr int kATileBytes = kBlockM * kBlockK * 2;   // 16 KiB
-constexpr int kNumThreads = 192;
+constexpr int kNumThreads = 320;             // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
+constexpr int kNumEpiWarps = 8;
 constexpr int kMaxStages = 8;
 constexpr int kAccStride = 256;              // TMEM columns between the two accumulator stages
 constexpr int kTmemCols = 512;
@@ -237,8 +238,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < P.num_stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, kTwoCta ? 256 : 128); }
-    for (int r = 0; r < 8; ++r) mbar_init(ctrl_addr + 192 + 8 * r, 1);     // residual ring: 4 warps x 2
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, (kTwoCta ? 2 : 1) * kNumEpiWarps * 32); }
+    for (int r = 0; r < 2 * kNumEpiWarps; ++r) mbar_init(ctrl_addr + 192 + 8 * r, 1);   // residual ring: 8 warps x 2
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     for (int i = 0; i < IOU_CONV_MAX_SRC; ++i)
@@ -361,22 +362,23 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
     // =============================== epilogue ===============================
     const int lane_group = warp & 3;                      // TMEM lanes 32*lane_group .. +31
     const int m_local = lane_group * 32 + lane;
-    const int ew = warp - 2;
+    const int ew = warp - 2;                               // 0..7
+    const int half = ew >> 2;                              // the two warps of a quadrant take alternate column groups
     const uint32_t st_out = tiles_addr + P.num_stages * P.stage_bytes + ew * P.staging_per_warp;
-    const uint32_t st_res = st_out + 8192;
+    const uint32_t st_res = st_out + 4096;
     const uint32_t bar_res = ctrl_addr + 192 + ew * 16;
     auto issue_res = [&](int tile_, int g_, int q_) {      // lane 0 only
       int mt, nt, s_;
       decode_tile(tile_, mt, nt, s_);
       const int row = P.seg[s_].row_start + (mt - P.seg_tile_off[s_]) * kBlockM + lane_group * 32;
-      const int col = nt * P.block_n + g_ * 64;
-      const uint32_t bar = bar_res + 8 * (q_ & 1), dst = st_res + (q_ & 1) * 8192;
-      mbar_expect_tx(bar, 8192u);
+      const int col = nt * P.block_n + g_ * 32;
+      const uint32_t bar = bar_res + 8 * (q_ & 1), dst = st_res + (q_ & 1) * 4096;
+      mbar_expect_tx(bar, 4096u);
       tma_load_2d(&P.tmap_res, bar, dst, col, row);
-      tma_load_2d(&P.tmap_res, bar, dst + 4096, P.cout + col, row);
+      tma_load_2d(&P.tmap_res, bar, dst + 2048, P.cout + col, row);
     };
     int rq = 0;                                            // running slab counter of the residual ring
-    if (P.res_staged && lane == 0 && w_first < w_total) issue_res(w_first, 0, 0);
+    if (P.res_staged && lane == 0 && w_first < w_total) issue_res(w_first, half, 0);
     int it = 0;
     for (int tile = w_first; tile < w_total; tile += w_stride, ++it) {
       const int acc = it & 1;
@@ -405,7 +407,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
       const uint32_t t_row = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(acc * kAccStride);
       const int n_chunks = P.block_n >> 4;
       if (!P.staged) {
-      for (int ch = 0; ch < n_chunks; ++ch) {
+      for (int ch = half; ch < n_chunks; ch += 2) {
         uint32_t v[16];
         tc_ld16(t_row + ch * 16, v);
         tc_wait_ld();
@@ -455,40 +457,43 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
         }
       }
       } else {
-        // ---- staged path (padded-rows output): 64 output channels per step.  Results go to a
-        // 128B-swizzled shared-memory tile and leave through TMA stores (fully coalesced, clipped at
-        // the end of the buffer); a same-geometry residual arrives through a 2-deep TMA-load ring.
+        // ---- staged path (padded-rows output): 32 output channels per step and warp.  Results go to a
+        // 64B-swizzled shared-memory tile (32 rows x 32 ch, hi and lo) and leave through TMA stores
+        // (coalesced, clipped at the end of the buffer); a same-geometry residual arrives through a
+        // 2-deep TMA-load ring per warp.
         const int row_tile0 = grow - lane;                 // first row of this warp's 32-row slab
-        const int n_groups = P.block_n >> 6;
-        for (int g = 0; g < n_groups; ++g, ++rq) {
-          const int c0 = n_tile * P.block_n + g * 64;
+        const int n_groups = P.block_n >> 5;
+        const uint32_t swz = (uint32_t)((lane >> 1) & 3);  // 64B swizzle: 16B chunk j of row r sits at j ^ ((r>>1)&3)
+        for (int g = half; g < n_groups; g += 2, ++rq) {
+          const int c0 = n_tile * P.block_n + g * 32;
           if (P.res_staged) {
-            if (lane == 0) {                               // prefetch the next slab of the ring
-              int nt = tile, ng = g + 1;
-              if (ng == n_groups) { nt = tile + w_stride; ng = 0; }
+            if (lane == 0) {                               // prefetch this warp's next slab
+              int nt = tile, ng = g + 2;
+              if (ng >= n_groups) { nt = tile + w_stride; ng = half; }
               if (nt < w_total) issue_res(nt, ng, rq + 1);
             }
             mbar_wait(bar_res + 8 * (rq & 1), (uint32_t)(rq >> 1) & 1u);
           }
-          uint32_t v[64];
-          tc_ld32(t_row + g * 64, v);
-          tc_ld32(t_row + g * 64 + 32, v + 32);
-          const float sc0 = P.scale ? __ldg(P.scale + c0 + lane) : 1.f, sc1 = P.scale ? __ldg(P.scale + c0 + 32 + lane) : 1.f;
-          const float sh0 = P.shift ? __ldg(P.shift + c0 + lane) : 0.f, sh1 = P.shift ? __ldg(P.shift + c0 + 32 + lane) : 0.f;
+          uint32_t v[32];
+          tc_ld32(t_row + g * 32, v);
+          const float sh_l = P.shift ? __ldg(P.shift + c0 + lane) : 0.f;
+          const float sc_l = P.scale ? __ldg(P.scale + c0 + lane) : 1.f;
           tc_wait_ld();
-          float f[64];
+          float f[32];
+          if (P.scale) {
 #pragma unroll
-          for (int q = 0; q < 64; ++q) {
-            const float sc = __shfl_sync(0xffffffffu, q < 32 ? sc0 : sc1, q & 31);
-            const float sh = __shfl_sync(0xffffffffu, q < 32 ? sh0 : sh1, q & 31);
-            f[q] = fmaf(__uint_as_float(v[q]), sc, sh);
+            for (int q = 0; q < 32; ++q)
+              f[q] = fmaf(__uint_as_float(v[q]), __shfl_sync(0xffffffffu, sc_l, q), __shfl_sync(0xffffffffu, sh_l, q));
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) f[q] = __uint_as_float(v[q]) + __shfl_sync(0xffffffffu, sh_l, q);
           }
           if (P.res_staged) {
-            const uint32_t rb = st_res + (rq & 1) * 8192 + lane * 128;
+            const uint32_t rb = st_res + (rq & 1) * 4096 + lane * 64;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint32_t sw = (uint32_t)((j ^ (lane & 7)) << 4);
-              const uint4 hv = lds128(rb + sw), lv = lds128(rb + 4096 + sw);
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t sw = (uint32_t)((j ^ swz) << 4);
+              const uint4 hv = lds128(rb + sw), lv = lds128(rb + 2048 + sw);
               const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -500,7 +505,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
             const uint4* rh = reinterpret_cast<const uint4*>(res_row + c0);
             const uint4* rl = reinterpret_cast<const uint4*>(res_row + P.cout + c0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 4; ++j) {
               const uint4 hv = __ldg(rh + j), lv = __ldg(rl + j);
               const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
 #pragma unroll
@@ -512,30 +517,31 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
           }
           if (lane == 0) tma_store_wait_read();            // previous slab has left the staging tile
           __syncwarp();
-          const uint32_t ob = st_out + lane * 128;
+          const uint32_t ob = st_out + lane * 64;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 4; ++j) {
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               float x0 = f[j * 8 + 2 * q], x1 = f[j * 8 + 2 * q + 1];
               if (P.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-              if (!interior) { x0 = 0.f; x1 = 0.f; }
-              const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-              const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
-              const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-              hi[q] = pack_bf16x2(h0, h1);
-              lo[q] = pack_bf16x2(l0, l1);
+              // packed fp32x2 -> bf16x2 conversions (F2FP): hi = bf16(x), lo = bf16(x - hi)
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+              const uint32_t hbits = *reinterpret_cast<const uint32_t*>(&h2);
+              const __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - __uint_as_float(hbits << 16),
+                                                              x1 - __uint_as_float(hbits & 0xffff0000u));
+              hi[q] = interior ? hbits : 0u;
+              lo[q] = interior ? *reinterpret_cast<const uint32_t*>(&l2) : 0u;
             }
-            const uint32_t sw = (uint32_t)((j ^ (lane & 7)) << 4);
+            const uint32_t sw = (uint32_t)((j ^ swz) << 4);
             sts128(ob + sw, make_uint4(hi[0], hi[1], hi[2], hi[3]));
-            sts128(ob + 4096 + sw, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+            sts128(ob + 2048 + sw, make_uint4(lo[0], lo[1], lo[2], lo[3]));
           }
           fence_async_smem();
           __syncwarp();
           if (lane == 0 && tile_valid) {
             tma_store_2d(&P.tmap_out, st_out, c0, row_tile0);
-            tma_store_2d(&P.tmap_out, st_out + 4096, P.cout + c0, row_tile0);
+            tma_store_2d(&P.tmap_out, st_out + 2048, P.cout + c0, row_tile0);
             tma_store_commit();
           }
         }
@@ -578,15 +584,16 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D bf16 matrix [rows][cols] (row-major), box = 64 cols x box_rows rows, 128B swizzle, zero OOB fill.
-static int encode_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+static int encode_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                     uint32_t box_cols = kBlockK, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(IOU_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstr[1] = {cols * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(IOU_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return IOU_OK;
@@ -672,12 +679,12 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   P.total_pair_tiles = ((P.num_m_tiles + 1) / 2) * P.num_n_tiles;
   P.b_tile_bytes = (P.two_cta ? d->block_n / 2 : d->block_n) * kBlockK * 2;
   P.stage_bytes = (d->passes >= 3 ? 2 : 1) * (kATileBytes + P.b_tile_bytes);
-  // padded-rows outputs leave through a per-warp 128B-swizzled staging tile (32 rows x 64 ch, hi + lo)
+  // padded-rows outputs leave through a per-warp 64B-swizzled staging tile (32 rows x 32 ch, hi + lo)
   // and TMA stores; a same-geometry residual arrives through a 2-deep TMA-load ring per warp
   P.staged = (d->out_mode == IOU_OUT_PADDED_BF16X2) && (d->block_n % 64 == 0);
   P.res_staged = P.staged && d->res_mode == IOU_RES_SAME;
-  P.staging_per_warp = P.staged ? (8192 + (P.res_staged ? 16384 : 0)) : 0;
-  int stages = (kSmemBudget - kCtrlBytes - 1024 - 4 * P.staging_per_warp) / P.stage_bytes;
+  P.staging_per_warp = P.staged ? (4096 + (P.res_staged ? 8192 : 0)) : 0;      // x 8 epilogue warps
+  int stages = (kSmemBudget - kCtrlBytes - 1024 - kNumEpiWarps * P.staging_per_warp) / P.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) { delete plan; return fail(IOU_ERR_INVALID, "tile does not fit shared memory (block_n %d, residual %d): use a smaller block_n", d->block_n, d->res_mode); }
   P.num_stages = stages;
@@ -695,12 +702,12 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   P.tmap_out = P.tmap_w; P.tmap_res = P.tmap_w;
   if (P.staged) {
     const uint64_t orow = d->out_rows > 0 ? (uint64_t)d->out_rows : (uint64_t)d->src_rows;
-    if (int e = encode_2d(&P.tmap_out, d->out, orow, (uint64_t)2 * d->cout, 32)) { delete plan; return e; }
+    if (int e = encode_2d(&P.tmap_out, d->out, orow, (uint64_t)2 * d->cout, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) { delete plan; return e; }
   }
   if (P.res_staged) {
     const uint64_t rrow = d->res_rows > 0 ? (uint64_t)d->res_rows : (uint64_t)d->src_rows;
     if (((uintptr_t)d->residual & 15) != 0) { delete plan; return fail(IOU_ERR_INVALID, "residual must be 16-byte aligned"); }
-    if (int e = encode_2d(&P.tmap_res, d->residual, rrow, (uint64_t)2 * d->cout, 32)) { delete plan; return e; }
+    if (int e = encode_2d(&P.tmap_res, d->residual, rrow, (uint64_t)2 * d->cout, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) { delete plan; return e; }
   }
   if (int e = encode_2d(&P.tmap_w, d->weight, (uint64_t)d->num_taps * d->cout_pad, (uint64_t)2 * P.b_cin, (uint32_t)(P.two_cta ? d->block_n / 2 : d->block_n))) { delete plan; return e; }
   int dev = 0, sms = 148;
@@ -711,7 +718,7 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   } else {
     plan->grid = P.total_tiles < sms ? P.total_tiles : sms;
   }
-  plan->smem_bytes = (size_t)kCtrlBytes + 1024 + (size_t)stages * P.stage_bytes + (size_t)4 * P.staging_per_warp;
+  plan->smem_bytes = (size_t)kCtrlBytes + 1024 + (size_t)stages * P.stage_bytes + (size_t)kNumEpiWarps * P.staging_per_warp;
   plan->flops = 2.0 * real_rows * d->cout * (double)(P.diag_k ? kBlockK : d->cin) * d->num_taps;
   static bool attr_set = false;
   if (!attr_set) {

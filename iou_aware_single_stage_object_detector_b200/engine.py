@@ -118,6 +118,12 @@ def bn_fold(sd, prefix, eps=1e-5):
 NUM_SMS = 148
 
 
+def fold_scale(w, scale):
+    """Fold the per-output-channel BN scale into the conv weight (y = conv(x; w*s) + shift), so that the
+    GEMM epilogue only adds the shift."""
+    return w.float() * scale.to(w.device).float().view(-1, 1, 1, 1)
+
+
 def pick_block_n(cout, m_tiles=None, max_bn=256):
     """(block_n, cout_pad) for the tap-GEMM.  With the number of 128-row tiles known, the N tile is
     chosen to minimise waves x per-tile cost on 148 SMs (small maps get narrower tiles so that more
@@ -258,8 +264,8 @@ class Engine(object):
         self.keep.append(img)
         self.ops.append(("stem.pack", lambda st: L.check(lib.iou_stem_pack(ip, n, h, w, pp, st))))
         scale, shift = bn_fold(sd, prefix + "bn1")
-        s1 = self.conv("stem.conv1", [packed], TAPS_STEM, pack_weight_stem(sd[prefix + "conv1.weight"]), 64, 64,
-                       scale=scale, shift=shift, relu=True, true_flops_scale=147.0 / 256.0)
+        s1 = self.conv("stem.conv1", [packed], TAPS_STEM, pack_weight_stem(fold_scale(sd[prefix + "conv1.weight"], scale)), 64, 64,
+                       shift=shift, relu=True, true_flops_scale=147.0 / 256.0)
         hp, wq = (ho - 1) // 2 + 1, (wo - 1) // 2 + 1
         x = self.new_map([(n, hp, wq)], 64)
         sp, xp = s1.ptr, x.ptr
@@ -278,37 +284,37 @@ class Engine(object):
                 cin = x.c
                 width = sd[p + "conv1.weight"].shape[0]          # == planes for ResNet (resnext.py:21-24)
                 sc1, sh1 = bn_fold(sd, p + "bn1")
-                t1 = self.conv(p + "conv1", [x], TAPS_1X1, pack_weight(sd[p + "conv1.weight"], width),
-                               cin, width, scale=sc1, shift=sh1, relu=True)
+                t1 = self.conv(p + "conv1", [x], TAPS_1X1, pack_weight(fold_scale(sd[p + "conv1.weight"], sc1), width),
+                               cin, width, shift=sh1, relu=True)
                 sc2, sh2 = bn_fold(sd, p + "bn2")
                 if groups == 1:
-                    w2, kw = pack_weight(sd[p + "conv2.weight"], width), {}
+                    w2, kw = pack_weight(fold_scale(sd[p + "conv2.weight"], sc2), width), {}
                 else:
                     cg = sd[p + "conv2.weight"].shape[1]
-                    w2 = pack_weight_grouped(sd[p + "conv2.weight"], groups)
+                    w2 = pack_weight_grouped(fold_scale(sd[p + "conv2.weight"], sc2), groups)
                     kw = dict(diag_k=True, true_flops_scale=cg / 64.0)
                 if stride == 2:
                     ph = self.phase_split(p + "conv2.phase", t1)
-                    t2 = self.conv(p + "conv2", ph, TAPS_3X3_S2, w2, width, width, scale=sc2, shift=sh2,
+                    t2 = self.conv(p + "conv2", ph, TAPS_3X3_S2, w2, width, width, shift=sh2,
                                    relu=True, **kw)
                 else:
-                    t2 = self.conv(p + "conv2", [t1], TAPS_3X3, w2, width, width, scale=sc2, shift=sh2,
+                    t2 = self.conv(p + "conv2", [t1], TAPS_3X3, w2, width, width, shift=sh2,
                                    relu=True, **kw)
                 idt = x
                 if (p + "downsample.0.weight") in sd:
                     scd, shd = bn_fold(sd, p + "downsample.1")
-                    wd = pack_weight(sd[p + "downsample.0.weight"], planes * 4)
+                    wd = pack_weight(fold_scale(sd[p + "downsample.0.weight"], scd), planes * 4)
                     if stride == 2:
                         xs = self.phase_split(p + "downsample.phase", x, mask=8)
                         srcs = [xs[3], xs[3], xs[3], xs[3]]
                         idt = self.conv(p + "downsample", srcs, TAPS_1X1_S2, wd, cin, planes * 4,
-                                        scale=scd, shift=shd)
+                                        shift=shd)
                     else:
                         idt = self.conv(p + "downsample", [x], TAPS_1X1, wd, cin, planes * 4,
-                                        scale=scd, shift=shd)
+                                        shift=shd)
                 sc3, sh3 = bn_fold(sd, p + "bn3")
-                x = self.conv(p + "conv3", [t2], TAPS_1X1, pack_weight(sd[p + "conv3.weight"], planes * 4),
-                              width, planes * 4, scale=sc3, shift=sh3, relu=True, residual=idt,
+                x = self.conv(p + "conv3", [t2], TAPS_1X1, pack_weight(fold_scale(sd[p + "conv3.weight"], sc3), planes * 4),
+                              width, planes * 4, shift=sh3, relu=True, residual=idt,
                               res_mode=L.RES_SAME)
             outs.append(x)
         return outs
