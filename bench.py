@@ -199,6 +199,29 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * BATCH * args.steps / float(t.item())
     h2d = img_host.numel() * 4 + BATCH * 8 * 4
+    # extra: the same end-to-end loop fed with raw uint8 frames (800x1333x3 BGR); normalise / pad / CHW run
+    # on the device (api.ImageTransform == mmdet/datasets/transforms.py:31-50 without the resize)
+    import iou_aware_single_stage_object_detector_b200 as P
+    tf = P.ImageTransform(cfg.img_norm_cfg["mean"], cfg.img_norm_cfg["std"], cfg.img_norm_cfg["to_rgb"], 32)
+    gen = torch.Generator().manual_seed(100 + rank)
+    frames = [torch.randint(0, 256, (BATCH, H, 1333, 3), generator=gen, dtype=torch.uint8).pin_memory() for _ in range(2)]
+
+    def run_e2e_u8(k):
+        gather = (lambda d, l, c: D.gather_detections(d, l, c, world)) if world > 1 else None
+        out = None
+        for out in det.detect_stream(((frames[i & 1], metas) for i in range(k)), rescale=True, device=dev,
+                                     gather=gather, img_transform=tf):
+            pass
+        return out
+    run_e2e_u8(2)
+    barrier()
+    t0 = time.perf_counter()
+    run_e2e_u8(args.steps)
+    barrier()
+    t = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_u8_value = world * BATCH * args.steps / float(t.item())
     d2h = sum(x.numel() * x.element_size() for x in res)
     # ---- live roofline of the dominant kernel (conv_tap_gemm_kernel), rank 0 ---------------------
     roof, extra = None, {}
@@ -257,6 +280,9 @@ def run_ours(args):
                            "cuda_graph": not args.no_graph},
                 "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h},
+                "e2e_uint8_frames": {"value": round(e2e_u8_value, 2), "unit": UNIT,
+                                     "h2d_bytes_per_step": frames[0].numel() + BATCH * 8 * 4,
+                                     "note": "extra: raw 800x1333x3 uint8 frames in, device-side ImageTransform"},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof}
         line.update(extra)
         if world == 1 and not args.no_cpu_baseline:

@@ -202,6 +202,15 @@ int iou_maxpool3x3s2(const void* src, int n, int c, int h, int w, void* dst, voi
 int iou_phase_split(const void* src, int n, int c, int h, int w, void* const* dst4,
                     int phase_mask, void* stream);
 
+/* ------------------------------------------------------------------ pre-processing ("next" row)
+ * ImageTransform without the resize (mmdet/datasets/transforms.py:31-50; mmcv 0.2.8 imnormalize,
+ * impad_to_multiple): src uint8 [n][h][w][3] (BGR, DEVICE pointer) -> dst fp32 [n][3][pad_h][pad_w] =
+ * (pixel - mean) / std per output channel (channel order reversed if to_rgb), optional horizontal flip,
+ * zero padding at the bottom / right.  mean3 / std3 are HOST pointers to 3 floats (output-channel order). */
+int iou_preprocess_u8(const unsigned char* src, int n, int h, int w, int pad_h, int pad_w,
+                      const float* mean3, const float* std3, int to_rgb, int flip, float* dst,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

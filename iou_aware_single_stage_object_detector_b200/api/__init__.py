@@ -4,7 +4,7 @@ from .builder import (build, build_backbone, build_neck, build_roi_extractor, bu
                       build_head, build_loss, build_detector)
 from .config import Config, ConfigDict
 from .anchor_generator import AnchorGenerator
-from .transforms import delta2bbox, bbox2result, multi_apply
+from .transforms import delta2bbox, bbox2result, multi_apply, ImageTransform
 from .bbox_nms import multiclass_nms
 from .losses import FocalLoss, SmoothL1Loss, CrossEntropyLoss
 from .conv_module import ConvModule, build_conv_layer, build_norm_layer
@@ -14,3 +14,4 @@ from .anchor_head import AnchorHead
 from .iou_aware_retina_head import IoUawareRetinaHead
 from .detectors import BaseDetector, SingleStageDetector, RetinaNet, FusedPlan
 from .ops import nms, soft_nms, sigmoid_focal_loss, SigmoidFocalLoss, nms_cuda, nms_cpu, sigmoid_focal_loss_cuda
+from .engine_cache import invalidate_plans

@@ -156,11 +156,13 @@ class SingleStageDetector(BaseDetector):
             plan.img_info.copy_(PP.make_img_info(img_metas, "cpu"), non_blocking=True)
         return plan.run()
 
-    def detect_stream(self, batches, rescale=False, device=None, gather=None):
+    def detect_stream(self, batches, rescale=False, device=None, gather=None, img_transform=None):
         """Pipelined batched inference over an iterable of (img, img_metas) with HOST (ideally pinned)
         images: the host->device copy of batch i+1 runs on a copy stream while batch i computes, then
         yields (dets, labels, counts) as CPU tensors per batch (one device->host read per batch).
-        `gather(dets, labels, counts)` (e.g. dist.gather_detections) is applied on the device first."""
+        `gather(dets, labels, counts)` (e.g. dist.gather_detections) is applied on the device first.
+        With `img_transform` (an api.ImageTransform) the batches are uint8 (n, h, w, 3) BGR frames: only
+        the raw bytes cross PCIe and normalisation / padding / CHW run on the device."""
         device = torch.device(device) if device is not None else next(self.parameters()).device
         if device.type != "cuda":
             raise RuntimeError("SingleStageDetector: move the model to a CUDA device first -- this path "
@@ -174,7 +176,7 @@ class SingleStageDetector(BaseDetector):
             def prefetch(slot, item):
                 img, metas = item
                 if stage[slot] is None or stage[slot].shape != img.shape:
-                    stage[slot] = torch.empty(img.shape, dtype=torch.float32, device=device)
+                    stage[slot] = torch.empty(img.shape, dtype=img.dtype, device=device)
                 with torch.cuda.stream(copy_stream):
                     if consumed[slot] is not None:
                         copy_stream.wait_event(consumed[slot])      # the previous use of this slot is over
@@ -193,9 +195,16 @@ class SingleStageDetector(BaseDetector):
                 nxt = next(it, None)
                 if nxt is not None:
                     prefetch(slot ^ 1, nxt)                          # overlaps with this batch's compute
-                plan = self.fused_plan(stage[slot].shape, device, rescale)
-                main.wait_event(ev)
-                plan.img.copy_(stage[slot], non_blocking=True)       # device->device, ~70 us for 103 MB
+                if img_transform is not None:
+                    n_, h_, w_, _ = stage[slot].shape
+                    hp_, wp_ = img_transform.pad_shape(h_, w_)
+                    plan = self.fused_plan((n_, 3, hp_, wp_), device, rescale)
+                    main.wait_event(ev)
+                    img_transform(stage[slot], out=plan.img)             # uint8 HWC -> normalised padded NCHW
+                else:
+                    plan = self.fused_plan(stage[slot].shape, device, rescale)
+                    main.wait_event(ev)
+                    plan.img.copy_(stage[slot], non_blocking=True)   # device->device, ~70 us for 103 MB
                 done = torch.cuda.Event()
                 done.record(main)
                 consumed[slot] = done

@@ -45,3 +45,39 @@ def multi_apply(func, *args, **kwargs):
     from functools import partial
     pfunc = partial(func, **kwargs) if kwargs else func
     return tuple(map(list, zip(*map(pfunc, *args))))
+
+
+class ImageTransform(object):
+    """Device-side ImageTransform (mmdet/datasets/transforms.py:11-50) for images that are ALREADY at
+    their test scale: normalize -> (flip) -> pad to size_divisor -> CHW, for a whole uint8 batch in one
+    kernel (iou_preprocess_u8).  Rescaling (mmcv.imrescale) is not part of the accelerated path."""
+
+    def __init__(self, mean=(0, 0, 0), std=(1, 1, 1), to_rgb=True, size_divisor=None):
+        import numpy as np
+        self.mean = np.array(mean, dtype=np.float32)
+        self.std = np.array(std, dtype=np.float32)
+        self.to_rgb = to_rgb
+        self.size_divisor = size_divisor
+
+    def pad_shape(self, h, w):
+        d = self.size_divisor
+        return (h, w) if d is None else ((h + d - 1) // d * d, (w + d - 1) // d * d)
+
+    def __call__(self, img_u8, flip=False, out=None):
+        """img_u8: CUDA uint8 tensor (n, h, w, 3) BGR -> fp32 (n, 3, hp, wp); returns (tensor, img_shape, pad_shape)."""
+        import ctypes
+        from .. import lib as L
+        if not img_u8.is_cuda or img_u8.dtype != torch.uint8 or img_u8.dim() != 4 or img_u8.shape[-1] != 3:
+            raise RuntimeError("ImageTransform: expected a CUDA uint8 tensor of shape (n, h, w, 3)")
+        img_u8 = img_u8.contiguous()
+        n, h, w, _ = img_u8.shape
+        hp, wp = self.pad_shape(h, w)
+        if out is None:
+            out = torch.empty(n, 3, hp, wp, dtype=torch.float32, device=img_u8.device)
+        mean = (ctypes.c_float * 3)(*[float(v) for v in self.mean])
+        std = (ctypes.c_float * 3)(*[float(v) for v in self.std])
+        with torch.cuda.device(img_u8.device):
+            L.check(L.load().iou_preprocess_u8(img_u8.data_ptr(), n, h, w, hp, wp, mean, std, int(self.to_rgb),
+                                               int(flip), out.data_ptr(), L.stream_ptr()))
+        L.launch_count += 1
+        return out, (h, w, 3), (hp, wp, 3)

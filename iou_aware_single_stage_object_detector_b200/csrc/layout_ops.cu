@@ -263,9 +263,48 @@ __global__ void __launch_bounds__(256) phase_split_kernel(const uint4* __restric
   }
 }
 
+// ---- image pre-processing (mmdet/datasets/transforms.py:31-50 minus the resize): uint8 HWC (BGR) ->
+// (img - mean) / std in fp32 (optionally BGR->RGB, optional horizontal flip), zero-padded to
+// (hp, wp), transposed to NCHW.  Arithmetic = numpy float32 `(img - mean) / std` (sub, then IEEE div).
+struct Norm3 { float mean[3], stdv[3]; };
+__global__ void __launch_bounds__(256) preprocess_u8_kernel(const unsigned char* __restrict__ src, int n, int h, int w,
+                                                            int hp, int wp, Norm3 nm, int to_rgb, int flip,
+                                                            float* __restrict__ dst) {
+  const size_t total = (size_t)n * 3 * hp * wp;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % wp);
+    size_t t = i / wp;
+    const int y = (int)(t % hp); t /= hp;
+    const int c = (int)(t % 3);
+    const int im = (int)(t / 3);
+    float v = 0.f;
+    if (y < h && x < w) {
+      const int xs = flip ? (w - 1 - x) : x;               // mmcv.imflip: horizontal
+      const int cs = to_rgb ? (2 - c) : c;                  // output channel c reads BGR channel 2-c
+      const float p = (float)src[(((size_t)im * h + y) * w + xs) * 3 + cs];
+      v = __fdiv_rn(__fsub_rn(p, nm.mean[c]), nm.stdv[c]);
+    }
+    dst[i] = v;
+  }
+}
+
 }  // namespace iou
 
 using namespace iou;
+
+extern "C" int iou_preprocess_u8(const unsigned char* src, int n, int h, int w, int pad_h, int pad_w,
+                                 const float* mean3, const float* std3, int to_rgb, int flip, float* dst,
+                                 void* stream) {
+  IOU_REQUIRE(src && dst && mean3 && std3 && n > 0 && h > 0 && w > 0, "bad argument");
+  IOU_REQUIRE(pad_h >= h && pad_w >= w, "pad shape smaller than the image");
+  Norm3 nm;
+  for (int c = 0; c < 3; ++c) { nm.mean[c] = mean3[c]; nm.stdv[c] = std3[c]; }
+  const size_t total = (size_t)n * 3 * pad_h * pad_w;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  preprocess_u8_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, n, h, w, pad_h, pad_w, nm, to_rgb, flip, dst);
+  return launch_status("preprocess_u8_kernel");
+}
+
 
 extern "C" int iou_pack_nchw(const float* src, int n, int c, int h, int w, void* dst, int64_t dst_row_start,
                              void* stream) {

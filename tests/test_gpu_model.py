@@ -146,3 +146,29 @@ def test_unpadded_input_raises_like_the_reference():
     meta = dict(ori_shape=(100, 136, 3), img_shape=(100, 136, 3), pad_shape=(100, 136, 3), scale_factor=1.0, flip=False)
     with pytest.raises(RuntimeError):
         det.simple_test_batch(img, [meta])
+
+
+def test_preprocess_kernel_bit_exact_and_uint8_stream():
+    """iou_preprocess_u8 == numpy ImageTransform restatement (oracle/preprocess.py), bit for bit; and
+    the uint8 streaming path gives the same detections as feeding the normalised fp32 tensor."""
+    from oracle import preprocess as opp
+    rs = np.random.RandomState(4)
+    mean, std = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+    tf = P.ImageTransform(mean, std, to_rgb=True, size_divisor=32)
+    for (h, w, flip) in ((90, 125, False), (96, 128, True), (33, 47, False)):
+        imgs = rs.randint(0, 256, size=(2, h, w, 3)).astype(np.uint8)
+        out, img_shape, pad_shape = tf(torch.from_numpy(imgs).to(DEV), flip=flip)
+        for i in range(2):
+            ref, rs_shape, rp_shape = opp.image_transform(imgs[i], mean, std, True, 32, flip)
+            assert tuple(out[i].shape) == ref.shape and pad_shape == rp_shape and img_shape == rs_shape
+            assert np.array_equal(out[i].cpu().numpy(), ref)
+    det, cfg = U.small_detector(seed=9)
+    det = det.to(DEV)
+    h, w = 90, 125
+    frames = [torch.from_numpy(rs.randint(0, 256, size=(2, h, w, 3)).astype(np.uint8)).pin_memory() for _ in range(3)]
+    meta = dict(ori_shape=(h, w, 3), img_shape=(h, w, 3), pad_shape=(96, 128, 3), scale_factor=1.0, flip=False)
+    got = list(det.detect_stream(((f, [meta, meta]) for f in frames), rescale=False, img_transform=tf))
+    for f, (d, l, c) in zip(frames, got):
+        x = torch.stack([torch.from_numpy(opp.image_transform(f[i].numpy(), mean, std, True, 32)[0]) for i in range(2)])
+        d2, l2, c2 = det.detect_device(x.to(DEV), [meta, meta], rescale=False)
+        assert torch.equal(c, c2.cpu()) and torch.equal(d, d2.cpu()) and torch.equal(l, l2.cpu())
