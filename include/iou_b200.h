@@ -57,7 +57,8 @@ typedef struct iou_postproc_cfg {
   float base_anchors[IOU_MAX_LEVELS][IOU_MAX_ANCHORS][4]; /* AnchorGenerator.base_anchors    */
   float target_means[4];
   float target_stds[4];
-  float alpha;                             /* score = cls^alpha * iou^(1-alpha); 0.5 at :510  */
+  float alpha;                             /* score = cls^alpha * iou^(1-alpha); 0.5 at :510;
+                                              1.0 = plain RetinaHead (iou maps may then be NULL) */
   float score_thr;                         /* test_cfg.score_thr (strict >)                   */
   float iou_thr;                           /* test_cfg.nms.iou_thr (strict >, nms_kernel.cu:60)*/
   float wh_ratio_clip;                     /* delta2bbox wh_ratio_clip, 16/1000               */

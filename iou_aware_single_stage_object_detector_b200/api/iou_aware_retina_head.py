@@ -118,7 +118,7 @@ class IoUawareRetinaHead(AnchorHead):
     def get_bboxes_device(self, cls_scores, bbox_preds, iou_preds, img_metas, cfg, rescale=False,
                           img_info=None):
         """Asynchronous form: returns padded device tensors (dets [n,K,5], labels [n,K], counts [n])."""
-        assert len(cls_scores) == len(bbox_preds) == len(iou_preds)
+        assert len(cls_scores) == len(bbox_preds) and (iou_preds is None or len(iou_preds) == len(cls_scores))
         n_img = len(img_metas)
         assert cls_scores[0].shape[0] == n_img
         sizes = [tuple(t.shape[-2:]) for t in cls_scores]

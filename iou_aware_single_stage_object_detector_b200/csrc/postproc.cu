@@ -42,7 +42,9 @@ __device__ __forceinline__ float sigmoidf_(float x) { return __fdiv_rn(1.0f, __f
 
 // score = sigmoid(cls)^alpha * sigmoid(iou)^(1-alpha)   (iou_aware_retina_head.py:510,531)
 __device__ __forceinline__ float fuse_score(float cls_logit, float iou_logit, float alpha) {
-  float s = sigmoidf_(cls_logit), q = sigmoidf_(iou_logit);
+  const float s = sigmoidf_(cls_logit);
+  if (alpha == 1.0f) return s;          // plain RetinaHead: score = sigmoid(cls) (anchor_head.py:404-407)
+  const float q = sigmoidf_(iou_logit);
   if (alpha == 0.5f) return __fmul_rn(__fsqrt_rn(s), __fsqrt_rn(q));
   return __fmul_rn(powf(s, alpha), powf(q, 1.0f - alpha));
 }
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(256) max_score_kernel(const __grid_constant__ 
     if (lane < v) {
       float m = -INFINITY;
       for (int t = 0; t < Q; ++t) m = fmaxf(m, sm[lane * Q + t]);
-      float q = __ldg(P.iou[l] + (size_t)img * n_l + a0 + lane);
+      const float q = P.iou[l] ? __ldg(P.iou[l] + (size_t)img * n_l + a0 + lane) : 0.f;
       maxscore[(size_t)img * P.A_total + P.anchor_off[l] + a0 + lane] = fuse_score(m, q, P.alpha);
     }
     __syncwarp();
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(256) gather_decode_kernel(const __grid_constan
     }
     const int n_l = P.n_anchor[l];
     const size_t row = (size_t)img * n_l + i;
-    const float ql = __ldg(P.iou[l] + row);
+    const float ql = P.iou[l] ? __ldg(P.iou[l] + row) : 0.f;
     const float* crow = P.cls[l] + row * P.C;
     for (int c = lane; c < P.C; c += 32) tile[c * 33 + t] = fuse_score(__ldg(crow + c), ql, P.alpha);
     if (lane == 0) {
@@ -909,10 +911,11 @@ static int run_decode(PostParams& P, const float* const* cls, const float* const
                       float* scores_cm, int32_t* cand_idx, float* maxscore, unsigned long long* topk_scratch,
                       cudaStream_t st) {
   for (int l = 0; l < P.num_levels; ++l) {
-    IOU_REQUIRE(cls[l] && reg[l] && iou[l], "NULL level pointer at level %d", l);
+    IOU_REQUIRE(cls[l] && reg[l], "NULL level pointer at level %d", l);
+    IOU_REQUIRE((iou && iou[l]) || P.alpha == 1.0f, "iou maps may only be omitted when alpha == 1 (level %d)", l);
     IOU_REQUIRE(((uintptr_t)cls[l] & 15) == 0 && ((uintptr_t)reg[l] & 15) == 0,
                 "cls/reg pointers must be 16-byte aligned (level %d)", l);
-    P.cls[l] = cls[l]; P.reg[l] = reg[l]; P.iou[l] = iou[l];
+    P.cls[l] = cls[l]; P.reg[l] = reg[l]; P.iou[l] = iou ? iou[l] : nullptr;
   }
   P.rescale = rescale;
   const long long groups = P.group_off[P.num_levels];
@@ -980,7 +983,7 @@ extern "C" int iou_decode_candidates(const iou_postproc_cfg* cfg, int n_img, con
                                      void* stream) {
   PostParams P;
   if (int e = fill_params(cfg, n_img, P)) return e;
-  IOU_REQUIRE(cls && reg && iou && img_info && boxes && scores_cm && cand_idx, "NULL argument");
+  IOU_REQUIRE(cls && reg && img_info && boxes && scores_cm && cand_idx, "NULL argument");
   PostWorkspace W = carve(P, workspace);
   if (!workspace || workspace_bytes < W.total)
     return fail(IOU_ERR_WORKSPACE, "workspace too small: need %zu bytes", W.total);
@@ -1006,7 +1009,7 @@ extern "C" int iou_get_bboxes(const iou_postproc_cfg* cfg, int n_img, const floa
                               void* workspace, size_t workspace_bytes, void* stream) {
   PostParams P;
   if (int e = fill_params(cfg, n_img, P)) return e;
-  IOU_REQUIRE(cls && reg && iou && img_info && dets && labels && counts, "NULL argument");
+  IOU_REQUIRE(cls && reg && img_info && dets && labels && counts, "NULL argument");
   PostWorkspace W = carve(P, workspace);
   if (!workspace || workspace_bytes < W.total)
     return fail(IOU_ERR_WORKSPACE, "workspace too small: need %zu bytes", W.total);

@@ -356,7 +356,7 @@ class Engine(object):
             src = F.view(i)                               # relu_before_extra_convs=False
         return F
 
-    def add_head(self, sd, F, prefix="bbox_head.", stacked=4, num_anchors=9, num_classes=80):
+    def add_head(self, sd, F, prefix="bbox_head.", stacked=4, num_anchors=9, num_classes=80, with_iou=True):
         """All levels in one launch per conv.  Returns (cls, reg, iou) lists of NHWC fp32 tensors
         exposed with the reference's logical shape (N, A*C, H, W)."""
         c = r = F
@@ -374,15 +374,20 @@ class Engine(object):
         bn_c, pad_c = pick_block_n(ncls)
         self.conv(prefix + "retina_cls", [c], TAPS_3X3, pack_weight(sd[prefix + "retina_cls.weight"], pad_c),
                   fc, ncls, shift=sd[prefix + "retina_cls.bias"], dense_out=cls_out)
-        # retina_reg and retina_iou read the same feature (shared_conv=4, :198-204): one GEMM, split store
-        w_ri = torch.cat([sd[prefix + "retina_reg.weight"], sd[prefix + "retina_iou.weight"]], dim=0)
-        b_ri = torch.cat([sd[prefix + "retina_reg.bias"], sd[prefix + "retina_iou.bias"]], dim=0)
-        _, pad_ri = pick_block_n(nreg + niou)
-        self.conv(prefix + "retina_reg+iou", [r], TAPS_3X3, pack_weight(w_ri, pad_ri), fc, nreg + niou,
-                  shift=b_ri, dense_out=reg_out, dense_out2=iou_out, dense_split=nreg)
+        if with_iou:
+            # retina_reg and retina_iou read the same feature (shared_conv=4, :198-204): one GEMM, split store
+            w_ri = torch.cat([sd[prefix + "retina_reg.weight"], sd[prefix + "retina_iou.weight"]], dim=0)
+            b_ri = torch.cat([sd[prefix + "retina_reg.bias"], sd[prefix + "retina_iou.bias"]], dim=0)
+            _, pad_ri = pick_block_n(nreg + niou)
+            self.conv(prefix + "retina_reg+iou", [r], TAPS_3X3, pack_weight(w_ri, pad_ri), fc, nreg + niou,
+                      shift=b_ri, dense_out=reg_out, dense_out2=iou_out, dense_split=nreg)
+        else:                                 # plain RetinaHead (retina_head.py:78-96)
+            _, pad_r = pick_block_n(nreg)
+            self.conv(prefix + "retina_reg", [r], TAPS_3X3, pack_weight(sd[prefix + "retina_reg.weight"], pad_r),
+                      fc, nreg, shift=sd[prefix + "retina_reg.bias"], dense_out=reg_out)
         self.keep += cls_out + reg_out + iou_out
         as_nchw = lambda ts: [t.permute(0, 3, 1, 2) for t in ts]
-        return as_nchw(cls_out), as_nchw(reg_out), as_nchw(iou_out)
+        return as_nchw(cls_out), as_nchw(reg_out), (as_nchw(iou_out) if with_iou else None)
 
     # ------------------------------------------------------------------ layout I/O
     def pack_input(self, x):

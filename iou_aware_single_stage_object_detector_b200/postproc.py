@@ -89,9 +89,10 @@ def get_bboxes_device(wsp, cls_list, reg_list, iou_list, img_info, rescale):
     lib = L.load()
     cls_list = [nhwc_rows(t) for t in cls_list]
     reg_list = [nhwc_rows(t) for t in reg_list]
-    iou_list = [nhwc_rows(t) for t in iou_list]
+    iou_list = [nhwc_rows(t) for t in iou_list] if iou_list is not None else None
     L.check(lib.iou_get_bboxes(ctypes.byref(wsp.cfg), wsp.n_img, _ptr_array(cls_list), _ptr_array(reg_list),
-                               _ptr_array(iou_list), img_info.data_ptr(), int(bool(rescale)),
+                               _ptr_array(iou_list) if iou_list is not None else None, img_info.data_ptr(),
+                               int(bool(rescale)),
                                wsp.dets.data_ptr(), wsp.labels.data_ptr(), wsp.counts.data_ptr(),
                                wsp.ws.data_ptr(), wsp.ws_bytes, L.stream_ptr()))
     L.launch_count += 5

@@ -183,9 +183,11 @@ def level_candidates(cls_map, reg_map, iou_map, stride, base, img_shape, nms_pre
     h, w = cls_map.shape[-2:]
     cls_rows = cls_map.permute(1, 2, 0).reshape(-1, num_classes)
     reg_rows = reg_map.permute(1, 2, 0).reshape(-1, 4)
-    iou_rows = iou_map.permute(1, 2, 0).reshape(-1)
     anchors = grid_anchors(base, h, w, stride)
-    scores = reweight_scores(cls_rows, iou_rows, alpha)
+    if iou_map is None:      # plain RetinaHead: scores = sigmoid(cls) (anchor_head.py:404-407)
+        scores = cls_rows.sigmoid()
+    else:
+        scores = reweight_scores(cls_rows, iou_map.permute(1, 2, 0).reshape(-1), alpha)
     idx = torch.arange(scores.shape[0])
     if nms_pre > 0 and scores.shape[0] > nms_pre:
         best = scores.max(dim=1)[0]
@@ -200,6 +202,8 @@ def get_bboxes_single(cls_maps, reg_maps, iou_maps, strides, bases, img_shape, s
     """iou_aware_retina_head.py:463-564 for one image; cfg needs nms_pre, score_thr,
     nms['iou_thr'], max_per_img."""
     bs, ss = [], []
+    if iou_maps is None:
+        iou_maps = [None] * len(cls_maps)
     for c, r, q, s, b in zip(cls_maps, reg_maps, iou_maps, strides, bases):
         bx, sc, _ = level_candidates(c, r, q, s, b, img_shape, cfg.get("nms_pre", -1),
                                      num_classes, **kw)

@@ -117,7 +117,35 @@ def main():
         out = run_postproc_case(head, case)
         np.savez_compressed(os.path.join(HERE, "postproc_%s.npz" % name), **out)
         print(name, {k: v.shape for k, v in out.items() if k.startswith("dets")})
+    gen_plain_retina()
+
+
+def gen_plain_retina():
+    """Sibling head: reference RetinaHead.get_bboxes on the 'small' case maps."""
+    ref_shim.load_reference()
+    from mmdet.models.anchor_heads import RetinaHead
+    torch.manual_seed(0)
+    head = RetinaHead(num_classes=81, in_channels=256, stacked_convs=4, feat_channels=256, octave_base_scale=4,
+                      scales_per_octave=3, anchor_ratios=[0.5, 1.0, 2.0], anchor_strides=[8, 16, 32, 64, 128],
+                      target_means=[.0, .0, .0, .0], target_stds=[1.0, 1.0, 1.0, 1.0],
+                      loss_cls=dict(type='FocalLoss', use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0),
+                      loss_bbox=dict(type='SmoothL1Loss', beta=0.11, loss_weight=1.0))
+    case = cases.postproc_case("small")
+    cfg = ref_shim._to_attr(case["cfg"])
+    n_img = case["cls"][0].shape[0]
+    with torch.no_grad():
+        res = head.get_bboxes(case["cls"], case["reg"], [torch.zeros(0, 4)] * n_img,
+                              [torch.zeros(0, dtype=torch.long)] * n_img, case["img_metas"], cfg,
+                              rescale=case["rescale"])
+    out = {}
+    for i, (d, l) in enumerate(res):
+        out["dets_%d" % i], out["labels_%d" % i] = d.numpy(), l.numpy()
+    np.savez_compressed(os.path.join(HERE, "postproc_plain_retina_small.npz"), **out)
+    print("plain retina", {k: v.shape for k, v in out.items()})
 
 
 if __name__ == "__main__":
+    if "--plain-retina-only" in sys.argv:
+        gen_plain_retina()
+        sys.exit(0)
     main()

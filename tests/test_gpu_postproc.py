@@ -158,3 +158,23 @@ def test_focal_loss_forward_backward_vs_oracle():
         x, t, torch.full_like(x, 1.0 / x.numel()), 2.0, 0.25), rtol=1e-4, atol=1e-9)
     assert P.SigmoidFocalLoss(2.0, 0.25)(x.cuda(), t.cuda()).item() == pytest.approx(
         op.sigmoid_focal_loss_forward(x, t, 2.0, 0.25).sum().item(), rel=1e-4)
+
+
+def test_plain_retina_head_get_bboxes_vs_reference_golden():
+    """RetinaHead (alpha = 1, no IoU maps) through the same kernels vs the reference's own RetinaHead."""
+    gold = np.load(os.path.join(U.GOLD, "postproc_plain_retina_small.npz"))
+    case = cases.postproc_case("small")
+    cfgd = dict(U.head_cfg(), type='RetinaHead')
+    torch.manual_seed(0)
+    head = P.build_head(cfgd)
+    assert sorted(k.split('.')[0] for k in head.state_dict()).count('retina_iou') == 0
+    dev = torch.device("cuda:0")
+    cls = [t.to(dev) for t in case["cls"]]
+    reg = [t.to(dev) for t in case["reg"]]
+    n = cls[0].shape[0]
+    res = head.get_bboxes(cls, reg, [None] * n, [None] * n, case["img_metas"], P.ConfigDict(case["cfg"]),
+                          rescale=case["rescale"])
+    for i, (d, l) in enumerate(res):
+        gd, gl = gold["dets_%d" % i], gold["labels_%d" % i]
+        assert d.shape[0] == gd.shape[0]
+        U.match_as_sets(d.cpu().numpy(), l.cpu().numpy(), gd, gl, min_frac=0.97)

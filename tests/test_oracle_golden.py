@@ -105,3 +105,16 @@ def test_focal_loss_matches_python_formula():
     (torch.nn.functional.binary_cross_entropy_with_logits(xg, onehot, reduction="none") * w2).sum().backward()
     grad = op.sigmoid_focal_loss_backward(x, t, torch.ones_like(x), g, a)
     assert torch.allclose(grad, xg.grad, rtol=1e-3, atol=1e-6)
+
+
+def test_plain_retina_head_matches_reference():
+    """Sibling RetinaHead (score = sigmoid(cls), anchor_head.py:364-450) on the 'small' maps."""
+    gold = np.load(os.path.join(G, "postproc_plain_retina_small.npz"))
+    case = cases.postproc_case("small")
+    bases = _bases()
+    for i in range(case["cls"][0].shape[0]):
+        m = case["img_metas"][i]
+        d, l = op.get_bboxes_single([c[i] for c in case["cls"]], [r[i] for r in case["reg"]], None,
+                                    cases.STRIDES, bases, m["img_shape"], m["scale_factor"], cfg=case["cfg"],
+                                    rescale=case["rescale"], nms_mode="cpu")
+        assert np.array_equal(l.numpy(), gold["labels_%d" % i]) and np.array_equal(d.numpy(), gold["dets_%d" % i])
