@@ -21,6 +21,8 @@
 // mmdet/models/necks/fpn.py:97-136, mmdet/models/anchor_heads/iou_aware_retina_head.py:171-219.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdio>
+#include <cstdlib>
 #include <new>
 #include "common.cuh"
 
@@ -52,7 +54,13 @@ struct ConvParams {
   int seg_tile_off[IOU_CONV_MAX_SEG + 1];
   int num_m_tiles, num_n_tiles, total_tiles;
   int two_cta, total_pair_tiles;   // cta_group::2: a CTA pair owns two consecutive 128-row tiles x BLOCK_N
-  int num_stages, stage_bytes, b_tile_bytes;
+  // A windows and B tiles travel through separate rings: taps that read the same source at the same dy
+  // (dx = dx0..dx0+2) share ONE (128+8)-row A window and address it through row-shifted descriptors
+  int num_groups;
+  int grp_src[IOU_CONV_MAX_TAPS], grp_dy[IOU_CONV_MAX_TAPS], grp_dx0[IOU_CONV_MAX_TAPS], grp_nt[IOU_CONV_MAX_TAPS];
+  int grp_tap[IOU_CONV_MAX_TAPS][3], grp_shift[IOU_CONV_MAX_TAPS][3];
+  int a_rows, a_entry_bytes, b_entry_bytes, num_a_stages, num_b_stages, ring_bytes, taps_per_tile;
+  int b_tile_bytes;
   int staged, res_staged, staging_per_warp;
   const float* scale;
   const float* shift;
@@ -199,9 +207,16 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 
 // K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 // start>>4 | LBO(16B)>>4 <<16 | SBO(1024B: 8 rows x 128B)>>4 <<32 | version=1 <<46 | SWIZZLE_128B(2) <<61
+// The start address may sit `shift` rows (shift*128 B) into a 1024-byte swizzle atom (the row-shifted A
+// windows of the dx taps): the tensor core applies the 128B XOR swizzle to ABSOLUTE shared-memory address
+// bits, exactly as TMA wrote them, so the base_offset field (bits 49..51) stays 0 -- measured on B200:
+// base_offset = shift gives wrong sums, 0 is exact (tests/test_gpu_conv.py).
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t umma_desc(uint32_t lo) { return ((uint64_t)0x40004040u << 32) | lo; }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
@@ -217,9 +232,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
   unsigned char* ctrl = smem_dyn + (base - raw);
   const uint32_t ctrl_addr = base;
   const uint32_t tiles_addr = base + kCtrlBytes;
-  // control block: full[8] @0, empty[8] @64, tfull[2] @128, tempty[2] @144, tmem ptr @160
+  // control block: B full[8] @0, B empty[8] @64, tfull[2] @128, tempty[2] @144, tmem ptr @160,
+  // residual ring @192..320, A full[8] @320, A empty[8] @384
   const uint32_t bar_full = ctrl_addr, bar_empty = ctrl_addr + 64, bar_tfull = ctrl_addr + 128,
-                 bar_tempty = ctrl_addr + 144;
+                 bar_tempty = ctrl_addr + 144, bar_afull = ctrl_addr + 320, bar_aempty = ctrl_addr + 384;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(ctrl + 160);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -237,7 +253,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
   };
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < P.num_stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < P.num_b_stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < P.num_a_stages; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, (kTwoCta ? 2 : 1) * kNumEpiWarps * 32); }
     for (int r = 0; r < 2 * kNumEpiWarps; ++r) mbar_init(ctrl_addr + 192 + 8 * r, 1);   // residual ring: 8 warps x 2
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -265,97 +282,132 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int k_iters = P.num_taps * P.k_slabs;
-  const uint32_t a_lo_off = kATileBytes;
-  const uint32_t b_hi_off = (P.passes == 3) ? 2 * kATileBytes : kATileBytes;
-  const uint32_t b_lo_off = b_hi_off + P.b_tile_bytes;
+  const uint32_t a_lo_off = (uint32_t)P.a_rows * 128u;       // A entry: hi window | lo window
+  const uint32_t b_lo_off = (uint32_t)P.b_tile_bytes;        // B entry: hi tile | lo tile
+  const uint32_t b_ring_addr = tiles_addr + (uint32_t)(P.num_a_stages * P.a_entry_bytes);
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      const uint32_t mult = kTwoCta ? 2u : 1u;   // pair: both CTAs' loads complete on the LEADER's barrier
       for (int tile = w_first; tile < w_total; tile += w_stride) {
         int m_tile, n_tile, s;
         decode_tile(tile, m_tile, n_tile, s);
         const int row0 = P.seg[s].row_start + (m_tile - P.seg_tile_off[s]) * kBlockM;
         const int wp = P.seg[s].w + 2;
         const int b_rows = kTwoCta ? (P.block_n >> 1) : P.block_n;     // a pair splits the B tile by rows
-        for (int t = 0; t < P.num_taps; ++t) {
-          const int arow = row0 + P.tap_dy[t] * wp + P.tap_dx[t];
-          const int wrow = t * P.cout_pad + n_tile * P.block_n + rank * b_rows;
-          const CUtensorMap* tm = &P.tmap_src[P.tap_src[t]];
+        for (int g = 0; g < P.num_groups; ++g) {
+          const int arow = row0 + P.grp_dy[g] * wp + P.grp_dx0[g];
+          const CUtensorMap* tm = &P.tmap_src[P.grp_src[g]];
+          const int nt = P.grp_nt[g];
           for (int ks = 0; ks < P.k_slabs; ++ks) {
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-            const uint32_t fb = bar_full + 8 * stage;
-            const uint32_t sa = tiles_addr + stage * P.stage_bytes;
+            // ---- one A window (hi, lo) serves all dx taps of the group
+            mbar_wait(bar_aempty + 8 * as, aph ^ 1u);
+            const uint32_t fa = bar_afull + 8 * as;
+            const uint32_t sa = tiles_addr + as * P.a_entry_bytes;
             const int a_col = P.diag_k ? n_tile * kBlockK : ks * kBlockK;
+            if (!kTwoCta || rank == 0) mbar_expect_tx(fa, mult * (uint32_t)P.a_entry_bytes);
             if constexpr (kTwoCta) {
-              // both CTAs' loads complete on the LEADER's full barrier; only the leader posts the byte count
-              if (rank == 0) mbar_expect_tx(fb, 2u * (uint32_t)P.stage_bytes);
-              tma_load_2d_pair(tm, fb, sa, a_col, arow);
-              tma_load_2d_pair(&P.tmap_w, fb, sa + b_hi_off, ks * kBlockK, wrow);
-              if (P.passes == 3) {
-                tma_load_2d_pair(tm, fb, sa + a_lo_off, P.cin + a_col, arow);
-                tma_load_2d_pair(&P.tmap_w, fb, sa + b_lo_off, P.b_cin + ks * kBlockK, wrow);
-              }
+              tma_load_2d_pair(tm, fa, sa, a_col, arow);
+              if (P.passes == 3) tma_load_2d_pair(tm, fa, sa + a_lo_off, P.cin + a_col, arow);
             } else {
-              mbar_expect_tx(fb, (uint32_t)P.stage_bytes);
-              tma_load_2d(tm, fb, sa, a_col, arow);
-              tma_load_2d(&P.tmap_w, fb, sa + b_hi_off, ks * kBlockK, wrow);
-              if (P.passes == 3) {
-                tma_load_2d(tm, fb, sa + a_lo_off, P.cin + a_col, arow);
-                tma_load_2d(&P.tmap_w, fb, sa + b_lo_off, P.b_cin + ks * kBlockK, wrow);
-              }
+              tma_load_2d(tm, fa, sa, a_col, arow);
+              if (P.passes == 3) tma_load_2d(tm, fa, sa + a_lo_off, P.cin + a_col, arow);
             }
-            if (++stage == P.num_stages) { stage = 0; phase ^= 1u; }
+            if (++as == P.num_a_stages) { as = 0; aph ^= 1u; }
+            // ---- one B tile (hi, lo) per tap
+            for (int j = 0; j < nt; ++j) {
+              const int wrow = P.grp_tap[g][j] * P.cout_pad + n_tile * P.block_n + rank * b_rows;
+              mbar_wait(bar_empty + 8 * bs, bph ^ 1u);
+              const uint32_t fb = bar_full + 8 * bs;
+              const uint32_t sb = b_ring_addr + bs * P.b_entry_bytes;
+              if (!kTwoCta || rank == 0) mbar_expect_tx(fb, mult * (uint32_t)P.b_entry_bytes);
+              if constexpr (kTwoCta) {
+                tma_load_2d_pair(&P.tmap_w, fb, sb, ks * kBlockK, wrow);
+                if (P.passes == 3) tma_load_2d_pair(&P.tmap_w, fb, sb + b_lo_off, P.b_cin + ks * kBlockK, wrow);
+              } else {
+                tma_load_2d(&P.tmap_w, fb, sb, ks * kBlockK, wrow);
+                if (P.passes == 3) tma_load_2d(&P.tmap_w, fb, sb + b_lo_off, P.b_cin + ks * kBlockK, wrow);
+              }
+              if (++bs == P.num_b_stages) { bs = 0; bph ^= 1u; }
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer (pair mode: leader CTA only) ===============================
-    int stage = 0;
-    uint32_t phase = 0;
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
     int it = 0;
+    const int mode = P.passes == 3 ? (P.lolo ? 4 : 3) : 1;
+    const uint32_t a_lo_d = a_lo_off >> 4, b_lo_d = b_lo_off >> 4;
+    auto mma = [&](uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t accum) {
+      if constexpr (kTwoCta) tc_mma_bf16_pair(d_tmem, ad, bd, P.idesc, accum);
+      else tc_mma_bf16(d_tmem, ad, bd, P.idesc, accum);
+    };
     for (int tile = w_first; tile < w_total && rank == 0; tile += w_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
-      for (int ki = 0; ki < k_iters; ++ki) {
-        mbar_wait(bar_full + 8 * stage, phase);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = tiles_addr + stage * P.stage_bytes;
+      int done = 0;                                    // taps x slabs issued for this tile
+      const int todo = P.taps_per_tile * P.k_slabs;
+      for (int g = 0; g < P.num_groups; ++g) {
+        const int nt = P.grp_nt[g];
+        for (int ks = 0; ks < P.k_slabs; ++ks) {
+          mbar_wait(bar_afull + 8 * as, aph);
+          const uint32_t sa = tiles_addr + as * P.a_entry_bytes;
+          for (int j = 0; j < nt; ++j, ++done) {
+            mbar_wait(bar_full + 8 * bs, bph);
+            tc_fence_after();
+            if (lane == 0) {
+              // descriptor low words: (addr >> 4) | LBO; every operand lives below 256 KiB, so advancing an
+              // address by x bytes is adding x >> 4 (the single issuing thread is the bottleneck of narrow-N
+              // tiles: 12 MMAs of 128 x 64 x 16 retire in ~400 cycles, so the loop body is kept minimal)
+              const uint32_t sb = b_ring_addr + bs * P.b_entry_bytes;
+              const uint32_t da = umma_desc_lo(sa + (uint32_t)P.grp_shift[g][j] * 128u), db = umma_desc_lo(sb);
+              const uint32_t dal = da + a_lo_d, dbl = db + b_lo_d;
+              const uint32_t first = done > 0 ? 1u : 0u;
+              if (mode == 3) {
 #pragma unroll
-          for (int kk = 0; kk < kBlockK / 16; ++kk) {
-            const uint64_t a_hi = umma_desc_sw128(sa + kk * 32);
-            const uint64_t b_hi = umma_desc_sw128(sa + b_hi_off + kk * 32);
-            auto mma = [&](uint64_t ad, uint64_t bd, uint32_t accum) {
-              if constexpr (kTwoCta) tc_mma_bf16_pair(d_tmem, ad, bd, P.idesc, accum);
-              else tc_mma_bf16(d_tmem, ad, bd, P.idesc, accum);
-            };
-            mma(a_hi, b_hi, (ki > 0 || kk > 0) ? 1u : 0u);
-            if (P.passes == 3) {
-              const uint64_t a_lo = umma_desc_sw128(sa + a_lo_off + kk * 32);
-              const uint64_t b_lo = umma_desc_sw128(sa + b_lo_off + kk * 32);
-              mma(a_hi, b_lo, 1u);
-              mma(a_lo, b_hi, 1u);
-              if (P.lolo) mma(a_lo, b_lo, 1u);
+                for (uint32_t kk = 0; kk < kBlockK / 16; ++kk) {
+                  mma(d_tmem, umma_desc(da + 2 * kk), umma_desc(db + 2 * kk), kk ? 1u : first);
+                  mma(d_tmem, umma_desc(da + 2 * kk), umma_desc(dbl + 2 * kk), 1u);
+                  mma(d_tmem, umma_desc(dal + 2 * kk), umma_desc(db + 2 * kk), 1u);
+                }
+              } else if (mode == 1) {
+#pragma unroll
+                for (uint32_t kk = 0; kk < kBlockK / 16; ++kk)
+                  mma(d_tmem, umma_desc(da + 2 * kk), umma_desc(db + 2 * kk), kk ? 1u : first);
+              } else {
+#pragma unroll
+                for (uint32_t kk = 0; kk < kBlockK / 16; ++kk) {
+                  mma(d_tmem, umma_desc(da + 2 * kk), umma_desc(db + 2 * kk), kk ? 1u : first);
+                  mma(d_tmem, umma_desc(da + 2 * kk), umma_desc(dbl + 2 * kk), 1u);
+                  mma(d_tmem, umma_desc(dal + 2 * kk), umma_desc(db + 2 * kk), 1u);
+                  mma(d_tmem, umma_desc(dal + 2 * kk), umma_desc(dbl + 2 * kk), 1u);
+                }
+              }
+              // commits fire when the MMAs issued so far retire (pair mode: multicast to BOTH CTAs)
+              if constexpr (kTwoCta) {
+                tc_commit_pair(bar_empty + 8 * bs);
+                if (j == nt - 1) tc_commit_pair(bar_aempty + 8 * as);
+                if (done == todo - 1) tc_commit_pair(bar_tfull + 8 * acc);
+              } else {
+                tc_commit(bar_empty + 8 * bs);                     // frees the B tile
+                if (j == nt - 1) tc_commit(bar_aempty + 8 * as);   // frees the A window
+                if (done == todo - 1) tc_commit(bar_tfull + 8 * acc);   // accumulator complete
+              }
             }
+            __syncwarp();
+            if (++bs == P.num_b_stages) { bs = 0; bph ^= 1u; }
           }
-          if constexpr (kTwoCta) {                     // multicast: frees the stage / publishes the accumulator in BOTH CTAs
-            tc_commit_pair(bar_empty + 8 * stage);
-            if (ki == k_iters - 1) tc_commit_pair(bar_tfull + 8 * acc);
-          } else {
-            tc_commit(bar_empty + 8 * stage);            // frees the smem stage when the MMAs retire
-            if (ki == k_iters - 1) tc_commit(bar_tfull + 8 * acc);   // accumulator complete
-          }
+          if (++as == P.num_a_stages) { as = 0; aph ^= 1u; }
         }
-        __syncwarp();
-        if (++stage == P.num_stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
@@ -364,7 +416,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
     const int m_local = lane_group * 32 + lane;
     const int ew = warp - 2;                               // 0..7
     const int half = ew >> 2;                              // the two warps of a quadrant take alternate column groups
-    const uint32_t st_out = tiles_addr + P.num_stages * P.stage_bytes + ew * P.staging_per_warp;
+    const uint32_t st_out = tiles_addr + P.ring_bytes + ew * P.staging_per_warp;
     const uint32_t st_res = st_out + 4096;
     const uint32_t bar_res = ctrl_addr + 192 + ew * 16;
     auto issue_res = [&](int tile_, int g_, int q_) {      // lane 0 only
@@ -678,16 +730,60 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   P.two_cta = (d->two_cta && d->block_n % 32 == 0 && !d->diag_k) ? 1 : 0;
   P.total_pair_tiles = ((P.num_m_tiles + 1) / 2) * P.num_n_tiles;
   P.b_tile_bytes = (P.two_cta ? d->block_n / 2 : d->block_n) * kBlockK * 2;
-  P.stage_bytes = (d->passes >= 3 ? 2 : 1) * (kATileBytes + P.b_tile_bytes);
   // padded-rows outputs leave through a per-warp 64B-swizzled staging tile (32 rows x 32 ch, hi + lo)
   // and TMA stores; a same-geometry residual arrives through a 2-deep TMA-load ring per warp
   P.staged = (d->out_mode == IOU_OUT_PADDED_BF16X2) && (d->block_n % 64 == 0);
   P.res_staged = P.staged && d->res_mode == IOU_RES_SAME;
   P.staging_per_warp = P.staged ? (4096 + (P.res_staged ? 8192 : 0)) : 0;      // x 8 epilogue warps
-  int stages = (kSmemBudget - kCtrlBytes - 1024 - kNumEpiWarps * P.staging_per_warp) / P.stage_bytes;
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) { delete plan; return fail(IOU_ERR_INVALID, "tile does not fit shared memory (block_n %d, residual %d): use a smaller block_n", d->block_n, d->res_mode); }
-  P.num_stages = stages;
+  const int nsplit = d->passes >= 3 ? 2 : 1;
+  P.b_entry_bytes = nsplit * P.b_tile_bytes;
+  if (P.b_tile_bytes % 1024 != 0) { delete plan; return fail(IOU_ERR_INVALID, "block_n %d: B tile is not a whole number of swizzle atoms", d->block_n); }
+  P.taps_per_tile = d->num_taps;
+  // tap groups: taps reading the same source at the same dy with dx within a span of 3 share one A window
+  // (tried first; if the rings do not fit shared memory that way, every tap loads its own 128-row window)
+  bool fits = false;
+  for (int share = getenv("IOU_NO_A_SHARE") ? 0 : 1; share >= 0 && !fits; --share) {
+    P.num_groups = 0;
+    bool used[IOU_CONV_MAX_TAPS] = {false};
+    for (int t = 0; t < d->num_taps; ++t) {
+      if (used[t]) continue;
+      const int g = P.num_groups++;
+      int members[3] = {t, -1, -1}, nm = 1, dxmin = d->tap_dx[t], dxmax = d->tap_dx[t];
+      used[t] = true;
+      for (int u = t + 1; u < d->num_taps && nm < 3 && share; ++u) {
+        if (used[u] || d->tap_src[u] != d->tap_src[t] || d->tap_dy[u] != d->tap_dy[t]) continue;
+        const int lo = d->tap_dx[u] < dxmin ? d->tap_dx[u] : dxmin, hi = d->tap_dx[u] > dxmax ? d->tap_dx[u] : dxmax;
+        if (hi - lo > 2) continue;
+        members[nm++] = u; used[u] = true; dxmin = lo; dxmax = hi;
+      }
+      P.grp_src[g] = d->tap_src[t]; P.grp_dy[g] = d->tap_dy[t]; P.grp_dx0[g] = dxmin; P.grp_nt[g] = nm;
+      for (int j = 0; j < nm; ++j) { P.grp_tap[g][j] = members[j]; P.grp_shift[g][j] = d->tap_dx[members[j]] - dxmin; }
+    }
+    P.a_rows = (P.num_groups == d->num_taps) ? kBlockM : kBlockM + 8;    // shifted windows need up to 2 extra rows
+    P.a_entry_bytes = nsplit * P.a_rows * kBlockK * 2;
+    // ring depths: the A ring is worth (taps per group) B tiles per entry; maximise the shallower of the two
+    const int budget = kSmemBudget - kCtrlBytes - 1024 - kNumEpiWarps * P.staging_per_warp;
+    int best_na = 0, best_nb = 0, best_score = 0;
+    for (int na = 2; na <= kMaxStages; ++na) {
+      int nb = (budget - na * P.a_entry_bytes) / P.b_entry_bytes;
+      if (nb > kMaxStages) nb = kMaxStages;
+      if (nb < 2) break;
+      const int cover = na * d->num_taps / P.num_groups;
+      const int score = cover < nb ? cover : nb;
+      if (score > best_score) { best_score = score; best_na = na; best_nb = nb; }
+    }
+    if (best_score > 0) {
+      fits = true;
+      P.num_a_stages = best_na; P.num_b_stages = best_nb;
+      P.ring_bytes = best_na * P.a_entry_bytes + best_nb * P.b_entry_bytes;
+    }
+    if (share == 0) break;
+  }
+  if (!fits) { delete plan; return fail(IOU_ERR_INVALID, "tile does not fit shared memory (block_n %d, residual %d): use a smaller block_n", d->block_n, d->res_mode); }
+  if (getenv("IOU_CONV_DEBUG"))
+    fprintf(stderr, "[iou_conv] cin %d cout %d taps %d block_n %d pair %d res %d staged %d | groups %d a_rows %d nA %d nB %d ring %d KB\n",
+            d->cin, d->cout, d->num_taps, d->block_n, P.two_cta, d->res_mode, P.staged, P.num_groups, P.a_rows,
+            P.num_a_stages, P.num_b_stages, P.ring_bytes / 1024);
   P.scale = d->scale; P.shift = d->shift; P.relu = d->relu; P.res_mode = d->res_mode;
   P.residual = (const __nv_bfloat16*)d->residual;
   P.out_mode = d->out_mode; P.out = (__nv_bfloat16*)d->out; P.dense_split = d->dense_split;
@@ -696,7 +792,7 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
             ((uint32_t)((P.two_cta ? 2 * kBlockM : kBlockM) >> 4) << 24);
   for (int i = 0; i < d->num_src; ++i) {
     if (!d->src[i] || ((uintptr_t)d->src[i] & 15)) { delete plan; return fail(IOU_ERR_INVALID, "src[%d] NULL or misaligned", i); }
-    if (int e = encode_2d(&P.tmap_src[i], d->src[i], (uint64_t)d->src_rows, (uint64_t)2 * d->cin, kBlockM)) { delete plan; return e; }
+    if (int e = encode_2d(&P.tmap_src[i], d->src[i], (uint64_t)d->src_rows, (uint64_t)2 * d->cin, (uint32_t)P.a_rows)) { delete plan; return e; }
   }
   for (int i = d->num_src; i < IOU_CONV_MAX_SRC; ++i) P.tmap_src[i] = P.tmap_src[0];
   P.tmap_out = P.tmap_w; P.tmap_res = P.tmap_w;
@@ -718,7 +814,7 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   } else {
     plan->grid = P.total_tiles < sms ? P.total_tiles : sms;
   }
-  plan->smem_bytes = (size_t)kCtrlBytes + 1024 + (size_t)stages * P.stage_bytes + (size_t)kNumEpiWarps * P.staging_per_warp;
+  plan->smem_bytes = (size_t)kCtrlBytes + 1024 + (size_t)P.ring_bytes + (size_t)kNumEpiWarps * P.staging_per_warp;
   plan->flops = 2.0 * real_rows * d->cout * (double)(P.diag_k ? kBlockK : d->cin) * d->num_taps;
   static bool attr_set = false;
   if (!attr_set) {
