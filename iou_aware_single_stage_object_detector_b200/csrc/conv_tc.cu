@@ -72,7 +72,8 @@ struct ConvParams {
   float* out_dense[IOU_CONV_MAX_SEG];
   float* out_dense2[IOU_CONV_MAX_SEG];
   int dense_split;
-  unsigned int idesc;
+  unsigned int idesc, idesc2;
+  int combine;               // narrow N: A_hi x [B_hi|B_lo] as ONE MMA of N = 2*block_n, A_lo x B_hi into a third column block
 };
 
 // ------------------------------------------------------------------------------------ PTX
@@ -215,6 +216,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// one lane of a converged warp (elect.sync): unlike `lane == 0`, the compiler knows the region is
+// single-threaded and emits tcgen05 / TMA instructions without a per-instruction ELECT loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ uint64_t umma_desc(uint32_t lo) { return ((uint64_t)0x40004040u << 32) | lo; }
 
@@ -288,7 +296,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    if (elect_one()) {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       const uint32_t mult = kTwoCta ? 2u : 1u;   // pair: both CTAs' loads complete on the LEADER's barrier
@@ -342,12 +350,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
     int as = 0, bs = 0;
     uint32_t aph = 0, bph = 0;
     int it = 0;
-    const int mode = P.passes == 3 ? (P.lolo ? 4 : 3) : 1;
+    const int mode = P.combine ? 5 : (P.passes == 3 ? (P.lolo ? 4 : 3) : 1);
     const uint32_t a_lo_d = a_lo_off >> 4, b_lo_d = b_lo_off >> 4;
-    auto mma = [&](uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t accum) {
-      if constexpr (kTwoCta) tc_mma_bf16_pair(d_tmem, ad, bd, P.idesc, accum);
-      else tc_mma_bf16(d_tmem, ad, bd, P.idesc, accum);
+    const uint32_t idesc = P.idesc, idesc2 = P.idesc2, col2 = 2u * (uint32_t)P.block_n;
+    auto mma_i = [&](uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t id, uint32_t accum) {
+      if constexpr (kTwoCta) tc_mma_bf16_pair(d_tmem, ad, bd, id, accum);
+      else tc_mma_bf16(d_tmem, ad, bd, id, accum);
     };
+    auto mma = [&](uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t accum) { mma_i(d_tmem, ad, bd, idesc, accum); };
     for (int tile = w_first; tile < w_total && rank == 0; tile += w_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
@@ -364,7 +374,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
           for (int j = 0; j < nt; ++j, ++done) {
             mbar_wait(bar_full + 8 * bs, bph);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
               // descriptor low words: (addr >> 4) | LBO; every operand lives below 256 KiB, so advancing an
               // address by x bytes is adding x >> 4 (the single issuing thread is the bottleneck of narrow-N
               // tiles: 12 MMAs of 128 x 64 x 16 retire in ~400 cycles, so the loop body is kept minimal)
@@ -372,7 +382,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
               const uint32_t da = umma_desc_lo(sa + (uint32_t)P.grp_shift[g][j] * 128u), db = umma_desc_lo(sb);
               const uint32_t dal = da + a_lo_d, dbl = db + b_lo_d;
               const uint32_t first = done > 0 ? 1u : 0u;
-              if (mode == 3) {
+              if (mode == 5) {
+                // back-to-back MMAs into the SAME accumulator serialise on its read-modify-write latency
+                // (~120 cycles, more than a 128 x 64 x 16 MMA computes for): B_hi and B_lo are adjacent in
+                // the B entry, so hi*hi and hi*lo are one N = 2*block_n MMA into columns [0, 2bn) and lo*hi
+                // goes to columns [2bn, 3bn); the epilogue adds the three column blocks
+#pragma unroll
+                for (uint32_t kk = 0; kk < kBlockK / 16; ++kk) {
+                  mma_i(d_tmem, umma_desc(da + 2 * kk), umma_desc(db + 2 * kk), idesc2, kk ? 1u : first);
+                  mma_i(d_tmem + col2, umma_desc(dal + 2 * kk), umma_desc(db + 2 * kk), idesc, kk ? 1u : first);
+                }
+              } else if (mode == 3) {
 #pragma unroll
                 for (uint32_t kk = 0; kk < kBlockK / 16; ++kk) {
                   mma(d_tmem, umma_desc(da + 2 * kk), umma_desc(db + 2 * kk), kk ? 1u : first);
@@ -419,7 +439,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
     const uint32_t st_out = tiles_addr + P.ring_bytes + ew * P.staging_per_warp;
     const uint32_t st_res = st_out + 4096;
     const uint32_t bar_res = ctrl_addr + 192 + ew * 16;
-    auto issue_res = [&](int tile_, int g_, int q_) {      // lane 0 only
+    auto issue_res = [&](int tile_, int g_, int q_) {      // one elected lane only
       int mt, nt, s_;
       decode_tile(tile_, mt, nt, s_);
       const int row = P.seg[s_].row_start + (mt - P.seg_tile_off[s_]) * kBlockM + lane_group * 32;
@@ -430,7 +450,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
       tma_load_2d(&P.tmap_res, bar, dst + 2048, P.cout + col, row);
     };
     int rq = 0;                                            // running slab counter of the residual ring
-    if (P.res_staged && lane == 0 && w_first < w_total) issue_res(w_first, half, 0);
+    if (P.res_staged && w_first < w_total && elect_one()) issue_res(w_first, half, 0);
     int it = 0;
     for (int tile = w_first; tile < w_total; tile += w_stride, ++it) {
       const int acc = it & 1;
@@ -463,6 +483,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
         uint32_t v[16];
         tc_ld16(t_row + ch * 16, v);
         tc_wait_ld();
+        if (P.combine) {                                   // sum the hi*hi, hi*lo and lo*hi column blocks
+          uint32_t w1[16], w2[16];
+          tc_ld16(t_row + P.block_n + ch * 16, w1);
+          tc_ld16(t_row + 2 * P.block_n + ch * 16, w2);
+          tc_wait_ld();
+#pragma unroll
+          for (int q = 0; q < 16; ++q)
+            v[q] = __float_as_uint(__uint_as_float(v[q]) + (__uint_as_float(w1[q]) + __uint_as_float(w2[q])));
+        }
         const int c0 = n_tile * P.block_n + ch * 16;      // first output channel of this chunk
         float f[16];
 #pragma unroll
@@ -519,7 +548,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
         for (int g = half; g < n_groups; g += 2, ++rq) {
           const int c0 = n_tile * P.block_n + g * 32;
           if (P.res_staged) {
-            if (lane == 0) {                               // prefetch this warp's next slab
+            if (elect_one()) {                             // prefetch this warp's next slab
               int nt = tile, ng = g + 2;
               if (ng >= n_groups) { nt = tile + w_stride; ng = half; }
               if (nt < w_total) issue_res(nt, ng, rq + 1);
@@ -531,6 +560,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
           const float sh_l = P.shift ? __ldg(P.shift + c0 + lane) : 0.f;
           const float sc_l = P.scale ? __ldg(P.scale + c0 + lane) : 1.f;
           tc_wait_ld();
+          if (P.combine) {                                 // sum the hi*hi, hi*lo and lo*hi column blocks
+            uint32_t w1[32];
+            tc_ld32(t_row + P.block_n + g * 32, w1);
+            tc_wait_ld();
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(w1[q]));
+            tc_ld32(t_row + 2 * P.block_n + g * 32, w1);
+            tc_wait_ld();
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(w1[q]));
+          }
           float f[32];
           if (P.scale) {
 #pragma unroll
@@ -591,7 +631,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
           }
           fence_async_smem();
           __syncwarp();
-          if (lane == 0 && tile_valid) {
+          if (tile_valid && elect_one()) {
             tma_store_2d(&P.tmap_out, st_out, c0, row_tile0);
             tma_store_2d(&P.tmap_out, st_out + 2048, P.cout + c0, row_tile0);
             tma_store_commit();
@@ -727,7 +767,7 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   P.total_tiles = P.num_m_tiles * P.num_n_tiles;
   // CTA-pair mode (tcgen05 cta_group::2): two CTAs of a cluster own two consecutive 128-row tiles and share
   // one BLOCK_N-wide B tile, each staging half of its rows -> half the B traffic per CTA and a deeper pipeline
-  P.two_cta = (d->two_cta && d->block_n % 32 == 0 && !d->diag_k) ? 1 : 0;
+  P.two_cta = (d->two_cta && d->block_n % 16 == 0 && !d->diag_k) ? 1 : 0;   // each CTA stages block_n/2 rows of B (whole 8-row swizzle atoms)
   P.total_pair_tiles = ((P.num_m_tiles + 1) / 2) * P.num_n_tiles;
   P.b_tile_bytes = (P.two_cta ? d->block_n / 2 : d->block_n) * kBlockK * 2;
   // padded-rows outputs leave through a per-warp 64B-swizzled staging tile (32 rows x 32 ch, hi + lo)
@@ -788,6 +828,8 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   P.residual = (const __nv_bfloat16*)d->residual;
   P.out_mode = d->out_mode; P.out = (__nv_bfloat16*)d->out; P.dense_split = d->dense_split;
   // cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=BF16 (1<<7, 1<<10), K-major both, N>>3 @17, M>>4 @24
+  P.combine = (d->passes == 3 && !P.two_cta && d->block_n <= 80 && !getenv("IOU_NO_COMBINE")) ? 1 : 0;
+  P.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * d->block_n) >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
   P.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d->block_n >> 3) << 17) |
             ((uint32_t)((P.two_cta ? 2 * kBlockM : kBlockM) >> 4) << 24);
   for (int i = 0; i < d->num_src; ++i) {

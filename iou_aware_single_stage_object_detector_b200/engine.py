@@ -153,7 +153,7 @@ class Engine(object):
         self.op_flops = {}
         import os
         self.two_cta = os.environ.get("IOU_TWO_CTA", "1") != "0"
-        self.pair_min_bn = int(os.environ.get("IOU_PAIR_MIN_BN", "240"))
+        self.pair_min_bn = int(os.environ.get("IOU_PAIR_MIN_BN", "64"))
         self.lib = L.load()
 
     # ------------------------------------------------------------------ primitive ops
@@ -193,7 +193,7 @@ class Engine(object):
         assert wp.shape == (len(taps) * cout_pad, 2 * (64 if diag_k else cin)), (name, wp.shape, len(taps), cout_pad, cin)
         d.diag_k = int(diag_k)
         # big maps with a wide N tile run as CTA pairs (cta_group::2): half the B traffic, deeper pipeline
-        d.two_cta = int(self.two_cta and not diag_k and block_n % 32 == 0 and block_n >= self.pair_min_bn
+        d.two_cta = int(self.two_cta and not diag_k and block_n % 16 == 0 and block_n >= self.pair_min_bn
                         and m_tiles >= NUM_SMS) if two_cta is None else int(two_cta)
         d.weight = wp.data_ptr()
 

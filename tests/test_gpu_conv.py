@@ -221,7 +221,10 @@ def test_grouped_conv_block_diagonal_vs_torch(width, groups, stride, hw):
                                                   (256, 256, 3, (1, 41, 59), False),     # odd: last pair half idle
                                                   (128, 512, 1, (2, 33, 47), False),     # two N tiles
                                                   (64, 128, 1, (2, 50, 70), True),       # residual ring, N tile 128
-                                                  (512, 256, 1, (3, 25, 42), False)])
+                                                  (512, 256, 1, (3, 25, 42), False),
+                                                  (64, 64, 3, (2, 50, 70), False),       # narrow N: 32 B rows per CTA
+                                                  (128, 128, 3, (1, 37, 53), False),
+                                                  (256, 64, 1, (2, 50, 70), False)])
 def test_cta_pair_mode_matches_torch(cin, cout, k, shape, res):
     """tcgen05 cta_group::2 path (a cluster of two CTAs shares the B tile) forced on small maps."""
     n, h, w = shape
