@@ -14,6 +14,7 @@ What each builder mirrors in the reference:
                                            mmdet/models/anchor_heads/iou_aware_retina_head.py:171-219
 """
 import ctypes
+import os
 
 import torch
 
@@ -124,10 +125,11 @@ def fold_scale(w, scale):
     return w.float() * scale.to(w.device).float().view(-1, 1, 1, 1)
 
 
-def pick_block_n(cout, m_tiles=None, max_bn=256):
+def pick_block_n(cout, m_tiles=None, max_bn=256, pair_min_tiles=None):
     """(block_n, cout_pad) for the tap-GEMM.  With the number of 128-row tiles known, the N tile is
     chosen to minimise waves x per-tile cost on 148 SMs (small maps get narrower tiles so that more
-    CTAs share the K loop; big maps keep N=256 so the A tile is loaded once)."""
+    CTAs share the K loop; big maps keep N=256 so the A tile is loaded once).  Maps with at least
+    `pair_min_tiles` tiles run as CTA pairs: the unit of work is then two 128-row tiles on one of 74 pairs."""
     if cout % 64 != 0:                       # head outputs: 720 -> 3 x 240, 45 -> 48
         if cout % 240 == 0:
             return 240, cout
@@ -138,8 +140,16 @@ def pick_block_n(cout, m_tiles=None, max_bn=256):
     cands = [bn for bn in (256, 128, 64) if cout % bn == 0 and bn <= max_bn]
     if m_tiles is None:
         return cands[0], cout
-    best = min(cands, key=lambda bn: (-(-(m_tiles * (cout // bn)) // NUM_SMS)) * (bn + 64))
-    return best, cout
+    pair = pair_min_tiles is not None and m_tiles >= pair_min_tiles
+
+    def cost(bn):
+        n_tiles = cout // bn
+        if pair:
+            waves = -(-(-(-m_tiles // 2) * n_tiles) // (NUM_SMS // 2))
+        else:
+            waves = -(-(m_tiles * n_tiles) // NUM_SMS)
+        return waves * (bn + 64)
+    return min(cands, key=cost), cout
 
 
 class Engine(object):
@@ -154,6 +164,7 @@ class Engine(object):
         import os
         self.two_cta = os.environ.get("IOU_TWO_CTA", "1") != "0"
         self.pair_min_bn = int(os.environ.get("IOU_PAIR_MIN_BN", "64"))
+        self.pair_min_tiles = int(os.environ.get("IOU_PAIR_MIN_TILES", "32"))
         self.lib = L.load()
 
     # ------------------------------------------------------------------ primitive ops
@@ -175,7 +186,9 @@ class Engine(object):
         geo = segs_from or srcs[0]
         m_tiles = sum(_round_up(n * (h + 2) * (w + 2), TILE_M) // TILE_M for (_, n, h, w) in geo.segs)
         # a same-geometry residual needs its TMA staging ring in shared memory: N tile <= 128
-        block_n, cout_pad = pick_block_n(cout, m_tiles, max_bn=128 if res_mode == L.RES_SAME else 256)
+        block_n, cout_pad = pick_block_n(cout, m_tiles, max_bn=128 if res_mode == L.RES_SAME else 256,
+                                         pair_min_tiles=self.pair_min_tiles if (self.two_cta and two_cta is None and
+                                                                                os.environ.get('IOU_PAIR_AWARE', '1') == '1') else None)
         if diag_k:
             block_n, cout_pad = 64, cout
         d = L.ConvDesc()
@@ -194,7 +207,7 @@ class Engine(object):
         d.diag_k = int(diag_k)
         # big maps with a wide N tile run as CTA pairs (cta_group::2): half the B traffic, deeper pipeline
         d.two_cta = int(self.two_cta and not diag_k and block_n % 16 == 0 and block_n >= self.pair_min_bn
-                        and m_tiles >= NUM_SMS) if two_cta is None else int(two_cta)
+                        and m_tiles >= self.pair_min_tiles) if two_cta is None else int(two_cta)
         d.weight = wp.data_ptr()
 
         def padc(v):
