@@ -105,6 +105,23 @@ size_t iou_nms_workspace_bytes(int n);
 int iou_nms(const float* dets, int n, float iou_thr, int64_t* keep_idx, int32_t* keep_count,
             void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ soft NMS ("next" row)
+ * Drop-in for mmdet.ops.nms.soft_nms_cpu.soft_nms_cpu (ops/nms/src/soft_nms_cpu.pyx:22-127; Python wrapper
+ * ops/nms/nms_wrapper.py:52-78).  dets [n][5] fp32 DEVICE rows (x1,y1,x2,y2,score); method 1 = linear,
+ * 2 = gaussian (the wrapper's method_codes), anything else the .pyx accepts = hard 0/1 weights (3 here).
+ * out_dets [n][5] receives the surviving rows with their decayed scores in SELECTION order, out_inds [n]
+ * (int64) their original row numbers, out_count the number of survivors.  n <= IOU_MAX_NMS_BOXES.
+ * Results are bit-identical to the reference's CPU loop, including its tie order (see csrc/postproc.cu). */
+int iou_soft_nms(const float* dets, int n, float iou_thr, int method, float sigma, float min_score,
+                 float* out_dets, int64_t* out_inds, int32_t* out_count, void* stream);
+
+/* multiclass_nms with nms_cfg = dict(type='soft_nms', iou_thr, method, sigma, min_score) for a whole batch
+ * (core/post_processing/bbox_nms.py:29-67 calling nms_wrapper.soft_nms per class).  Same buffers as
+ * iou_batched_nms; cfg->iou_thr is the soft-NMS iou_thr.  Rows of one class keep their selection order. */
+int iou_batched_soft_nms(const iou_postproc_cfg* cfg, int n_img, const float* boxes, const float* scores_cm,
+                         int method, float sigma, float min_score, float* dets, int64_t* labels,
+                         int32_t* counts, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ focal loss
  * Drop-in for sigmoid_focal_loss_cuda.forward / .backward
  * (ops/sigmoid_focal_loss/src/sigmoid_focal_loss.cpp:17-43,

@@ -14,5 +14,6 @@ from .anchor_head import AnchorHead
 from .iou_aware_retina_head import IoUawareRetinaHead
 from .retina_head import RetinaHead
 from .detectors import BaseDetector, SingleStageDetector, RetinaNet, FusedPlan
-from .ops import nms, soft_nms, sigmoid_focal_loss, SigmoidFocalLoss, nms_cuda, nms_cpu, sigmoid_focal_loss_cuda
+from .ops import (nms, soft_nms, sigmoid_focal_loss, SigmoidFocalLoss, nms_cuda, nms_cpu, soft_nms_cpu,
+                  sigmoid_focal_loss_cuda)
 from .engine_cache import invalidate_plans

@@ -18,9 +18,15 @@ def multiclass_nms(multi_bboxes, multi_scores, score_thr, nms_cfg, max_num=-1, s
         raise NotImplementedError("per-class boxes (n, C*4) are not on the RetinaNet path")
     cfg_ = dict(nms_cfg)
     nms_type = cfg_.pop('type', 'nms')
-    if nms_type != 'nms':
+    if nms_type not in ('nms', 'soft_nms'):
         raise NotImplementedError("nms type '%s' is outside the accelerated path" % nms_type)
     iou_thr = cfg_.get('iou_thr', 0.5)
+    soft = None
+    if nms_type == 'soft_nms':                 # nms_wrapper.soft_nms keyword defaults (nms_wrapper.py:52)
+        method = cfg_.get('method', 'linear')
+        if method not in PP.SOFT_NMS_METHODS:
+            raise ValueError('Invalid method for SoftNMS: {}'.format(method))
+        soft = (PP.SOFT_NMS_METHODS[method], float(cfg_.get('sigma', 0.5)), float(cfg_.get('min_score', 1e-3)))
     n, c1 = multi_scores.shape
     C = c1 - 1
     if n == 0 or C == 0:
@@ -42,6 +48,9 @@ def multiclass_nms(multi_bboxes, multi_scores, score_thr, nms_cfg, max_num=-1, s
         _ws_cache[key] = PP.PostprocWorkspace(cfg, 1, multi_bboxes.device)
     wsp = _ws_cache[key]
     with torch.cuda.device(multi_bboxes.device):
-        dets, labels, counts = PP.batched_nms(wsp, multi_bboxes.float().reshape(1, n, 4), scores_cm)
+        if soft is None:
+            dets, labels, counts = PP.batched_nms(wsp, multi_bboxes.float().reshape(1, n, 4), scores_cm)
+        else:
+            dets, labels, counts = PP.batched_soft_nms(wsp, multi_bboxes.float().reshape(1, n, 4), scores_cm, *soft)
     k = int(counts.item())
     return dets[0, :k].clone(), labels[0, :k].clone()

@@ -2,7 +2,7 @@
 
 nms                -> iou_nms                (ops/nms/nms_wrapper.py:8-49, nms_kernel.cu:70-131)
 sigmoid_focal_loss -> iou_sigmoid_focal_loss_* (ops/sigmoid_focal_loss/functions/sigmoid_focal_loss.py:8-42)
-soft_nms           -> not on the north-star path: importable, raises when called.
+soft_nms           -> iou_soft_nms           (ops/nms/nms_wrapper.py:52-78, ops/nms/src/soft_nms_cpu.pyx:22-127)
 There is no CPU implementation here: CPU tensors raise (the CPU path is the oracle's job).
 """
 import types
@@ -47,10 +47,41 @@ def nms(dets, iou_thr, device_id=None):
     return dets[inds, :], inds
 
 
+def _soft_nms_device(dets_np_or_tensor, iou_thr, method=1, sigma=0.5, min_score=0.001):
+    """Stands where the reference's Cython module function soft_nms_cpu.soft_nms_cpu stood (same arguments and
+    return order); the rows are processed on the current CUDA device."""
+    if isinstance(dets_np_or_tensor, np.ndarray):
+        if not torch.cuda.is_available():
+            raise RuntimeError("libiou_b200 implements soft_nms on a CUDA device only (no CPU fallback)")
+        d = torch.from_numpy(np.ascontiguousarray(dets_np_or_tensor, dtype=np.float32)).cuda()
+        new_dets, inds = PP.soft_nms_cuda(d, iou_thr, method, sigma, min_score)
+        return new_dets.cpu().numpy(), inds.cpu().numpy()
+    return PP.soft_nms_cuda(dets_np_or_tensor, iou_thr, method, sigma, min_score)
+
+
+soft_nms_cpu = types.SimpleNamespace(soft_nms_cpu=_soft_nms_device)
+
+
 def soft_nms(dets, iou_thr, method='linear', sigma=0.5, min_score=1e-3):
-    if method not in ('linear', 'gaussian'):
+    """Same contract as nms_wrapper.soft_nms (ops/nms/nms_wrapper.py:52-78): Tensor or ndarray in,
+    (new_dets with decayed scores, inds) out, in selection order.  CUDA tensors stay on their device; CPU
+    tensors raise (there is no CPU implementation in this library); ndarrays go through the current device."""
+    if isinstance(dets, torch.Tensor):
+        is_tensor = True
+        if not dets.is_cuda:
+            raise RuntimeError("libiou_b200 implements soft_nms for CUDA tensors only (no CPU fallback)")
+    elif isinstance(dets, np.ndarray):
+        is_tensor = False
+    else:
+        raise TypeError('dets must be either a Tensor or numpy array, but got {}'.format(type(dets)))
+    method_codes = PP.SOFT_NMS_METHODS
+    if method not in method_codes:
         raise ValueError('Invalid method for SoftNMS: {}'.format(method))
-    raise NotImplementedError("soft_nms is outside the accelerated path (SURVEY.md 8(f) rank 3)")
+    new_dets, inds = soft_nms_cpu.soft_nms_cpu(dets, iou_thr, method=method_codes[method], sigma=sigma,
+                                               min_score=min_score)
+    if is_tensor:
+        return new_dets.to(dets.dtype), inds
+    return new_dets.astype(np.float32), inds.astype(np.int64)
 
 
 class _FocalLossCuda(object):

@@ -723,7 +723,10 @@ __global__ void __launch_bounds__(1024) final_select_kernel(const __grid_constan
                                                             const int32_t* __restrict__ kept_cnt,
                                                             float* __restrict__ dets,
                                                             long long* __restrict__ labels,
-                                                            int32_t* __restrict__ counts) {
+                                                            int32_t* __restrict__ counts,
+                                                            const int rank_order) {
+  // rank_order (soft NMS): rows of a class keep their SELECTION order (the order soft_nms returns them in),
+  // so the unsorted key is (class, rank) and the candidate index is looked up again afterwards
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(smem_raw);   // [Pcap]
   __shared__ int s_off[257];
@@ -745,7 +748,8 @@ __global__ void __launch_bounds__(1024) final_select_kernel(const __grid_constan
       const unsigned long long key = kk[r];
       const unsigned int sbits = (unsigned int)(key >> 32);
       const unsigned int j = 0xffffffffu - (unsigned int)(key & 0xffffffffull);
-      const unsigned int pos = (unsigned int)c * (unsigned int)P.M + j;   // class-major, row-minor
+      const unsigned int pos = rank_order ? (unsigned int)(c * P.kcap + r)
+                                          : (unsigned int)c * (unsigned int)P.M + j;   // class-major, row-minor
       const int e = s_off[c] + r;
       // payload (pos) must survive the sort: by_score -> key = (score, ~pos); else key = (~pos, score)
       sortbuf[e] = by_score ? (((unsigned long long)sbits << 32) | (0xffffffffu - pos))
@@ -763,7 +767,14 @@ __global__ void __launch_bounds__(1024) final_select_kernel(const __grid_constan
       const unsigned int hi = (unsigned int)(key >> 32), lo = (unsigned int)(key & 0xffffffffull);
       const unsigned int sbits = by_score ? hi : lo;
       const unsigned int pos = 0xffffffffu - (by_score ? lo : hi);
-      const unsigned int c = pos / (unsigned int)P.M, j = pos - c * (unsigned int)P.M;
+      unsigned int c, j;
+      if (rank_order) {
+        c = pos / (unsigned int)P.kcap;
+        const unsigned long long k2 = kept_keys[((size_t)img * P.C + c) * P.kcap + (pos - c * (unsigned int)P.kcap)];
+        j = 0xffffffffu - (unsigned int)(k2 & 0xffffffffull);
+      } else {
+        c = pos / (unsigned int)P.M; j = pos - c * (unsigned int)P.M;
+      }
       const float4 b = __ldg(bx + j);
       d_out[r * 5 + 0] = b.x; d_out[r * 5 + 1] = b.y; d_out[r * 5 + 2] = b.z; d_out[r * 5 + 3] = b.w;
       d_out[r * 5 + 4] = ordered_to_float(sbits);
@@ -833,6 +844,225 @@ __global__ void __launch_bounds__(512) single_nms_kernel(const float* __restrict
     __syncthreads();
   }
   if (tid == 0) *keep_count = (int32_t)s_run;
+}
+
+
+// ---------------------------------------------------------------------------------------- soft NMS
+// Drop-in for soft_nms_cpu (mmdet/ops/nms/src/soft_nms_cpu.pyx:22-127), SURVEY 8(f) rank 3.  The reference is
+// a sequential in-place loop; what is kept here is its exact OUTPUT, including the order that its swap /
+// swap-with-last bookkeeping produces (that order decides ties between equal scores):
+//   select  : first maximum of score over positions [i, N)            (strict '<', :52)  -> block arg-max
+//   swap    : rows i <-> maxpos                                        (:57-72)
+//   rescore : every later box that overlaps the selected one           (:82-113)          -> one box per thread
+//   remove  : boxes whose new score < min_score; the sequential "overwrite with the last live box and look
+//             again" loop (:116-124) is a two-pointer partition: survivors in front stay where they are and the
+//             holes, in ascending order, receive the surviving boxes of the tail in DESCENDING position order
+// Precision follows the C that Cython generates: '+ 1' is emitted as the double 1.0, so areas and the union are
+// double expressions rounded to float once, iw*ih and the division are float, 1 - ov is a double subtraction;
+// np.exp runs in double on the float argument.  Explicit _rn intrinsics keep nvcc from contracting into FMAs.
+struct SoftSmem {
+  float4* box;           // [cap]
+  float* score;          // [cap]
+  int* idx;              // [cap] original row
+  int* list;             // [2*cap] holes | fillers
+  unsigned char* drop;   // [cap]
+};
+__host__ __device__ inline size_t soft_smem_bytes(int cap) { return (size_t)cap * (16 + 4 + 4 + 8 + 1) + 16; }
+__device__ __forceinline__ SoftSmem soft_carve(unsigned char* base, int cap) {
+  SoftSmem S;
+  S.box = reinterpret_cast<float4*>(base);
+  S.score = reinterpret_cast<float*>(base + (size_t)cap * 16);
+  S.idx = reinterpret_cast<int*>(base + (size_t)cap * 20);
+  S.list = reinterpret_cast<int*>(base + (size_t)cap * 24);
+  S.drop = base + (size_t)cap * 32;
+  return S;
+}
+
+__device__ __forceinline__ float soft_rescore(const float4 t, const double t_area, const float4 b, const float s,
+                                              const int method, const float thr, const float sigma, bool& touched) {
+  touched = false;
+  const float iw = (float)__dadd_rn((double)__fsub_rn(fminf(t.z, b.z), fmaxf(t.x, b.x)), 1.0);        // :91
+  if (!(iw > 0.f)) return s;
+  const float ih = (float)__dadd_rn((double)__fsub_rn(fminf(t.w, b.w), fmaxf(t.y, b.y)), 1.0);        // :93
+  if (!(ih > 0.f)) return s;
+  touched = true;
+  const float area = (float)__dmul_rn(__dadd_rn((double)__fsub_rn(b.z, b.x), 1.0),
+                                      __dadd_rn((double)__fsub_rn(b.w, b.y), 1.0));                    // :90
+  const float inter = __fmul_rn(iw, ih);
+  const float ua = (float)__dsub_rn(__dadd_rn(t_area, (double)area), (double)inter);                  // :95
+  const float ov = __fdiv_rn(inter, ua);                                                             // :96
+  float w;
+  if (method == 1) w = (ov > thr) ? (float)__dsub_rn(1.0, (double)ov) : 1.f;                         // :98-102
+  else if (method == 2) w = (float)exp((double)__fdiv_rn(-__fmul_rn(ov, ov), sigma));                // :103-104
+  else w = (ov > thr) ? 0.f : 1.f;                                                                   // :105-109
+  return __fmul_rn(w, s);                                                                            // :111
+}
+
+// Exclusive rank of `flag` among the block's threads (thread order) + block total; two barriers.
+__device__ __forceinline__ int block_rank(const bool flag, int* warp_cnt, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const unsigned int b = __ballot_sync(0xffffffffu, flag);
+  if (lane == 0) warp_cnt[warp] = __popc(b);
+  __syncthreads();
+  int off = 0, tot = 0;
+  for (int w = 0; w < nw; ++w) { const int c = warp_cnt[w]; tot += c; if (w < warp) off += c; }
+  __syncthreads();
+  total = tot;
+  return off + __popc(b & ((1u << lane) - 1u));
+}
+
+// Runs the loop on n boxes staged in S; returns the number of live boxes N (positions [0, N) hold the result in
+// selection order).  stop_after > 0 ends the loop after that many selections (later rows are then unfinished).
+__device__ int soft_nms_core(const SoftSmem S, const int n, const int stop_after, const int method,
+                             const float thr, const float sigma, const float min_score) {
+  __shared__ float w_s[32];
+  __shared__ int w_p[32], warp_cnt[32];
+  __shared__ int s_drops;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, T = blockDim.x, nw = T >> 5;
+  int N = n;
+  __syncthreads();
+  for (int i = 0; i < N; ++i) {
+    if (stop_after > 0 && i >= stop_after) break;
+    // ---- select: first maximum over [i, N)
+    float bs = -INFINITY;
+    int bp = 0x7fffffff;
+    for (int p = i + tid; p < N; p += T) {
+      const float s = S.score[p];
+      if (s > bs || bp == 0x7fffffff) { bs = s; bp = p; }       // ascending p per thread: strict > keeps the first
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int op = __shfl_xor_sync(0xffffffffu, bp, o);
+      if (op != 0x7fffffff && (bp == 0x7fffffff || os > bs || (os == bs && op < bp))) { bs = os; bp = op; }
+    }
+    if (lane == 0) { w_s[warp] = bs; w_p[warp] = bp; }
+    __syncthreads();
+    if (warp == 0) {
+      bs = lane < nw ? w_s[lane] : -INFINITY;
+      bp = lane < nw ? w_p[lane] : 0x7fffffff;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+        const int op = __shfl_xor_sync(0xffffffffu, bp, o);
+        if (op != 0x7fffffff && (bp == 0x7fffffff || os > bs || (os == bs && op < bp))) { bs = os; bp = op; }
+      }
+      if (lane == 0) {                                           // swap rows i <-> maxpos (:57-72)
+        const float4 tb = S.box[i]; const float ts = S.score[i]; const int ti = S.idx[i];
+        S.box[i] = S.box[bp]; S.score[i] = S.score[bp]; S.idx[i] = S.idx[bp];
+        S.box[bp] = tb; S.score[bp] = ts; S.idx[bp] = ti;
+        s_drops = 0;
+      }
+    }
+    __syncthreads();
+    // ---- rescore positions (i, N)
+    const float4 t = S.box[i];
+    const double t_area = __dmul_rn(__dadd_rn((double)__fsub_rn(t.z, t.x), 1.0), __dadd_rn((double)__fsub_rn(t.w, t.y), 1.0));
+    int my_drops = 0;
+    for (int p = i + 1 + tid; p < N; p += T) {
+      bool touched;
+      const float ns = soft_rescore(t, t_area, S.box[p], S.score[p], method, thr, sigma, touched);
+      S.score[p] = ns;
+      const bool d = touched && (ns < min_score);                // :114 (only rescored boxes are examined)
+      S.drop[p] = d ? 1 : 0;
+      my_drops += d ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_drops += __shfl_xor_sync(0xffffffffu, my_drops, o);
+    if (lane == 0 && my_drops) atomicAdd(&s_drops, my_drops);
+    __syncthreads();
+    const int D = s_drops;
+    if (D > 0) {
+      // ---- remove: two-pointer partition of (i, N)
+      const int Nn = N - D;
+      int H = 0, run = 0;
+      for (int base = i + 1; base < Nn; base += T) {             // holes, ascending
+        const int p = base + tid;
+        const bool f = p < Nn && S.drop[p];
+        int tot;
+        const int r = block_rank(f, warp_cnt, tot);
+        if (f) S.list[run + r] = p;
+        run += tot;
+      }
+      H = run; run = 0;
+      for (int base = 0; base < D; base += T) {                  // surviving tail boxes, descending
+        const int q = N - 1 - (base + tid);
+        const bool f = q >= Nn && !S.drop[q];
+        int tot;
+        const int r = block_rank(f, warp_cnt, tot);
+        if (f) S.list[n + run + r] = q;
+        run += tot;
+      }
+      __syncthreads();
+      for (int k = tid; k < H; k += T) {
+        const int dst = S.list[k], src = S.list[n + k];
+        S.box[dst] = S.box[src]; S.score[dst] = S.score[src]; S.idx[dst] = S.idx[src];
+      }
+      N = Nn;
+    }
+    __syncthreads();
+  }
+  return N;
+}
+
+__global__ void __launch_bounds__(1024) soft_nms_kernel(const float* __restrict__ dets, const int n, const float thr,
+                                                        const int method, const float sigma, const float min_score,
+                                                        float* __restrict__ out_dets, long long* __restrict__ out_inds,
+                                                        int32_t* __restrict__ out_count) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SoftSmem S = soft_carve(smem_raw, n);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    S.box[i] = make_float4(dets[(size_t)i * 5], dets[(size_t)i * 5 + 1], dets[(size_t)i * 5 + 2], dets[(size_t)i * 5 + 3]);
+    S.score[i] = dets[(size_t)i * 5 + 4];
+    S.idx[i] = i;
+  }
+  const int N = soft_nms_core(S, n, 0, method, thr, sigma, min_score);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float4 b = S.box[i];
+    out_dets[(size_t)i * 5] = b.x; out_dets[(size_t)i * 5 + 1] = b.y; out_dets[(size_t)i * 5 + 2] = b.z;
+    out_dets[(size_t)i * 5 + 3] = b.w; out_dets[(size_t)i * 5 + 4] = S.score[i];
+    out_inds[i] = (long long)S.idx[i];
+  }
+  if (threadIdx.x == 0) *out_count = N;
+}
+
+// multiclass_nms with nms_cfg type 'soft_nms' (bbox_nms.py:29-54): one CTA per (class, image).  Selection scores
+// never increase, so only the first max_per_img+1 selections of a class can reach the final top max_per_img.
+__global__ void __launch_bounds__(512) class_soft_nms_kernel(const __grid_constant__ PostParams P,
+                                                             const float* __restrict__ boxes,
+                                                             const float* __restrict__ scores_cm,
+                                                             unsigned long long* __restrict__ kept_keys,
+                                                             int32_t* __restrict__ kept_cnt, const int method,
+                                                             const float sigma, const float min_score) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SoftSmem S = soft_carve(smem_raw, P.M);
+  __shared__ int warp_cnt[32];
+  const int c = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
+  const float* sc = scores_cm + ((size_t)img * P.C + c) * P.M;
+  const float4* bx = reinterpret_cast<const float4*>(boxes) + (size_t)img * P.M;
+  int n = 0;
+  for (int base = 0; base < P.M; base += blockDim.x) {            // rows with score > score_thr, ascending (bbox_nms.py:37)
+    const int j = base + tid;
+    const float s = (j < P.M) ? __ldg(sc + j) : 0.f;
+    const bool pass = (j < P.M) && (s > P.score_thr);
+    int tot;
+    const int r = block_rank(pass, warp_cnt, tot);
+    if (pass) { S.box[n + r] = __ldg(bx + j); S.score[n + r] = s; S.idx[n + r] = j; }
+    n += tot;
+  }
+  int32_t* cnt_out = kept_cnt + (size_t)img * P.C + c;
+  if (n == 0) {
+    if (tid == 0) *cnt_out = 0;
+    return;
+  }
+  // S.list is indexed with the capacity the core is given; the staged count n <= P.M
+  const int N = soft_nms_core(S, n, P.kcap, method, P.iou_thr, sigma, min_score);
+  const int k = min(N, P.kcap);
+  unsigned long long* keys_out = kept_keys + ((size_t)img * P.C + c) * P.kcap;
+  for (int r = tid; r < k; r += blockDim.x)
+    keys_out[r] = ((unsigned long long)float_to_ordered(S.score[r]) << 32) |
+                  (unsigned long long)(0xffffffffu - (unsigned int)S.idx[r]);
+  if (tid == 0) *cnt_out = k;
 }
 
 // ---------------------------------------------------------------------------------------- host
@@ -956,7 +1186,7 @@ static int run_nms(const PostParams& P, const float* boxes, const float* scores_
   const size_t sm5 = (size_t)next_pow2_host(P.C * P.kcap) * 8 + 64;
   IOU_CHECK_CUDA(cudaFuncSetAttribute(final_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm5));
   final_select_kernel<<<P.n_img, 1024, sm5, st>>>(P, boxes, kept_keys, kept_cnt, dets,
-                                                   reinterpret_cast<long long*>(labels), counts);
+                                                   reinterpret_cast<long long*>(labels), counts, 0);
   return launch_status("final_select_kernel");
 }
 
@@ -1042,4 +1272,50 @@ extern "C" int iou_nms(const float* dets, int n, float iou_thr, int64_t* keep_id
   single_nms_kernel<<<1, 512, sm, st>>>(dets, n, iou_thr, reinterpret_cast<long long*>(keep_idx),
                                         keep_count, Pmax);
   return launch_status("single_nms_kernel");
+}
+
+extern "C" int iou_soft_nms(const float* dets, int n, float iou_thr, int method, float sigma, float min_score,
+                            float* out_dets, int64_t* out_inds, int32_t* out_count, void* stream) {
+  IOU_REQUIRE(n >= 0, "n must be >= 0");
+  IOU_REQUIRE(out_count != nullptr, "out_count is NULL");
+  IOU_REQUIRE(method >= 1 && method <= 3, "method must be 1 (linear), 2 (gaussian) or 3 (hard)");
+  IOU_REQUIRE(method != 2 || sigma != 0.f, "sigma must be non-zero for the gaussian method");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    IOU_CHECK_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int32_t), st));
+    return IOU_OK;
+  }
+  IOU_REQUIRE(dets && out_dets && out_inds, "NULL argument");
+  if (n > IOU_MAX_NMS_BOXES)
+    return fail(IOU_ERR_UNSUPPORTED, "iou_soft_nms supports at most %d boxes per call (got %d)", IOU_MAX_NMS_BOXES, n);
+  const size_t sm = soft_smem_bytes(n);
+  IOU_CHECK_CUDA(cudaFuncSetAttribute(soft_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)soft_smem_bytes(IOU_MAX_NMS_BOXES)));
+  soft_nms_kernel<<<1, n > 512 ? 1024 : 256, sm, st>>>(dets, n, iou_thr, method, sigma, min_score, out_dets,
+                                                       reinterpret_cast<long long*>(out_inds), out_count);
+  return launch_status("soft_nms_kernel");
+}
+
+extern "C" int iou_batched_soft_nms(const iou_postproc_cfg* cfg, int n_img, const float* boxes,
+                                    const float* scores_cm, int method, float sigma, float min_score,
+                                    float* dets, int64_t* labels, int32_t* counts, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  PostParams P;
+  if (int e = fill_params(cfg, n_img, P)) return e;
+  IOU_REQUIRE(boxes && scores_cm && dets && labels && counts, "NULL argument");
+  IOU_REQUIRE(method >= 1 && method <= 3, "method must be 1 (linear), 2 (gaussian) or 3 (hard)");
+  IOU_REQUIRE(method != 2 || sigma != 0.f, "sigma must be non-zero for the gaussian method");
+  PostWorkspace W = carve(P, workspace);
+  if (!workspace || workspace_bytes < W.total)
+    return fail(IOU_ERR_WORKSPACE, "workspace too small: need %zu bytes", W.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t sm = soft_smem_bytes(P.M);
+  IOU_CHECK_CUDA(cudaFuncSetAttribute(class_soft_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  class_soft_nms_kernel<<<dim3(P.C, P.n_img), 512, sm, st>>>(P, boxes, scores_cm, W.kept_keys, W.kept_cnt, method,
+                                                             sigma, min_score);
+  if (int e = launch_status("class_soft_nms_kernel")) return e;
+  const size_t sm5 = (size_t)next_pow2_host(P.C * P.kcap) * 8 + 64;
+  IOU_CHECK_CUDA(cudaFuncSetAttribute(final_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm5));
+  final_select_kernel<<<P.n_img, 1024, sm5, st>>>(P, boxes, W.kept_keys, W.kept_cnt, dets,
+                                                   reinterpret_cast<long long*>(labels), counts, 1);
+  return launch_status("final_select_kernel");
 }

@@ -114,6 +114,13 @@ _SIGS = {
     "iou_nms_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int]),
     "iou_nms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_void_p,
                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "iou_soft_nms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_float,
+                                    ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.c_void_p]),
+    "iou_batched_soft_nms": (ctypes.c_int, [ctypes.POINTER(PostprocCfg), ctypes.c_int, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_size_t, ctypes.c_void_p]),
     "iou_sigmoid_focal_loss_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                                       ctypes.c_int, ctypes.c_float, ctypes.c_float,
                                                       ctypes.c_void_p, ctypes.c_void_p]),

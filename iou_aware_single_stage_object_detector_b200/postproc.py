@@ -128,6 +128,41 @@ def batched_nms(wsp, boxes, scores_cm):
     return wsp.dets, wsp.labels, wsp.counts
 
 
+SOFT_NMS_METHODS = {'linear': 1, 'gaussian': 2}
+
+
+def batched_soft_nms(wsp, boxes, scores_cm, method=1, sigma=0.5, min_score=1e-3):
+    """Stage 2 with nms type 'soft_nms': same buffers as batched_nms (wsp.cfg.iou_thr is the soft-NMS iou_thr)."""
+    lib = L.load()
+    boxes, scores_cm = boxes.contiguous(), scores_cm.contiguous()
+    L.check(lib.iou_batched_soft_nms(ctypes.byref(wsp.cfg), wsp.n_img, boxes.data_ptr(), scores_cm.data_ptr(),
+                                     int(method), float(sigma), float(min_score),
+                                     wsp.dets.data_ptr(), wsp.labels.data_ptr(), wsp.counts.data_ptr(),
+                                     wsp.ws.data_ptr(), wsp.ws_bytes, L.stream_ptr()))
+    L.launch_count += 2
+    return wsp.dets, wsp.labels, wsp.counts
+
+
+def soft_nms_cuda(dets, iou_thr, method=1, sigma=0.5, min_score=1e-3):
+    """Device counterpart of soft_nms_cpu.soft_nms_cpu (ops/nms/src/soft_nms_cpu.pyx:22-127): returns
+    (new_dets (k,5) with decayed scores in selection order, inds (k,) int64), both on dets.device."""
+    if not dets.is_cuda:
+        raise RuntimeError("soft_nms_cuda: dets must be a CUDA tensor")
+    d = dets.detach().float().contiguous()
+    n = d.shape[0]
+    out = torch.empty(n, 5, dtype=torch.float32, device=d.device)
+    inds = torch.empty(n, dtype=torch.int64, device=d.device)
+    cnt = torch.zeros(1, dtype=torch.int32, device=d.device)
+    if n > 0:
+        with torch.cuda.device(d.device):
+            L.check(L.load().iou_soft_nms(d.data_ptr(), n, float(iou_thr), int(method), float(sigma),
+                                          float(min_score), out.data_ptr(), inds.data_ptr(), cnt.data_ptr(),
+                                          L.stream_ptr()))
+        L.launch_count += 1
+    k = int(cnt.item())
+    return out[:k], inds[:k]
+
+
 def split_results(dets, labels, counts):
     """One D2H sync: list[(Tensor(k,5), Tensor(k,))] as get_bboxes returns (:461)."""
     cnt = counts.cpu().tolist()

@@ -132,8 +132,12 @@ def iou_pair(a, b):
     return float(_lib().oracle_iou(a.ctypes.data, b.ctypes.data))
 
 
-def multiclass_nms(boxes, scores, score_thr, iou_thr, max_num, mode="cuda", return_index=False):
+def multiclass_nms(boxes, scores, score_thr, iou_thr, max_num, mode="cuda", return_index=False, soft=None):
     """mmdet/core/post_processing/bbox_nms.py:6-67.
+
+    soft = None: nms_cfg type 'nms'.  soft = dict(method=, sigma=, min_score=): type 'soft_nms'
+    (nms_wrapper.soft_nms per class, :48-54): rows of a class then come in soft-NMS selection order with
+    their decayed scores.
 
     boxes (n,4); scores (n, 1+C) with background column 0.  Returns dets (k,5),
     labels (k,) int64 and, if asked, the candidate row index of every det.
@@ -149,6 +153,13 @@ def multiclass_nms(boxes, scores, score_thr, iou_thr, max_num, mode="cuda", retu
         if rows.numel() == 0:
             continue
         d = torch.cat([boxes[rows], scores[rows, c, None]], dim=1)
+        if soft is not None:
+            from . import soft_nms as SN
+            nd, keep = SN.soft_nms(d.numpy(), iou_thr, **soft)
+            out_d.append(torch.from_numpy(nd))
+            out_l.append(torch.full((len(keep),), c - 1, dtype=torch.long))
+            out_i.append(rows[torch.from_numpy(keep)])
+            continue
         keep = nms(d, iou_thr, mode)
         out_d.append(d[keep])
         out_l.append(torch.full((keep.numel(),), c - 1, dtype=torch.long))

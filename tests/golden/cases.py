@@ -133,3 +133,30 @@ def _rows_iou(b, s, e):
     w = np.maximum(right - left + one, np.float32(0)); h = np.maximum(bot - top + one, np.float32(0))
     inter = w * h
     return inter / (area[s:e, None] + area[None, :] - inter)
+
+
+def soft_nms_inputs():
+    """name -> (dets (n,5) float32, iou_thr, method, sigma, min_score) for the Soft-NMS goldens: dense and
+    sparse scenes, duplicated scores (tie order), integer coordinates, every method and removal regime."""
+    rs = np.random.RandomState(20240607)
+    out = {}
+    specs = [("linear_64", 64, 200.0, 60.0, 0.5, 'linear', 0.5, 1e-3),
+             ("linear_dense_300", 300, 120.0, 80.0, 0.3, 'linear', 0.5, 0.05),
+             ("gauss_200", 200, 300.0, 100.0, 0.5, 'gaussian', 0.5, 1e-3),
+             ("gauss_dense_500", 500, 150.0, 90.0, 0.5, 'gaussian', 0.3, 0.05),
+             ("linear_ties_257", 257, 200.0, 70.0, 0.5, 'linear', 0.5, 0.02),
+             ("gauss_ties_int_129", 129, 100.0, 50.0, 0.7, 'gaussian', 1.0, 0.2),
+             ("linear_1", 1, 50.0, 20.0, 0.5, 'linear', 0.5, 1e-3),
+             ("linear_2", 2, 10.0, 20.0, 0.5, 'linear', 0.5, 0.3),
+             ("gauss_1500", 1500, 600.0, 120.0, 0.5, 'gaussian', 0.5, 1e-3)]
+    for name, n, extent, size, thr, method, sigma, min_score in specs:
+        d = random_dets(rs, n, extent, size)
+        if "ties" in name:
+            d[:, 4] = np.round(d[:, 4] * 16) / 16
+        if "int" in name:
+            d[:, :4] = np.round(d[:, :4])
+        out[name] = (d.astype(np.float32), thr, method, sigma, min_score)
+    return out
+
+
+SOFT_MULTICLASS = dict(type='soft_nms', iou_thr=0.5, method='linear', sigma=0.5, min_score=0.05)

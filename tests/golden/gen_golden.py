@@ -118,6 +118,30 @@ def main():
         np.savez_compressed(os.path.join(HERE, "postproc_%s.npz" % name), **out)
         print(name, {k: v.shape for k, v in out.items() if k.startswith("dets")})
     gen_plain_retina()
+    gen_soft_nms()
+
+
+def gen_soft_nms():
+    """the reference's own soft_nms (nms_wrapper.soft_nms -> soft_nms_cpu.pyx compiled with
+    Cython) on cases.soft_nms_inputs(), and its multiclass_nms with nms_cfg type 'soft_nms' on the candidates
+    of the 'small' get_bboxes case."""
+    ref_shim.load_reference()
+    nw = sys.modules["mmdet.ops.nms.nms_wrapper"]
+    from mmdet.core import multiclass_nms
+    out = {}
+    for name, (d, thr, method, sigma, min_score) in cases.soft_nms_inputs().items():
+        nd, inds = nw.soft_nms(d, thr, method=method, sigma=sigma, min_score=min_score)
+        out[name + "_dets"], out[name + "_inds"] = nd, inds
+    g = np.load(os.path.join(HERE, "postproc_small.npz"))
+    n_img = sum(1 for k in g.files if k.startswith("cand_boxes_"))
+    for i in range(n_img):
+        boxes = torch.from_numpy(g["cand_boxes_%d" % i])
+        scores = torch.from_numpy(g["cand_scores_%d" % i])
+        padded = torch.cat([scores.new_zeros(scores.shape[0], 1), scores], dim=1)
+        d, l = multiclass_nms(boxes, padded, 0.05, ref_shim._to_attr(dict(cases.SOFT_MULTICLASS)), 100)
+        out["mc_dets_%d" % i], out["mc_labels_%d" % i] = d.numpy(), l.numpy()
+    np.savez_compressed(os.path.join(HERE, "soft_nms.npz"), **out)
+    print("soft nms", {k: v.shape for k, v in out.items() if k.endswith("_dets") or k.startswith("mc_dets")})
 
 
 def gen_plain_retina():
@@ -147,5 +171,8 @@ def gen_plain_retina():
 if __name__ == "__main__":
     if "--plain-retina-only" in sys.argv:
         gen_plain_retina()
+        sys.exit(0)
+    if "--soft-nms-only" in sys.argv:
+        gen_soft_nms()
         sys.exit(0)
     main()

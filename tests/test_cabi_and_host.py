@@ -214,7 +214,10 @@ def test_all_gather_of_detections_world2_gloo():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29641
+    import socket
+    with socket.socket() as sk:            # a free port: a fixed one collides with a lingering earlier run
+        sk.bind(('127.0.0.1', 0))
+        port = sk.getsockname()[1]
     procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()

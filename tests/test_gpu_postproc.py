@@ -178,3 +178,73 @@ def test_plain_retina_head_get_bboxes_vs_reference_golden():
         gd, gl = gold["dets_%d" % i], gold["labels_%d" % i]
         assert d.shape[0] == gd.shape[0]
         U.match_as_sets(d.cpu().numpy(), l.cpu().numpy(), gd, gl, min_frac=0.97)
+
+
+# ------------------------------------------------------------------ Soft-NMS
+@pytest.mark.parametrize("name", list(cases.soft_nms_inputs().keys()))
+def test_soft_nms_bit_exact_vs_reference_golden(name):
+    """iou_soft_nms == the reference's soft_nms_cpu.pyx: survivors, order and decayed scores, bit for bit."""
+    g = np.load(os.path.join(U.GOLD, "soft_nms.npz"))
+    d, thr, method, sigma, min_score = cases.soft_nms_inputs()[name]
+    nd, inds = P.soft_nms(torch.from_numpy(d).cuda(), thr, method=method, sigma=sigma, min_score=min_score)
+    assert nd.is_cuda and inds.is_cuda and inds.dtype == torch.int64
+    assert np.array_equal(inds.cpu().numpy(), g[name + "_inds"])
+    assert np.array_equal(nd.cpu().numpy().view(np.uint32), g[name + "_dets"].view(np.uint32))
+    # numpy in -> numpy out (nms_wrapper.py:53-58,75-78)
+    nd2, i2 = P.soft_nms(d, thr, method=method, sigma=sigma, min_score=min_score)
+    assert isinstance(nd2, np.ndarray) and nd2.dtype == np.float32 and i2.dtype == np.int64
+    assert np.array_equal(i2, g[name + "_inds"])
+
+
+def test_soft_nms_random_vs_oracle_and_errors():
+    from oracle import soft_nms as SN
+    rs = np.random.RandomState(21)
+    for trial in range(40):
+        n = int(rs.choice([1, 2, 31, 33, 255, 256, 257, 600, 1025, 2500]))
+        d = cases.random_dets(rs, n, float(rs.choice([60., 300.])), float(rs.choice([40., 120.])))
+        if trial % 3 == 0:
+            d[:, 4] = np.round(d[:, 4] * 8) / 8                         # tie order must follow the swap bookkeeping
+        method = ['linear', 'gaussian'][trial % 2]
+        thr, sig, ms = float(rs.choice([0.3, 0.5])), float(rs.choice([0.3, 0.5])), float(rs.choice([1e-3, 0.05, 0.3]))
+        want_d, want_i = SN.soft_nms(d, thr, method=method, sigma=sig, min_score=ms)
+        got_d, got_i = P.soft_nms(torch.from_numpy(d).cuda(), thr, method=method, sigma=sig, min_score=ms)
+        assert np.array_equal(got_i.cpu().numpy(), want_i), (trial, n, method)
+        assert np.array_equal(got_d.cpu().numpy().view(np.uint32), want_d.view(np.uint32)), (trial, n, method)
+    e_d, e_i = P.soft_nms(torch.zeros(0, 5, device="cuda"), 0.5)
+    assert e_d.shape == (0, 5) and e_i.shape == (0,)
+    with pytest.raises(ValueError):
+        P.soft_nms(torch.zeros(3, 5, device="cuda"), 0.5, method='bogus')
+    with pytest.raises(TypeError):
+        P.soft_nms([[0, 0, 1, 1, 0.5]], 0.5)
+    with pytest.raises(RuntimeError):
+        P.soft_nms(torch.zeros(3, 5), 0.5)                               # CPU tensor: no fallback
+    with pytest.raises(RuntimeError):
+        P.soft_nms(torch.zeros(7000, 5, device="cuda"), 0.5)             # above IOU_MAX_NMS_BOXES
+
+
+def test_multiclass_soft_nms_vs_reference_golden():
+    """multiclass_nms(nms_cfg type 'soft_nms') == the reference's on the 'small' case candidates."""
+    g = np.load(os.path.join(U.GOLD, "soft_nms.npz"))
+    c = np.load(os.path.join(U.GOLD, "postproc_small.npz"))
+    for i in range(2):
+        boxes = torch.from_numpy(c["cand_boxes_%d" % i]).cuda()
+        scores = torch.from_numpy(c["cand_scores_%d" % i]).cuda()
+        padded = torch.cat([scores.new_zeros(scores.shape[0], 1), scores], dim=1)
+        d, l = P.multiclass_nms(boxes, padded, 0.05, dict(cases.SOFT_MULTICLASS), 100)
+        want_d, want_l = g["mc_dets_%d" % i], g["mc_labels_%d" % i]
+        # the final top-100 cut sorts by score (torch.sort, unstable in the reference): compare as sorted sets
+        assert d.shape == want_d.shape
+        key = lambda D, Lb: sorted(map(tuple, np.concatenate([D, Lb[:, None].astype(np.float32)], 1).tolist()))
+        assert key(d.cpu().numpy(), l.cpu().numpy()) == key(want_d, want_l)
+    # few candidates (no top-100 cut): class-major, selection order inside a class, exactly as the oracle
+    rs = np.random.RandomState(3)
+    n, C = 300, 8
+    boxes = cases.random_dets(rs, n, 300, 120)[:, :4]
+    scores = (rs.rand(n, C + 1) ** 8).astype(np.float32)
+    scores[:, 0] = 0
+    want_d, want_l = op.multiclass_nms(torch.from_numpy(boxes), torch.from_numpy(scores), 0.3, 0.5, 1000,
+                                       soft=dict(method='gaussian', sigma=0.5, min_score=0.05))
+    d, l = P.multiclass_nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), 0.3,
+                            dict(type='soft_nms', iou_thr=0.5, method='gaussian', sigma=0.5, min_score=0.05), 1000)
+    assert np.array_equal(l.cpu().numpy(), want_l.numpy())
+    assert np.array_equal(d.cpu().numpy().view(np.uint32), want_d.numpy().view(np.uint32))

@@ -118,3 +118,56 @@ def test_plain_retina_head_matches_reference():
                                     cases.STRIDES, bases, m["img_shape"], m["scale_factor"], cfg=case["cfg"],
                                     rescale=case["rescale"], nms_mode="cpu")
         assert np.array_equal(l.numpy(), gold["labels_%d" % i]) and np.array_equal(d.numpy(), gold["dets_%d" % i])
+
+
+# ------------------------------------------------------------------ Soft-NMS
+@pytest.mark.parametrize("name", list(cases.soft_nms_inputs().keys()))
+def test_soft_nms_oracle_matches_reference_pyx(name):
+    """oracle/soft_nms.py == the reference's own soft_nms_cpu.pyx (compiled with Cython) bit for bit:
+    decayed scores, survivors and their order."""
+    from oracle import soft_nms as SN
+    g = np.load(os.path.join(G, "soft_nms.npz"))
+    d, thr, method, sigma, min_score = cases.soft_nms_inputs()[name]
+    nd, inds = SN.soft_nms(d, thr, method=method, sigma=sigma, min_score=min_score)
+    assert nd.dtype == np.float32 and inds.dtype == np.int64
+    assert np.array_equal(inds, g[name + "_inds"])
+    assert np.array_equal(nd.view(np.uint32), g[name + "_dets"].view(np.uint32))
+
+
+def test_soft_nms_oracle_multiclass_matches_reference():
+    """multiclass_nms with nms_cfg type 'soft_nms' (bbox_nms.py:29-67) on the 'small' case candidates."""
+    g = np.load(os.path.join(G, "soft_nms.npz"))
+    c = np.load(os.path.join(G, "postproc_small.npz"))
+    cfg = dict(cases.SOFT_MULTICLASS)
+    for i in range(2):
+        boxes = torch.from_numpy(c["cand_boxes_%d" % i])
+        scores = torch.from_numpy(c["cand_scores_%d" % i])
+        padded = torch.cat([scores.new_zeros(scores.shape[0], 1), scores], dim=1)
+        d, l = op.multiclass_nms(boxes, padded, 0.05, cfg['iou_thr'], 100,
+                                 soft=dict(method=cfg['method'], sigma=cfg['sigma'], min_score=cfg['min_score']))
+        assert np.array_equal(l.numpy(), g["mc_labels_%d" % i])
+        assert np.array_equal(d.numpy().view(np.uint32), g["mc_dets_%d" % i].view(np.uint32))
+
+
+def test_soft_nms_oracle_rejects_unknown_method():
+    from oracle import soft_nms as SN
+    with pytest.raises(ValueError):
+        SN.soft_nms(np.zeros((1, 5), np.float32), 0.5, method='bogus')
+
+
+@pytest.mark.reference
+def test_soft_nms_oracle_vs_compiled_reference_random():
+    """Build-container only: 200 random scenes through oracle/_ref/soft_nms_cpu*.so and the oracle."""
+    from oracle import build_ref, soft_nms as SN
+    ref = build_ref.load_ref_soft_nms_cpu()
+    rs = np.random.RandomState(11)
+    for trial in range(200):
+        n = int(rs.randint(1, 250))
+        d = cases.random_dets(rs, n, float(rs.choice([50., 200., 600.])), float(rs.choice([30., 120.])))
+        if trial % 5 == 0:
+            d[:, 4] = np.round(d[:, 4] * 8) / 8
+        method = int(rs.randint(1, 4))
+        thr, sig, ms = float(rs.choice([0.3, 0.5, 0.7])), float(rs.choice([0.3, 0.5, 1.0])), float(rs.choice([1e-3, 0.05, 0.2]))
+        rb, ri = ref.soft_nms_cpu(d, thr, method=method, sigma=sig, min_score=ms)
+        ob, oi = SN.soft_nms_cpu(d, thr, method, sig, ms)
+        assert np.array_equal(ri, oi) and np.array_equal(rb.view(np.uint32), ob.view(np.uint32)), (trial, method, n)
