@@ -6,6 +6,7 @@ from .config import Config, ConfigDict
 from .anchor_generator import AnchorGenerator
 from .transforms import delta2bbox, bbox2result, multi_apply, ImageTransform
 from .bbox_nms import multiclass_nms
+from .results import batch_bbox2result, xyxy2xywh, det2json, results2json, dump_results
 from .losses import FocalLoss, SmoothL1Loss, CrossEntropyLoss
 from .conv_module import ConvModule, build_conv_layer, build_norm_layer
 from .resnet import ResNet, ResNeXt, Bottleneck, make_res_layer

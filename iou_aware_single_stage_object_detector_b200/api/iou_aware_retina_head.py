@@ -102,17 +102,26 @@ class IoUawareRetinaHead(AnchorHead):
     # ---- get_bboxes --------------------------------------------------------------------------
     def postproc_workspace(self, featmap_sizes, n_img, cfg, device):
         key = (tuple(featmap_sizes), n_img, cfg.get('nms_pre', -1), cfg['score_thr'],
-               cfg['nms'].get('iou_thr', 0.5), cfg['max_per_img'], str(device))
+               tuple(sorted(dict(cfg['nms']).items())), cfg['max_per_img'], str(device))
         if key not in self._post:
             nms_cfg = dict(cfg['nms'])
-            if nms_cfg.pop('type', 'nms') != 'nms':
-                raise NotImplementedError("only nms type 'nms' is on the accelerated path")
+            nms_type = nms_cfg.pop('type', 'nms')
+            if nms_type not in ('nms', 'soft_nms'):
+                raise NotImplementedError("nms type '%s' is not on the accelerated path" % nms_type)
+            soft = None
+            if nms_type == 'soft_nms':             # keyword defaults of nms_wrapper.soft_nms (nms_wrapper.py:52)
+                method = nms_cfg.get('method', 'linear')
+                if method not in PP.SOFT_NMS_METHODS:
+                    raise ValueError('Invalid method for SoftNMS: {}'.format(method))
+                soft = (PP.SOFT_NMS_METHODS[method], float(nms_cfg.get('sigma', 0.5)),
+                        float(nms_cfg.get('min_score', 1e-3)))
             pcfg = PP.make_cfg(featmap_sizes, self.anchor_strides,
                                [g.base_anchors for g in self.anchor_generators], self.cls_out_channels,
                                cfg.get('nms_pre', -1), cfg['max_per_img'], cfg['score_thr'],
                                nms_cfg.get('iou_thr', 0.5), self.target_means, self.target_stds, self.alpha)
             self._post.clear()
             self._post[key] = PP.PostprocWorkspace(pcfg, n_img, device)
+            self._post[key].soft = soft
         return self._post[key]
 
     def get_bboxes_device(self, cls_scores, bbox_preds, iou_preds, img_metas, cfg, rescale=False,
@@ -127,6 +136,11 @@ class IoUawareRetinaHead(AnchorHead):
         if img_info is None:
             img_info = PP.make_img_info(img_metas, dev)
         with torch.cuda.device(dev):
+            if getattr(wsp, 'soft', None) is not None:      # test_cfg.nms = dict(type='soft_nms', ...)
+                if iou_preds is None:
+                    iou_preds = [t.new_zeros((t.shape[0], self.num_anchors) + tuple(t.shape[-2:])) for t in cls_scores]
+                boxes, scores_cm, _ = PP.decode_candidates(wsp, cls_scores, bbox_preds, iou_preds, img_info, rescale)
+                return PP.batched_soft_nms(wsp, boxes, scores_cm, *wsp.soft)
             return PP.get_bboxes_device(wsp, cls_scores, bbox_preds, iou_preds, img_info, rescale)
 
     def get_bboxes(self, cls_scores, bbox_preds, iou_preds, gt_bboxes, gt_labels, img_metas, cfg,

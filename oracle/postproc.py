@@ -225,8 +225,13 @@ def get_bboxes_single(cls_maps, reg_maps, iou_maps, strides, bases, img_shape, s
         boxes = boxes / boxes.new_tensor(scale_factor)   # :553-554 (after the clamp)
     scores = torch.cat(ss)
     scores = torch.cat([scores.new_zeros(scores.shape[0], 1), scores], dim=1)  # :556-558
-    return multiclass_nms(boxes, scores, cfg["score_thr"], cfg["nms"]["iou_thr"],
-                          cfg["max_per_img"], nms_mode, return_index)
+    nms_cfg = dict(cfg["nms"])
+    soft = None
+    if nms_cfg.get("type", "nms") == "soft_nms":      # bbox_nms.py:29-31 -> nms_wrapper.soft_nms defaults
+        soft = dict(method=nms_cfg.get("method", "linear"), sigma=nms_cfg.get("sigma", 0.5),
+                    min_score=nms_cfg.get("min_score", 1e-3))
+    return multiclass_nms(boxes, scores, cfg["score_thr"], nms_cfg.get("iou_thr", 0.5),
+                          cfg["max_per_img"], nms_mode, return_index, soft=soft)
 
 
 def candidates_single(cls_maps, reg_maps, iou_maps, strides, bases, img_shape, scale_factor,

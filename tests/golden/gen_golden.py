@@ -119,6 +119,7 @@ def main():
         print(name, {k: v.shape for k, v in out.items() if k.startswith("dets")})
     gen_plain_retina()
     gen_soft_nms()
+    gen_results_json()
 
 
 def gen_soft_nms():
@@ -140,8 +141,34 @@ def gen_soft_nms():
         padded = torch.cat([scores.new_zeros(scores.shape[0], 1), scores], dim=1)
         d, l = multiclass_nms(boxes, padded, 0.05, ref_shim._to_attr(dict(cases.SOFT_MULTICLASS)), 100)
         out["mc_dets_%d" % i], out["mc_labels_%d" % i] = d.numpy(), l.numpy()
+    # the head's own get_bboxes with test_cfg.nms = dict(type='soft_nms', ...) on the 'small' case maps
+    head = ref_head()
+    case = cases.postproc_case("small")
+    cfgd = dict(case["cfg"])
+    cfgd["nms"] = dict(cases.SOFT_MULTICLASS)
+    n_img = case["cls"][0].shape[0]
+    with torch.no_grad():
+        res = head.get_bboxes(case["cls"], case["reg"], case["iou"], [torch.zeros(0, 4)] * n_img,
+                              [torch.zeros(0, dtype=torch.long)] * n_img, case["img_metas"],
+                              ref_shim._to_attr(cfgd), rescale=case["rescale"])
+    for i, (d, l) in enumerate(res):
+        out["gb_dets_%d" % i], out["gb_labels_%d" % i] = d.numpy(), l.numpy()
     np.savez_compressed(os.path.join(HERE, "soft_nms.npz"), **out)
     print("soft nms", {k: v.shape for k, v in out.items() if k.endswith("_dets") or k.startswith("mc_dets")})
+
+
+from gen_golden_fixtures import results_fixture  # noqa: E402
+
+
+def gen_results_json():
+    """the reference's det2json / xyxy2xywh (core/evaluation/coco_utils.py:78-117)."""
+    ref_shim.load_reference()
+    import json
+    from mmdet.core.evaluation.coco_utils import det2json
+    ds, results = results_fixture()
+    with open(os.path.join(HERE, "results_det2json.json"), "w") as f:
+        json.dump(det2json(ds, results), f)
+    print("results json written")
 
 
 def gen_plain_retina():
@@ -171,6 +198,9 @@ def gen_plain_retina():
 if __name__ == "__main__":
     if "--plain-retina-only" in sys.argv:
         gen_plain_retina()
+        sys.exit(0)
+    if "--results-only" in sys.argv:
+        gen_results_json()
         sys.exit(0)
     if "--soft-nms-only" in sys.argv:
         gen_soft_nms()

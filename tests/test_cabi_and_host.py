@@ -231,3 +231,37 @@ def test_all_gather_of_detections_world2_gloo():
             assert torch.equal(gd[src * 3:(src + 1) * 3], got[src][4])
             assert torch.equal(gl[src * 3:(src + 1) * 3], got[src][5])
             assert torch.equal(gc[src * 3:(src + 1) * 3], got[src][6])
+
+
+def test_result_formats_match_reference(tmp_path):
+    """det2json / xyxy2xywh / results2json vs the golden written by the reference's own functions
+    (tests/golden/gen_golden.py::gen_results_json); batch_bbox2result == per-image bbox2result."""
+    import json
+    import pickle
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import gen_golden_fixtures as GF
+    ds, results = GF.results_fixture()
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "results_det2json.json")))
+    assert P.det2json(ds, results) == want
+    out = str(tmp_path / "r.pkl.json")
+    assert P.results2json(ds, results, out) == want and json.load(open(out)) == want
+    P.dump_results(results, str(tmp_path / "r.pkl"))
+    back = pickle.load(open(str(tmp_path / "r.pkl"), "rb"))
+    assert all(np.array_equal(a, b) for ra, rb in zip(results, back) for a, b in zip(ra, rb))
+    with pytest.raises(TypeError):
+        P.results2json(ds, [3], out)
+    with pytest.raises(TypeError):
+        P.dump_results(results, str(tmp_path / "r.txt"))
+    # padded batch tensors -> per-image per-class arrays
+    rs = np.random.RandomState(2)
+    n, K = 3, 100
+    dets = rs.rand(n, K, 5).astype(np.float32)
+    labels = rs.randint(0, 80, size=(n, K)).astype(np.int64)
+    counts = np.array([100, 0, 37], dtype=np.int32)
+    got = P.batch_bbox2result(torch.from_numpy(dets), torch.from_numpy(labels), torch.from_numpy(counts), 81)
+    for i in range(n):
+        k = counts[i]
+        want_i = P.bbox2result(torch.from_numpy(dets[i, :k]), torch.from_numpy(labels[i, :k]), 81)
+        assert len(got[i]) == 80
+        for a, b in zip(got[i], want_i):
+            assert a.dtype == np.float32 and a.shape == b.shape and np.array_equal(a, b)

@@ -248,3 +248,26 @@ def test_multiclass_soft_nms_vs_reference_golden():
                             dict(type='soft_nms', iou_thr=0.5, method='gaussian', sigma=0.5, min_score=0.05), 1000)
     assert np.array_equal(l.cpu().numpy(), want_l.numpy())
     assert np.array_equal(d.cpu().numpy().view(np.uint32), want_d.numpy().view(np.uint32))
+
+
+def test_head_get_bboxes_with_soft_nms_test_cfg():
+    """IoUawareRetinaHead.get_bboxes with test_cfg.nms = dict(type='soft_nms', ...) vs the reference's own
+    output on the 'small' case maps (scores/boxes within the fp32 tolerance of the decode stage)."""
+    g = np.load(os.path.join(U.GOLD, "soft_nms.npz"))
+    case = cases.postproc_case("small")
+    cfgd = dict(case["cfg"])
+    cfgd["nms"] = dict(cases.SOFT_MULTICLASS)
+    head = U.get_head()
+    dev = torch.device("cuda:0")
+    n_img = case["cls"][0].shape[0]
+    res = head.get_bboxes([t.to(dev) for t in case["cls"]], [t.to(dev) for t in case["reg"]],
+                          [t.to(dev) for t in case["iou"]], [None] * n_img, [None] * n_img, case["img_metas"],
+                          P.ConfigDict(cfgd), rescale=case["rescale"])
+    for i, (d, l) in enumerate(res):
+        gd, gl = g["gb_dets_%d" % i], g["gb_labels_%d" % i]
+        assert d.shape == gd.shape and l.dtype == torch.int64
+        d, l = d.cpu().numpy(), l.cpu().numpy()
+        o1 = np.lexsort((d[:, 0], l, -d[:, 4]))
+        o2 = np.lexsort((gd[:, 0], gl, -gd[:, 4]))
+        assert np.array_equal(l[o1], gl[o2])
+        assert np.allclose(d[o1], gd[o2], rtol=U.RTOL, atol=U.ATOL), np.abs(d[o1] - gd[o2]).max()

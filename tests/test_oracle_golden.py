@@ -171,3 +171,18 @@ def test_soft_nms_oracle_vs_compiled_reference_random():
         rb, ri = ref.soft_nms_cpu(d, thr, method=method, sigma=sig, min_score=ms)
         ob, oi = SN.soft_nms_cpu(d, thr, method, sig, ms)
         assert np.array_equal(ri, oi) and np.array_equal(rb.view(np.uint32), ob.view(np.uint32)), (trial, method, n)
+
+
+def test_soft_nms_oracle_get_bboxes_matches_reference():
+    """get_bboxes with test_cfg.nms type 'soft_nms' on the 'small' case vs the reference's own output."""
+    g = np.load(os.path.join(G, "soft_nms.npz"))
+    case = cases.postproc_case("small")
+    cfgd = dict(case["cfg"])
+    cfgd["nms"] = dict(cases.SOFT_MULTICLASS)
+    strides, bases = [8, 16, 32, 64, 128], _bases()
+    for i, meta in enumerate(case["img_metas"]):
+        d, l = op.get_bboxes_single([t[i] for t in case["cls"]], [t[i] for t in case["reg"]],
+                                    [t[i] for t in case["iou"]], strides, bases, meta["img_shape"],
+                                    meta["scale_factor"], cfgd, rescale=case["rescale"], nms_mode="cpu")
+        assert np.array_equal(l.numpy(), g["gb_labels_%d" % i])
+        assert np.array_equal(d.numpy().view(np.uint32), g["gb_dets_%d" % i].view(np.uint32))
