@@ -62,7 +62,12 @@ typedef struct iou_postproc_cfg {
   float score_thr;                         /* test_cfg.score_thr (strict >)                   */
   float iou_thr;                           /* test_cfg.nms.iou_thr (strict >, nms_kernel.cu:60)*/
   float wh_ratio_clip;                     /* delta2bbox wh_ratio_clip, 16/1000               */
+  int32_t decode_mode;                     /* IOU_DECODE_DELTA: anchors + delta2bbox (transforms.py:44-78);
+                                              IOU_DECODE_DISTANCE: FCOS points (x*s + s/2, y*s + s/2) +
+                                              distance2bbox (transforms.py:169-190, iou_aware_fcos_head.py:392-401),
+                                              num_anchors must be 1 and reg holds (l, t, r, b) distances   */
 } iou_postproc_cfg;
+enum { IOU_DECODE_DELTA = 0, IOU_DECODE_DISTANCE = 1 };
 
 /* Number of candidate rows per image that enter NMS: sum_l min(H_l*W_l*A, nms_pre). */
 int iou_postproc_num_candidates(const iou_postproc_cfg* cfg);

@@ -14,6 +14,7 @@ from .fpn import FPN
 from .anchor_head import AnchorHead
 from .iou_aware_retina_head import IoUawareRetinaHead
 from .retina_head import RetinaHead
+from .iou_aware_fcos_head import IoUawareFCOSHead
 from .detectors import BaseDetector, SingleStageDetector, RetinaNet, FusedPlan
 from .ops import (nms, soft_nms, sigmoid_focal_loss, SigmoidFocalLoss, nms_cuda, nms_cpu, soft_nms_cpu,
                   sigmoid_focal_loss_cuda)

@@ -10,7 +10,8 @@ import torch.nn as nn
 
 from .weight_init import constant_init, kaiming_init
 
-_NORMS = {'BN': ('bn', nn.BatchNorm2d), 'SyncBN': ('bn', nn.BatchNorm2d)}
+# GN is a parameter container only (IoUawareFCOSHead): the conv engine does not plan GroupNorm layers
+_NORMS = {'BN': ('bn', nn.BatchNorm2d), 'SyncBN': ('bn', nn.BatchNorm2d), 'GN': ('gn', nn.GroupNorm)}
 
 
 def build_norm_layer(cfg, num_features, postfix=''):
@@ -22,7 +23,11 @@ def build_norm_layer(cfg, num_features, postfix=''):
     abbr, cls = _NORMS[layer_type]
     requires_grad = cfg_.pop('requires_grad', True)
     cfg_.setdefault('eps', 1e-5)
-    layer = cls(num_features, **cfg_)
+    if layer_type == 'GN':                      # norm.py:48-50
+        assert 'num_groups' in cfg_
+        layer = cls(num_channels=num_features, **cfg_)
+    else:
+        layer = cls(num_features, **cfg_)
     for p in layer.parameters():
         p.requires_grad = requires_grad
     return abbr + str(postfix), layer

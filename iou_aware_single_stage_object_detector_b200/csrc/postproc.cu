@@ -35,7 +35,7 @@ struct PostParams {
   float base[IOU_MAX_LEVELS][IOU_MAX_ANCHORS][4];
   float mean[4], stdv[4];
   float alpha, score_thr, iou_thr, max_ratio;
-  int rescale;
+  int rescale, decode_mode;
 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
@@ -390,6 +390,13 @@ __global__ void __launch_bounds__(256) gather_decode_kernel(const __grid_constan
       const float ax1 = __fadd_rn(P.base[l][a][0], sx), ay1 = __fadd_rn(P.base[l][a][1], sy);
       const float ax2 = __fadd_rn(P.base[l][a][2], sx), ay2 = __fadd_rn(P.base[l][a][3], sy);
       const float4 d = __ldg(reinterpret_cast<const float4*>(P.reg[l]) + row);
+      float x1, y1, x2, y2;
+      if (P.decode_mode == IOU_DECODE_DISTANCE) {
+        // FCOS point (iou_aware_fcos_head.py:392-401) + distance2bbox (transforms.py:181-184)
+        const float ptx = __fadd_rn(sx, (float)(P.stride[l] / 2)), pty = __fadd_rn(sy, (float)(P.stride[l] / 2));
+        x1 = __fsub_rn(ptx, d.x); y1 = __fsub_rn(pty, d.y);
+        x2 = __fadd_rn(ptx, d.z); y2 = __fadd_rn(pty, d.w);
+      } else {
       // delta2bbox (transforms.py:44-78)
       const float dx = __fadd_rn(__fmul_rn(d.x, P.stdv[0]), P.mean[0]);
       const float dy = __fadd_rn(__fmul_rn(d.y, P.stdv[1]), P.mean[1]);
@@ -402,8 +409,9 @@ __global__ void __launch_bounds__(256) gather_decode_kernel(const __grid_constan
       const float gw = __fmul_rn(pw, expf(dw)), gh = __fmul_rn(ph, expf(dh));
       const float gx = __fadd_rn(px, __fmul_rn(pw, dx)), gy = __fadd_rn(py, __fmul_rn(ph, dy));
       const float hw = __fmul_rn(gw, 0.5f), hh = __fmul_rn(gh, 0.5f);
-      float x1 = __fadd_rn(__fsub_rn(gx, hw), 0.5f), y1 = __fadd_rn(__fsub_rn(gy, hh), 0.5f);
-      float x2 = __fsub_rn(__fadd_rn(gx, hw), 0.5f), y2 = __fsub_rn(__fadd_rn(gy, hh), 0.5f);
+      x1 = __fadd_rn(__fsub_rn(gx, hw), 0.5f); y1 = __fadd_rn(__fsub_rn(gy, hh), 0.5f);
+      x2 = __fsub_rn(__fadd_rn(gx, hw), 0.5f); y2 = __fsub_rn(__fadd_rn(gy, hh), 0.5f);
+      }
       const float xmax = __fsub_rn(info[1], 1.0f), ymax = __fsub_rn(info[0], 1.0f);
       x1 = clampf_(x1, 0.f, xmax); y1 = clampf_(y1, 0.f, ymax);
       x2 = clampf_(x2, 0.f, xmax); y2 = clampf_(y2, 0.f, ymax);
@@ -1111,6 +1119,9 @@ static int fill_params(const iou_postproc_cfg* cfg, int n_img, PostParams& P) {
   for (int q = 0; q < 4; ++q) { P.mean[q] = cfg->target_means[q]; P.stdv[q] = cfg->target_stds[q]; }
   P.alpha = cfg->alpha; P.score_thr = cfg->score_thr; P.iou_thr = cfg->iou_thr;
   P.max_ratio = (float)fabs(log((double)cfg->wh_ratio_clip));
+  IOU_REQUIRE(cfg->decode_mode == IOU_DECODE_DELTA || cfg->decode_mode == IOU_DECODE_DISTANCE, "bad decode_mode %d", cfg->decode_mode);
+  IOU_REQUIRE(cfg->decode_mode == IOU_DECODE_DELTA || cfg->num_anchors == 1, "distance decoding needs num_anchors == 1");
+  P.decode_mode = cfg->decode_mode;
   return IOU_OK;
 }
 

@@ -61,6 +61,9 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+DECODE_DELTA, DECODE_DISTANCE = 0, 1      # iou_postproc_cfg.decode_mode
+
+
 class PostprocCfg(ctypes.Structure):
     _fields_ = [("num_levels", ctypes.c_int32), ("num_anchors", ctypes.c_int32),
                 ("num_classes", ctypes.c_int32), ("nms_pre", ctypes.c_int32),
@@ -70,7 +73,7 @@ class PostprocCfg(ctypes.Structure):
                 ("base_anchors", ((ctypes.c_float * 4) * MAX_ANCHORS) * MAX_LEVELS),
                 ("target_means", ctypes.c_float * 4), ("target_stds", ctypes.c_float * 4),
                 ("alpha", ctypes.c_float), ("score_thr", ctypes.c_float), ("iou_thr", ctypes.c_float),
-                ("wh_ratio_clip", ctypes.c_float)]
+                ("wh_ratio_clip", ctypes.c_float), ("decode_mode", ctypes.c_int32)]
 
 
 class ConvSegment(ctypes.Structure):

@@ -13,8 +13,9 @@ from . import lib as L
 
 def make_cfg(feat_sizes, strides, base_anchors, num_classes, nms_pre, max_per_img, score_thr, iou_thr,
              target_means=(0., 0., 0., 0.), target_stds=(1., 1., 1., 1.), alpha=0.5,
-             wh_ratio_clip=16 / 1000):
+             wh_ratio_clip=16 / 1000, decode_mode=0):
     cfg = L.PostprocCfg()
+    cfg.decode_mode = int(decode_mode)
     cfg.num_levels = len(feat_sizes)
     cfg.num_anchors = int(base_anchors[0].shape[0])
     cfg.num_classes = int(num_classes)

@@ -234,6 +234,58 @@ def get_bboxes_single(cls_maps, reg_maps, iou_maps, strides, bases, img_shape, s
                           cfg["max_per_img"], nms_mode, return_index, soft=soft)
 
 
+def distance2bbox(points, distance, max_shape=None):
+    """mmdet/core/bbox/transforms.py:169-190."""
+    x1 = points[:, 0] - distance[:, 0]
+    y1 = points[:, 1] - distance[:, 1]
+    x2 = points[:, 0] + distance[:, 2]
+    y2 = points[:, 1] + distance[:, 3]
+    if max_shape is not None:
+        x1 = x1.clamp(min=0, max=max_shape[1] - 1)
+        y1 = y1.clamp(min=0, max=max_shape[0] - 1)
+        x2 = x2.clamp(min=0, max=max_shape[1] - 1)
+        y2 = y2.clamp(min=0, max=max_shape[0] - 1)
+    return torch.stack([x1, y1, x2, y2], -1)
+
+
+def fcos_points(feat_h, feat_w, stride):
+    """IoUawareFCOSHead.get_points_single (iou_aware_fcos_head.py:392-401): (x*s + s//2, y*s + s//2), row-major."""
+    xs = torch.arange(0, feat_w * stride, stride, dtype=torch.float32)
+    ys = torch.arange(0, feat_h * stride, stride, dtype=torch.float32)
+    y, x = torch.meshgrid(ys, xs, indexing="ij")
+    return torch.stack((x.reshape(-1), y.reshape(-1)), dim=-1) + stride // 2
+
+
+def fcos_get_bboxes_single(cls_maps, reg_maps, iou_maps, strides, img_shape, scale_factor, cfg, rescale=False,
+                           num_classes=80, alpha=0.3, nms_mode="cuda", return_candidates=False):
+    """IoUawareFCOSHead.get_bboxes_single (iou_aware_fcos_head.py:270-366) for one image: score =
+    sigmoid(cls)^alpha * sigmoid(iou)^(1-alpha) (:312-316), per-level top-k of the best class (:321-331),
+    distance2bbox (:332), rescale after the clamp (:338-339), multiclass_nms (:347-352).  The centerness maps
+    do not enter the result (their uses are commented out in the reference)."""
+    bs, ss, ii = [], [], []
+    nms_pre = cfg.get("nms_pre", -1)
+    for c, r, q, s in zip(cls_maps, reg_maps, iou_maps, strides):
+        scores = c.permute(1, 2, 0).reshape(-1, num_classes).sigmoid()
+        iou = q.permute(1, 2, 0).reshape(-1).sigmoid()
+        scores = scores.pow(alpha) * iou.view(-1, 1).expand(-1, scores.size(-1)).pow(1 - alpha)
+        bbox_pred = r.permute(1, 2, 0).reshape(-1, 4)
+        points = fcos_points(c.shape[-2], c.shape[-1], s)
+        idx = torch.arange(scores.shape[0])
+        if nms_pre > 0 and scores.shape[0] > nms_pre:
+            idx = scores.max(dim=1)[0].topk(nms_pre)[1]
+        bs.append(distance2bbox(points[idx], bbox_pred[idx], max_shape=img_shape))
+        ss.append(scores[idx])
+        ii.append(idx)
+    boxes = torch.cat(bs)
+    if rescale:
+        boxes = boxes / boxes.new_tensor(scale_factor)
+    scores = torch.cat(ss)
+    if return_candidates:
+        return boxes, scores, torch.cat(ii)
+    padded = torch.cat([scores.new_zeros(scores.shape[0], 1), scores], dim=1)
+    return multiclass_nms(boxes, padded, cfg["score_thr"], cfg["nms"]["iou_thr"], cfg["max_per_img"], nms_mode)
+
+
 def candidates_single(cls_maps, reg_maps, iou_maps, strides, bases, img_shape, scale_factor,
                       nms_pre, rescale=False, num_classes=80, **kw):
     """The (boxes (M,4), scores (M,C), level-local index (M,)) that enter multiclass_nms."""

@@ -160,3 +160,27 @@ def soft_nms_inputs():
 
 
 SOFT_MULTICLASS = dict(type='soft_nms', iou_thr=0.5, method='linear', sigma=0.5, min_score=0.05)
+
+
+FCOS_STRIDES = (8, 16, 32, 64, 128)
+
+
+def fcos_case():
+    """Maps for IoUawareFCOSHead.get_bboxes: one location per cell, 80 class logits,
+    positive (l, t, r, b) distances (the head's forward already applied exp, iou_aware_fcos_head.py:108),
+    centerness and IoU logits; 2 images of different test scales."""
+    rs = np.random.RandomState(4321)
+    sizes = level_sizes(224, 288)
+    cls, reg, cen, iou = [], [], [], []
+    for (h, w), s in zip(sizes, FCOS_STRIDES):
+        cls.append(torch.from_numpy((rs.randn(2, 80, h, w) * 2.0 - 3.0).astype(np.float32)))
+        reg.append(torch.from_numpy(np.exp(rs.randn(2, 4, h, w) * 0.6 + np.log(1.5 * s)).astype(np.float32)))
+        cen.append(torch.from_numpy(rs.randn(2, 1, h, w).astype(np.float32)))
+        iou.append(torch.from_numpy((rs.randn(2, 1, h, w) * 1.5).astype(np.float32)))
+    cfg = dict(TEST_CFG)
+    cfg["nms_pre"] = 300
+    metas = [dict(ori_shape=(125, 163, 3), img_shape=(200, 261, 3), pad_shape=(224, 288, 3), scale_factor=1.6,
+                  flip=False),
+             dict(ori_shape=(238, 313, 3), img_shape=(190, 250, 3), pad_shape=(224, 288, 3), scale_factor=0.8,
+                  flip=False)]
+    return dict(cls=cls, reg=reg, cen=cen, iou=iou, img_metas=metas, cfg=cfg, rescale=True, sizes=sizes)

@@ -120,6 +120,7 @@ def main():
     gen_plain_retina()
     gen_soft_nms()
     gen_results_json()
+    gen_fcos()
 
 
 def gen_soft_nms():
@@ -160,6 +161,46 @@ def gen_soft_nms():
 from gen_golden_fixtures import results_fixture  # noqa: E402
 
 
+def gen_fcos():
+    """the reference IoUawareFCOSHead.get_bboxes on cases.fcos_case(), plus the candidates
+    that enter multiclass_nms (re-running the reference's own statements, iou_aware_fcos_head.py:303-339)."""
+    ref_shim.load_reference()
+    from mmdet.models.anchor_heads import IoUawareFCOSHead
+    from mmdet.core import distance2bbox
+    torch.manual_seed(0)
+    head = IoUawareFCOSHead(num_classes=81, in_channels=256, stacked_convs=4, feat_channels=256,
+                            strides=list(cases.FCOS_STRIDES))
+    case = cases.fcos_case()
+    cfg = ref_shim._to_attr(case["cfg"])
+    n_img = case["cls"][0].shape[0]
+    with torch.no_grad():
+        res = head.get_bboxes(case["cls"], case["reg"], case["cen"], case["iou"], [torch.zeros(0, 4)] * n_img,
+                              [torch.zeros(0, dtype=torch.long)] * n_img, case["img_metas"], cfg,
+                              rescale=case["rescale"])
+    out = {}
+    for i, (d, l) in enumerate(res):
+        out["dets_%d" % i], out["labels_%d" % i] = d.numpy(), l.numpy()
+    points = head.get_points([t.shape[-2:] for t in case["cls"]], torch.float32, torch.device("cpu"))
+    for i in range(n_img):
+        bs, ss, ii = [], [], []
+        for l in range(len(case["cls"])):
+            scores = case["cls"][l][i].permute(1, 2, 0).reshape(-1, 80).sigmoid()
+            iou = case["iou"][l][i].permute(1, 2, 0).reshape(-1).sigmoid()
+            scores = scores.pow(0.3) * iou.view(-1, 1).expand(-1, 80).pow(1 - 0.3)
+            bp = case["reg"][l][i].permute(1, 2, 0).reshape(-1, 4)
+            idx = torch.arange(scores.shape[0])
+            if scores.shape[0] > cfg.nms_pre:
+                idx = scores.max(dim=1)[0].topk(cfg.nms_pre)[1]
+            bs.append(distance2bbox(points[l][idx], bp[idx], max_shape=case["img_metas"][i]["img_shape"]))
+            ss.append(scores[idx]), ii.append(idx)
+        boxes = torch.cat(bs)
+        boxes /= boxes.new_tensor(case["img_metas"][i]["scale_factor"])
+        out["cand_boxes_%d" % i], out["cand_scores_%d" % i] = boxes.numpy(), torch.cat(ss).numpy()
+        out["cand_idx_%d" % i] = torch.cat(ii).numpy()
+    np.savez_compressed(os.path.join(HERE, "postproc_fcos.npz"), **out)
+    print("fcos", {k: v.shape for k, v in out.items() if k.startswith("dets")})
+
+
 def gen_results_json():
     """the reference's det2json / xyxy2xywh (core/evaluation/coco_utils.py:78-117)."""
     ref_shim.load_reference()
@@ -198,6 +239,9 @@ def gen_plain_retina():
 if __name__ == "__main__":
     if "--plain-retina-only" in sys.argv:
         gen_plain_retina()
+        sys.exit(0)
+    if "--fcos-only" in sys.argv:
+        gen_fcos()
         sys.exit(0)
     if "--results-only" in sys.argv:
         gen_results_json()

@@ -35,7 +35,7 @@ def test_library_builds_and_exports_header_symbols():
         assert hasattr(lib, n), "symbol %s declared in the header is not exported" % n
     assert set(names) == set(L.EXPORTED_SYMBOLS)
     lib.iou_abi_version.restype = ctypes.c_int
-    assert lib.iou_abi_version() == 1
+    assert lib.iou_abi_version() == 2
 
 
 def test_sass_is_blackwell_native():
@@ -49,7 +49,7 @@ def test_sass_is_blackwell_native():
 def test_struct_layouts_match_header():
     # sizes the C side computes for the same structs (plain-C layout rules)
     assert ctypes.sizeof(L.ConvSegment) == 16
-    assert ctypes.sizeof(L.PostprocCfg) == 5 * 4 + 3 * 8 * 4 + 8 * 16 * 4 * 4 + 8 * 4 + 4 * 4
+    assert ctypes.sizeof(L.PostprocCfg) == 5 * 4 + 3 * 8 * 4 + 8 * 16 * 4 * 4 + 8 * 4 + 4 * 4 + 4   # + decode_mode (ABI 2)
     assert L.ConvDesc.src.offset % 8 == 0 and L.ConvDesc.weight.offset % 8 == 0
     lib = L.load()                                   # the compiled C structs agree with the ctypes mirror
     assert lib.iou_sizeof(0) == ctypes.sizeof(L.PostprocCfg)

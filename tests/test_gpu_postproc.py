@@ -271,3 +271,51 @@ def test_head_get_bboxes_with_soft_nms_test_cfg():
         o2 = np.lexsort((gd[:, 0], gl, -gd[:, 4]))
         assert np.array_equal(l[o1], gl[o2])
         assert np.allclose(d[o1], gd[o2], rtol=U.RTOL, atol=U.ATOL), np.abs(d[o1] - gd[o2]).max()
+
+
+def test_fcos_head_get_bboxes_vs_reference_golden():
+    """IoUawareFCOSHead.get_bboxes (alpha = 0.3, one location per cell, distance2bbox) through the same kernels.
+    Candidates: same set/order as the reference (near-ties aside), boxes/scores within the fp32 tolerance (pow with
+    a non-trivial exponent differs by ~1 ulp between torch-CPU and CUDA); stage 2 on the GOLDEN candidates is
+    bit-exact; the head's public get_bboxes matches the reference detections within tolerance."""
+    g = np.load(os.path.join(U.GOLD, "postproc_fcos.npz"))
+    case = cases.fcos_case()
+    dev = torch.device("cuda:0")
+    head = P.IoUawareFCOSHead(81, 256, strides=cases.FCOS_STRIDES)
+    cfg = P.ConfigDict(case["cfg"])
+    cls = [t.to(dev) for t in case["cls"]]
+    reg = [t.to(dev) for t in case["reg"]]
+    cen = [t.to(dev) for t in case["cen"]]
+    iou = [t.to(dev) for t in case["iou"]]
+    n_img = 2
+    wsp = head.postproc_workspace([tuple(t.shape[-2:]) for t in cls], n_img, cfg, dev)
+    info = PP.make_img_info(case["img_metas"], dev)
+    boxes, scores_cm, idx = PP.decode_candidates(wsp, cls, reg, iou, info, True)
+    for i in range(n_img):
+        my_idx, g_idx = idx[i].cpu().numpy(), g["cand_idx_%d" % i]
+        bad = int((my_idx != g_idx).sum())
+        assert bad <= 8 and sorted(my_idx.tolist()) == sorted(g_idx.tolist()), bad
+        if bad == 0:
+            assert np.allclose(boxes[i].cpu().numpy(), g["cand_boxes_%d" % i], rtol=U.RTOL, atol=U.ATOL)
+            assert np.allclose(scores_cm[i].t().cpu().numpy(), g["cand_scores_%d" % i], rtol=U.RTOL, atol=U.ATOL)
+    gb = torch.stack([torch.from_numpy(g["cand_boxes_%d" % i]) for i in range(n_img)]).to(dev)
+    gs = torch.stack([torch.from_numpy(g["cand_scores_%d" % i]).t().contiguous() for i in range(n_img)]).to(dev)
+    dets, labels, counts = PP.batched_nms(wsp, gb, gs)
+    for i in range(n_img):
+        want_d, want_l = op.multiclass_nms(torch.from_numpy(g["cand_boxes_%d" % i]),
+                                           torch.cat([torch.zeros(gs.shape[2], 1), torch.from_numpy(g["cand_scores_%d" % i])], 1),
+                                           0.05, 0.5, 100)
+        k = int(counts[i])
+        assert k == want_d.shape[0]
+        assert np.array_equal(labels[i, :k].cpu().numpy(), want_l.numpy())
+        assert np.array_equal(dets[i, :k].cpu().numpy(), want_d.numpy())
+    res = head.get_bboxes(cls, reg, cen, iou, [None] * n_img, [None] * n_img, case["img_metas"], cfg, rescale=True)
+    for i, (d, l) in enumerate(res):
+        gd, gl = g["dets_%d" % i], g["labels_%d" % i]
+        d, l = d.cpu().numpy(), l.cpu().numpy()
+        assert d.shape == gd.shape
+        o1, o2 = np.lexsort((d[:, 0], l, -d[:, 4])), np.lexsort((gd[:, 0], gl, -gd[:, 4]))
+        assert np.array_equal(l[o1], gl[o2])
+        assert np.allclose(d[o1], gd[o2], rtol=U.RTOL, atol=U.ATOL), np.abs(d[o1] - gd[o2]).max()
+    with pytest.raises(NotImplementedError):
+        head.forward(tuple(cls))

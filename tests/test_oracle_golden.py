@@ -186,3 +186,21 @@ def test_soft_nms_oracle_get_bboxes_matches_reference():
                                     meta["scale_factor"], cfgd, rescale=case["rescale"], nms_mode="cpu")
         assert np.array_equal(l.numpy(), g["gb_labels_%d" % i])
         assert np.array_equal(d.numpy().view(np.uint32), g["gb_dets_%d" % i].view(np.uint32))
+
+
+# ------------------------------------------------------------------ IoUawareFCOSHead.get_bboxes
+def test_fcos_get_bboxes_oracle_matches_reference():
+    g = np.load(os.path.join(G, "postproc_fcos.npz"))
+    case = cases.fcos_case()
+    for i, meta in enumerate(case["img_metas"]):
+        args = ([t[i] for t in case["cls"]], [t[i] for t in case["reg"]], [t[i] for t in case["iou"]],
+                cases.FCOS_STRIDES, meta["img_shape"], meta["scale_factor"], case["cfg"])
+        b, s, idx = op.fcos_get_bboxes_single(*args, rescale=True, return_candidates=True)
+        assert np.array_equal(idx.numpy(), g["cand_idx_%d" % i])
+        assert np.array_equal(b.numpy().view(np.uint32), g["cand_boxes_%d" % i].view(np.uint32))
+        assert np.array_equal(s.numpy().view(np.uint32), g["cand_scores_%d" % i].view(np.uint32))
+        d, l = op.fcos_get_bboxes_single(*args, rescale=True, nms_mode="cpu")
+        assert np.array_equal(l.numpy(), g["labels_%d" % i])
+        assert np.array_equal(d.numpy().view(np.uint32), g["dets_%d" % i].view(np.uint32))
+    # known answer for the points (iou_aware_fcos_head.py:392-401)
+    assert op.fcos_points(2, 3, 8).tolist() == [[4, 4], [12, 4], [20, 4], [4, 12], [12, 12], [20, 12]]
