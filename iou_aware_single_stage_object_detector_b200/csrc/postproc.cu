@@ -447,6 +447,7 @@ __device__ __forceinline__ float box_area(const float4 a) {
 }
 
 #define NMS_ROUND 1024
+#define NMS_FIRST 256
 struct NmsSmem {
   unsigned long long* sortbuf;   // [P]
   float4* sbox;                  // [n]
@@ -604,10 +605,15 @@ __global__ void __launch_bounds__(512) class_nms_kernel(const __grid_constant__ 
                                                         unsigned long long* __restrict__ kept_keys,
                                                         int32_t* __restrict__ kept_cnt, const int Pmax) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  NmsSmem S;
-  S.sortbuf = reinterpret_cast<unsigned long long*>(smem_raw);                 // [Pmax] composite keys
-  float4* kbox = reinterpret_cast<float4*>(smem_raw + (size_t)Pmax * 8);       // [kcap] kept boxes
-  float* karea = reinterpret_cast<float*>(smem_raw + (size_t)Pmax * 8 + (size_t)P.kcap * 16);
+  // candidates above the threshold, compacted: score bits (u32) and row (u16) = 6 bytes each (composite 64-bit
+  // keys are only materialised for the <= NMS_ROUND members of a round, in rb)
+  unsigned int* c_bits = reinterpret_cast<unsigned int*>(smem_raw);                              // [Pmax]
+  unsigned short* c_row = reinterpret_cast<unsigned short*>(smem_raw + (size_t)Pmax * 4);          // [Pmax]
+  float4* kbox = reinterpret_cast<float4*>(smem_raw + (size_t)Pmax * 6);       // [kcap] kept boxes
+  float* karea = reinterpret_cast<float*>(smem_raw + (size_t)Pmax * 6 + (size_t)P.kcap * 16);
+  auto key_at = [&](int i) {
+    return ((unsigned long long)c_bits[i] << 32) | (unsigned long long)(0xffffffffu - (unsigned int)c_row[i]);
+  };
   __shared__ unsigned int s_n, warp_cnt[16];
   const int c = blockIdx.x, img = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -626,8 +632,8 @@ __global__ void __launch_bounds__(512) class_nms_kernel(const __grid_constant__ 
     for (int w = 0; w < warp; ++w) off += warp_cnt[w];
     if (pass) {
       const unsigned int slot = off + __popc(b & ((1u << lane) - 1u));
-      S.sortbuf[slot] = ((unsigned long long)float_to_ordered(s) << 32) |
-                        (unsigned long long)(0xffffffffu - (unsigned int)j);
+      c_bits[slot] = float_to_ordered(s);
+      c_row[slot] = (unsigned short)j;
     }
     __syncthreads();
     if (tid == 0) {
@@ -647,19 +653,80 @@ __global__ void __launch_bounds__(512) class_nms_kernel(const __grid_constant__ 
   unsigned long long* keys_out = kept_keys + ((size_t)img * P.C + c) * P.kcap;
   __shared__ int s_total;
   if (tid == 0) s_total = 0;
-  if (n <= NMS_ROUND) {
+  // Bucket histogram of the class's scores: bucket(s) is monotone in s, so "all candidates of buckets
+  // [blo, bhi)" is a contiguous slice of the score order.  The scan stops after max_per_img+1 kept boxes, so
+  // the order is consumed from the top in rounds: a first round of <= NMS_FIRST candidates (one cheap 256-wide
+  // sort usually already yields the 101 kept boxes), then rounds of <= NMS_ROUND.  One histogram pass + a scan
+  // of 1024 bins replaces the 8-pass exact radix select, which remains the fallback when a single bucket holds
+  // more than a round (many near-equal scores).
+  __shared__ unsigned int bh[1024];
+  __shared__ unsigned int s_maxb;
+  __shared__ int s_blo, s_teff;
+  __shared__ unsigned long long rb[NMS_ROUND];
+  const float b_scale = 1024.0f / fmaxf(1.0f - P.score_thr, 1e-6f);
+  auto bucket_of = [&](unsigned long long key) {
+    const float sv = ordered_to_float((unsigned int)(key >> 32));
+    const int bq = (int)((sv - P.score_thr) * b_scale);
+    return min(1023, max(0, bq));
+  };
+  bool use_buckets = false;
+  if (n > NMS_FIRST) {
+    for (int i = tid; i < 1024; i += 512) bh[i] = 0;
+    if (tid == 0) s_maxb = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 512) atomicAdd(&bh[bucket_of(key_at(i))], 1u);
+    __syncthreads();
+    for (int i = tid; i < 1024; i += 512) if (bh[i] > NMS_FIRST) atomicMax(&s_maxb, bh[i]);
+    __syncthreads();
+    use_buckets = (s_maxb == 0);               // every bucket fits the first (smallest) round
+  }
+  if (n <= NMS_FIRST) {
     // small class: sort everything once
     const int Ps = next_pow2(n);
-    for (int i = n + tid; i < Ps; i += 512) S.sortbuf[i] = 0ull;
-    bitonic_sort_desc(S.sortbuf, Ps);
-    const unsigned long long* sb = S.sortbuf;
+    for (int i = tid; i < Ps; i += 512) rb[i] = (i < n) ? key_at(i) : 0ull;
+    bitonic_sort_desc(rb, Ps);
+    const unsigned long long* sb = rb;
     greedy_nms_bounded(sb, n, bx, P.iou_thr, P.kcap, &s_total, kbox, karea,
                        [&](int r, int pos) { keys_out[pos] = sb[r]; });
+  } else if (use_buckets) {
+    __shared__ unsigned int s_slot2;
+    int bhi = 1024, cap = NMS_FIRST;
+    while (bhi > 0) {
+      __syncthreads();
+      if (tid == 0) {
+        int bq = bhi, cum = 0;
+        while (bq > 0 && cum + (int)bh[bq - 1] <= cap) cum += (int)bh[--bq];
+        s_blo = bq; s_teff = cum; s_slot2 = 0;
+      }
+      __syncthreads();
+      const int blo = s_blo, teff = s_teff;
+      if (teff > 0) {
+        for (int base = 0; base < n; base += 512) {
+          const int i = base + tid;
+          const unsigned long long u = (i < n) ? key_at(i) : 0ull;
+          const int bq = (i < n) ? bucket_of(u) : -1;
+          const bool take = bq >= blo && bq < bhi;
+          const unsigned int bt = __ballot_sync(0xffffffffu, take);
+          unsigned int slot0 = 0;
+          if (lane == 0 && bt) slot0 = atomicAdd(&s_slot2, __popc(bt));
+          slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+          if (take) rb[slot0 + __popc(bt & ((1u << lane) - 1u))] = u;
+        }
+        __syncthreads();
+        const int Ps = next_pow2(teff);
+        for (int i = teff + tid; i < Ps; i += 512) rb[i] = 0ull;
+        bitonic_sort_desc(rb, Ps);
+        const int total = greedy_nms_bounded(rb, teff, bx, P.iou_thr, P.kcap, &s_total, kbox, karea,
+                                             [&](int r, int pos) { keys_out[pos] = rb[r]; });
+        if (total >= P.kcap) break;
+      }
+      bhi = blo;
+      cap = NMS_ROUND;
+    }
   } else {
     // big class: the scan stops after max_per_img+1 kept boxes, so only the head of the score order is
     // ever needed.  Rounds of NMS_ROUND boxes: exact radix select of the round's lowest composite key
     // (keys are unique: score bits | ~index), compaction, a 1024-wide sort, then the lazy greedy scan.
-    __shared__ unsigned long long rb[NMS_ROUND];
     __shared__ unsigned int hist[256];
     __shared__ unsigned long long s_prefix;
     __shared__ unsigned int s_kleft, s_slot;
@@ -676,7 +743,7 @@ __global__ void __launch_bounds__(512) class_nms_kernel(const __grid_constant__ 
         const unsigned long long prefix = s_prefix;
         for (int base = 0; base < n; base += 512) {
           const int i = base + tid;
-          const unsigned long long u = (i < n) ? S.sortbuf[i] : 0ull;
+          const unsigned long long u = (i < n) ? key_at(i) : 0ull;
           const bool valid = (i < n) && (u < bound) && ((u & mask) == prefix);
           const unsigned int d = valid ? (unsigned int)((u >> shift) & 255ull) : (256u + lane);
           const unsigned int peers = __match_any_sync(0xffffffffu, d);
@@ -699,7 +766,7 @@ __global__ void __launch_bounds__(512) class_nms_kernel(const __grid_constant__ 
       const unsigned long long kt = s_prefix;   // the teff-th largest key below `bound`
       for (int base = 0; base < n; base += 512) {
         const int i = base + tid;
-        const unsigned long long u = (i < n) ? S.sortbuf[i] : 0ull;
+        const unsigned long long u = (i < n) ? key_at(i) : 0ull;
         const bool take = (i < n) && (u < bound) && (u >= kt);
         const unsigned int bt = __ballot_sync(0xffffffffu, take);
         unsigned int slot0 = 0;
@@ -739,9 +806,11 @@ __global__ void __launch_bounds__(1024) final_select_kernel(const __grid_constan
   unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(smem_raw);   // [Pcap]
   __shared__ int s_off[257];
   const int img = blockIdx.x, tid = threadIdx.x;
+  if (tid < 256) s_off[tid + 1] = (tid < P.C) ? kept_cnt[(size_t)img * P.C + tid] : 0;   // parallel loads, serial scan
+  __syncthreads();
   if (tid == 0) {
     int t = 0;
-    for (int c = 0; c < P.C; ++c) { s_off[c] = t; t += kept_cnt[(size_t)img * P.C + c]; }
+    for (int c = 0; c < P.C; ++c) { const int n_c = s_off[c + 1]; s_off[c] = t; t += n_c; }
     s_off[P.C] = t;
   }
   __syncthreads();
@@ -764,8 +833,56 @@ __global__ void __launch_bounds__(1024) final_select_kernel(const __grid_constan
                             : (((unsigned long long)(0xffffffffu - pos) << 32) | sbits);
     }
   }
-  bitonic_sort_desc(sortbuf, Ps);
   const int k = min(total, P.max_per_img);
+  if (by_score && total > 4 * P.max_per_img) {
+    // Only the max_per_img largest keys are needed: exact radix select of the k-th largest key (keys are unique:
+    // score bits | ~position), compaction of the keys >= it to the front, and a sort of just those --
+    // instead of a bitonic sort of up to 8192 keys (91 barrier-separated stages on one SM per image).
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned int s_kleft, s_slot;
+    __syncthreads();
+    if (tid == 0) { s_prefix = 0ull; s_kleft = (unsigned int)k; s_slot = 0; }
+    unsigned long long mask = 0ull;
+    for (int pass = 0; pass < 8; ++pass) {
+      const int shift = 56 - 8 * pass;
+      if (tid < 256) hist[tid] = 0;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      for (int i = tid; i < total; i += 1024) {
+        const unsigned long long u = sortbuf[i];
+        if ((u & mask) == prefix) atomicAdd(&hist[(unsigned int)((u >> shift) & 255ull)], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        unsigned int cacc = 0, kl = s_kleft;
+        int d = 255;
+        for (; d > 0; --d) {
+          if (cacc + hist[d] >= kl) break;
+          cacc += hist[d];
+        }
+        s_kleft = kl - cacc;
+        s_prefix = prefix | ((unsigned long long)d << shift);
+      }
+      mask |= 255ull << shift;
+      __syncthreads();
+    }
+    const unsigned long long kth = s_prefix;                     // exactly k keys are >= kth
+    unsigned long long mine[8];                                  // total <= 8192 = 8 x 1024 (checked by the host)
+    int nm = 0;
+    for (int i = tid; i < total; i += 1024) {
+      const unsigned long long u = sortbuf[i];
+      if (u >= kth) mine[nm++] = u;
+    }
+    __syncthreads();
+    const int Pk = next_pow2(k);
+    for (int q = 0; q < nm; ++q) sortbuf[atomicAdd(&s_slot, 1u)] = mine[q];
+    __syncthreads();
+    for (int i = k + tid; i < Pk; i += 1024) sortbuf[i] = 0ull;
+    bitonic_sort_desc(sortbuf, Pk);
+  } else {
+    bitonic_sort_desc(sortbuf, Ps);
+  }
   float* d_out = dets + (size_t)img * P.max_per_img * 5;
   long long* l_out = labels + (size_t)img * P.max_per_img;
   const float4* bx = reinterpret_cast<const float4*>(boxes) + (size_t)img * P.M;
@@ -1188,9 +1305,8 @@ static int run_decode(PostParams& P, const float* const* cls, const float* const
 static int run_nms(const PostParams& P, const float* boxes, const float* scores_cm, float* dets,
                    int64_t* labels, int32_t* counts, unsigned long long* kept_keys, int32_t* kept_cnt,
                    cudaStream_t st) {
-  // key buffer: all M candidates (unsorted) or a <= NMS_ROUND-wide full sort; even length keeps kbox 16B-aligned
-  const int Pmax = ((P.M > NMS_ROUND ? P.M : NMS_ROUND) + 1) & ~1;
-  const size_t sm4 = (size_t)Pmax * 8 + (size_t)P.kcap * 20 + 16;
+  const int Pmax = (P.M + 7) & ~7;          // multiple of 8 keeps kbox 16-byte aligned behind the 6-byte entries
+  const size_t sm4 = (size_t)Pmax * 6 + (size_t)P.kcap * 20 + 16;
   IOU_CHECK_CUDA(cudaFuncSetAttribute(class_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4));
   class_nms_kernel<<<dim3(P.C, P.n_img), 512, sm4, st>>>(P, boxes, scores_cm, kept_keys, kept_cnt, Pmax);
   if (int e = launch_status("class_nms_kernel")) return e;
