@@ -172,3 +172,52 @@ def test_preprocess_kernel_bit_exact_and_uint8_stream():
         x = torch.stack([torch.from_numpy(opp.image_transform(f[i].numpy(), mean, std, True, 32)[0]) for i in range(2)])
         d2, l2, c2 = det.detect_device(x.to(DEV), [meta, meta], rescale=False)
         assert torch.equal(c, c2.cpu()) and torch.equal(d, d2.cpu()) and torch.equal(l, l2.cpu())
+
+
+def test_full_size_dense_path_properties():
+    """BASELINE size (800x1344, R50-FPN): size-independent properties of the whole dense path + get_bboxes, and
+    one image's head maps against a torch fp32 reference of the same network evaluated on the GPU (cuDNN, TF32
+    off) -- the CPU oracle needs ~10 s per full-size image, which is what tests/test_gpu_model.py's small cases
+    and bench.py's cpu_baseline spend it on."""
+    from oracle import model as om
+    det, cfg = U.small_detector()
+    sd = {k: v.clone() for k, v in det.state_dict().items()}
+    dev = torch.device("cuda:0")
+    det = det.to(dev)
+    n, h, w = 4, 800, 1344
+    g = torch.Generator().manual_seed(11)
+    img = torch.randn(n, 3, h, w, generator=g).to(dev)
+    metas = [dict(ori_shape=(h, 1333, 3), img_shape=(h, 1333, 3), pad_shape=(h, w, 3), scale_factor=1.0,
+                  flip=False) for _ in range(n)]
+
+    def run(x):
+        d, l, c = det.detect_device(x, metas, rescale=False)
+        torch.cuda.synchronize()
+        return d.clone(), l.clone(), c.clone()
+    d0, l0, c0 = run(img)
+    assert int(c0.min()) > 0
+    # (1) idempotence: the same launch sequence gives the same bits
+    d1, l1, c1 = run(img)
+    assert torch.equal(d0, d1) and torch.equal(l0, l1) and torch.equal(c0, c1)
+    # (2) images are independent (iou_aware_retina_head.py:434-460): permuting the batch permutes the detections
+    perm = torch.tensor([2, 0, 3, 1], device=dev)
+    dp, lp, cp = run(img[perm].contiguous())
+    assert torch.equal(dp, d0[perm]) and torch.equal(lp, l0[perm]) and torch.equal(cp, c0[perm])
+    # (3) linearity of the conv engine at full size is not observable through ReLU/NMS, so pin the dense maps:
+    # image 0 through the same weights in torch fp32 on the GPU
+    run(img)                                         # the plan's output maps now hold the un-permuted batch again
+    plan = det.fused_plan(img.shape, dev, False)
+    mine = [[t[:1].clone() for t in plan.outs[k]] for k in range(3)]
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            ref = om.detector_forward({k: v.to(dev) for k, v in sd.items()}, img[:1])
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    for name, a_l, b_l in zip(("cls", "reg", "iou"), mine, ref):
+        for lvl, (a, b) in enumerate(zip(a_l, b_l)):
+            err = (a - b).abs().max().item()
+            scale = max(b.abs().max().item(), 1.0)
+            assert err <= 2e-4 * scale, "full-size head %s level %d: max|d| %g of range %g" % (name, lvl, err, scale)
