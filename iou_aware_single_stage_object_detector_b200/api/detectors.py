@@ -185,6 +185,19 @@ class SingleStageDetector(BaseDetector):
                     ev.record(copy_stream)
                 ready[slot] = (ev, metas)
 
+            host, pending = [None, None], None      # pinned result buffers per slot; (slot, event) not yet yielded
+
+            def read_back(slot, tensors):
+                """Async device->host copy of this batch's results into the slot's pinned buffers (enqueued on
+                the main stream BEFORE the next batch's launches overwrite the plan's output tensors)."""
+                if host[slot] is None or any(hb.shape != t.shape for hb, t in zip(host[slot], tensors)):
+                    host[slot] = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in tensors]
+                for hb, t in zip(host[slot], tensors):
+                    hb.copy_(t, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                return ev
+
             nxt = next(it, None)
             if nxt is None:
                 return
@@ -212,8 +225,18 @@ class SingleStageDetector(BaseDetector):
                 dets, labels, counts = plan.run()
                 if gather is not None:
                     dets, labels, counts = gather(dets, labels, counts)
-                yield dets.cpu(), labels.cpu(), counts.cpu()
+                rb_ev = read_back(slot, (dets, labels, counts))
+                # the previous batch is handed out only now, after this batch's launches are queued: the GPU never
+                # waits for the host between batches
+                if pending is not None:
+                    pslot, pev = pending
+                    pev.synchronize()
+                    yield tuple(hb.clone() for hb in host[pslot])
+                pending = (slot, rb_ev)
                 if nxt is None:
+                    pslot, pev = pending
+                    pev.synchronize()
+                    yield tuple(hb.clone() for hb in host[pslot])
                     return
                 slot ^= 1
 
