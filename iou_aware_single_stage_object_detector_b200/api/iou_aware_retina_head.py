@@ -137,8 +137,6 @@ class IoUawareRetinaHead(AnchorHead):
             img_info = PP.make_img_info(img_metas, dev)
         with torch.cuda.device(dev):
             if getattr(wsp, 'soft', None) is not None:      # test_cfg.nms = dict(type='soft_nms', ...)
-                if iou_preds is None:
-                    iou_preds = [t.new_zeros((t.shape[0], self.num_anchors) + tuple(t.shape[-2:])) for t in cls_scores]
                 boxes, scores_cm, _ = PP.decode_candidates(wsp, cls_scores, bbox_preds, iou_preds, img_info, rescale)
                 return PP.batched_soft_nms(wsp, boxes, scores_cm, *wsp.soft)
             return PP.get_bboxes_device(wsp, cls_scores, bbox_preds, iou_preds, img_info, rescale)

@@ -106,12 +106,13 @@ def decode_candidates(wsp, cls_list, reg_list, iou_list, img_info, rescale):
     cfg, n = wsp.cfg, wsp.n_img
     cls_list = [nhwc_rows(t) for t in cls_list]
     reg_list = [nhwc_rows(t) for t in reg_list]
-    iou_list = [nhwc_rows(t) for t in iou_list]
+    iou_list = [nhwc_rows(t) for t in iou_list] if iou_list is not None else None     # None: alpha == 1 heads
     boxes = torch.empty(n, wsp.M, 4, dtype=torch.float32, device=wsp.device)
     scores = torch.empty(n, cfg.num_classes, wsp.M, dtype=torch.float32, device=wsp.device)
     idx = torch.empty(n, wsp.M, dtype=torch.int32, device=wsp.device)
     L.check(lib.iou_decode_candidates(ctypes.byref(cfg), n, _ptr_array(cls_list), _ptr_array(reg_list),
-                                      _ptr_array(iou_list), img_info.data_ptr(), int(bool(rescale)),
+                                      _ptr_array(iou_list) if iou_list is not None else None,
+                                      img_info.data_ptr(), int(bool(rescale)),
                                       boxes.data_ptr(), scores.data_ptr(), idx.data_ptr(),
                                       wsp.ws.data_ptr(), wsp.ws_bytes, L.stream_ptr()))
     L.launch_count += 3

@@ -131,10 +131,14 @@ def test_detect_stream_matches_detect_device():
     for im in imgs:
         d, l, c = det.detect_device(im, [meta, meta], rescale=True)
         want.append((d.cpu().clone(), l.cpu().clone(), c.cpu().clone()))
-    got = list(det.detect_stream(((im, [meta, meta]) for im in imgs), rescale=True))
-    assert len(got) == 4
-    for (d, l, c), (d2, l2, c2) in zip(want, got):
-        assert torch.equal(c, c2) and torch.equal(d, d2) and torch.equal(l, l2)
+    imgs5 = imgs + [imgs[1]]                       # odd count: the last batch sits alone in its pipeline slot
+    want5 = want + [want[1]]
+    for depth in (2, 1):                           # two plans on two streams / one plan on the caller's stream
+        got = list(det.detect_stream(((im, [meta, meta]) for im in imgs5), rescale=True, depth=depth))
+        assert len(got) == 5
+        for (d, l, c), (d2, l2, c2) in zip(want5, got):
+            assert torch.equal(c, c2) and torch.equal(d, d2) and torch.equal(l, l2)
+    assert list(det.detect_stream(iter(()), rescale=True)) == []
 
 
 def test_unpadded_input_raises_like_the_reference():
