@@ -430,10 +430,10 @@ class Engine(object):
 
     def profile(self, iters=3):
         """Eager pass with a CUDA event pair around every launch (on the launching stream).
-        Returns [(name, avg_ms)] in launch order; used by bench.py for the live roofline."""
+        Returns [(name, median_ms)] in launch order; used by bench.py for the live roofline."""
         st_t = torch.cuda.current_stream()
         st = L.stream_ptr()
-        acc = [0.0] * len(self.ops)
+        acc = [[] for _ in self.ops]
         for _ in range(iters):
             evs = []
             for _, fn in self.ops:
@@ -444,9 +444,9 @@ class Engine(object):
                 evs.append((a, b))
             torch.cuda.synchronize()
             for i, (a, b) in enumerate(evs):
-                acc[i] += a.elapsed_time(b)
+                acc[i].append(a.elapsed_time(b))
         L.launch_count += iters * len(self.ops)
-        return [(name, t / iters) for (name, _), t in zip(self.ops, acc)]
+        return [(name, sorted(t)[len(t) // 2]) for (name, _), t in zip(self.ops, acc)]      # median over the passes
 
     def num_launches(self):
         return len(self.ops)
