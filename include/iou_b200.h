@@ -234,6 +234,14 @@ int iou_preprocess_u8(const unsigned char* src, int n, int h, int w, int pad_h, 
                       const float* mean3, const float* std3, int to_rgb, int flip, float* dst,
                       void* stream);
 
+/* The same with the resize of ImageTransform.__call__ in front (transforms.py:33-40: mmcv.imrescale / imresize =
+ * cv2.resize(..., INTER_LINEAR) on the uint8 frame): src [n][src_h][src_w][3] is resized to dst_h x dst_w with
+ * OpenCV's 8-bit fixed-point bilinear arithmetic (bit-identical to cv2.resize), then normalised, flipped, padded
+ * and transposed exactly as iou_preprocess_u8 does.  The caller computes dst_h/dst_w (mmcv imrescale rule). */
+int iou_preprocess_resize_u8(const unsigned char* src, int n, int src_h, int src_w, int dst_h, int dst_w,
+                             int pad_h, int pad_w, const float* mean3, const float* std3, int to_rgb, int flip,
+                             float* dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

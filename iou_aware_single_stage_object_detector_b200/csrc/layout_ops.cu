@@ -288,9 +288,76 @@ __global__ void __launch_bounds__(256) preprocess_u8_kernel(const unsigned char*
   }
 }
 
+// ---- the same with mmcv.imrescale / imresize in front (transforms.py:33-40): bilinear resize of the uint8 frame
+// exactly as cv2.resize(..., INTER_LINEAR) computes it for 8-bit images (OpenCV imgproc/resize.cpp, the fixed-point
+// path): per destination column fx = (float)((dx+0.5)*scale_x - 0.5), sx = floor(fx), weights
+// saturate_cast<short>((1-fx)*2048), saturate_cast<short>(fx*2048) (fraction zeroed where sx is clamped); per row
+// the same WITHOUT zeroing the fraction (rows are clipped instead); horizontal pass in int32, vertical pass
+// ((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2) >> 2.  The resized pixel is then normalised as above.
+struct ResizeCoef { int s0, s1, w0, w1; };
+__device__ __forceinline__ ResizeCoef resize_coef(int d, double scale, int sn, bool zero_frac_at_clamp) {
+  const float f0 = (float)__dsub_rn(__dmul_rn((double)d + 0.5, scale), 0.5);
+  int s = (int)floorf(f0);
+  float fr = __fsub_rn(f0, (float)s);
+  ResizeCoef c;
+  if (zero_frac_at_clamp) {
+    if (s < 0) { s = 0; fr = 0.f; }
+    if (s >= sn - 1) { s = sn - 1; fr = 0.f; }
+    c.s0 = s; c.s1 = min(s + 1, sn - 1);
+  } else {
+    c.s0 = min(max(s, 0), sn - 1); c.s1 = min(max(s + 1, 0), sn - 1);
+  }
+  c.w0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, fr), 2048.f));
+  c.w1 = __float2int_rn(__fmul_rn(fr, 2048.f));
+  return c;
+}
+
+__global__ void __launch_bounds__(256) preprocess_resize_u8_kernel(const unsigned char* __restrict__ src, int n, int sh,
+                                                                   int sw, int dh, int dw, int hp, int wp, double scale_x,
+                                                                   double scale_y, Norm3 nm, int to_rgb, int flip,
+                                                                   float* __restrict__ dst) {
+  const size_t total = (size_t)n * 3 * hp * wp;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % wp);
+    size_t t = i / wp;
+    const int y = (int)(t % hp); t /= hp;
+    const int c = (int)(t % 3);
+    const int im = (int)(t / 3);
+    float v = 0.f;
+    if (y < dh && x < dw) {
+      const int xs = flip ? (dw - 1 - x) : x;              // mmcv.imflip acts on the resized image
+      const int cs = to_rgb ? (2 - c) : c;
+      const ResizeCoef cx = resize_coef(xs, scale_x, sw, true), cy = resize_coef(y, scale_y, sh, false);
+      const unsigned char* r0 = src + ((size_t)im * sh + cy.s0) * sw * 3 + cs;
+      const unsigned char* r1 = src + ((size_t)im * sh + cy.s1) * sw * 3 + cs;
+      const int h0 = (int)r0[(size_t)cx.s0 * 3] * cx.w0 + (int)r0[(size_t)cx.s1 * 3] * cx.w1;
+      const int h1 = (int)r1[(size_t)cx.s0 * 3] * cx.w0 + (int)r1[(size_t)cx.s1 * 3] * cx.w1;
+      int q = (((cy.w0 * (h0 >> 4)) >> 16) + ((cy.w1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      q = min(max(q, 0), 255);
+      v = __fdiv_rn(__fsub_rn((float)q, nm.mean[c]), nm.stdv[c]);
+    }
+    dst[i] = v;
+  }
+}
+
 }  // namespace iou
 
 using namespace iou;
+
+extern "C" int iou_preprocess_resize_u8(const unsigned char* src, int n, int src_h, int src_w, int dst_h, int dst_w,
+                                        int pad_h, int pad_w, const float* mean3, const float* std3, int to_rgb,
+                                        int flip, float* dst, void* stream) {
+  IOU_REQUIRE(src && dst && mean3 && std3 && n > 0 && src_h > 0 && src_w > 0 && dst_h > 0 && dst_w > 0, "bad argument");
+  IOU_REQUIRE(pad_h >= dst_h && pad_w >= dst_w, "pad shape smaller than the resized image");
+  Norm3 nm;
+  for (int c = 0; c < 3; ++c) { nm.mean[c] = mean3[c]; nm.stdv[c] = std3[c]; }
+  const double inv_x = (double)dst_w / src_w, inv_y = (double)dst_h / src_h;      // cv::resize: scale = 1 / inv_scale
+  const size_t total = (size_t)n * 3 * pad_h * pad_w;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  preprocess_resize_u8_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, n, src_h, src_w, dst_h, dst_w, pad_h, pad_w,
+                                                                        1.0 / inv_x, 1.0 / inv_y, nm, to_rgb, flip, dst);
+  return launch_status("preprocess_resize_u8_kernel");
+}
 
 extern "C" int iou_preprocess_u8(const unsigned char* src, int n, int h, int w, int pad_h, int pad_w,
                                  const float* mean3, const float* std3, int to_rgb, int flip, float* dst,

@@ -121,6 +121,7 @@ def main():
     gen_soft_nms()
     gen_results_json()
     gen_fcos()
+    gen_resize()
 
 
 def gen_soft_nms():
@@ -201,6 +202,18 @@ def gen_fcos():
     print("fcos", {k: v.shape for k, v in out.items() if k.startswith("dets")})
 
 
+def gen_resize():
+    """cv2.resize(..., INTER_LINEAR) -- the call inside mmcv.imrescale / imresize that
+    ImageTransform makes (transforms.py:33-40) -- on the frames of gen_golden_fixtures.resize_cases()."""
+    import cv2
+    from gen_golden_fixtures import resize_cases
+    out = {"cv2_version": np.array(cv2.__version__)}
+    for name, (img, (dw, dh)) in resize_cases().items():
+        out[name] = cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR)
+    np.savez_compressed(os.path.join(HERE, "resize_cv2.npz"), **out)
+    print("resize", {k: v.shape for k, v in out.items() if k != "cv2_version"})
+
+
 def gen_results_json():
     """the reference's det2json / xyxy2xywh (core/evaluation/coco_utils.py:78-117)."""
     ref_shim.load_reference()
@@ -239,6 +252,9 @@ def gen_plain_retina():
 if __name__ == "__main__":
     if "--plain-retina-only" in sys.argv:
         gen_plain_retina()
+        sys.exit(0)
+    if "--resize-only" in sys.argv:
+        gen_resize()
         sys.exit(0)
     if "--fcos-only" in sys.argv:
         gen_fcos()

@@ -23,3 +23,14 @@ def results_fixture():
         def __len__(self):
             return 3
     return DS(), results
+
+
+def resize_cases():
+    """name -> (uint8 BGR frame (h, w, 3), (dst_w, dst_h)): up- and down-scaling, odd sizes, the 2x special case."""
+    rs = np.random.RandomState(31)
+    out = {}
+    for name, (sh, sw), (dw, dh) in [("up_60x80", (60, 80), (133, 100)), ("down_97x131", (97, 131), (53, 37)),
+                                     ("up2x_32x48", (32, 48), (96, 64)), ("down2x_64x64", (64, 64), (32, 32)),
+                                     ("aspect_50x120", (50, 120), (77, 201)), ("row_1x40", (1, 40), (90, 3))]:
+        out[name] = (rs.randint(0, 256, (sh, sw, 3)).astype(np.uint8), (dw, dh))
+    return out

@@ -225,3 +225,28 @@ def test_full_size_dense_path_properties():
             err = (a - b).abs().max().item()
             scale = max(b.abs().max().item(), 1.0)
             assert err <= 2e-4 * scale, "full-size head %s level %d: max|d| %g of range %g" % (name, lvl, err, scale)
+
+
+def test_preprocess_resize_kernel_bit_exact_vs_cv2_restatement():
+    """iou_preprocess_resize_u8 (resize + normalise + flip + pad + CHW in one kernel) == the oracle's restatement of
+    ImageTransform.__call__ with mmcv.imrescale -> cv2.resize(INTER_LINEAR), bit for bit, incl. the cv2 goldens."""
+    from oracle import preprocess as OP
+    from gen_golden_fixtures import resize_cases
+    mean, std = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+    g = np.load(os.path.join(U.GOLD, "resize_cv2.npz"))
+    for name, (img, (dw, dh)) in resize_cases().items():        # keep_ratio=False: exact (w, h) as in the goldens
+        tf = P.ImageTransform(mean, std, to_rgb=True, size_divisor=32, scale=(dw, dh), keep_ratio=False)
+        out, img_shape, pad_shape, factor = tf(torch.from_numpy(img[None]).to(DEV))
+        want, w_shape, w_pad = OP.image_transform(g[name], mean, std, True, 32, False)
+        assert img_shape == (dh, dw, 3) and tuple(pad_shape) == tuple(w_pad)
+        assert np.array_equal(out[0].cpu().numpy().view(np.uint32), want.view(np.uint32)), name
+    rs = np.random.RandomState(9)
+    frames = rs.randint(0, 256, (3, 120, 160, 3)).astype(np.uint8)            # a batch, keep_ratio, flip
+    tf = P.ImageTransform(mean, std, to_rgb=True, size_divisor=32, scale=(333, 200))
+    for flip in (False, True):
+        out, img_shape, pad_shape, factor = tf(torch.from_numpy(frames).to(DEV), flip=flip)
+        for i in range(3):
+            want, w_shape, w_pad, w_f = OP.image_transform_rescaled(frames[i], (333, 200), mean, std, True, 32, flip)
+            assert tuple(img_shape) == tuple(w_shape) and tuple(pad_shape) == tuple(w_pad) and factor == w_f
+            assert np.array_equal(out[i].cpu().numpy().view(np.uint32), want.view(np.uint32)), (i, flip)
+    assert tf.pad_shape(120, 160) == (224, 288) and tf.out_shape(120, 160)[:2] == (200, 267)

@@ -204,3 +204,31 @@ def test_fcos_get_bboxes_oracle_matches_reference():
         assert np.array_equal(d.numpy().view(np.uint32), g["dets_%d" % i].view(np.uint32))
     # known answer for the points (iou_aware_fcos_head.py:392-401)
     assert op.fcos_points(2, 3, 8).tolist() == [[4, 4], [12, 4], [20, 4], [4, 12], [12, 12], [20, 12]]
+
+
+# ------------------------------------------------------------------ ImageTransform resize
+def test_resize_oracle_matches_cv2_golden():
+    """oracle.preprocess.resize_linear_u8 == cv2.resize(INTER_LINEAR) on uint8 frames, bit for bit (goldens written by
+    cv2 itself in the build container; when cv2 is importable, 30 random sizes are checked live as well)."""
+    from oracle import preprocess as OP
+    from gen_golden_fixtures import resize_cases
+    g = np.load(os.path.join(G, "resize_cv2.npz"))
+    for name, (img, (dw, dh)) in resize_cases().items():
+        assert np.array_equal(OP.resize_linear_u8(img, dw, dh), g[name]), name
+    try:
+        import cv2
+    except ImportError:
+        cv2 = None
+    if cv2 is not None:
+        rs = np.random.RandomState(5)
+        for _ in range(30):
+            sh, sw, dh, dw = (int(v) for v in rs.randint(8, 400, size=4))
+            img = rs.randint(0, 256, (sh, sw, 3)).astype(np.uint8)
+            assert np.array_equal(OP.resize_linear_u8(img, dw, dh), cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR))
+    # mmcv 0.2.8 imrescale size rule: COCO 480x640 -> 800x1067, 427x640 -> 800x1199
+    assert OP.rescale_size(480, 640, (1333, 800))[:2] == (800, 1067)
+    assert OP.rescale_size(427, 640, (1333, 800))[:2] == (800, 1199)
+    assert OP.rescale_size(640, 427, (1333, 800))[:2] == (1199, 800)
+    assert OP.rescale_size(100, 200, 0.5)[:2] == (50, 100)
+    nh, nw, f = OP.rescale_size(100, 200, (300, 150), keep_ratio=False)
+    assert (nh, nw) == (150, 300) and np.allclose(f, [1.5, 1.5, 1.5, 1.5])
