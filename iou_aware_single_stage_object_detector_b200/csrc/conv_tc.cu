@@ -767,7 +767,7 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   P.total_tiles = P.num_m_tiles * P.num_n_tiles;
   // CTA-pair mode (tcgen05 cta_group::2): two CTAs of a cluster own two consecutive 128-row tiles and share
   // one BLOCK_N-wide B tile, each staging half of its rows -> half the B traffic per CTA and a deeper pipeline
-  P.two_cta = (d->two_cta && d->block_n % 16 == 0 && !d->diag_k) ? 1 : 0;   // each CTA stages block_n/2 rows of B (whole 8-row swizzle atoms)
+  P.two_cta = (d->two_cta && d->block_n % 16 == 0) ? 1 : 0;   // each CTA stages block_n/2 rows of B (whole 8-row swizzle atoms)
   P.total_pair_tiles = ((P.num_m_tiles + 1) / 2) * P.num_n_tiles;
   P.b_tile_bytes = (P.two_cta ? d->block_n / 2 : d->block_n) * kBlockK * 2;
   // padded-rows outputs leave through a per-warp 64B-swizzled staging tile (32 rows x 32 ch, hi + lo)

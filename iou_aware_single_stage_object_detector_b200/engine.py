@@ -165,6 +165,7 @@ class Engine(object):
         self.two_cta = os.environ.get("IOU_TWO_CTA", "1") != "0"
         self.pair_min_bn = int(os.environ.get("IOU_PAIR_MIN_BN", "64"))
         self.pair_min_tiles = int(os.environ.get("IOU_PAIR_MIN_TILES", "32"))
+        self.pair_diag = os.environ.get("IOU_PAIR_DIAG", "1") != "0"       # grouped (block-diagonal) convs as CTA pairs
         self.lib = L.load()
 
     # ------------------------------------------------------------------ primitive ops
@@ -206,7 +207,7 @@ class Engine(object):
         assert wp.shape == (len(taps) * cout_pad, 2 * (64 if diag_k else cin)), (name, wp.shape, len(taps), cout_pad, cin)
         d.diag_k = int(diag_k)
         # big maps with a wide N tile run as CTA pairs (cta_group::2): half the B traffic, deeper pipeline
-        d.two_cta = int(self.two_cta and not diag_k and block_n % 16 == 0 and block_n >= self.pair_min_bn
+        d.two_cta = int(self.two_cta and (not diag_k or self.pair_diag) and block_n % 16 == 0 and block_n >= self.pair_min_bn
                         and m_tiles >= self.pair_min_tiles) if two_cta is None else int(two_cta)
         d.weight = wp.data_ptr()
 

@@ -192,10 +192,11 @@ def test_conv_rejects_bad_descriptors_loudly():
         eng.conv("bad", [m], E.TAPS_1X1, torch.zeros(64, 96, dtype=torch.bfloat16), 48, 64)
 
 
+@pytest.mark.parametrize("pair", [None, True])
 @pytest.mark.parametrize("width,groups,stride,hw", [(128, 32, 1, (14, 18)), (256, 64, 1, (9, 13)),
                                                     (256, 32, 2, (20, 28)), (512, 64, 2, (13, 21)),
                                                     (1024, 32, 1, (7, 11))])
-def test_grouped_conv_block_diagonal_vs_torch(width, groups, stride, hw):
+def test_grouped_conv_block_diagonal_vs_torch(width, groups, stride, hw, pair):
     """ResNeXt 3x3 grouped conv (resnext.py:47-56) as a block-diagonal tap-GEMM."""
     g = torch.Generator().manual_seed(width + groups + stride)
     cg = width // groups
@@ -207,9 +208,10 @@ def test_grouped_conv_block_diagonal_vs_torch(width, groups, stride, hw):
     m = eng.pack_input(x.to(DEV).contiguous())
     wp = E.pack_weight_grouped(w, groups)
     if stride == 1:
-        out = eng.conv("g", [m], E.TAPS_3X3, wp, width, width, shift=b, diag_k=True)
+        out = eng.conv("g", [m], E.TAPS_3X3, wp, width, width, shift=b, diag_k=True, two_cta=pair)
     else:
-        out = eng.conv("g", eng.phase_split("p", m), E.TAPS_3X3_S2, wp, width, width, shift=b, diag_k=True)
+        out = eng.conv("g", eng.phase_split("p", m), E.TAPS_3X3_S2, wp, width, width, shift=b, diag_k=True,
+                       two_cta=pair)
     y = eng.unpack_output(out)
     eng.run()
     torch.cuda.synchronize()
