@@ -225,6 +225,19 @@ int iou_maxpool3x3s2(const void* src, int n, int c, int h, int w, void* dst, voi
 int iou_phase_split(const void* src, int n, int c, int h, int w, void* const* dst4,
                     int phase_mask, void* stream);
 
+/* ------------------------------------------------------------------ GroupNorm towers (IoUawareFCOSHead, "next" row rank 4)
+ * In-place GroupNorm (+ReLU) of a padded-rows map holding num_seg segments (FPN levels): the norm layer of
+ * ConvModule with norm_cfg type 'GN' (mmdet/models/utils/conv_module.py:140-163, norm.py:7,44-50;
+ * torch.nn.GroupNorm: per (image, group) mean / biased variance over H x W x C/groups, eps inside the sqrt).
+ * gamma/beta: device [c].  workspace: iou_group_norm_workspace_bytes(sum of n_img over segments, groups). */
+size_t iou_group_norm_workspace_bytes(int total_images, int groups);
+int iou_group_norm_relu(void* map, int c, int num_seg, const iou_conv_segment* seg, int groups,
+                        const float* gamma, const float* beta, float eps, int relu, void* workspace,
+                        size_t workspace_bytes, void* stream);
+/* x[i] = exp(x[i] * scale) on n dense fp32 values: bbox_pred = scale(fcos_reg(feat)).exp()
+ * (mmdet/models/anchor_heads/iou_aware_fcos_head.py:108). */
+int iou_scale_exp(float* x, size_t n, float scale, void* stream);
+
 /* ------------------------------------------------------------------ pre-processing ("next" row)
  * ImageTransform without the resize (mmdet/datasets/transforms.py:31-50; mmcv 0.2.8 imnormalize,
  * impad_to_multiple): src uint8 [n][h][w][3] (BGR, DEVICE pointer) -> dst fp32 [n][3][pad_h][pad_w] =

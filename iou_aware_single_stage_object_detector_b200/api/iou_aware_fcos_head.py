@@ -7,17 +7,18 @@ rescale, multiclass NMS -- the SAME kernels as the RetinaNet path with alpha = 0
 distance decoder (iou_postproc_cfg.decode_mode = IOU_DECODE_DISTANCE).  The centerness maps are accepted and,
 exactly as in the reference (:342-366, the centerness variants are commented out), do not influence the result.
 
-The dense half (towers with GroupNorm, Scale, exp; :92-113) is NOT planned on the tap-GEMM engine: GroupNorm
-needs per-sample statistics between the convolutions.  The layers are built so that configs and state_dicts
-load; ``forward`` raises.
+The dense half (:92-113) runs on the conv engine too: every tower layer is a tap-GEMM (no bias) followed by an
+in-place GroupNorm+ReLU pass over all levels (iou_group_norm_relu), fcos_cls + fcos_centerness share one GEMM with
+a split store, fcos_reg + fcos_iou likewise, and bbox_pred = exp(scale_l * fcos_reg) is one small kernel per level.
 """
 import torch
 import torch.nn as nn
 
+from .. import engine as E
 from .. import lib as L
 from .. import postproc as PP
 from .conv_module import ConvModule
-from .engine_cache import require_cuda
+from .engine_cache import PlanCache, cuda_state_dict, param_stamp, require_cuda
 from .registry import HEADS
 from .weight_init import bias_init_with_prob, normal_init
 
@@ -49,6 +50,7 @@ class IoUawareFCOSHead(nn.Module):
         self.strides, self.regress_ranges = strides, regress_ranges
         self.conv_cfg, self.norm_cfg = conv_cfg, norm_cfg
         self._post = {}
+        self._plans = PlanCache()
         self._init_layers()
 
     def _init_layers(self):
@@ -72,9 +74,50 @@ class IoUawareFCOSHead(nn.Module):
         normal_init(self.fcos_centerness, std=0.01)
         normal_init(self.fcos_iou, std=0.01)
 
+    # ---- forward -----------------------------------------------------------------------------
+    def plan_into(self, eng, sd, F, prefix=""):
+        if self.norm_cfg is None or self.norm_cfg.get('type') != 'GN':
+            raise NotImplementedError("IoUawareFCOSHead is planned with its default GroupNorm towers only")
+        if self.conv_cfg is not None and self.conv_cfg.get('type', 'Conv') != 'Conv':
+            raise NotImplementedError("conv type %r is outside the accelerated path" % self.conv_cfg.get('type'))
+        gn = self.cls_convs[0].gn
+        return eng.add_fcos_head(sd, F, prefix=prefix, stacked=self.stacked_convs,
+                                 num_classes=self.cls_out_channels, groups=gn.num_groups, eps=gn.eps)
+
     def forward(self, feats):
-        raise NotImplementedError("IoUawareFCOSHead.forward (GroupNorm towers) is not planned on the tap-GEMM engine; "
-                                  "only get_bboxes runs on libiou_b200 (SURVEY.md 8(f) rank 4)")
+        """feats: tuple of (N, C, H, W) CUDA tensors -> (cls_scores, bbox_preds, centernesses, ious), lists per
+        level with logical shapes (N, 80, H, W), (N, 4, H, W), (N, 1, H, W), (N, 1, H, W) (:89-113); NHWC storage."""
+        for t in feats:
+            require_cuda(t, "IoUawareFCOSHead.forward")
+        assert len(feats) == len(self.strides)
+        feats = [t.float().contiguous() for t in feats]
+        dev = feats[0].device
+        key = (tuple(tuple(t.shape) for t in feats), dev, param_stamp(self))
+
+        def build():
+            eng = E.Engine(dev)
+            ins = [torch.empty_like(t) for t in feats]
+            F = eng.new_map([(t.shape[0], t.shape[2], t.shape[3]) for t in ins], ins[0].shape[1])
+            for s_, t in enumerate(ins):
+                n, c, h, w = t.shape
+                rs = F.segs[s_][0]
+                lib, tp, fp = eng.lib, t.data_ptr(), F.ptr
+                eng.ops.append(("pack", lambda st, tp=tp, n=n, c=c, h=h, w=w, rs=rs, fp=fp, lib=lib:
+                                E.L.check(lib.iou_pack_nchw(tp, n, c, h, w, fp, rs, st))))
+            outs = self.plan_into(eng, cuda_state_dict(self, dev), F)
+            return eng, ins, outs
+        eng, ins, outs = self._plans.get(key, build)
+        for a_, b_ in zip(ins, feats):
+            a_.copy_(b_)
+        with torch.cuda.device(dev):
+            eng.run()
+        return outs
+
+    def forward_single(self, x, scale=None):
+        if len(self.strides) != 1:
+            raise NotImplementedError("forward_single needs the level's Scale: call forward(feats) with all levels")
+        c, r, q, u = self.forward((x,))
+        return c[0], r[0], q[0], u[0]
 
     # ---- get_bboxes --------------------------------------------------------------------------
     def postproc_workspace(self, featmap_sizes, n_img, cfg, device):

@@ -288,6 +288,107 @@ __global__ void __launch_bounds__(256) preprocess_u8_kernel(const unsigned char*
   }
 }
 
+// ---- GroupNorm (+ReLU) on padded-rows maps, all segments (FPN levels) of a map in one launch (IoUawareFCOSHead
+// towers: conv -> GN(32 groups) -> ReLU, mmdet/models/utils/conv_module.py:140-163 with norm_cfg type 'GN').
+// Statistics are per (image, group) over the H x W interior pixels (torch.nn.GroupNorm, biased variance), summed
+// in double; one block per image row, thread t owns the 8-channel chunk t % (C/8) of every (256 / (C/8))-th pixel.
+struct GnSegs {
+  int num_seg;
+  int row_start[IOU_CONV_MAX_SEG], n[IOU_CONV_MAX_SEG], h[IOU_CONV_MAX_SEG], w[IOU_CONV_MAX_SEG];
+  int blk_off[IOU_CONV_MAX_SEG + 1];      // prefix of n*h (one block per image row)
+  int img_off[IOU_CONV_MAX_SEG + 1];      // prefix of n   (stats index)
+};
+__device__ __forceinline__ void gn_locate(const GnSegs& G, int blk, int& s, int& img, int& y) {
+  s = 0;
+  while (s + 1 < G.num_seg && blk >= G.blk_off[s + 1]) ++s;
+  const int r = blk - G.blk_off[s];
+  img = r / G.h[s];
+  y = r - img * G.h[s];
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* px, int c, int ch8, float (&v)[8]) {
+  const uint4 hv = __ldg(reinterpret_cast<const uint4*>(px) + ch8);
+  const uint4 lv = __ldg(reinterpret_cast<const uint4*>(px + c) + ch8);
+  const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    v[2 * q] = __uint_as_float(hw[q] << 16) + __uint_as_float(lw[q] << 16);
+    v[2 * q + 1] = __uint_as_float(hw[q] & 0xffff0000u) + __uint_as_float(lw[q] & 0xffff0000u);
+  }
+}
+
+__global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __restrict__ map, const GnSegs G, int c,
+                                                       int groups, double* __restrict__ stats) {
+  __shared__ double acc[2 * 256];                          // [group][sum, sumsq], groups <= 256
+  int s, img, y;
+  gn_locate(G, blockIdx.x, s, img, y);
+  const int chunks = c >> 3, cpg = c / groups;
+  const int ch8 = threadIdx.x % chunks, px0 = threadIdx.x / chunks, pstride = blockDim.x / chunks;
+  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) acc[i] = 0.0;
+  __syncthreads();
+  const int wp = G.w[s] + 2;
+  const __nv_bfloat16* row = map + ((size_t)G.row_start[s] + ((size_t)img * (G.h[s] + 2) + y + 1) * wp + 1) * (2 * c);
+  double sum = 0.0, sq = 0.0;
+  for (int x = px0; x < G.w[s]; x += pstride) {
+    float v[8];
+    load8(row + (size_t)x * 2 * c, c, ch8, v);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { sum += (double)v[q]; sq += (double)v[q] * (double)v[q]; }
+  }
+  const int g = (ch8 * 8) / cpg;
+  atomicAdd(&acc[2 * g], sum);
+  atomicAdd(&acc[2 * g + 1], sq);
+  __syncthreads();
+  double* out = stats + ((size_t)(G.img_off[s] + img) * groups) * 2;
+  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) atomicAdd(out + i, acc[i]);
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(__nv_bfloat16* __restrict__ map, const GnSegs G, int c, int groups,
+                                                       const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float eps, int relu) {
+  int s, img, y;
+  gn_locate(G, blockIdx.x, s, img, y);
+  const int chunks = c >> 3, cpg = c / groups;
+  const int ch8 = threadIdx.x % chunks, px0 = threadIdx.x / chunks, pstride = blockDim.x / chunks;
+  const int g = (ch8 * 8) / cpg;
+  const double cnt = (double)G.h[s] * G.w[s] * cpg;
+  const double* st = stats + ((size_t)(G.img_off[s] + img) * groups + g) * 2;
+  const double mean = st[0] / cnt;
+  const double var = fmax(st[1] / cnt - mean * mean, 0.0);
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps)), meanf = (float)mean;
+  float sc[8], bi[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {                            // y = x * (rstd * gamma) + (beta - mean * rstd * gamma)
+    sc[q] = rstd * __ldg(gamma + ch8 * 8 + q);
+    bi[q] = __ldg(beta + ch8 * 8 + q) - meanf * sc[q];
+  }
+  const int wp = G.w[s] + 2;
+  __nv_bfloat16* row = map + ((size_t)G.row_start[s] + ((size_t)img * (G.h[s] + 2) + y + 1) * wp + 1) * (2 * c);
+  for (int x = px0; x < G.w[s]; x += pstride) {
+    __nv_bfloat16* px = row + (size_t)x * 2 * c;
+    float v[8];
+    load8(px, c, ch8, v);
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float a = fmaf(v[2 * q], sc[2 * q], bi[2 * q]), b = fmaf(v[2 * q + 1], sc[2 * q + 1], bi[2 * q + 1]);
+      if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(a, h0, l0);
+      split_bf16(b, h1, l1);
+      hi[q] = pack2_bf16(h0, h1);
+      lo[q] = pack2_bf16(l0, l1);
+    }
+    reinterpret_cast<uint4*>(px)[ch8] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    reinterpret_cast<uint4*>(px + c)[ch8] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// y = exp(x * scale) on a dense fp32 tensor (FCOS: bbox_pred = scale(fcos_reg(x)).exp(), iou_aware_fcos_head.py:108)
+__global__ void __launch_bounds__(256) scale_exp_kernel(float* __restrict__ x, size_t n, float scale) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    x[i] = expf(__fmul_rn(x[i], scale));
+}
+
 // ---- the same with mmcv.imrescale / imresize in front (transforms.py:33-40): bilinear resize of the uint8 frame
 // exactly as cv2.resize(..., INTER_LINEAR) computes it for 8-bit images (OpenCV imgproc/resize.cpp, the fixed-point
 // path): per destination column fx = (float)((dx+0.5)*scale_x - 0.5), sx = floor(fx), weights
@@ -357,6 +458,47 @@ extern "C" int iou_preprocess_resize_u8(const unsigned char* src, int n, int src
   preprocess_resize_u8_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, n, src_h, src_w, dst_h, dst_w, pad_h, pad_w,
                                                                         1.0 / inv_x, 1.0 / inv_y, nm, to_rgb, flip, dst);
   return launch_status("preprocess_resize_u8_kernel");
+}
+
+extern "C" size_t iou_group_norm_workspace_bytes(int total_images, int groups) {
+  return (size_t)total_images * groups * 2 * sizeof(double);
+}
+
+extern "C" int iou_group_norm_relu(void* map, int c, int num_seg, const iou_conv_segment* seg, int groups,
+                                   const float* gamma, const float* beta, float eps, int relu, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  IOU_REQUIRE(map && seg && gamma && beta && workspace, "NULL argument");
+  IOU_REQUIRE(num_seg >= 1 && num_seg <= IOU_CONV_MAX_SEG, "num_seg out of range");
+  IOU_REQUIRE(c >= 8 && c % 8 == 0 && groups >= 1 && groups <= 256 && c % groups == 0 && (c / groups) % 8 == 0,
+              "GroupNorm needs channels per group to be a multiple of 8 (c %d, groups %d)", c, groups);
+  IOU_REQUIRE(256 % (c / 8) == 0, "GroupNorm supports power-of-two channel counts up to 2048 (got %d)", c);
+  GnSegs G;
+  memset(&G, 0, sizeof(G));
+  G.num_seg = num_seg;
+  int boff = 0, ioff = 0;
+  for (int s = 0; s < num_seg; ++s) {
+    IOU_REQUIRE(seg[s].n_img >= 1 && seg[s].h >= 1 && seg[s].w >= 1, "empty segment %d", s);
+    G.row_start[s] = seg[s].row_start; G.n[s] = seg[s].n_img; G.h[s] = seg[s].h; G.w[s] = seg[s].w;
+    G.blk_off[s] = boff; G.img_off[s] = ioff;
+    boff += seg[s].n_img * seg[s].h; ioff += seg[s].n_img;
+  }
+  for (int s = num_seg; s <= IOU_CONV_MAX_SEG; ++s) { G.blk_off[s] = boff; G.img_off[s] = ioff; }
+  const size_t need = iou_group_norm_workspace_bytes(ioff, groups);
+  if (workspace_bytes < need) return fail(IOU_ERR_WORKSPACE, "workspace too small: need %zu bytes", need);
+  cudaStream_t st = (cudaStream_t)stream;
+  IOU_CHECK_CUDA(cudaMemsetAsync(workspace, 0, need, st));
+  gn_stats_kernel<<<boff, 256, 0, st>>>((const __nv_bfloat16*)map, G, c, groups, (double*)workspace);
+  if (int e = launch_status("gn_stats_kernel")) return e;
+  gn_apply_kernel<<<boff, 256, 0, st>>>((__nv_bfloat16*)map, G, c, groups, (const double*)workspace, gamma, beta, eps, relu);
+  return launch_status("gn_apply_kernel");
+}
+
+extern "C" int iou_scale_exp(float* x, size_t n, float scale, void* stream) {
+  IOU_REQUIRE(x != nullptr || n == 0, "NULL argument");
+  if (n == 0) return IOU_OK;
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  scale_exp_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n, scale);
+  return launch_status("scale_exp_kernel");
 }
 
 extern "C" int iou_preprocess_u8(const unsigned char* src, int n, int h, int w, int pad_h, int pad_w,

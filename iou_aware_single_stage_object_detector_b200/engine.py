@@ -404,6 +404,60 @@ class Engine(object):
         as_nchw = lambda ts: [t.permute(0, 3, 1, 2) for t in ts]
         return as_nchw(cls_out), as_nchw(reg_out), (as_nchw(iou_out) if with_iou else None)
 
+    def group_norm(self, name, m, gamma, beta, groups, eps=1e-5, relu=True):
+        """In-place GroupNorm(+ReLU) of every segment of FlatMap m (ConvModule with norm_cfg type 'GN')."""
+        g, b = self._dev(gamma), self._dev(beta)
+        segs = (L.ConvSegment * len(m.segs))()
+        for i, (rs, n, h, w) in enumerate(m.segs):
+            segs[i].row_start, segs[i].n_img, segs[i].h, segs[i].w = rs, n, h, w
+        nbytes = self.lib.iou_group_norm_workspace_bytes(sum(n for (_, n, _, _) in m.segs), groups)
+        ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=self.device)
+        self.keep += [ws, segs]
+        lib, mp, c, ns, gp, bp, wp = self.lib, m.ptr, m.c, len(m.segs), g.data_ptr(), b.data_ptr(), ws.data_ptr()
+        self.ops.append((name, lambda st: L.check(lib.iou_group_norm_relu(mp, c, ns, segs, groups, gp, bp, float(eps),
+                                                                          int(relu), wp, nbytes, st))))
+        self.extra_launches = getattr(self, "extra_launches", 0) + 2      # memset + 2 kernels behind one op
+        return m
+
+    def scale_exp(self, name, t, scale):
+        """t <- exp(t * scale) on a dense fp32 tensor owned by this engine."""
+        lib, tp, n, sc = self.lib, t.data_ptr(), t.numel(), float(scale)
+        self.ops.append((name, lambda st: L.check(lib.iou_scale_exp(tp, n, sc, st))))
+
+    def add_fcos_head(self, sd, F, prefix="bbox_head.", stacked=4, num_classes=80, groups=32, eps=1e-5):
+        """IoUawareFCOSHead.forward_single for all levels at once (iou_aware_fcos_head.py:92-113): towers of
+        conv(no bias) -> GN -> ReLU; fcos_cls + fcos_centerness share cls_feat (one GEMM, split store), fcos_reg +
+        fcos_iou share reg_feat; bbox_pred = exp(scale_l * fcos_reg).  Returns (cls, bbox_pred, centerness, iou)."""
+        c = r = F
+        fc = sd[prefix + "cls_convs.0.conv.weight"].shape[0]
+        for i in range(stacked):
+            for tower in ("cls", "reg"):
+                k = "%s%s_convs.%d." % (prefix, tower, i)
+                src = c if tower == "cls" else r
+                out = self.conv(k + "conv", [src], TAPS_3X3, pack_weight(sd[k + "conv.weight"], fc), src.c, fc)
+                self.group_norm(k + "gn", out, sd[k + "gn.weight"], sd[k + "gn.bias"], groups, eps, relu=True)
+                if tower == "cls":
+                    c = out
+                else:
+                    r = out
+        mk = lambda ch: [torch.empty(n, h, w, ch, dtype=torch.float32, device=self.device) for (_, n, h, w) in F.segs]
+        cls_out, cen_out, reg_out, iou_out = mk(num_classes), mk(1), mk(4), mk(1)
+        w_cc = torch.cat([sd[prefix + "fcos_cls.weight"], sd[prefix + "fcos_centerness.weight"]], dim=0)
+        b_cc = torch.cat([sd[prefix + "fcos_cls.bias"], sd[prefix + "fcos_centerness.bias"]], dim=0)
+        _, pad_cc = pick_block_n(num_classes + 1)
+        self.conv(prefix + "fcos_cls+centerness", [c], TAPS_3X3, pack_weight(w_cc, pad_cc), fc, num_classes + 1,
+                  shift=b_cc, dense_out=cls_out, dense_out2=cen_out, dense_split=num_classes)
+        w_ri = torch.cat([sd[prefix + "fcos_reg.weight"], sd[prefix + "fcos_iou.weight"]], dim=0)
+        b_ri = torch.cat([sd[prefix + "fcos_reg.bias"], sd[prefix + "fcos_iou.bias"]], dim=0)
+        _, pad_ri = pick_block_n(5)
+        self.conv(prefix + "fcos_reg+iou", [r], TAPS_3X3, pack_weight(w_ri, pad_ri), fc, 5, shift=b_ri,
+                  dense_out=reg_out, dense_out2=iou_out, dense_split=4)
+        for l, t in enumerate(reg_out):
+            self.scale_exp("%sscales.%d.exp" % (prefix, l), t, float(sd["%sscales.%d.scale" % (prefix, l)]))
+        self.keep += cls_out + cen_out + reg_out + iou_out
+        as_nchw = lambda ts: [t.permute(0, 3, 1, 2) for t in ts]
+        return as_nchw(cls_out), as_nchw(reg_out), as_nchw(cen_out), as_nchw(iou_out)
+
     # ------------------------------------------------------------------ layout I/O
     def pack_input(self, x):
         """(N,C,H,W) fp32 cuda tensor -> FlatMap (op appended)."""

@@ -151,6 +151,11 @@ _SIGS = {
                                                 ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                                 ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                                 ctypes.c_void_p]),
+    "iou_group_norm_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "iou_group_norm_relu": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_int,
+                                           ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "iou_scale_exp": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_float, ctypes.c_void_p]),
     "iou_phase_split": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
 }

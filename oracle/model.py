@@ -82,6 +82,31 @@ def head_forward(sd, feats, prefix="bbox_head."):
     return tuple(map(list, zip(*outs)))
 
 
+def fcos_head_forward(sd, feats, prefix="bbox_head.", stacked=4, groups=32, eps=1e-5):
+    """IoUawareFCOSHead.forward (iou_aware_fcos_head.py:89-113): per level, towers of conv(no bias) -> GroupNorm ->
+    ReLU; cls_score / centerness from cls_feat; bbox_pred = exp(scale_l * fcos_reg(reg_feat)); iou from reg_feat.
+    Returns (cls list, bbox_pred list, centerness list, iou list)."""
+    outs = []
+    for l, x in enumerate(feats):
+        c = r = x
+        for i in range(stacked):
+            for tower in ("cls", "reg"):
+                k = "%s%s_convs.%d." % (prefix, tower, i)
+                t = F.conv2d(c if tower == "cls" else r, sd[k + "conv.weight"], None, padding=1)
+                t = F.relu(F.group_norm(t, groups, sd[k + "gn.weight"], sd[k + "gn.bias"], eps))
+                if tower == "cls":
+                    c = t
+                else:
+                    r = t
+        cls = F.conv2d(c, sd[prefix + "fcos_cls.weight"], sd[prefix + "fcos_cls.bias"], padding=1)
+        cen = F.conv2d(c, sd[prefix + "fcos_centerness.weight"], sd[prefix + "fcos_centerness.bias"], padding=1)
+        reg = (F.conv2d(r, sd[prefix + "fcos_reg.weight"], sd[prefix + "fcos_reg.bias"], padding=1) *
+               sd["%sscales.%d.scale" % (prefix, l)]).exp()
+        iou = F.conv2d(r, sd[prefix + "fcos_iou.weight"], sd[prefix + "fcos_iou.bias"], padding=1)
+        outs.append((cls, reg, cen, iou))
+    return tuple(map(list, zip(*outs)))
+
+
 @torch.no_grad()
 def detector_forward(sd, img, depth=50, groups=1):
     """extract_feat + bbox_head (single_stage.py:39-43, 86-87)."""

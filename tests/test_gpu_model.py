@@ -8,6 +8,7 @@ import torch
 import cases
 import parity_util as U
 from oracle import model as om
+from oracle import postproc as op
 
 pytestmark = pytest.mark.gpu
 P = U.P
@@ -250,3 +251,77 @@ def test_preprocess_resize_kernel_bit_exact_vs_cv2_restatement():
             assert tuple(img_shape) == tuple(w_shape) and tuple(pad_shape) == tuple(w_pad) and factor == w_f
             assert np.array_equal(out[i].cpu().numpy().view(np.uint32), want.view(np.uint32)), (i, flip)
     assert tf.pad_shape(120, 160) == (224, 288) and tf.out_shape(120, 160)[:2] == (200, 267)
+
+
+def _spread_fcos_head(seed=5):
+    head = P.IoUawareFCOSHead(81, 256, strides=cases.FCOS_STRIDES)
+    head.init_weights()
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for k, v in head.state_dict().items():
+            if ".gn.weight" in k:
+                v.copy_(torch.rand(v.shape, generator=g) + 0.5)
+            elif ".gn.bias" in k:
+                v.copy_(torch.randn(v.shape, generator=g) * 0.1)
+            elif k.endswith(".scale"):
+                v.copy_(torch.rand(v.shape, generator=g) + 0.5)
+            elif k.endswith("conv.weight"):
+                v.copy_(torch.randn(v.shape, generator=g) * 0.03)
+    return head.eval(), g
+
+
+def test_group_norm_kernel_vs_torch():
+    """iou_group_norm_relu on a two-segment padded-rows map vs torch.nn.functional.group_norm (+ReLU)."""
+    import torch.nn.functional as F
+    from iou_aware_single_stage_object_detector_b200 import engine as E
+    g = torch.Generator().manual_seed(1)
+    xs = [torch.randn(2, 256, 13, 17, generator=g) * 3 + 1, torch.randn(2, 256, 5, 7, generator=g)]
+    gamma, beta = torch.rand(256, generator=g) + 0.5, torch.randn(256, generator=g) * 0.2
+    for groups, relu in ((32, True), (8, False)):
+        eng = E.Engine(DEV)
+        Fm = eng.new_map([(2, 13, 17), (2, 5, 7)], 256)
+        from iou_aware_single_stage_object_detector_b200 import lib as L
+        for s_, x in enumerate(xs):
+            xd = x.to(DEV).contiguous()
+            eng.keep.append(xd)
+            L.check(eng.lib.iou_pack_nchw(xd.data_ptr(), 2, 256, x.shape[2], x.shape[3], Fm.ptr, Fm.segs[s_][0],
+                                          L.stream_ptr()))
+        eng.group_norm("gn", Fm, gamma, beta, groups, 1e-5, relu=relu)
+        outs = [eng.unpack_output(Fm, s_) for s_ in range(2)]
+        eng.run()
+        torch.cuda.synchronize()
+        for x, y in zip(xs, outs):
+            ref = F.group_norm(x, groups, gamma, beta, 1e-5)
+            ref = F.relu(ref) if relu else ref
+            # inputs/outputs live as bf16 hi+lo pairs (16 mantissa bits): 2e-5 of the range
+            assert (y.cpu() - ref).abs().max().item() <= 2e-5 * max(ref.abs().max().item(), 1.0)
+
+
+def test_fcos_head_forward_vs_oracle_and_get_bboxes():
+    """IoUawareFCOSHead.forward on the conv engine (GN towers, split output GEMMs, exp(scale * reg)) vs the oracle
+    restatement that equals the reference module bit for bit; then forward -> get_bboxes end to end vs the oracle."""
+    head, g = _spread_fcos_head()
+    sd = {"bbox_head." + k: v.clone() for k, v in head.state_dict().items()}
+    sizes = [(16, 20), (8, 10), (4, 5), (2, 3), (1, 2)]
+    feats = [torch.randn(2, 256, h, w, generator=g) for (h, w) in sizes]
+    ref = om.fcos_head_forward(sd, feats)
+    head = head.to(DEV)
+    outs = head([f.to(DEV) for f in feats])
+    torch.cuda.synchronize()
+    for name, a_l, b_l in zip(("cls", "bbox_pred", "centerness", "iou"), outs, ref):
+        for lvl, (a, b) in enumerate(zip(a_l, b_l)):
+            assert tuple(a.shape) == tuple(b.shape), (name, lvl, a.shape, b.shape)
+            err = (a.cpu() - b).abs().max().item()
+            assert err <= 2e-4 * max(b.abs().max().item(), 1.0), (name, lvl, err)
+    # end to end through the reference signature
+    cfg = P.ConfigDict(dict(cases.TEST_CFG, nms_pre=300))
+    metas = [dict(ori_shape=(128, 157, 3), img_shape=(128, 157, 3), pad_shape=(128, 160, 3), scale_factor=1.0,
+                  flip=False)] * 2
+    res = head.get_bboxes(outs[0], outs[1], outs[2], outs[3], [None] * 2, [None] * 2, metas, cfg, rescale=False)
+    for i, (d, l) in enumerate(res):
+        want_d, want_l = op.fcos_get_bboxes_single([t[i] for t in ref[0]], [t[i] for t in ref[1]], [t[i] for t in ref[3]],
+                                                   cases.FCOS_STRIDES, metas[i]["img_shape"], 1.0, dict(cfg))
+        assert abs(d.shape[0] - want_d.shape[0]) <= 2
+        if want_d.shape[0]:
+            frac, ms, mb = U.match_as_sets(d.cpu().numpy(), l.cpu().numpy(), want_d.numpy(), want_l.numpy(),
+                                           min_frac=0.97, score_tol=1e-4, box_tol=1e-4 * 160)

@@ -49,3 +49,43 @@ def test_oracle_model_equals_reference_modules():
     out = subprocess.run([sys.executable, "-c", CODE % ROOT], capture_output=True, text=True, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-3000:]
     assert "WORST 0.0" in out.stdout
+
+
+FCOS_CODE = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from oracle import ref_shim, model as om
+ref_shim.load_reference()
+from mmdet.models.anchor_heads import IoUawareFCOSHead
+torch.manual_seed(0)
+head = IoUawareFCOSHead(num_classes=81, in_channels=256, stacked_convs=4, feat_channels=256, strides=[8, 16, 32, 64, 128])
+head.init_weights()
+g = torch.Generator().manual_seed(5)
+with torch.no_grad():
+    for k, v in head.state_dict().items():          # spread the affine GN / Scale parameters and the convs
+        if ".gn.weight" in k: v.copy_(torch.rand(v.shape, generator=g) + 0.5)
+        elif ".gn.bias" in k: v.copy_(torch.randn(v.shape, generator=g) * 0.1)
+        elif k.endswith(".scale"): v.copy_(torch.rand(v.shape, generator=g) + 0.5)
+        elif k.endswith("conv.weight"): v.copy_(torch.randn(v.shape, generator=g) * 0.03)
+head.eval()
+feats = [torch.randn(2, 256, h, w, generator=g) for (h, w) in [(16, 20), (8, 10), (4, 5), (2, 3), (1, 2)]]
+with torch.no_grad():
+    outs = head(feats)
+sd = {"bbox_head." + k: v for k, v in head.state_dict().items()}
+mine = om.fcos_head_forward(sd, feats)
+worst = 0.0
+for a_list, b_list in zip(outs, mine):
+    for a, b in zip(a_list, b_list):
+        assert a.shape == b.shape
+        worst = max(worst, (a - b).abs().max().item())
+print("WORST", worst)
+assert worst == 0.0, worst
+'''
+
+
+@pytest.mark.reference
+def test_oracle_fcos_head_equals_reference_module():
+    """oracle.model.fcos_head_forward == the reference IoUawareFCOSHead.forward, bit for bit."""
+    out = subprocess.run([sys.executable, "-c", FCOS_CODE % ROOT], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-3000:]
+    assert "WORST 0.0" in out.stdout
