@@ -223,7 +223,7 @@ int iou_maxpool3x3s2(const void* src, int n, int c, int h, int w, void* dst, voi
 /* Splits a padded-rows map into the 4 stride-2 phase maps laid out in the OUTPUT
  * geometry ((h+1)/2 x (w+1)/2): phase[py][px][u][v] = in_padded[2(u-1)+py][2(v-1)+px]. */
 int iou_phase_split(const void* src, int n, int c, int h, int w, void* const* dst4,
-                    int phase_mask, void* stream);
+                    int phase_mask, void* stream);   /* bits 0..3: phases to write; bit 4: apply ReLU while copying */
 
 /* ------------------------------------------------------------------ GroupNorm towers (IoUawareFCOSHead, "next" row rank 4)
  * In-place GroupNorm (+ReLU) of a padded-rows map holding num_seg segments (FPN levels): the norm layer of

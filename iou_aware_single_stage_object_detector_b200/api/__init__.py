@@ -15,7 +15,7 @@ from .anchor_head import AnchorHead
 from .iou_aware_retina_head import IoUawareRetinaHead
 from .retina_head import RetinaHead
 from .iou_aware_fcos_head import IoUawareFCOSHead
-from .detectors import BaseDetector, SingleStageDetector, RetinaNet, FusedPlan
+from .detectors import BaseDetector, SingleStageDetector, RetinaNet, FCOS, FusedPlan
 from .ops import (nms, soft_nms, sigmoid_focal_loss, SigmoidFocalLoss, nms_cuda, nms_cpu, soft_nms_cpu,
                   sigmoid_focal_loss_cuda)
 from .engine_cache import invalidate_plans

@@ -71,6 +71,9 @@ class FusedPlan(object):
             raise RuntimeError("SingleStageDetector was built without test_cfg (nms_pre, score_thr, nms, "
                                "max_per_img): pass test_cfg=cfg.test_cfg to build_detector")
         self.eng = eng
+        # heads return their forward() tuple; get_bboxes' kernels take (cls, reg, iou-or-None)
+        to_post = getattr(det.bbox_head, "postproc_inputs", None)
+        self.post_in = to_post(self.outs) if to_post is not None else (self.outs[0], self.outs[1], self.outs[2])
         sizes = [tuple(t.shape[-2:]) for t in self.outs[0]]
         shared = det.bbox_head.postproc_workspace(sizes, n, det.test_cfg, self.device)
         # the head caches ONE workspace per configuration; a plan owns its scratch and outputs so that two plans
@@ -85,11 +88,12 @@ class FusedPlan(object):
     def _launch(self):
         self.eng.run()
         if self.wsp.soft is not None:            # test_cfg.nms = dict(type='soft_nms', ...)
-            boxes, scores_cm, _ = PP.decode_candidates(self.wsp, self.outs[0], self.outs[1], self.outs[2],
+            boxes, scores_cm, _ = PP.decode_candidates(self.wsp, self.post_in[0], self.post_in[1], self.post_in[2],
                                                        self.img_info, self.rescale)
             PP.batched_soft_nms(self.wsp, boxes, scores_cm, *self.wsp.soft)
         else:
-            PP.get_bboxes_device(self.wsp, self.outs[0], self.outs[1], self.outs[2], self.img_info, self.rescale)
+            PP.get_bboxes_device(self.wsp, self.post_in[0], self.post_in[1], self.post_in[2], self.img_info,
+                                 self.rescale)
 
     def run(self):
         """Enqueue one pass on the current stream (inputs: self.img, self.img_info)."""
@@ -279,6 +283,14 @@ class SingleStageDetector(BaseDetector):
 
     def aug_test(self, imgs, img_metas, rescale=False):
         raise NotImplementedError
+
+
+@DETECTORS.register_module
+class FCOS(SingleStageDetector):
+    """mmdet/models/detectors/fcos.py:6-16 (with IoUawareFCOSHead: configs/fcos/iou_aware_fcos_r50_caffe_fpn_gn_1x_4gpu.py)."""
+
+    def __init__(self, backbone, neck, bbox_head, train_cfg=None, test_cfg=None, pretrained=None):
+        super(FCOS, self).__init__(backbone, neck, bbox_head, train_cfg, test_cfg, pretrained)
 
 
 @DETECTORS.register_module

@@ -50,17 +50,17 @@ class FPN(nn.Module):
                 xavier_init(m, distribution='uniform')
 
     def _check_supported(self):
-        if not (self.add_extra_convs and self.extra_convs_on_inputs) or self.relu_before_extra_convs \
-                or self.activation is not None or self.end_level != -1:
-            raise NotImplementedError("only the RetinaNet FPN variant (extra convs on inputs, no "
-                                      "activation) is planned")
+        if not self.add_extra_convs or self.activation is not None or self.end_level != -1:
+            raise NotImplementedError("only FPNs whose extra levels are stride-2 convs (RetinaNet / FCOS variants, "
+                                      "no activation) are planned")
         if any(m.with_norm for m in self.lateral_convs):
             raise NotImplementedError("FPN with norm layers is not planned")
 
     def plan_into(self, eng, sd, feats, prefix=""):
         self._check_supported()
         return eng.add_fpn(sd, feats, prefix=prefix, start_level=self.start_level, num_outs=self.num_outs,
-                           out_channels=self.out_channels)
+                           out_channels=self.out_channels, extra_convs_on_inputs=self.extra_convs_on_inputs,
+                           relu_before_extra_convs=self.relu_before_extra_convs)
 
     def forward(self, inputs):
         assert len(inputs) == len(self.in_channels)

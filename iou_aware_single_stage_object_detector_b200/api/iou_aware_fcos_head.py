@@ -113,6 +113,12 @@ class IoUawareFCOSHead(nn.Module):
             eng.run()
         return outs
 
+    @staticmethod
+    def postproc_inputs(outs):
+        """(cls_scores, bbox_preds, ious) out of forward()'s (cls, bbox_pred, centerness, iou): the centerness maps
+        do not enter get_bboxes (iou_aware_fcos_head.py:342-366)."""
+        return outs[0], outs[1], outs[3]
+
     def forward_single(self, x, scale=None):
         if len(self.strides) != 1:
             raise NotImplementedError("forward_single needs the level's Scale: call forward(feats) with all levels")

@@ -24,13 +24,14 @@ class Bottleneck(nn.Module):
                  base_width=4, conv_cfg=None, norm_cfg=dict(type='BN')):
         super(Bottleneck, self).__init__()
         assert style in ['pytorch', 'caffe']
-        if style != 'pytorch':
-            raise NotImplementedError("caffe-style bottlenecks are not used by the IoU-aware configs")
         width = planes if groups == 1 else math.floor(planes * (base_width / 64)) * groups
         self.inplanes, self.planes, self.stride, self.groups, self.width = inplanes, planes, stride, groups, width
-        self.conv1 = build_conv_layer(conv_cfg, inplanes, width, kernel_size=1, stride=1, bias=False)
+        self.style = style
+        # resnet.py:129-134: 'pytorch' strides the 3x3 conv2, 'caffe' the 1x1 conv1
+        s1, s2 = (1, stride) if style == 'pytorch' else (stride, 1)
+        self.conv1 = build_conv_layer(conv_cfg, inplanes, width, kernel_size=1, stride=s1, bias=False)
         self.add_module('bn1', build_norm_layer(norm_cfg, width, postfix=1)[1])
-        self.conv2 = build_conv_layer(conv_cfg, width, width, kernel_size=3, stride=stride, padding=1,
+        self.conv2 = build_conv_layer(conv_cfg, width, width, kernel_size=3, stride=s2, padding=1,
                                       groups=groups, bias=False)
         self.add_module('bn2', build_norm_layer(norm_cfg, width, postfix=2)[1])
         self.conv3 = build_conv_layer(conv_cfg, width, planes * self.expansion, kernel_size=1, bias=False)
@@ -135,7 +136,7 @@ class ResNet(nn.Module):
     def plan_into(self, eng, sd, img, prefix=""):
         if self.num_stages != 4:
             raise NotImplementedError("only 4-stage backbones are planned")
-        feats = eng.add_backbone(sd, img, depth=self.depth, groups=self.groups, prefix=prefix)
+        feats = eng.add_backbone(sd, img, depth=self.depth, groups=self.groups, prefix=prefix, style=self.style)
         return feats
 
     def forward(self, x):

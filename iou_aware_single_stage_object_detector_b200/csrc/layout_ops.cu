@@ -257,7 +257,22 @@ __global__ void __launch_bounds__(256) phase_split_kernel(const uint4* __restric
       const int py = ph >> 1, px = ph & 1;
       const int sy = 2 * (u - 1) + py, sx = 2 * (v - 1) + px;
       uint4 val = make_uint4(0, 0, 0, 0);
-      if (u >= 1 && v >= 1 && sy < hp && sx < wp) val = __ldg(src + (((size_t)img * hp + sy) * wp + sx) * vec + q);
+      if (u >= 1 && v >= 1 && sy < hp && sx < wp) {
+        const uint4* px = src + (((size_t)img * hp + sy) * wp + sx) * vec;
+        val = __ldg(px + q);
+        if (phase_mask & 16) {                       // fused ReLU (FPN relu_before_extra_convs, fpn.py:124-127):
+          // x = hi + lo is negative exactly when hi is; the lo half is cleared with the hi half's sign bits
+          const int half = vec >> 1;
+          const uint4 hv = q < half ? val : __ldg(px + (q - half));
+          const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+          uint32_t* vw = reinterpret_cast<uint32_t*>(&val);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t neg = ((hw[e] & 0x8000u) ? 0xffffu : 0u) | ((hw[e] & 0x80000000u) ? 0xffff0000u : 0u);
+            vw[e] &= ~neg;
+          }
+        }
+      }
       dst.p[ph][i] = val;
     }
   }
@@ -573,7 +588,8 @@ extern "C" int iou_maxpool3x3s2(const void* src, int n, int c, int h, int w, voi
 extern "C" int iou_phase_split(const void* src, int n, int c, int h, int w, void* const* dst4, int phase_mask,
                                void* stream) {
   IOU_REQUIRE(src && dst4 && n > 0 && c > 0 && (c % 4) == 0 && h > 0 && w > 0, "bad argument");
-  IOU_REQUIRE(phase_mask > 0 && phase_mask < 16, "phase_mask out of range");
+  IOU_REQUIRE((phase_mask & 15) != 0 && phase_mask < 32, "phase_mask out of range (bits 0..3: phases, bit 4: ReLU)");
+  IOU_REQUIRE(!(phase_mask & 16) || (c % 8) == 0, "the fused ReLU needs c %% 8 == 0");
   PhasePtrs P;
   for (int i = 0; i < 4; ++i) {
     P.p[i] = (uint4*)dst4[i];

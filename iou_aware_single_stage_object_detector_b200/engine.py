@@ -256,8 +256,9 @@ class Engine(object):
         self.ops.append((name, lambda st, p=plan: L.check(lib.iou_conv_run(p, st))))
         return out
 
-    def phase_split(self, name, src, mask=15):
-        """-> list of 4 FlatMaps (None where masked out) in the stride-2 output geometry."""
+    def phase_split(self, name, src, mask=15, relu=False):
+        """-> list of 4 FlatMaps (None where masked out) in the stride-2 output geometry; relu=True clamps the
+        copied values at zero (FPN relu_before_extra_convs)."""
         assert len(src.segs) == 1
         _, n, h, w = src.segs[0]
         ho, wo = (h + 1) // 2, (w + 1) // 2
@@ -265,7 +266,8 @@ class Engine(object):
         arr = (ctypes.c_void_p * 4)(*[(o.ptr if o is not None else None) for o in outs])
         self.keep.append(arr)
         lib, c, sp = self.lib, src.c, src.ptr
-        self.ops.append((name, lambda st: L.check(lib.iou_phase_split(sp, n, c, h, w, arr, mask, st))))
+        kmask = mask | (16 if relu else 0)
+        self.ops.append((name, lambda st: L.check(lib.iou_phase_split(sp, n, c, h, w, arr, kmask, st))))
         return outs
 
     # ------------------------------------------------------------------ network builders
@@ -287,8 +289,9 @@ class Engine(object):
         self.ops.append(("stem.maxpool", lambda st: L.check(lib.iou_maxpool3x3s2(sp, n, 64, ho, wo, xp, st))))
         return x
 
-    def add_backbone(self, sd, img, depth=50, groups=1, prefix="backbone."):
-        """ResNet (groups == 1) or ResNeXt (grouped 3x3 run as a block-diagonal tap-GEMM)."""
+    def add_backbone(self, sd, img, depth=50, groups=1, prefix="backbone.", style="pytorch"):
+        """ResNet (groups == 1) or ResNeXt (grouped 3x3 run as a block-diagonal tap-GEMM).  style 'pytorch' puts a
+        block's stride in the 3x3 conv2, 'caffe' in the 1x1 conv1 (resnet.py:129-134)."""
         x = self.add_stem(sd, img, prefix)
         outs = []
         for s, nblocks in enumerate(STAGE_BLOCKS[depth]):
@@ -299,8 +302,13 @@ class Engine(object):
                 cin = x.c
                 width = sd[p + "conv1.weight"].shape[0]          # == planes for ResNet (resnext.py:21-24)
                 sc1, sh1 = bn_fold(sd, p + "bn1")
-                t1 = self.conv(p + "conv1", [x], TAPS_1X1, pack_weight(fold_scale(sd[p + "conv1.weight"], sc1), width),
-                               cin, width, shift=sh1, relu=True)
+                w1 = pack_weight(fold_scale(sd[p + "conv1.weight"], sc1), width)
+                xs = None
+                if stride == 2 and style == "caffe":        # 1x1 stride 2 reads phase (1,1) of x; conv2 has stride 1
+                    xs = self.phase_split(p + "conv1.phase", x, mask=8)
+                    t1 = self.conv(p + "conv1", [xs[3]] * 4, TAPS_1X1_S2, w1, cin, width, shift=sh1, relu=True)
+                else:
+                    t1 = self.conv(p + "conv1", [x], TAPS_1X1, w1, cin, width, shift=sh1, relu=True)
                 sc2, sh2 = bn_fold(sd, p + "bn2")
                 if groups == 1:
                     w2, kw = pack_weight(fold_scale(sd[p + "conv2.weight"], sc2), width), {}
@@ -308,7 +316,7 @@ class Engine(object):
                     cg = sd[p + "conv2.weight"].shape[1]
                     w2 = pack_weight_grouped(fold_scale(sd[p + "conv2.weight"], sc2), groups)
                     kw = dict(diag_k=True, true_flops_scale=cg / 64.0)
-                if stride == 2:
+                if stride == 2 and style != "caffe":
                     ph = self.phase_split(p + "conv2.phase", t1)
                     t2 = self.conv(p + "conv2", ph, TAPS_3X3_S2, w2, width, width, shift=sh2,
                                    relu=True, **kw)
@@ -320,7 +328,8 @@ class Engine(object):
                     scd, shd = bn_fold(sd, p + "downsample.1")
                     wd = pack_weight(fold_scale(sd[p + "downsample.0.weight"], scd), planes * 4)
                     if stride == 2:
-                        xs = self.phase_split(p + "downsample.phase", x, mask=8)
+                        if xs is None:
+                            xs = self.phase_split(p + "downsample.phase", x, mask=8)
                         srcs = [xs[3], xs[3], xs[3], xs[3]]
                         idt = self.conv(p + "downsample", srcs, TAPS_1X1_S2, wd, cin, planes * 4,
                                         shift=shd)
@@ -334,8 +343,11 @@ class Engine(object):
             outs.append(x)
         return outs
 
-    def add_fpn(self, sd, feats, prefix="neck.", start_level=1, num_outs=5, out_channels=256):
-        """feats: list of FlatMaps C2..C5.  Returns one multi-segment FlatMap (P3..P7)."""
+    def add_fpn(self, sd, feats, prefix="neck.", start_level=1, num_outs=5, out_channels=256,
+                extra_convs_on_inputs=True, relu_before_extra_convs=False):
+        """feats: list of FlatMaps C2..C5.  Returns one multi-segment FlatMap (P3..P7).  The extra stride-2 levels
+        read C5 (RetinaNet configs) or the last FPN output (FCOS, extra_convs_on_inputs=False), optionally through
+        a ReLU (relu_before_extra_convs; fpn.py:117-128)."""
         used = feats[start_level:]
         nl = len(used)
         lat = [None] * nl
@@ -362,13 +374,14 @@ class Engine(object):
             kp = "%sfpn_convs.%d.conv." % (prefix, i)
             self.conv(kp[:-1], [lat[i]], TAPS_3X3, pack_weight(sd[kp + "weight"], out_channels),
                       out_channels, out_channels, out=F.view(i), shift=sd[kp + "bias"])
-        src = feats[-1]                                   # extra_convs_on_inputs=True: P6 from C5
+        src = feats[-1] if extra_convs_on_inputs else F.view(nl - 1)     # fpn.py:118-122
         for i in range(nl, num_outs):
             kp = "%sfpn_convs.%d.conv." % (prefix, i)
-            ph = self.phase_split(kp + "phase", src)
+            # fpn.py:123-128: ReLU only in front of the extra convs AFTER the first one
+            ph = self.phase_split(kp + "phase", src, relu=(relu_before_extra_convs and i > nl))
             self.conv(kp[:-1], ph, TAPS_3X3_S2, pack_weight(sd[kp + "weight"], out_channels), src.c,
                       out_channels, out=F.view(i), shift=sd[kp + "bias"])
-            src = F.view(i)                               # relu_before_extra_convs=False
+            src = F.view(i)
         return F
 
     def add_head(self, sd, F, prefix="bbox_head.", stacked=4, num_anchors=9, num_classes=80, with_iou=True):

@@ -325,3 +325,40 @@ def test_fcos_head_forward_vs_oracle_and_get_bboxes():
         if want_d.shape[0]:
             frac, ms, mb = U.match_as_sets(d.cpu().numpy(), l.cpu().numpy(), want_d.numpy(), want_l.numpy(),
                                            min_frac=0.97, score_tol=1e-4, box_tol=1e-4 * 160)
+
+
+def test_fcos_detector_end_to_end_small():
+    """configs/fcos/iou_aware_fcos_r50_caffe_fpn_gn_1x_4gpu.py through build_detector: caffe-style ResNet (stride in
+    the 1x1), FPN with P6 from P5 and ReLU before P7, GroupNorm head, distance decode, alpha 0.3 -- head maps and
+    detections vs the oracle (which equals the reference FCOS detector bit for bit)."""
+    cfg = P.Config.fromfile(os.path.join(U.ROOT, "configs", "fcos", "iou_aware_fcos_r50_caffe_fpn_gn_1x_4gpu.py"))
+    cfg.model.pretrained = None
+    torch.manual_seed(0)
+    det = P.build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg).eval()
+    assert type(det).__name__ == "FCOS"
+    sd = det.state_dict()
+    om.spread_fcos_weights_(sd, seed=1)
+    det.load_state_dict(sd)
+    sd = {k: v.clone() for k, v in det.state_dict().items()}
+    det = det.to(DEV)
+    n, h, w = 2, 128, 160
+    img = torch.randn(n, 3, h, w, generator=torch.Generator().manual_seed(3))
+    metas = [dict(ori_shape=(h, w - 3, 3), img_shape=(h, w - 3, 3), pad_shape=(h, w, 3), scale_factor=1.0,
+                  flip=False) for _ in range(n)]
+    results = det.simple_test_batch(img.to(DEV), metas, rescale=False)
+    results = det.simple_test_batch(img.to(DEV), metas, rescale=False)        # second call replays the CUDA graph
+    plan = det.fused_plan(img.shape, torch.device(DEV), False)
+    torch.cuda.synchronize()
+    ref = om.fcos_detector_forward(sd, img)
+    for name, mine, r in zip(("cls", "bbox_pred", "centerness", "iou"), plan.outs, ref):
+        for lvl, (a, b) in enumerate(zip(mine, r)):
+            err = (a.cpu() - b).abs().max().item()
+            assert err <= 3e-4 * max(b.abs().max().item(), 1.0), (name, lvl, err, b.abs().max().item())
+    for i in range(n):
+        d_ref, l_ref = op.fcos_get_bboxes_single([c[i] for c in ref[0]], [r_[i] for r_ in ref[1]],
+                                                 [q[i] for q in ref[3]], cases.FCOS_STRIDES, metas[i]["img_shape"],
+                                                 1.0, dict(cfg.test_cfg), rescale=False)
+        d_my, l_my = U.results_to_arrays(results[i])
+        assert abs(len(d_my) - d_ref.shape[0]) <= 3 and d_ref.shape[0] > 0
+        U.match_as_sets(d_my, l_my, d_ref.numpy(), l_ref.numpy(), min_frac=0.97, score_tol=1e-4,
+                        box_tol=1e-4 * max(h, w))

@@ -317,5 +317,3 @@ def test_fcos_head_get_bboxes_vs_reference_golden():
         o1, o2 = np.lexsort((d[:, 0], l, -d[:, 4])), np.lexsort((gd[:, 0], gl, -gd[:, 4]))
         assert np.array_equal(l[o1], gl[o2])
         assert np.allclose(d[o1], gd[o2], rtol=U.RTOL, atol=U.ATOL), np.abs(d[o1] - gd[o2]).max()
-    with pytest.raises(NotImplementedError):
-        head.forward(tuple(cls))

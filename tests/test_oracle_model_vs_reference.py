@@ -89,3 +89,43 @@ def test_oracle_fcos_head_equals_reference_module():
     out = subprocess.run([sys.executable, "-c", FCOS_CODE % ROOT], capture_output=True, text=True, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-3000:]
     assert "WORST 0.0" in out.stdout
+
+
+FCOS_DET_CODE = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from oracle import ref_shim, model as om, postproc as op
+ref_shim.load_reference()
+cfg = ref_shim.load_config("/root/reference/configs/fcos/iou_aware_fcos_r50_caffe_fpn_gn_1x_4gpu.py")
+torch.manual_seed(0)
+m, cfg = ref_shim.build_reference_detector(cfg)
+sd = {k: v.clone() for k, v in m.state_dict().items()}
+om.spread_fcos_weights_(sd, seed=1)
+m.load_state_dict(sd)
+img = torch.randn(1, 3, 128, 160)
+with torch.no_grad():
+    outs = m.bbox_head(m.extract_feat(img))
+mine = om.fcos_detector_forward(sd, img)
+worst = 0.0
+for a_list, b_list in zip(outs, mine):
+    for a, b in zip(a_list, b_list):
+        assert a.shape == b.shape
+        worst = max(worst, (a - b).abs().max().item())
+print("WORST", worst)
+assert worst == 0.0, worst
+meta = dict(ori_shape=(128,157,3), img_shape=(128,157,3), pad_shape=(128,160,3), scale_factor=1.0, flip=False)
+with torch.no_grad():
+    res = m.bbox_head.get_bboxes(*outs, [torch.zeros(0,4)], [torch.zeros(0,dtype=torch.long)], [meta], cfg.test_cfg, rescale=True)
+d, l = op.fcos_get_bboxes_single([c[0] for c in outs[0]], [r[0] for r in outs[1]], [q[0] for q in outs[3]],
+                                 [8, 16, 32, 64, 128], meta["img_shape"], 1.0, dict(cfg.test_cfg), rescale=True, nms_mode="cpu")
+assert torch.equal(d, res[0][0]) and torch.equal(l, res[0][1]), (d.shape, res[0][0].shape)
+print("DETS", d.shape[0])
+'''
+
+
+@pytest.mark.reference
+def test_oracle_fcos_detector_equals_reference():
+    """caffe-style ResNet + FCOS FPN variant + IoUawareFCOSHead + get_bboxes == the reference FCOS detector."""
+    out = subprocess.run([sys.executable, "-c", FCOS_DET_CODE % ROOT], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-3000:]
+    assert "WORST 0.0" in out.stdout
