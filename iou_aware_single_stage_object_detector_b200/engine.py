@@ -165,6 +165,7 @@ class Engine(object):
         self.two_cta = os.environ.get("IOU_TWO_CTA", "1") != "0"
         self.pair_min_bn = int(os.environ.get("IOU_PAIR_MIN_BN", "64"))
         self.pair_min_tiles = int(os.environ.get("IOU_PAIR_MIN_TILES", "32"))
+        self.res_bn256 = os.environ.get("IOU_RES_BN256", "1") != "0"        # N = 256 tiles for residual convs in pair mode
         self.pair_diag = os.environ.get("IOU_PAIR_DIAG", "1") != "0"       # grouped (block-diagonal) convs as CTA pairs
         self.lib = L.load()
 
@@ -186,10 +187,15 @@ class Engine(object):
         """srcs: list[FlatMap] (same geometry); out: FlatMap or None (dense).  Returns out."""
         geo = segs_from or srcs[0]
         m_tiles = sum(_round_up(n * (h + 2) * (w + 2), TILE_M) // TILE_M for (_, n, h, w) in geo.segs)
-        # a same-geometry residual needs its TMA staging ring in shared memory: N tile <= 128
-        block_n, cout_pad = pick_block_n(cout, m_tiles, max_bn=128 if res_mode == L.RES_SAME else 256,
-                                         pair_min_tiles=self.pair_min_tiles if (self.two_cta and two_cta is None and
-                                                                                os.environ.get('IOU_PAIR_AWARE', '1') == '1') else None)
+        # a same-geometry residual needs its TMA staging ring in shared memory: N tile <= 128, or 256 when the conv
+        # runs as a CTA pair (half a B tile per CTA); plan_create decides, so 256 is tried first and 128 is the retry
+        pair_aware = self.pair_min_tiles if (self.two_cta and two_cta is None and
+                                             os.environ.get('IOU_PAIR_AWARE', '1') == '1') else None
+        res_wide = (res_mode == L.RES_SAME and self.res_bn256 and self.two_cta and two_cta is None and
+                    m_tiles >= self.pair_min_tiles and cout % 256 == 0)
+        block_n, cout_pad = pick_block_n(cout, m_tiles, max_bn=128 if (res_mode == L.RES_SAME and not res_wide) else 256,
+                                         pair_min_tiles=pair_aware)
+        retry_bn = 128 if (res_wide and block_n == 256) else None
         if diag_k:
             block_n, cout_pad = 64, cout
         d = L.ConvDesc()
@@ -247,7 +253,11 @@ class Engine(object):
                     d.out_dense2[i] = t.data_ptr()
         d.passes = self.passes
         plan = ctypes.c_void_p()
-        L.check(self.lib.iou_conv_plan_create(ctypes.byref(d), ctypes.byref(plan)))
+        rc = self.lib.iou_conv_plan_create(ctypes.byref(d), ctypes.byref(plan))
+        if rc != 0 and retry_bn is not None:         # the wide residual tile did not fit next to the staging rings
+            d.block_n = retry_bn
+            rc = self.lib.iou_conv_plan_create(ctypes.byref(d), ctypes.byref(plan))
+        L.check(rc)
         self.plans.append(plan)
         f = self.lib.iou_conv_plan_flops(plan) * true_flops_scale
         self.flops += f
