@@ -557,7 +557,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
           }
           uint32_t v[32];
           tc_ld32(t_row + g * 32, v);
-          const float sh_l = P.shift ? __ldg(P.shift + c0 + lane) : 0.f;
+          // per-channel shift (and optional scale) of the slab's 32 channels: 8 broadcast 16-byte loads (every lane
+          // reads the same address) instead of one load + 32 shuffles
+          float shv[32];
+          if (P.shift) {
+            const float4* sp = reinterpret_cast<const float4*>(P.shift + c0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 t4 = __ldg(sp + q);
+              shv[4 * q] = t4.x; shv[4 * q + 1] = t4.y; shv[4 * q + 2] = t4.z; shv[4 * q + 3] = t4.w;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) shv[q] = 0.f;
+          }
           const float sc_l = P.scale ? __ldg(P.scale + c0 + lane) : 1.f;
           tc_wait_ld();
           if (P.combine) {                                 // sum the hi*hi, hi*lo and lo*hi column blocks
@@ -575,10 +588,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
           if (P.scale) {
 #pragma unroll
             for (int q = 0; q < 32; ++q)
-              f[q] = fmaf(__uint_as_float(v[q]), __shfl_sync(0xffffffffu, sc_l, q), __shfl_sync(0xffffffffu, sh_l, q));
+              f[q] = fmaf(__uint_as_float(v[q]), __shfl_sync(0xffffffffu, sc_l, q), shv[q]);
           } else {
 #pragma unroll
-            for (int q = 0; q < 32; ++q) f[q] = __uint_as_float(v[q]) + __shfl_sync(0xffffffffu, sh_l, q);
+            for (int q = 0; q < 32; ++q) f[q] = __uint_as_float(v[q]) + shv[q];
           }
           if (P.res_staged) {
             const uint32_t rb = st_res + (rq & 1) * 4096 + lane * 64;
