@@ -218,6 +218,9 @@ int iou_im2col_stem(const float* img, int n, int h, int w, int kpad, void* dst, 
  * neighbouring pixels x'-2..x'+1 of the 2x2 space-to-depth image (16 channels each, 12 real):
  * kk = j*16 + (py*2+px)*3 + ch.  The 7x7/s2 conv is then 4 taps (dy=-2..1) of K=64 on iou_conv_run. */
 int iou_stem_pack(const float* img, int n, int h, int w, void* dst, void* stream);
+/* The same with the four VERTICAL neighbours y'-2..y'+1 at column x' in the 64 channels: the conv is then the 4 taps
+ * dx = -2..1 at dy = 0, which share ONE A window in iou_conv_run (half the shared-memory fill of the stem conv). */
+int iou_stem_pack_v(const float* img, int n, int h, int w, void* dst, void* stream);
 /* 3x3 stride-2 pad-1 max pool (resnet.py:466) on padded rows (inputs >= 0). */
 int iou_maxpool3x3s2(const void* src, int n, int c, int h, int w, void* dst, void* stream);
 /* Splits a padded-rows map into the 4 stride-2 phase maps laid out in the OUTPUT

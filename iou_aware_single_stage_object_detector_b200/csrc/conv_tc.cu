@@ -58,7 +58,7 @@ struct ConvParams {
   // (dx = dx0..dx0+2) share ONE (128+8)-row A window and address it through row-shifted descriptors
   int num_groups;
   int grp_src[IOU_CONV_MAX_TAPS], grp_dy[IOU_CONV_MAX_TAPS], grp_dx0[IOU_CONV_MAX_TAPS], grp_nt[IOU_CONV_MAX_TAPS];
-  int grp_tap[IOU_CONV_MAX_TAPS][3], grp_shift[IOU_CONV_MAX_TAPS][3];
+  int grp_tap[IOU_CONV_MAX_TAPS][4], grp_shift[IOU_CONV_MAX_TAPS][4];   // up to 4 taps per window (shift 0..3 rows)
   int a_rows, a_entry_bytes, b_entry_bytes, num_a_stages, num_b_stages, ring_bytes, taps_per_tile;
   int b_tile_bytes;
   int staged, res_staged, staging_per_warp;
@@ -792,7 +792,7 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   P.b_entry_bytes = nsplit * P.b_tile_bytes;
   if (P.b_tile_bytes % 1024 != 0) { delete plan; return fail(IOU_ERR_INVALID, "block_n %d: B tile is not a whole number of swizzle atoms", d->block_n); }
   P.taps_per_tile = d->num_taps;
-  // tap groups: taps reading the same source at the same dy with dx within a span of 3 share one A window
+  // tap groups: taps reading the same source at the same dy with dx within a span of 4 share one A window
   // (tried first; if the rings do not fit shared memory that way, every tap loads its own 128-row window)
   bool fits = false;
   for (int share = getenv("IOU_NO_A_SHARE") ? 0 : 1; share >= 0 && !fits; --share) {
@@ -801,12 +801,12 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
     for (int t = 0; t < d->num_taps; ++t) {
       if (used[t]) continue;
       const int g = P.num_groups++;
-      int members[3] = {t, -1, -1}, nm = 1, dxmin = d->tap_dx[t], dxmax = d->tap_dx[t];
+      int members[4] = {t, -1, -1, -1}, nm = 1, dxmin = d->tap_dx[t], dxmax = d->tap_dx[t];
       used[t] = true;
-      for (int u = t + 1; u < d->num_taps && nm < 3 && share; ++u) {
+      for (int u = t + 1; u < d->num_taps && nm < 4 && share; ++u) {
         if (used[u] || d->tap_src[u] != d->tap_src[t] || d->tap_dy[u] != d->tap_dy[t]) continue;
         const int lo = d->tap_dx[u] < dxmin ? d->tap_dx[u] : dxmin, hi = d->tap_dx[u] > dxmax ? d->tap_dx[u] : dxmax;
-        if (hi - lo > 2) continue;
+        if (hi - lo > 3) continue;                      // the window has 8 spare rows; the stem uses dx = -2..1
         members[nm++] = u; used[u] = true; dxmin = lo; dxmax = hi;
       }
       P.grp_src[g] = d->tap_src[t]; P.grp_dy[g] = d->tap_dy[t]; P.grp_dx0[g] = dxmin; P.grp_nt[g] = nm;

@@ -196,6 +196,65 @@ __device__ __forceinline__ void max8(float (&m)[8], const uint4 hv, const uint4 
   }
 }
 
+// ---- stem, vertical variant: the 64 "channels" of output pixel (y', x') are the four VERTICALLY neighbouring
+// pixels y'-2..y'+1 of the 2x2 space-to-depth image at column x' (kk = j*16 + (py*2+px)*3 + ch).  The 7x7/s2 conv
+// is then four taps dx = -2..1 at dy = 0 -- ONE shared A window per tile (row-shifted descriptors) instead of
+// four separate windows: the stem conv is bound by shared-memory fill bandwidth, this halves it.
+constexpr int kStemChunk = 112;                  // padded output pixels per block (224 input columns)
+constexpr int kStemRows = 4;                     // padded output rows per block: 2*4 + 6 input rows staged once
+constexpr int kStemRowStride = 2 * kStemChunk + 1;   // odd stride: staged rows fall into different banks
+__global__ void __launch_bounds__(256) stem_pack_v_kernel(const float* __restrict__ img, int n, int h, int w,
+                                                          int ho, int wo, __nv_bfloat16* __restrict__ dst) {
+  constexpr int kIn = 2 * kStemRows + 6;          // input rows 2(y0'-2) .. 2(y0'+R-1+1)+1
+  __shared__ float rows[3 * kIn * kStemRowStride];
+  const int yp0 = blockIdx.x * kStemRows, im = blockIdx.y;
+  const int wop = wo + 2;
+  const int xp0 = blockIdx.z * kStemChunk, xp1 = min(xp0 + kStemChunk, wop);
+  const int ys0 = yp0 - 1;                        // s2d row of the block's first padded output row
+  const int col0 = 2 * (xp0 - 1);                 // first input column of the chunk
+  for (int i = threadIdx.x; i < 3 * kIn * 2 * kStemChunk; i += blockDim.x) {
+    const int ch = i / (kIn * 2 * kStemChunk), rem = i - ch * kIn * 2 * kStemChunk;
+    const int r = rem / (2 * kStemChunk), xx = rem - r * 2 * kStemChunk;
+    const int y = 2 * (ys0 - 2) + r, x = col0 + xx;
+    rows[(ch * kIn + r) * kStemRowStride + xx] =
+        (y >= 0 && y < h && x >= 0 && x < w) ? __ldg(img + (((size_t)im * 3 + ch) * h + y) * w + x) : 0.f;
+  }
+  __syncthreads();
+  const int nx = xp1 - xp0;
+  for (int i = threadIdx.x; i < kStemRows * nx * 8; i += blockDim.x) {
+    const int rr = i / (nx * 8), rem = i - rr * nx * 8;
+    const int xl = rem >> 3, v = rem & 7;         // vector v holds kk = 8v .. 8v+7
+    const int yp = yp0 + rr, xp = xp0 + xl;
+    if (yp > ho + 1) continue;
+    uint32_t hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
+    if (yp >= 1 && yp <= ho && xp >= 1 && xp <= wo) {
+      const int j = v >> 1, q0 = (v & 1) * 8;     // j: vertical neighbour y' - 2 + j
+      float val[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int q = q0 + e;
+        float t = 0.f;
+        if (q < 12) {
+          const int pp = q / 3, ch = q - pp * 3, py = pp >> 1, px = pp & 1;
+          t = rows[(ch * kIn + 2 * (rr + j) + py) * kStemRowStride + 2 * xl + px];
+        }
+        val[e] = t;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(val[2 * e], h0, l0);
+        split_bf16(val[2 * e + 1], h1, l1);
+        hi[e] = pack2_bf16(h0, h1);
+        lo[e] = pack2_bf16(l0, l1);
+      }
+    }
+    uint4* drow = reinterpret_cast<uint4*>(dst + ((size_t)im * (ho + 2) + yp) * wop * 128);
+    drow[(size_t)xp * 16 + v] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    drow[(size_t)xp * 16 + 8 + v] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
 __global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* __restrict__ src, int n, int c, int h,
                                                       int w, int ho, int wo, __nv_bfloat16* __restrict__ dst) {
   const int c8 = c >> 3;
@@ -559,6 +618,15 @@ extern "C" int iou_im2col_stem(const float* img, int n, int h, int w, int kpad, 
   }
   im2col_stem_kernel<<<dim3(ho + 2, n), 256, sm, (cudaStream_t)stream>>>(img, n, h, w, ho, wo, kpad, (__nv_bfloat16*)dst);
   return launch_status("im2col_stem_kernel");
+}
+
+extern "C" int iou_stem_pack_v(const float* img, int n, int h, int w, void* dst, void* stream) {
+  IOU_REQUIRE(img && dst && n > 0 && h > 0 && w > 0, "bad argument");
+  const int ho = (h + 6 - 7) / 2 + 1, wo = (w + 6 - 7) / 2 + 1;
+  const int chunks = (wo + 2 + kStemChunk - 1) / kStemChunk;
+  IOU_REQUIRE(n <= 65535 && chunks <= 65535, "batch / width out of range for the stem pack kernel");
+  stem_pack_v_kernel<<<dim3((ho + 2 + kStemRows - 1) / kStemRows, n, chunks), 256, 0, (cudaStream_t)stream>>>(img, n, h, w, ho, wo, (__nv_bfloat16*)dst);
+  return launch_status("stem_pack_v_kernel");
 }
 
 extern "C" int iou_stem_pack(const float* img, int n, int h, int w, void* dst, void* stream) {

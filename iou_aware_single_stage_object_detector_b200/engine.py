@@ -26,7 +26,8 @@ TAPS_1X1 = [(0, 0, 0)]
 TAPS_3X3 = [(0, r - 1, s - 1) for r in range(3) for s in range(3)]                    # stride 1, pad 1
 TAPS_3X3_S2 = [((r & 1) * 2 + (s & 1), r >> 1, s >> 1) for r in range(3) for s in range(3)]  # on phase maps
 TAPS_1X1_S2 = [(3, 0, 0)]
-TAPS_STEM = [(0, r - 2, 0) for r in range(4)]                                          # stem: dy = -2..1                                                             # phase (1,1)
+TAPS_STEM = [(0, r - 2, 0) for r in range(4)]
+TAPS_STEM_V = [(0, 0, s - 2) for s in range(4)]                                        # stem, vertical pack: dx = -2..1                                          # stem: dy = -2..1                                                             # phase (1,1)
 
 
 def _round_up(x, m):
@@ -90,6 +91,23 @@ def pack_weight_stem(w):
                     if 0 <= ky <= 6 and 0 <= kx <= 6:
                         k0 = j * 16 + (py * 2 + px) * 3
                         t[r, :, k0:k0 + 3] = w[:, :, ky, kx].float()
+    hi, lo = split_hi_lo(t)
+    return torch.cat([hi, lo], dim=2).reshape(4 * cout, 128).contiguous()
+
+
+def pack_weight_stem_v(w):
+    """(64, 3, 7, 7) stem weight -> [4 taps * 64][2*64] for iou_stem_pack_v: tap s (dx = s-2), K index
+    kk = j*16 + (py*2+px)*3 + ch  <->  w[o, ch, 2j+py-1, 2s+px-1] (j = vertical neighbour y'-2+j)."""
+    cout = w.shape[0]
+    t = torch.zeros(4, cout, 64, dtype=torch.float32, device=w.device)
+    for s_ in range(4):
+        for j in range(4):
+            for py in range(2):
+                for px in range(2):
+                    ky, kx = 2 * j + py - 1, 2 * s_ + px - 1
+                    if 0 <= ky <= 6 and 0 <= kx <= 6:
+                        k0 = j * 16 + (py * 2 + px) * 3
+                        t[s_, :, k0:k0 + 3] = w[:, :, ky, kx].float()
     hi, lo = split_hi_lo(t)
     return torch.cat([hi, lo], dim=2).reshape(4 * cout, 128).contiguous()
 
@@ -165,6 +183,7 @@ class Engine(object):
         self.two_cta = os.environ.get("IOU_TWO_CTA", "1") != "0"
         self.pair_min_bn = int(os.environ.get("IOU_PAIR_MIN_BN", "64"))
         self.pair_min_tiles = int(os.environ.get("IOU_PAIR_MIN_TILES", "32"))
+        self.stem_vertical = os.environ.get("IOU_STEM_VERTICAL", "1") != "0"
         self.res_bn256 = os.environ.get("IOU_RES_BN256", "1") != "0"        # N = 256 tiles for residual convs in pair mode
         self.pair_diag = os.environ.get("IOU_PAIR_DIAG", "1") != "0"       # grouped (block-diagonal) convs as CTA pairs
         self.lib = L.load()
@@ -289,10 +308,16 @@ class Engine(object):
         packed = self.new_map([(n, ho, wo)], 64)
         lib, ip, pp = self.lib, img.data_ptr(), packed.ptr
         self.keep.append(img)
-        self.ops.append(("stem.pack", lambda st: L.check(lib.iou_stem_pack(ip, n, h, w, pp, st))))
         scale, shift = bn_fold(sd, prefix + "bn1")
-        s1 = self.conv("stem.conv1", [packed], TAPS_STEM, pack_weight_stem(fold_scale(sd[prefix + "conv1.weight"], scale)), 64, 64,
-                       shift=shift, relu=True, true_flops_scale=147.0 / 256.0)
+        wf = fold_scale(sd[prefix + "conv1.weight"], scale)
+        if self.stem_vertical:      # four dx taps sharing one A window (half the shared-memory fill of the stem conv)
+            self.ops.append(("stem.pack", lambda st: L.check(lib.iou_stem_pack_v(ip, n, h, w, pp, st))))
+            s1 = self.conv("stem.conv1", [packed], TAPS_STEM_V, pack_weight_stem_v(wf), 64, 64, shift=shift, relu=True,
+                           true_flops_scale=147.0 / 256.0)
+        else:
+            self.ops.append(("stem.pack", lambda st: L.check(lib.iou_stem_pack(ip, n, h, w, pp, st))))
+            s1 = self.conv("stem.conv1", [packed], TAPS_STEM, pack_weight_stem(wf), 64, 64, shift=shift, relu=True,
+                           true_flops_scale=147.0 / 256.0)
         hp, wq = (ho - 1) // 2 + 1, (wo - 1) // 2 + 1
         x = self.new_map([(n, hp, wq)], 64)
         sp, xp = s1.ptr, x.ptr
