@@ -301,8 +301,8 @@ def run_ours(args):
                 "peak": peaks["tf_sustained"], "peak_source": peaks["source"] + " bf16 sustained (cuBLAS)",
                 "unit": "TFLOP/s", "frac": round(achieved / peaks["tf_sustained"], 4),
                 # dram__bytes_read+write summed over the 71 conv launches of one step / 71, from the ncu pass
-                # committed as profiles/r01_v8_launches_ncu_dram.csv (22.06 GB per step)
-                "traffic": 310.7e6, "traffic_source": "ncu, profiles/r01_v8_launches_ncu_dram.csv",
+                # committed as profiles/r01_v11_launches_ncu_dram.csv (22.01 GB per step)
+                "traffic": 310.0e6, "traffic_source": "ncu, profiles/r01_v11_launches_ncu_dram.csv",
                 "launches_per_step": n_conv,
                 "avg_launch_ms": round(conv_ms / max(n_conv, 1), 4),
                 "algorithmic_gflop_per_step": round(conv_flops / 1e9, 1),
