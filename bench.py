@@ -333,7 +333,8 @@ def run_ours(args):
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "fp32 (bf16x3 split on tcgen05, fp32 accumulate)" if args.passes == 3 else "bf16",
+                "dtype": {3: "fp32 (bf16x3 split on tcgen05, fp32 accumulate)",
+                          2: "fp32 (fp16 + 2x e4m3 split on tcgen05, fp32 accumulate)"}.get(args.passes, "bf16"),
                 "data": "synthetic",
                 "config": {"workload": "IoU-aware RetinaNet %s-FPN inference bs=%d/GPU, synthetic 800x1344 "
                                        "(img_shape 800x1333), backbone+FPN+head+get_bboxes" % (MODEL.upper(), BATCH),
@@ -445,7 +446,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--weights", default="spread", choices=["spread", "reference-init"])
-    ap.add_argument("--passes", type=int, default=3, choices=[1, 3, 4])
+    ap.add_argument("--passes", type=int, default=3, choices=[1, 2, 3, 4],
+                    help="3: bf16 hi|lo x3 (default); 2: fp16 + e4m3 corrections (2 bf16-pass equivalents); 1: bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu launch lists)")
     ap.add_argument("--no-pipeline", action="store_true", help="one launch plan on one stream (no step overlap)")

@@ -149,7 +149,10 @@ int iou_sigmoid_focal_loss_backward(const float* logits, const int64_t* targets,
  * columns [0,Cch) hold hi = bf16(v), columns [Cch,2Cch) hold lo = bf16(v - hi);
  * the one-pixel border rows are zero.  Several maps (FPN levels) may be
  * concatenated as "segments", each starting at a multiple of 128 rows.
- * Weight layout: bf16 [taps*cout_pad][2*Cin] (hi | lo), tap-major, K contiguous. */
+ * Weight layout: bf16 [taps*cout_pad][2*Cin] (hi | lo), tap-major, K contiguous.
+ * passes == 2 (IOU_FMT_F16F8, declared with the layout kernels): the same row sizes hold
+ * [Wh: Cin x fp16][per 8 input channels: Wl8 x 8 | W8 x 8], Wl8 = e4m3((w - Wh) * 2^11 * s_n),
+ * W8 = e4m3(w * s_n), s_n a power of two per output channel; acc = Wh*hi + scale[n] * (Wl8*x8 + W8*l8). */
 #define IOU_CONV_MAX_SEG 8
 #define IOU_CONV_MAX_TAPS 9
 #define IOU_CONV_MAX_SRC 4
@@ -173,7 +176,8 @@ typedef struct iou_conv_desc {
   const void* src[IOU_CONV_MAX_SRC];        /* bf16 [src_rows][2*cin]                    */
   int64_t src_rows;
   const void* weight;                       /* bf16 [num_taps*cout_pad][2*cin]           */
-  const float* scale;                       /* [cout_pad] per-channel multiplier (BN fold) or NULL */
+  const float* scale;                       /* [cout_pad] per-channel multiplier (BN fold) or NULL; passes == 2: REQUIRED,
+                                               the multiplier of the e4m3 correction accumulator (2^-11 / s_n) */
   const float* shift;                       /* [cout_pad] bias / BN shift or NULL        */
   int32_t relu;
   int32_t res_mode;
@@ -186,7 +190,9 @@ typedef struct iou_conv_desc {
   void* out_dense2[IOU_CONV_MAX_SEG];
   int32_t num_seg;
   iou_conv_segment seg[IOU_CONV_MAX_SEG];
-  int32_t passes;                           /* 3 = hi*hi+hi*lo+lo*hi (fp32-grade), 4 = +lo*lo, 1 = bf16 */
+  int32_t passes;                           /* 3 = hi*hi+hi*lo+lo*hi (fp32-grade), 4 = +lo*lo, 1 = bf16;
+                                               2 = IOU_FMT_F16F8 maps and weights: one fp16 MMA pass + one e4m3
+                                               pass of doubled K (two bf16-pass equivalents), see below          */
   int64_t out_rows;                         /* PADDED: rows allocated behind `out` (TMA store clips there) */
   int64_t res_rows;                         /* rows allocated behind `residual`                             */
   int32_t diag_k;                           /* grouped conv (cin == cout, block_n == 64): output tile j contracts
@@ -227,6 +233,19 @@ int iou_maxpool3x3s2(const void* src, int n, int c, int h, int w, void* dst, voi
  * geometry ((h+1)/2 x (w+1)/2): phase[py][px][u][v] = in_padded[2(u-1)+py][2(v-1)+px]. */
 int iou_phase_split(const void* src, int n, int c, int h, int w, void* const* dst4,
                     int phase_mask, void* stream);   /* bits 0..3: phases to write; bit 4: apply ReLU while copying */
+/* The same layout kernels for either element format of a padded-rows map (ABI version 3).  Both formats spend
+ * 4 bytes per element as [hi plane: c x 16 bit][lo plane: c x 16 bit], one 16-byte vector per 8 channels and plane:
+ *   IOU_FMT_BF16X2: hi = bf16(v), lo = bf16(v - hi)                          (conv passes = 3; the *_fmt-less calls)
+ *   IOU_FMT_F16F8 : hi = fp16(v), lo vector = [x8 x 8 | l8 x 8], x8 = e4m3(v), l8 = e4m3((v - hi) * 2^11)
+ *                                                                            (conv passes = 2; needs c % 8 == 0)
+ * iou_phase_split copies bytes and serves both (its fused ReLU only IOU_FMT_BF16X2). */
+enum { IOU_FMT_BF16X2 = 0, IOU_FMT_F16F8 = 1 };
+int iou_pack_nchw_fmt(const float* src, int n, int c, int h, int w, void* dst, int64_t dst_row_start, int fmt,
+                      void* stream);
+int iou_unpack_nchw_fmt(const void* src, int64_t src_row_start, int n, int c, int h, int w, float* dst, int fmt,
+                        void* stream);
+int iou_stem_pack_v_fmt(const float* img, int n, int h, int w, void* dst, int fmt, void* stream);
+int iou_maxpool3x3s2_fmt(const void* src, int n, int c, int h, int w, void* dst, int fmt, void* stream);
 
 /* ------------------------------------------------------------------ GroupNorm towers (IoUawareFCOSHead, "next" row rank 4)
  * In-place GroupNorm (+ReLU) of a padded-rows map holding num_seg segments (FPN levels): the norm layer of

@@ -16,6 +16,10 @@
 // fp32-grade accuracy comes from three bf16 MMAs per K step (hi*hi + hi*lo + lo*hi) into the
 // same fp32 accumulator; `passes = 1` runs plain bf16.  Two TMEM accumulator stages let the
 // epilogue of tile i overlap the MMAs of tile i+1.
+// `passes = 2` (template kF8) is the fp16 + e4m3 scheme of split_fmt.cuh: per K step one kind::f16 MMA
+// (fp16 hi x fp16 Whi) into the main accumulator and one kind::f8f6f4 MMA ([x8|l8] x [Wl8;W8], K = 32) into a
+// second accumulator that the epilogue folds in with a per-channel power-of-two scale: two bf16-pass
+// equivalents of tensor-pipe time instead of three.
 //
 // Replaces the F.conv2d / cuDNN calls of mmdet/models/backbones/resnet.py:224-267,
 // mmdet/models/necks/fpn.py:97-136, mmdet/models/anchor_heads/iou_aware_retina_head.py:171-219.
@@ -25,6 +29,7 @@
 #include <cstdlib>
 #include <new>
 #include "common.cuh"
+#include "split_fmt.cuh"
 
 namespace iou {
 
@@ -74,6 +79,9 @@ struct ConvParams {
   int dense_split;
   unsigned int idesc, idesc2;
   int combine;               // narrow N: A_hi x [B_hi|B_lo] as ONE MMA of N = 2*block_n, A_lo x B_hi into a third column block
+  int f8;                    // passes == 2: fp16 main pass + e4m3 correction pass (split_fmt.cuh); `scale` = 2^-11 / s_n
+  int num_acc;               // TMEM accumulator stages (2, or 1 when main + correction fill all 512 columns)
+  int corr_off;              // f8: TMEM column offset of the correction accumulator inside a stage
 };
 
 // ------------------------------------------------------------------------------------ PTX
@@ -170,6 +178,25 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uin
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void tc_mma_f8_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -231,8 +258,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
 }
 
 // ------------------------------------------------------------------------------------ kernel
-template <bool kTwoCta>
+template <bool kTwoCta, bool kF8>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __grid_constant__ ConvParams P) {
+  constexpr int kFmt = kF8 ? kFmtF16F8 : kFmtBf16x2;
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte alignment is required by the 128B swizzle atoms
   const uint32_t raw = smem_u32(smem_dyn);
@@ -350,7 +378,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
     int as = 0, bs = 0;
     uint32_t aph = 0, bph = 0;
     int it = 0;
-    const int mode = P.combine ? 5 : (P.passes == 3 ? (P.lolo ? 4 : 3) : 1);
+    const int mode = kF8 ? 6 : (P.combine ? 5 : (P.passes == 3 ? (P.lolo ? 4 : 3) : 1));
+    const uint32_t corr_off = (uint32_t)P.corr_off;
+    const bool two_acc = P.num_acc == 2;
     const uint32_t a_lo_d = a_lo_off >> 4, b_lo_d = b_lo_off >> 4;
     const uint32_t idesc = P.idesc, idesc2 = P.idesc2, col2 = 2u * (uint32_t)P.block_n;
     auto mma_i = [&](uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t id, uint32_t accum) {
@@ -359,8 +389,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
     };
     auto mma = [&](uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t accum) { mma_i(d_tmem, ad, bd, idesc, accum); };
     for (int tile = w_first; tile < w_total && rank == 0; tile += w_stride, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int acc = two_acc ? (it & 1) : 0;
+      const uint32_t acc_phase = (uint32_t)(two_acc ? (it >> 1) : it) & 1u;
       mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
@@ -382,7 +412,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
               const uint32_t da = umma_desc_lo(sa + (uint32_t)P.grp_shift[g][j] * 128u), db = umma_desc_lo(sb);
               const uint32_t dal = da + a_lo_d, dbl = db + b_lo_d;
               const uint32_t first = done > 0 ? 1u : 0u;
-              if (mode == 5) {
+              if constexpr (kF8) {
+                // fp16 hi x Whi -> main accumulator; [x8|l8] x [Wl8;W8] (e4m3, K = 32 per 32 bytes) -> correction
+                // accumulator.  Both instruction descriptors have the same bits (formats 0 = F16 / E4M3).
+#pragma unroll
+                for (uint32_t kk = 0; kk < kBlockK / 16; ++kk) {
+                  mma_i(d_tmem, umma_desc(da + 2 * kk), umma_desc(db + 2 * kk), idesc, kk ? 1u : first);
+                  if constexpr (kTwoCta) tc_mma_f8_pair(d_tmem + corr_off, umma_desc(dal + 2 * kk), umma_desc(dbl + 2 * kk), idesc, kk ? 1u : first);
+                  else tc_mma_f8(d_tmem + corr_off, umma_desc(dal + 2 * kk), umma_desc(dbl + 2 * kk), idesc, kk ? 1u : first);
+                }
+              } else if (mode == 5) {
                 // back-to-back MMAs into the SAME accumulator serialise on its read-modify-write latency
                 // (~120 cycles, more than a 128 x 64 x 16 MMA computes for): B_hi and B_lo are adjacent in
                 // the B entry, so hi*hi and hi*lo are one N = 2*block_n MMA into columns [0, 2bn) and lo*hi
@@ -452,9 +491,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
     int rq = 0;                                            // running slab counter of the residual ring
     if (P.res_staged && w_first < w_total && elect_one()) issue_res(w_first, half, 0);
     int it = 0;
+    const bool two_acc = P.num_acc == 2;
     for (int tile = w_first; tile < w_total; tile += w_stride, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int acc = two_acc ? (it & 1) : 0;
+      const uint32_t acc_phase = (uint32_t)(two_acc ? (it >> 1) : it) & 1u;
       int m_tile, n_tile, s;
       decode_tile(tile, m_tile, n_tile, s);
       const bool tile_valid = m_tile < P.num_m_tiles;        // pair mode: the odd CTA of the last pair may idle
@@ -483,7 +523,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
         uint32_t v[16];
         tc_ld16(t_row + ch * 16, v);
         tc_wait_ld();
-        if (P.combine) {                                   // sum the hi*hi, hi*lo and lo*hi column blocks
+        const int c0 = n_tile * P.block_n + ch * 16;      // first output channel of this chunk
+        if constexpr (kF8) {                               // + correction accumulator x per-channel 2^-11 / s_n
+          uint32_t w1[16];
+          tc_ld16(t_row + P.corr_off + ch * 16, w1);
+          tc_wait_ld();
+#pragma unroll
+          for (int q = 0; q < 16; ++q)
+            v[q] = __float_as_uint(fmaf(__uint_as_float(w1[q]), __ldg(P.scale + c0 + q), __uint_as_float(v[q])));
+        } else if (P.combine) {                            // sum the hi*hi, hi*lo and lo*hi column blocks
           uint32_t w1[16], w2[16];
           tc_ld16(t_row + P.block_n + ch * 16, w1);
           tc_ld16(t_row + 2 * P.block_n + ch * 16, w2);
@@ -492,12 +540,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
           for (int q = 0; q < 16; ++q)
             v[q] = __float_as_uint(__uint_as_float(v[q]) + (__uint_as_float(w1[q]) + __uint_as_float(w2[q])));
         }
-        const int c0 = n_tile * P.block_n + ch * 16;      // first output channel of this chunk
         float f[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
           float x = __uint_as_float(v[q]);
-          if (P.scale) x *= __ldg(P.scale + c0 + q);
+          if (!kF8 && P.scale) x *= __ldg(P.scale + c0 + q);
           if (P.shift) x += __ldg(P.shift + c0 + q);
           f[q] = x;
         }
@@ -506,13 +553,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
           const uint4* rl = reinterpret_cast<const uint4*>(res_row + P.cout + c0);
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
-            const uint4 hv = __ldg(rh + h2), lv = __ldg(rl + h2);
-            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+            float t8[8];
+            decode8<kFmt>(__ldg(rh + h2), __ldg(rl + h2), t8);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              f[h2 * 8 + q * 2 + 0] += __uint_as_float(hw[q] << 16) + __uint_as_float(lw[q] << 16);
-              f[h2 * 8 + q * 2 + 1] += __uint_as_float(hw[q] & 0xffff0000u) + __uint_as_float(lw[q] & 0xffff0000u);
-            }
+            for (int q = 0; q < 8; ++q) f[h2 * 8 + q] += t8[q];
           }
         }
         if (P.relu) {
@@ -557,6 +601,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
           }
           uint32_t v[32];
           tc_ld32(t_row + g * 32, v);
+          uint32_t wc[kF8 ? 32 : 1];
+          if constexpr (kF8) tc_ld32(t_row + P.corr_off + g * 32, wc);
           // per-channel shift (and optional scale) of the slab's 32 channels: 8 broadcast 16-byte loads (every lane
           // reads the same address) instead of one load + 32 shuffles
           float shv[32];
@@ -571,9 +617,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
 #pragma unroll
             for (int q = 0; q < 32; ++q) shv[q] = 0.f;
           }
-          const float sc_l = P.scale ? __ldg(P.scale + c0 + lane) : 1.f;
+          const float sc_l = (!kF8 && P.scale) ? __ldg(P.scale + c0 + lane) : 1.f;
           tc_wait_ld();
-          if (P.combine) {                                 // sum the hi*hi, hi*lo and lo*hi column blocks
+          if constexpr (kF8) {                             // + correction accumulator x per-channel 2^-11 / s_n
+            const float4* cp = reinterpret_cast<const float4*>(P.scale + c0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 t4 = __ldg(cp + q);
+              const int qq = kF8 ? 4 * q : 0;
+              v[4 * q] = __float_as_uint(fmaf(__uint_as_float(wc[qq]), t4.x, __uint_as_float(v[4 * q])));
+              v[4 * q + 1] = __float_as_uint(fmaf(__uint_as_float(wc[kF8 ? qq + 1 : 0]), t4.y, __uint_as_float(v[4 * q + 1])));
+              v[4 * q + 2] = __float_as_uint(fmaf(__uint_as_float(wc[kF8 ? qq + 2 : 0]), t4.z, __uint_as_float(v[4 * q + 2])));
+              v[4 * q + 3] = __float_as_uint(fmaf(__uint_as_float(wc[kF8 ? qq + 3 : 0]), t4.w, __uint_as_float(v[4 * q + 3])));
+            }
+          } else if (P.combine) {                          // sum the hi*hi, hi*lo and lo*hi column blocks
             uint32_t w1[32];
             tc_ld32(t_row + P.block_n + g * 32, w1);
             tc_wait_ld();
@@ -585,7 +642,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
             for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(w1[q]));
           }
           float f[32];
-          if (P.scale) {
+          if (!kF8 && P.scale) {
 #pragma unroll
             for (int q = 0; q < 32; ++q)
               f[q] = fmaf(__uint_as_float(v[q]), __shfl_sync(0xffffffffu, sc_l, q), shv[q]);
@@ -598,26 +655,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint32_t sw = (uint32_t)((j ^ swz) << 4);
-              const uint4 hv = lds128(rb + sw), lv = lds128(rb + 2048 + sw);
-              const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+              float t8[8];
+              decode8<kFmt>(lds128(rb + sw), lds128(rb + 2048 + sw), t8);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                f[j * 8 + q * 2 + 0] += __uint_as_float(hw[q] << 16) + __uint_as_float(lw[q] << 16);
-                f[j * 8 + q * 2 + 1] += __uint_as_float(hw[q] & 0xffff0000u) + __uint_as_float(lw[q] & 0xffff0000u);
-              }
+              for (int q = 0; q < 8; ++q) f[j * 8 + q] += t8[q];
             }
           } else if (res_row != nullptr && interior) {     // nearest-2x upsampled residual (FPN laterals)
             const uint4* rh = reinterpret_cast<const uint4*>(res_row + c0);
             const uint4* rl = reinterpret_cast<const uint4*>(res_row + P.cout + c0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint4 hv = __ldg(rh + j), lv = __ldg(rl + j);
-              const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+              float t8[8];
+              decode8<kFmt>(__ldg(rh + j), __ldg(rl + j), t8);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                f[j * 8 + q * 2 + 0] += __uint_as_float(hw[q] << 16) + __uint_as_float(lw[q] << 16);
-                f[j * 8 + q * 2 + 1] += __uint_as_float(hw[q] & 0xffff0000u) + __uint_as_float(lw[q] & 0xffff0000u);
-              }
+              for (int q = 0; q < 8; ++q) f[j * 8 + q] += t8[q];
             }
           }
           if (lane == 0) tma_store_wait_read();            // previous slab has left the staging tile
@@ -625,22 +676,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
           const uint32_t ob = st_out + lane * 64;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            uint32_t hi[4], lo[4];
+            float x8[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float x0 = f[j * 8 + 2 * q], x1 = f[j * 8 + 2 * q + 1];
-              if (P.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-              // packed fp32x2 -> bf16x2 conversions (F2FP): hi = bf16(x), lo = bf16(x - hi)
-              const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
-              const uint32_t hbits = *reinterpret_cast<const uint32_t*>(&h2);
-              const __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - __uint_as_float(hbits << 16),
-                                                              x1 - __uint_as_float(hbits & 0xffff0000u));
-              hi[q] = interior ? hbits : 0u;
-              lo[q] = interior ? *reinterpret_cast<const uint32_t*>(&l2) : 0u;
-            }
+            for (int q = 0; q < 8; ++q) x8[q] = P.relu ? fmaxf(f[j * 8 + q], 0.f) : f[j * 8 + q];
+            // packed conversions (F2FP): bf16 hi | lo, or fp16 hi | e4m3 pairs (split_fmt.cuh); border rows are zero
+            uint4 hi, lo;
+            encode8<kFmt>(x8, hi, lo);
+            if (!interior) { hi = make_uint4(0, 0, 0, 0); lo = hi; }
             const uint32_t sw = (uint32_t)((j ^ swz) << 4);
-            sts128(ob + sw, make_uint4(hi[0], hi[1], hi[2], hi[3]));
-            sts128(ob + 2048 + sw, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+            sts128(ob + sw, hi);
+            sts128(ob + 2048 + sw, lo);
           }
           fence_async_smem();
           __syncwarp();
@@ -723,7 +768,8 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   IOU_REQUIRE(d->num_taps >= 1 && d->num_taps <= IOU_CONV_MAX_TAPS, "num_taps out of range");
   IOU_REQUIRE(d->num_src >= 1 && d->num_src <= IOU_CONV_MAX_SRC, "num_src out of range");
   IOU_REQUIRE(d->num_seg >= 1 && d->num_seg <= IOU_CONV_MAX_SEG, "num_seg out of range");
-  IOU_REQUIRE(d->passes == 1 || d->passes == 3 || d->passes == 4, "passes must be 1, 3 or 4");
+  IOU_REQUIRE(d->passes >= 1 && d->passes <= 4, "passes must be 1, 2 (fp16 + e4m3), 3 or 4");
+  IOU_REQUIRE(d->passes != 2 || d->scale != nullptr, "passes == 2 needs `scale` = the per-channel correction scale 2^-11 / s_n");
   IOU_REQUIRE(d->weight != nullptr, "weight is NULL");
   IOU_REQUIRE(!d->diag_k || (d->block_n == 64 && d->cin == d->cout), "diag_k (grouped conv) needs block_n == 64 and cin == cout");
   IOU_REQUIRE(d->src_rows > 0 && d->src_rows < (1ll << 31), "src_rows out of range");
@@ -750,6 +796,10 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   P.k_slabs = P.diag_k ? 1 : d->cin / kBlockK;
   P.passes = d->passes == 1 ? 1 : 3;   // 3 = hi/lo operands staged; lolo adds the fourth product
   P.lolo = d->passes == 4;
+  P.f8 = d->passes == 2;
+  // f8: main + correction accumulators per stage; wide tiles fill all 512 TMEM columns -> one stage
+  P.num_acc = (P.f8 && d->block_n > 128) ? 1 : 2;
+  P.corr_off = d->block_n > 128 ? 256 : 128;
   for (int t = 0; t < d->num_taps; ++t) {
     if (d->tap_src[t] < 0 || d->tap_src[t] >= d->num_src) { delete plan; return fail(IOU_ERR_INVALID, "tap_src out of range"); }
     P.tap_src[t] = d->tap_src[t]; P.tap_dy[t] = d->tap_dy[t]; P.tap_dx[t] = d->tap_dx[t];
@@ -788,7 +838,7 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   P.staged = (d->out_mode == IOU_OUT_PADDED_BF16X2) && (d->block_n % 64 == 0);
   P.res_staged = P.staged && d->res_mode == IOU_RES_SAME;
   P.staging_per_warp = P.staged ? (4096 + (P.res_staged ? 8192 : 0)) : 0;      // x 8 epilogue warps
-  const int nsplit = d->passes >= 3 ? 2 : 1;
+  const int nsplit = d->passes >= 2 ? 2 : 1;
   P.b_entry_bytes = nsplit * P.b_tile_bytes;
   if (P.b_tile_bytes % 1024 != 0) { delete plan; return fail(IOU_ERR_INVALID, "block_n %d: B tile is not a whole number of swizzle atoms", d->block_n); }
   P.taps_per_tile = d->num_taps;
@@ -842,8 +892,10 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   P.out_mode = d->out_mode; P.out = (__nv_bfloat16*)d->out; P.dense_split = d->dense_split;
   // cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=BF16 (1<<7, 1<<10), K-major both, N>>3 @17, M>>4 @24
   P.combine = (d->passes == 3 && !P.two_cta && d->block_n <= 80 && !getenv("IOU_NO_COMBINE")) ? 1 : 0;
-  P.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * d->block_n) >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
-  P.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d->block_n >> 3) << 17) |
+  // f8: a/b format fields 0 = F16 (kind::f16) and 0 = E4M3 (kind::f8f6f4): one descriptor serves both MMAs
+  const uint32_t fmt_bits = P.f8 ? 0u : ((1u << 7) | (1u << 10));
+  P.idesc2 = (1u << 4) | fmt_bits | ((uint32_t)((2 * d->block_n) >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+  P.idesc = (1u << 4) | fmt_bits | ((uint32_t)(d->block_n >> 3) << 17) |
             ((uint32_t)((P.two_cta ? 2 * kBlockM : kBlockM) >> 4) << 24);
   for (int i = 0; i < d->num_src; ++i) {
     if (!d->src[i] || ((uintptr_t)d->src[i] & 15)) { delete plan; return fail(IOU_ERR_INVALID, "src[%d] NULL or misaligned", i); }
@@ -873,9 +925,13 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   plan->flops = 2.0 * real_rows * d->cout * (double)(P.diag_k ? kBlockK : d->cin) * d->num_taps;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tap_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    cudaError_t e = cudaFuncSetAttribute(conv_tap_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_tap_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+      e = cudaFuncSetAttribute(conv_tap_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_tap_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_tap_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     if (e != cudaSuccess) { delete plan; return fail(IOU_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
     attr_set = true;
   }
@@ -895,11 +951,15 @@ extern "C" int iou_conv_run(const iou_conv_plan* plan, void* stream) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tap_gemm_kernel<true>, plan->params);
+    cudaError_t e = plan->params.f8 ? cudaLaunchKernelEx(&cfg, conv_tap_gemm_kernel<true, true>, plan->params)
+                                    : cudaLaunchKernelEx(&cfg, conv_tap_gemm_kernel<true, false>, plan->params);
     if (e != cudaSuccess) return fail(IOU_ERR_CUDA, "conv_tap_gemm_kernel<pair> launch failed: %s", cudaGetErrorString(e));
     return IOU_OK;
   }
-  conv_tap_gemm_kernel<false><<<plan->grid, kNumThreads, plan->smem_bytes, (cudaStream_t)stream>>>(plan->params);
+  if (plan->params.f8)
+    conv_tap_gemm_kernel<false, true><<<plan->grid, kNumThreads, plan->smem_bytes, (cudaStream_t)stream>>>(plan->params);
+  else
+    conv_tap_gemm_kernel<false, false><<<plan->grid, kNumThreads, plan->smem_bytes, (cudaStream_t)stream>>>(plan->params);
   return launch_status("conv_tap_gemm_kernel");
 }
 

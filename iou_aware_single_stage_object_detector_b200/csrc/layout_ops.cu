@@ -3,6 +3,7 @@
 // max pool and the stride-2 phase split.  Layout definition: include/iou_b200.h.
 #include <cuda_bf16.h>
 #include "common.cuh"
+#include "split_fmt.cuh"
 
 namespace iou {
 
@@ -15,6 +16,7 @@ __device__ __forceinline__ float join_bf16(__nv_bfloat16 hi, __nv_bfloat16 lo) {
 }
 
 // ---- NCHW fp32 -> padded rows.  One CTA per (padded row y, image); tile transpose via smem.
+template <int kFmt>
 __global__ void __launch_bounds__(256) pack_nchw_kernel(const float* __restrict__ src, int n, int c, int h, int w,
                                                         __nv_bfloat16* __restrict__ dst) {
   extern __shared__ float tile[];                 // [32 channels][w + 1]
@@ -39,16 +41,27 @@ __global__ void __launch_bounds__(256) pack_nchw_kernel(const float* __restrict_
     __syncthreads();
     for (int i = threadIdx.x; i < cc * w; i += blockDim.x) {
       const int x = i / cc, ch = i - x * cc;
-      __nv_bfloat16 hi, lo;
-      split_bf16(tile[ch * (w + 1) + x], hi, lo);
       __nv_bfloat16* px = drow + (size_t)(x + 1) * 2 * c;
-      px[c0 + ch] = hi;
-      px[c + c0 + ch] = lo;
+      if constexpr (kFmt == kFmtBf16x2) {
+        __nv_bfloat16 hi, lo;
+        split_bf16(tile[ch * (w + 1) + x], hi, lo);
+        px[c0 + ch] = hi;
+        px[c + c0 + ch] = lo;
+      } else {                                   // fp16 | per 8-channel group [x8 x 8 | l8 x 8] (split_fmt.cuh)
+        const int ca = c0 + ch;
+        const float v = fminf(fmaxf(tile[ch * (w + 1) + x], -65504.f), 65504.f);
+        const __half hh = __float2half_rn(v);
+        reinterpret_cast<__half*>(px)[ca] = hh;
+        unsigned char* lob = reinterpret_cast<unsigned char*>(px + c) + (ca >> 3) * 16 + (ca & 7);
+        lob[0] = (unsigned char)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3);
+        lob[8] = (unsigned char)__nv_cvt_float_to_fp8((v - __half2float(hh)) * kF8LoScale, __NV_SATFINITE, __NV_E4M3);
+      }
     }
     __syncthreads();
   }
 }
 
+template <int kFmt>
 __global__ void __launch_bounds__(256) unpack_nchw_kernel(const __nv_bfloat16* __restrict__ src, int n, int c,
                                                           int h, int w, float* __restrict__ dst) {
   extern __shared__ float tile[];                 // [32 channels][w + 1]
@@ -60,7 +73,15 @@ __global__ void __launch_bounds__(256) unpack_nchw_kernel(const __nv_bfloat16* _
     for (int i = threadIdx.x; i < cc * w; i += blockDim.x) {
       const int x = i / cc, ch = i - x * cc;
       const __nv_bfloat16* px = srow + (size_t)(x + 1) * 2 * c;
-      tile[ch * (w + 1) + x] = join_bf16(px[c0 + ch], px[c + c0 + ch]);
+      if constexpr (kFmt == kFmtBf16x2) {
+        tile[ch * (w + 1) + x] = join_bf16(px[c0 + ch], px[c + c0 + ch]);
+      } else {
+        const int ca = c0 + ch;
+        const unsigned char* lob = reinterpret_cast<const unsigned char*>(px + c) + (ca >> 3) * 16 + (ca & 7);
+        const __half_raw lr = __nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)lob[8], __NV_E4M3);
+        tile[ch * (w + 1) + x] = fmaf(__half2float(*reinterpret_cast<const __half*>(&lr)), kF8LoInv,
+                                      __half2float(reinterpret_cast<const __half*>(px)[ca]));
+      }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < cc * w; i += blockDim.x) {
@@ -203,6 +224,7 @@ __device__ __forceinline__ void max8(float (&m)[8], const uint4 hv, const uint4 
 constexpr int kStemChunk = 112;                  // padded output pixels per block (224 input columns)
 constexpr int kStemRows = 4;                     // padded output rows per block: 2*4 + 6 input rows staged once
 constexpr int kStemRowStride = 2 * kStemChunk + 1;   // odd stride: staged rows fall into different banks
+template <int kFmt>
 __global__ void __launch_bounds__(256) stem_pack_v_kernel(const float* __restrict__ img, int n, int h, int w,
                                                           int ho, int wo, __nv_bfloat16* __restrict__ dst) {
   constexpr int kIn = 2 * kStemRows + 6;          // input rows 2(y0'-2) .. 2(y0'+R-1+1)+1
@@ -226,7 +248,7 @@ __global__ void __launch_bounds__(256) stem_pack_v_kernel(const float* __restric
     const int xl = rem >> 3, v = rem & 7;         // vector v holds kk = 8v .. 8v+7
     const int yp = yp0 + rr, xp = xp0 + xl;
     if (yp > ho + 1) continue;
-    uint32_t hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
+    uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
     if (yp >= 1 && yp <= ho && xp >= 1 && xp <= wo) {
       const int j = v >> 1, q0 = (v & 1) * 8;     // j: vertical neighbour y' - 2 + j
       float val[8];
@@ -240,21 +262,15 @@ __global__ void __launch_bounds__(256) stem_pack_v_kernel(const float* __restric
         }
         val[e] = t;
       }
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(val[2 * e], h0, l0);
-        split_bf16(val[2 * e + 1], h1, l1);
-        hi[e] = pack2_bf16(h0, h1);
-        lo[e] = pack2_bf16(l0, l1);
-      }
+      encode8<kFmt>(val, hi, lo);
     }
     uint4* drow = reinterpret_cast<uint4*>(dst + ((size_t)im * (ho + 2) + yp) * wop * 128);
-    drow[(size_t)xp * 16 + v] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    drow[(size_t)xp * 16 + 8 + v] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    drow[(size_t)xp * 16 + v] = hi;
+    drow[(size_t)xp * 16 + 8 + v] = lo;
   }
 }
 
+template <int kFmt>
 __global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* __restrict__ src, int n, int c, int h,
                                                       int w, int ho, int wo, __nv_bfloat16* __restrict__ dst) {
   const int c8 = c >> 3;
@@ -277,22 +293,23 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* __res
           const int py = py0 + r, px = px0 + s;
           if (py <= h + 1 && px <= w + 1) {
             const __nv_bfloat16* p = src + (((size_t)img * (h + 2) + py) * wp + px) * (2 * c);
-            max8(m, __ldg(reinterpret_cast<const uint4*>(p) + cg), __ldg(reinterpret_cast<const uint4*>(p + c) + cg));
+            const uint4 hv = __ldg(reinterpret_cast<const uint4*>(p) + cg), lv = __ldg(reinterpret_cast<const uint4*>(p + c) + cg);
+            if constexpr (kFmt == kFmtBf16x2) {
+              max8(m, hv, lv);
+            } else {
+              float t8[8];
+              decode8<kFmt>(hv, lv, t8);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) m[q] = fmaxf(m[q], t8[q]);
+            }
           }
         }
     }
-    uint32_t hi[4], lo[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(m[2 * q], h0, l0);
-      split_bf16(m[2 * q + 1], h1, l1);
-      hi[q] = pack2_bf16(h0, h1);
-      lo[q] = pack2_bf16(l0, l1);
-    }
+    uint4 hi, lo;
+    encode8<kFmt>(m, hi, lo);
     __nv_bfloat16* o = dst + (((size_t)img * (ho + 2) + yp) * wop + xp) * (2 * c);
-    reinterpret_cast<uint4*>(o)[cg] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    reinterpret_cast<uint4*>(o + c)[cg] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    reinterpret_cast<uint4*>(o)[cg] = hi;
+    reinterpret_cast<uint4*>(o + c)[cg] = lo;
   }
 }
 
@@ -589,20 +606,38 @@ extern "C" int iou_preprocess_u8(const unsigned char* src, int n, int h, int w, 
 }
 
 
-extern "C" int iou_pack_nchw(const float* src, int n, int c, int h, int w, void* dst, int64_t dst_row_start,
-                             void* stream) {
+#define IOU_REQUIRE_FMT(fmt) IOU_REQUIRE((fmt) == kFmtBf16x2 || (fmt) == kFmtF16F8, "fmt must be 0 (bf16 hi|lo) or 1 (fp16 | e4m3 pairs)")
+
+extern "C" int iou_pack_nchw_fmt(const float* src, int n, int c, int h, int w, void* dst, int64_t dst_row_start,
+                                 int fmt, void* stream) {
   IOU_REQUIRE(src && dst && n > 0 && c > 0 && h > 0 && w > 0, "bad argument");
+  IOU_REQUIRE_FMT(fmt);
+  IOU_REQUIRE(fmt == kFmtBf16x2 || (c & 7) == 0, "the fp16|e4m3 format needs c %% 8 == 0");
   __nv_bfloat16* d = (__nv_bfloat16*)dst + (size_t)dst_row_start * 2 * c;
-  pack_nchw_kernel<<<dim3(h + 2, n), 256, (size_t)32 * (w + 1) * 4, (cudaStream_t)stream>>>(src, n, c, h, w, d);
+  const size_t sm = (size_t)32 * (w + 1) * 4;
+  if (fmt == kFmtBf16x2) pack_nchw_kernel<kFmtBf16x2><<<dim3(h + 2, n), 256, sm, (cudaStream_t)stream>>>(src, n, c, h, w, d);
+  else pack_nchw_kernel<kFmtF16F8><<<dim3(h + 2, n), 256, sm, (cudaStream_t)stream>>>(src, n, c, h, w, d);
   return launch_status("pack_nchw_kernel");
 }
+extern "C" int iou_pack_nchw(const float* src, int n, int c, int h, int w, void* dst, int64_t dst_row_start,
+                             void* stream) {
+  return iou_pack_nchw_fmt(src, n, c, h, w, dst, dst_row_start, kFmtBf16x2, stream);
+}
 
+extern "C" int iou_unpack_nchw_fmt(const void* src, int64_t src_row_start, int n, int c, int h, int w, float* dst,
+                                   int fmt, void* stream) {
+  IOU_REQUIRE(src && dst && n > 0 && c > 0 && h > 0 && w > 0, "bad argument");
+  IOU_REQUIRE_FMT(fmt);
+  IOU_REQUIRE(fmt == kFmtBf16x2 || (c & 7) == 0, "the fp16|e4m3 format needs c %% 8 == 0");
+  const __nv_bfloat16* s = (const __nv_bfloat16*)src + (size_t)src_row_start * 2 * c;
+  const size_t sm = (size_t)32 * (w + 1) * 4;
+  if (fmt == kFmtBf16x2) unpack_nchw_kernel<kFmtBf16x2><<<dim3(h, n), 256, sm, (cudaStream_t)stream>>>(s, n, c, h, w, dst);
+  else unpack_nchw_kernel<kFmtF16F8><<<dim3(h, n), 256, sm, (cudaStream_t)stream>>>(s, n, c, h, w, dst);
+  return launch_status("unpack_nchw_kernel");
+}
 extern "C" int iou_unpack_nchw(const void* src, int64_t src_row_start, int n, int c, int h, int w, float* dst,
                                void* stream) {
-  IOU_REQUIRE(src && dst && n > 0 && c > 0 && h > 0 && w > 0, "bad argument");
-  const __nv_bfloat16* s = (const __nv_bfloat16*)src + (size_t)src_row_start * 2 * c;
-  unpack_nchw_kernel<<<dim3(h, n), 256, (size_t)32 * (w + 1) * 4, (cudaStream_t)stream>>>(s, n, c, h, w, dst);
-  return launch_status("unpack_nchw_kernel");
+  return iou_unpack_nchw_fmt(src, src_row_start, n, c, h, w, dst, kFmtBf16x2, stream);
 }
 
 extern "C" int iou_im2col_stem(const float* img, int n, int h, int w, int kpad, void* dst, void* stream) {
@@ -620,13 +655,19 @@ extern "C" int iou_im2col_stem(const float* img, int n, int h, int w, int kpad, 
   return launch_status("im2col_stem_kernel");
 }
 
-extern "C" int iou_stem_pack_v(const float* img, int n, int h, int w, void* dst, void* stream) {
+extern "C" int iou_stem_pack_v_fmt(const float* img, int n, int h, int w, void* dst, int fmt, void* stream) {
   IOU_REQUIRE(img && dst && n > 0 && h > 0 && w > 0, "bad argument");
+  IOU_REQUIRE_FMT(fmt);
   const int ho = (h + 6 - 7) / 2 + 1, wo = (w + 6 - 7) / 2 + 1;
   const int chunks = (wo + 2 + kStemChunk - 1) / kStemChunk;
   IOU_REQUIRE(n <= 65535 && chunks <= 65535, "batch / width out of range for the stem pack kernel");
-  stem_pack_v_kernel<<<dim3((ho + 2 + kStemRows - 1) / kStemRows, n, chunks), 256, 0, (cudaStream_t)stream>>>(img, n, h, w, ho, wo, (__nv_bfloat16*)dst);
+  const dim3 grid((ho + 2 + kStemRows - 1) / kStemRows, n, chunks);
+  if (fmt == kFmtBf16x2) stem_pack_v_kernel<kFmtBf16x2><<<grid, 256, 0, (cudaStream_t)stream>>>(img, n, h, w, ho, wo, (__nv_bfloat16*)dst);
+  else stem_pack_v_kernel<kFmtF16F8><<<grid, 256, 0, (cudaStream_t)stream>>>(img, n, h, w, ho, wo, (__nv_bfloat16*)dst);
   return launch_status("stem_pack_v_kernel");
+}
+extern "C" int iou_stem_pack_v(const float* img, int n, int h, int w, void* dst, void* stream) {
+  return iou_stem_pack_v_fmt(img, n, h, w, dst, kFmtBf16x2, stream);
 }
 
 extern "C" int iou_stem_pack(const float* img, int n, int h, int w, void* dst, void* stream) {
@@ -643,14 +684,20 @@ extern "C" int iou_stem_pack(const float* img, int n, int h, int w, void* dst, v
   return launch_status("stem_pack_kernel");
 }
 
-extern "C" int iou_maxpool3x3s2(const void* src, int n, int c, int h, int w, void* dst, void* stream) {
+extern "C" int iou_maxpool3x3s2_fmt(const void* src, int n, int c, int h, int w, void* dst, int fmt, void* stream) {
   IOU_REQUIRE(src && dst && n > 0 && c > 0 && (c & 7) == 0 && h > 0 && w > 0, "bad argument (c % 8)");
+  IOU_REQUIRE_FMT(fmt);
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
   const size_t total = (size_t)n * (ho + 2) * (wo + 2) * (c / 8);
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  maxpool_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, n, c, h, w, ho, wo,
-                                                           (__nv_bfloat16*)dst);
+  if (fmt == kFmtBf16x2)
+    maxpool_kernel<kFmtBf16x2><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, n, c, h, w, ho, wo, (__nv_bfloat16*)dst);
+  else
+    maxpool_kernel<kFmtF16F8><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, n, c, h, w, ho, wo, (__nv_bfloat16*)dst);
   return launch_status("maxpool_kernel");
+}
+extern "C" int iou_maxpool3x3s2(const void* src, int n, int c, int h, int w, void* dst, void* stream) {
+  return iou_maxpool3x3s2_fmt(src, n, c, h, w, dst, kFmtBf16x2, stream);
 }
 
 extern "C" int iou_phase_split(const void* src, int n, int c, int h, int w, void* const* dst4, int phase_mask,

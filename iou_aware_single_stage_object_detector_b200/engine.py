@@ -65,6 +65,53 @@ def split_hi_lo(x):
     return hi, lo
 
 
+def _hi_lo_rows(t):
+    """fp32 [taps, cout_pad, K] -> the C ABI's bf16 weight matrix [taps*cout_pad][2*K] (hi | lo).  The fp32 source
+    rides along as ``.src32`` so that Engine.conv can repack it for the fp16 + e4m3 scheme (passes == 2)."""
+    hi, lo = split_hi_lo(t)
+    out = torch.cat([hi, lo], dim=2).reshape(t.shape[0] * t.shape[1], 2 * t.shape[2]).contiguous()
+    out.src32 = t
+    return out
+
+
+F8_LO_SCALE = 2048.0      # 2^11, csrc/split_fmt.cuh
+
+
+def pack_f16f8(t):
+    """fp32 [taps, cout_pad, K] -> (weight matrix for passes == 2, per-channel correction scale).
+
+    Row layout mirrors the activations (csrc/split_fmt.cuh): [Wh: K x fp16][per 8 channels: Wl8 x 8 | W8 x 8] with
+    Wh = fp16(w), Wl8 = e4m3((w - Wh) * 2^11 * s_n), W8 = e4m3(w * s_n); s_n is a power of two per OUTPUT channel
+    that puts the row maximum in (64, 128].  The activation bytes [x8 x 8 | l8 x 8] meet [Wl8 x 8 | W8 x 8] in one
+    e4m3 MMA, so the correction accumulator holds 2^11 * s_n * (x*Wl + xl*W); the epilogue multiplies it by the
+    returned 2^-11 / s_n.  Returned as a bf16-typed [taps*cout_pad][2*K] tensor (same bytes per row as hi | lo)."""
+    taps, co, k = t.shape
+    assert k % 8 == 0, k
+    t = t.float()
+    wh = t.clamp(-65504.0, 65504.0).to(torch.float16)
+    wl = t - wh.float()
+    m = t.abs().amax(dim=(0, 2))
+    s = torch.where(m > 0, torch.exp2(torch.floor(torch.log2(64.0 / m.clamp_min(1e-38))) + 1.0), torch.ones_like(m))
+    s = s.clamp(2.0 ** -60, 2.0 ** 60)
+    sv = s.view(1, co, 1)
+    w8 = (t * sv).clamp(-448.0, 448.0).to(torch.float8_e4m3fn).view(torch.uint8)
+    wl8 = (wl * (F8_LO_SCALE * sv)).clamp(-448.0, 448.0).to(torch.float8_e4m3fn).view(torch.uint8)
+    lo = torch.stack([wl8.view(taps, co, k // 8, 8), w8.view(taps, co, k // 8, 8)], dim=3).reshape(taps, co, 2 * k)
+    hi = wh.contiguous().view(torch.uint8).view(taps, co, 2 * k)
+    rows = torch.cat([hi, lo], dim=2).contiguous().view(torch.bfloat16).reshape(taps * co, 2 * k)
+    return rows, (1.0 / (F8_LO_SCALE * s)).float().contiguous()
+
+
+def unpack_f16f8_rows(rows, k):
+    """Inverse view of pack_f16f8 for tests: -> (Wh fp32, Wl8 fp32, W8 fp32), each [rows, K]."""
+    b = rows.contiguous().view(torch.uint8).view(rows.shape[0], 4 * k)
+    wh = b[:, :2 * k].contiguous().view(torch.float16).float()
+    lo = b[:, 2 * k:].reshape(rows.shape[0], k // 8, 2, 8)
+    wl8 = lo[:, :, 0].contiguous().view(torch.float8_e4m3fn).float().reshape(rows.shape[0], k)
+    w8 = lo[:, :, 1].contiguous().view(torch.float8_e4m3fn).float().reshape(rows.shape[0], k)
+    return wh, wl8, w8
+
+
 def pack_weight(w, cout_pad, kpad=None):
     """(Cout, Cin, kh, kw) fp32 -> bf16 [kh*kw*cout_pad][2*Cin'] (hi | lo), tap-major, K contiguous."""
     cout, cin, kh, kw = w.shape
@@ -74,8 +121,7 @@ def pack_weight(w, cout_pad, kpad=None):
         cin = kpad
     if cout_pad != cout:
         t = torch.nn.functional.pad(t, (0, 0, 0, cout_pad - cout))
-    hi, lo = split_hi_lo(t)
-    return torch.cat([hi, lo], dim=2).reshape(kh * kw * cout_pad, 2 * cin).contiguous()
+    return _hi_lo_rows(t)
 
 
 def pack_weight_stem(w):
@@ -91,8 +137,7 @@ def pack_weight_stem(w):
                     if 0 <= ky <= 6 and 0 <= kx <= 6:
                         k0 = j * 16 + (py * 2 + px) * 3
                         t[r, :, k0:k0 + 3] = w[:, :, ky, kx].float()
-    hi, lo = split_hi_lo(t)
-    return torch.cat([hi, lo], dim=2).reshape(4 * cout, 128).contiguous()
+    return _hi_lo_rows(t)
 
 
 def pack_weight_stem_v(w):
@@ -108,8 +153,7 @@ def pack_weight_stem_v(w):
                     if 0 <= ky <= 6 and 0 <= kx <= 6:
                         k0 = j * 16 + (py * 2 + px) * 3
                         t[s_, :, k0:k0 + 3] = w[:, :, ky, kx].float()
-    hi, lo = split_hi_lo(t)
-    return torch.cat([hi, lo], dim=2).reshape(4 * cout, 128).contiguous()
+    return _hi_lo_rows(t)
 
 
 def pack_weight_grouped(w, groups):
@@ -123,8 +167,7 @@ def pack_weight_grouped(w, groups):
     base = (o // cg) * cg - (o // 64) * 64                     # first local input channel of o's group
     idx = (base[:, None] + torch.arange(cg, device=w.device)[None, :])          # (cout, cg)
     t.scatter_(2, idx[None].expand(kh * kw, cout, cg), wt)
-    hi, lo = split_hi_lo(t)
-    return torch.cat([hi, lo], dim=2).reshape(kh * kw * cout, 128).contiguous()
+    return _hi_lo_rows(t)
 
 
 def bn_fold(sd, prefix, eps=1e-5):
@@ -173,7 +216,8 @@ def pick_block_n(cout, m_tiles=None, max_bn=256, pair_min_tiles=None):
 class Engine(object):
     def __init__(self, device, passes=3):
         self.device = torch.device(device)
-        self.passes = passes
+        self.passes = passes        # 3: bf16 hi|lo x3 (default), 2: fp16 + e4m3 corrections (csrc/split_fmt.cuh), 1: bf16
+        self.fmt = 1 if passes == 2 else 0
         self.ops = []            # (name, callable(stream_ptr))
         self.plans = []
         self.keep = []           # tensors that must outlive the plan
@@ -214,6 +258,12 @@ class Engine(object):
                     m_tiles >= self.pair_min_tiles and cout % 256 == 0)
         block_n, cout_pad = pick_block_n(cout, m_tiles, max_bn=128 if (res_mode == L.RES_SAME and not res_wide) else 256,
                                          pair_min_tiles=pair_aware)
+        # passes == 2: main + correction accumulators of an N > 128 tile fill all 512 TMEM columns, so the epilogue of
+        # tile i no longer overlaps the MMAs of tile i+1.  Convs with a short K loop (1x1 convs, where the epilogue IS
+        # the work) keep two accumulator stages with N = 128 instead; deep K loops (3x3 towers) amortise it
+        if (self.passes == 2 and block_n > 128 and cout % 128 == 0 and not diag_k and
+                len(taps) * (cin // 64) <= int(os.environ.get("IOU_F8_SHALLOW", "8"))):
+            block_n, cout_pad = 128, cout
         retry_bn = 128 if (res_wide and block_n == 256) else None
         if diag_k:
             block_n, cout_pad = 64, cout
@@ -227,9 +277,19 @@ class Engine(object):
             assert m.c == cin, (name, m.c, cin)
             d.src[i] = m.ptr
         d.src_rows = min(m.rows for m in srcs)
+        kdim = 64 if diag_k else cin
+        assert weight.shape == (len(taps) * cout_pad, 2 * kdim), (name, weight.shape, len(taps), cout_pad, cin)
+        corr_scale = None
+        if self.passes == 2:                     # repack for the fp16 + e4m3 scheme, from the fp32 source if it rode along
+            src32 = getattr(weight, "src32", None)
+            if src32 is None:
+                src32 = (weight[:, :kdim].float() + weight[:, kdim:].float())
+            assert scale is None, "passes == 2 uses `scale` for the correction accumulator"
+            weight, corr_scale = pack_f16f8(src32.reshape(len(taps), cout_pad, kdim))
+        elif hasattr(weight, "src32"):
+            del weight.src32
         wp = weight.to(self.device)
         self.keep.append(wp)
-        assert wp.shape == (len(taps) * cout_pad, 2 * (64 if diag_k else cin)), (name, wp.shape, len(taps), cout_pad, cin)
         d.diag_k = int(diag_k)
         # big maps with a wide N tile run as CTA pairs (cta_group::2): half the B traffic, deeper pipeline
         d.two_cta = int(self.two_cta and (not diag_k or self.pair_diag) and block_n % 16 == 0 and block_n >= self.pair_min_bn
@@ -242,7 +302,9 @@ class Engine(object):
                 v = torch.nn.functional.pad(v, (0, cout_pad - v.numel())).contiguous()
                 self.keep.append(v)
             return v
-        if scale is not None:
+        if corr_scale is not None:
+            d.scale = padc(corr_scale).data_ptr()
+        elif scale is not None:
             d.scale = padc(scale).data_ptr()
         if shift is not None:
             d.shift = padc(shift).data_ptr()
@@ -289,6 +351,8 @@ class Engine(object):
         """-> list of 4 FlatMaps (None where masked out) in the stride-2 output geometry; relu=True clamps the
         copied values at zero (FPN relu_before_extra_convs)."""
         assert len(src.segs) == 1
+        if relu and self.fmt != 0:
+            raise RuntimeError("the fused-ReLU phase split is only built for the bf16 hi|lo format (passes == 3)")
         _, n, h, w = src.segs[0]
         ho, wo = (h + 1) // 2, (w + 1) // 2
         outs = [self.new_map([(n, ho, wo)], src.c) if (mask >> i) & 1 else None for i in range(4)]
@@ -310,8 +374,11 @@ class Engine(object):
         self.keep.append(img)
         scale, shift = bn_fold(sd, prefix + "bn1")
         wf = fold_scale(sd[prefix + "conv1.weight"], scale)
+        fmt = self.fmt
+        if fmt != 0 and not self.stem_vertical:
+            raise RuntimeError("passes == 2 needs the vertical stem pack (IOU_STEM_VERTICAL=1)")
         if self.stem_vertical:      # four dx taps sharing one A window (half the shared-memory fill of the stem conv)
-            self.ops.append(("stem.pack", lambda st: L.check(lib.iou_stem_pack_v(ip, n, h, w, pp, st))))
+            self.ops.append(("stem.pack", lambda st: L.check(lib.iou_stem_pack_v_fmt(ip, n, h, w, pp, fmt, st))))
             s1 = self.conv("stem.conv1", [packed], TAPS_STEM_V, pack_weight_stem_v(wf), 64, 64, shift=shift, relu=True,
                            true_flops_scale=147.0 / 256.0)
         else:
@@ -321,7 +388,7 @@ class Engine(object):
         hp, wq = (ho - 1) // 2 + 1, (wo - 1) // 2 + 1
         x = self.new_map([(n, hp, wq)], 64)
         sp, xp = s1.ptr, x.ptr
-        self.ops.append(("stem.maxpool", lambda st: L.check(lib.iou_maxpool3x3s2(sp, n, 64, ho, wo, xp, st))))
+        self.ops.append(("stem.maxpool", lambda st: L.check(lib.iou_maxpool3x3s2_fmt(sp, n, 64, ho, wo, xp, fmt, st))))
         return x
 
     def add_backbone(self, sd, img, depth=50, groups=1, prefix="backbone.", style="pytorch"):
@@ -454,6 +521,8 @@ class Engine(object):
 
     def group_norm(self, name, m, gamma, beta, groups, eps=1e-5, relu=True):
         """In-place GroupNorm(+ReLU) of every segment of FlatMap m (ConvModule with norm_cfg type 'GN')."""
+        if self.fmt != 0:
+            raise RuntimeError("GroupNorm is only built for the bf16 hi|lo format (passes == 3)")
         g, b = self._dev(gamma), self._dev(beta)
         segs = (L.ConvSegment * len(m.segs))()
         for i, (rs, n, h, w) in enumerate(m.segs):
@@ -511,17 +580,17 @@ class Engine(object):
         """(N,C,H,W) fp32 cuda tensor -> FlatMap (op appended)."""
         n, c, h, w = x.shape
         m = self.new_map([(n, h, w)], c)
-        lib, xp, mp = self.lib, x.data_ptr(), m.ptr
+        lib, xp, mp, fmt = self.lib, x.data_ptr(), m.ptr, self.fmt
         self.keep.append(x)
-        self.ops.append(("pack", lambda st: L.check(lib.iou_pack_nchw(xp, n, c, h, w, mp, 0, st))))
+        self.ops.append(("pack", lambda st: L.check(lib.iou_pack_nchw_fmt(xp, n, c, h, w, mp, 0, fmt, st))))
         return m
 
     def unpack_output(self, m, s=0):
         rs, n, h, w = m.segs[s]
         out = torch.empty(n, m.c, h, w, dtype=torch.float32, device=self.device)
         self.keep.append(out)
-        lib, mp, op, c = self.lib, m.ptr, out.data_ptr(), m.c
-        self.ops.append(("unpack", lambda st: L.check(lib.iou_unpack_nchw(mp, rs, n, c, h, w, op, st))))
+        lib, mp, op, c, fmt = self.lib, m.ptr, out.data_ptr(), m.c, self.fmt
+        self.ops.append(("unpack", lambda st: L.check(lib.iou_unpack_nchw_fmt(mp, rs, n, c, h, w, op, fmt, st))))
         return out
 
     # ------------------------------------------------------------------ execution

@@ -172,7 +172,7 @@ def results_to_arrays(per_class):
     return d, l
 
 
-def check_detector_small(h=128, w=160, n=2, verbose=True, use_graph=False):
+def check_detector_small(h=128, w=160, n=2, verbose=True, use_graph=False, passes=3):
     """Whole path on a small image: CUDA head maps vs oracle (torch-CPU fp32) maps, then detections."""
     det, cfg = small_detector()
     sd = {k: v.clone() for k, v in det.state_dict().items()}
@@ -183,6 +183,7 @@ def check_detector_small(h=128, w=160, n=2, verbose=True, use_graph=False):
     metas = [dict(ori_shape=(h, w - 3, 3), img_shape=(h, w - 3, 3), pad_shape=(h, w, 3), scale_factor=1.0,
                   flip=False) for _ in range(n)]
     det.use_cuda_graph = use_graph
+    det.passes = passes
     results = det.simple_test_batch(img.to(dev), metas, rescale=False)
     if use_graph:   # second call replays the captured graph
         results = det.simple_test_batch(img.to(dev), metas, rescale=False)

@@ -35,7 +35,7 @@ def test_library_builds_and_exports_header_symbols():
         assert hasattr(lib, n), "symbol %s declared in the header is not exported" % n
     assert set(names) == set(L.EXPORTED_SYMBOLS)
     lib.iou_abi_version.restype = ctypes.c_int
-    assert lib.iou_abi_version() == 2
+    assert lib.iou_abi_version() == 3
 
 
 def test_sass_is_blackwell_native():
@@ -187,6 +187,31 @@ def test_weight_packing_and_layout_helpers():
     tg = (pg[:, :64].float() + pg[:, 64:].float()).reshape(9, 256, 64)
     assert torch.allclose(tg[4, 70, 4:8], wg[70, :, 1, 1], rtol=2e-5, atol=1e-30)
     assert float(tg[4, 70, :4].abs().max()) == 0 and float(tg[4, 70, 8:].abs().max()) == 0
+
+
+def test_f16f8_weight_packing_pairs_with_the_activation_bytes():
+    """engine.pack_f16f8 (conv passes = 2) against the byte-level emulation of the two tensor-core passes in
+    oracle/split_fmt.py: the K order of [Wl8 | W8] must meet the activations' [x8 | l8], the per-channel power-of-two
+    scale must be undone by the returned correction scale, and the result must be fp32-grade (~2^-16 per product)."""
+    from oracle import split_fmt as SF
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(300, 128, generator=g) * torch.exp(torch.randn(300, 128, generator=g))
+    w = torch.randn(40, 128, generator=g) * 0.05 * torch.exp(2 * torch.randn(40, 1, generator=g))
+    w[7] = 0                                                    # an all-zero (padding) output channel
+    rows, cs = E.pack_f16f8(w.view(1, 40, 128))
+    assert rows.shape == (40, 256) and rows.dtype == torch.bfloat16 and cs.shape == (40,)
+    assert bool((torch.log2(cs) == torch.log2(cs).round()).all())          # powers of two
+    wh, wl8, w8 = E.unpack_f16f8_rows(rows, 128)
+    assert float(w8.abs().max()) <= 128 and float(w8.abs().amax(1)[w.abs().amax(1) > 0].min()) > 56
+    y = SF.emulate_gemm(SF.encode_rows(x), rows, cs)
+    ref = x.double() @ w.double().t()
+    bound = x.double().abs() @ w.double().abs().t()
+    assert float(((y - ref).abs() / bound.clamp_min(1e-30)).max()) < 4e-5
+    assert float(y[:, 7].abs().max()) == 0
+    # the packed default weights carry their fp32 source for the repack in Engine.conv
+    p = E.pack_weight(torch.randn(16, 64, 3, 3, generator=g), 16)
+    assert p.src32.shape == (9, 16, 64)
+    assert float((SF.decode_rows(SF.encode_rows(x)) - x).abs().max() / x.abs().max()) < 2.0 ** -15
 
 
 def test_shard_ranges_cover_batch():

@@ -1,0 +1,184 @@
+"""-m gpu tests of conv `passes = 2` (IOU_FMT_F16F8: one fp16 tensor-core pass + one e4m3 pass of doubled K,
+csrc/split_fmt.cuh): the layout kernels' encode/decode bit for bit against oracle/split_fmt.py, the conv engine
+against plain PyTorch fp32 (CPU) convs, the whole detector against the CPU oracle at the north-star tolerance."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import parity_util as U  # noqa: F401  (sets sys.path)
+from oracle import split_fmt as SF
+from iou_aware_single_stage_object_detector_b200 import engine as E
+from iou_aware_single_stage_object_detector_b200 import lib as L
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+# fp16 main pass + e4m3 corrections: ~2^-16 relative per product (tools/numerics_sim.py), fp32 accumulate
+TOL = 2e-4
+
+
+def rel_err(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-6)).item()
+
+
+def test_pack_encode_is_bit_exact_and_unpack_decodes():
+    g = torch.Generator().manual_seed(0)
+    for shape in ((2, 64, 7, 11), (1, 256, 13, 21), (3, 8, 5, 4)):
+        n, c, h, w = shape
+        x = torch.randn(*shape, generator=g) * torch.exp(2 * torch.randn(*shape, generator=g))
+        x[0, 0, 0, 0], x[0, 1, 0, 0], x[0, 2, 0, 0] = 1e5, -3e-7, 500.0       # fp16 / e4m3 saturation, underflow
+        eng = E.Engine(DEV, passes=2)
+        m = eng.pack_input(x.to(DEV))
+        y = eng.unpack_output(m)
+        eng.run()
+        torch.cuda.synchronize()
+        t = m.tensor[: n * (h + 2) * (w + 2)].view(torch.uint8).view(n, h + 2, w + 2, 4 * c).cpu()
+        want = SF.encode_rows(x.permute(0, 2, 3, 1).reshape(-1, c)).view(n, h, w, 4 * c)
+        assert torch.equal(t[:, 1:-1, 1:-1], want)
+        assert int(t[:, 0].max()) == 0 and int(t[:, -1].max()) == 0 and int(t[:, :, 0].max()) == 0 and int(t[:, :, -1].max()) == 0
+        dec = SF.decode_rows(want.view(-1, 4 * c)).view(n, h, w, c).permute(0, 3, 1, 2)
+        assert torch.equal(y.cpu(), dec)
+        xs = x.clamp(-65504, 65504)
+        # hi (11 bits) + l8 (4 bits): ~2^-16 relative inside the format's window; below |x| ~ 2^-5 the e4m3 residual is
+        # subnormal (abs 2^-21), above |x| ~ 448 it saturates and the value falls back to fp16 precision (2^-12)
+        big = xs.abs() > 448
+        assert torch.allclose(y.cpu()[~big], xs[~big], rtol=2.0 ** -15, atol=5e-7)
+        assert torch.allclose(y.cpu()[big], xs[big], rtol=2.0 ** -11)
+
+
+def run_conv(x, w, bias=None, stride=1, relu=False, residual=None, two_cta=None):
+    eng = E.Engine(DEV, passes=2)
+    m = eng.pack_input(x.to(DEV).contiguous())
+    k, co = w.shape[-1], w.shape[0]
+    wp = E.pack_weight(w, E.pick_block_n(co)[1])
+    res = eng.pack_input(residual.to(DEV).contiguous()) if residual is not None else None
+    kw = dict(shift=bias, relu=relu, two_cta=two_cta)
+    if stride == 1:
+        out = eng.conv("t", [m], E.TAPS_1X1 if k == 1 else E.TAPS_3X3, wp, x.shape[1], co, residual=res,
+                       res_mode=L.RES_SAME if res is not None else L.RES_NONE, **kw)
+    elif k == 1:
+        out = eng.conv("t", [eng.phase_split("p", m, mask=8)[3]] * 4, E.TAPS_1X1_S2, wp, x.shape[1], co, **kw)
+    else:
+        out = eng.conv("t", eng.phase_split("p", m), E.TAPS_3X3_S2, wp, x.shape[1], co, **kw)
+    y = eng.unpack_output(out)
+    eng.run()
+    torch.cuda.synchronize()
+    return y.cpu()
+
+
+@pytest.mark.parametrize("cin,cout,k,hw", [(64, 64, 1, (9, 13)), (64, 256, 1, (17, 23)), (256, 64, 1, (8, 8)),
+                                           (64, 64, 3, (12, 20)), (128, 128, 3, (25, 42)),
+                                           (256, 256, 3, (13, 21)), (2048, 256, 1, (5, 6))])
+def test_conv_stride1_vs_torch(cin, cout, k, hw):
+    g = torch.Generator().manual_seed(cin + cout + k)
+    x = torch.randn(2, cin, *hw, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    w *= torch.exp(torch.randn(cout, 1, 1, 1, generator=g))          # per-channel scales differ (BN fold)
+    b = torch.randn(cout, generator=g)
+    ref = F.conv2d(x, w, b, padding=k // 2)
+    y = run_conv(x, w, bias=b)
+    assert y.shape == ref.shape
+    assert rel_err(y, ref) < TOL, rel_err(y, ref)
+
+
+@pytest.mark.parametrize("cin,cout,k,hw", [(128, 128, 3, (25, 42)), (256, 512, 1, (20, 28)), (2048, 256, 3, (25, 42))])
+def test_conv_stride2_vs_torch(cin, cout, k, hw):
+    g = torch.Generator().manual_seed(cin * 3 + cout + k)
+    x = torch.randn(2, cin, *hw, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = F.conv2d(x, w, b, stride=2, padding=k // 2)
+    y = run_conv(x, w, bias=b, stride=2)
+    assert y.shape == ref.shape and rel_err(y, ref) < TOL, rel_err(y, ref)
+
+
+@pytest.mark.parametrize("cin,cout,k,shape,res", [(64, 256, 1, (2, 50, 70), True),      # pair, N = 256: ONE accumulator stage
+                                                  (64, 128, 1, (2, 50, 70), True),      # pair, residual ring, two stages
+                                                  (256, 256, 3, (2, 50, 70), False),    # the head-tower shape
+                                                  (64, 64, 3, (2, 50, 70), False)])
+def test_cta_pair_mode_matches_torch(cin, cout, k, shape, res):
+    n, h, w = shape
+    g = torch.Generator().manual_seed(cin + cout + h)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    b = torch.randn(cout, generator=g)
+    r = torch.randn(n, cout, h, w, generator=g) if res else None
+    ref = F.conv2d(x, wt, b, padding=k // 2)
+    if res:
+        ref = F.relu(ref + r)
+    y = run_conv(x, wt, bias=b, relu=res, residual=r, two_cta=True)
+    assert rel_err(y, ref) < TOL, rel_err(y, ref)
+
+
+@pytest.mark.parametrize("pair", [False, True])
+def test_multi_segment_head_style_dense_outputs(pair):
+    """Shared weights over several levels in ONE launch, dense fp32 NHWC outputs (N = 240 tiles and a 48-wide split)."""
+    g = torch.Generator().manual_seed(21)
+    sizes = [(2, 30, 44), (2, 15, 22), (2, 8, 11), (2, 2, 3), (2, 1, 2)]
+    xs = [torch.randn(n, 256, h, w, generator=g) for (n, h, w) in sizes]
+    w_cls, b_cls = torch.randn(720, 256, 3, 3, generator=g) * 0.02, torch.randn(720, generator=g)
+    w_ri, b_ri = torch.randn(45, 256, 3, 3, generator=g) * 0.02, torch.randn(45, generator=g)
+    eng = E.Engine(DEV, passes=2)
+    Fm = eng.new_map(sizes, 256)
+    for s, x in enumerate(xs):
+        n, c, h, w = x.shape
+        xd = x.to(DEV)
+        eng.keep.append(xd)
+        L.check(eng.lib.iou_pack_nchw_fmt(xd.data_ptr(), n, c, h, w, Fm.ptr, Fm.segs[s][0], 1, L.stream_ptr()))
+    cls_out = [torch.zeros(n, h, w, 720, device=DEV) for (n, h, w) in sizes]
+    reg_out = [torch.zeros(n, h, w, 36, device=DEV) for (n, h, w) in sizes]
+    iou_out = [torch.zeros(n, h, w, 9, device=DEV) for (n, h, w) in sizes]
+    eng.conv("cls", [Fm], E.TAPS_3X3, E.pack_weight(w_cls, 720), 256, 720, shift=b_cls, dense_out=cls_out,
+             two_cta=pair)
+    eng.conv("ri", [Fm], E.TAPS_3X3, E.pack_weight(w_ri, 48), 256, 45, shift=b_ri, dense_out=reg_out,
+             dense_out2=iou_out, dense_split=36, two_cta=False)
+    eng.run()
+    torch.cuda.synchronize()
+    for s, x in enumerate(xs):
+        ref = F.conv2d(x, w_cls, b_cls, padding=1).permute(0, 2, 3, 1)
+        assert rel_err(cls_out[s].cpu(), ref) < TOL
+        ref = F.conv2d(x, w_ri, b_ri, padding=1).permute(0, 2, 3, 1)
+        assert rel_err(reg_out[s].cpu(), ref[..., :36]) < TOL and rel_err(iou_out[s].cpu(), ref[..., 36:]) < TOL
+
+
+def test_fpn_upsample_residual_and_stem():
+    g = torch.Generator().manual_seed(5)
+    # lateral 1x1 + nearest-2x top-down add (fpn.py:108-110)
+    xf, xc = torch.randn(2, 512, 12, 20, generator=g), torch.randn(2, 256, 6, 10, generator=g)
+    w, b = torch.randn(256, 512, 1, 1, generator=g) * 0.05, torch.randn(256, generator=g)
+    eng = E.Engine(DEV, passes=2)
+    mf, mc = eng.pack_input(xf.to(DEV)), eng.pack_input(xc.to(DEV))
+    out = eng.conv("lat", [mf], E.TAPS_1X1, E.pack_weight(w, 256), 512, 256, shift=b, residual=mc,
+                   res_mode=L.RES_UPSAMPLE2)
+    y = eng.unpack_output(out)
+    # stem: 7x7/s2 conv + BN + ReLU + 3x3/s2 max pool (resnet.py:508-511)
+    img = torch.randn(2, 3, 70, 90, generator=g)
+    sd = {"backbone.conv1.weight": torch.randn(64, 3, 7, 7, generator=g) * 0.1,
+          "backbone.bn1.weight": torch.rand(64, generator=g) + 0.5, "backbone.bn1.bias": torch.randn(64, generator=g) * 0.1,
+          "backbone.bn1.running_mean": torch.randn(64, generator=g) * 0.1,
+          "backbone.bn1.running_var": torch.rand(64, generator=g) + 0.5}
+    ys = eng.unpack_output(eng.add_stem(sd, img.to(DEV)))
+    eng.run()
+    torch.cuda.synchronize()
+    ref = F.conv2d(xf, w, b) + F.interpolate(xc, scale_factor=2, mode="nearest")
+    assert rel_err(y.cpu(), ref) < TOL, rel_err(y.cpu(), ref)
+    t = F.conv2d(img, sd["backbone.conv1.weight"], None, stride=2, padding=3)
+    t = F.batch_norm(t, sd["backbone.bn1.running_mean"], sd["backbone.bn1.running_var"], sd["backbone.bn1.weight"],
+                     sd["backbone.bn1.bias"], False, 0.0, 1e-5)
+    ref = F.max_pool2d(F.relu(t), 3, 2, 1)
+    assert ys.shape == ref.shape and rel_err(ys.cpu(), ref) < TOL, rel_err(ys.cpu(), ref)
+
+
+def test_whole_detector_small_passes2():
+    """Backbone + FPN + head + get_bboxes with passes = 2 against the CPU oracle: head maps within 2e-4 of range,
+    detections within 1e-4 (scores) / 1e-4 * max(H, W) px (boxes) -- the same bar as the default path."""
+    worst = U.check_detector_small(128, 160, 2, verbose=False, passes=2)
+    assert worst <= 2e-4
+
+
+def test_unsupported_ops_raise_in_f16f8_format():
+    eng = E.Engine(DEV, passes=2)
+    m = eng.pack_input(torch.randn(1, 64, 4, 4, device=DEV))
+    with pytest.raises(RuntimeError):
+        eng.phase_split("p", m, relu=True)
+    with pytest.raises(RuntimeError):
+        eng.group_norm("gn", m, torch.ones(64), torch.zeros(64), 32)
