@@ -125,7 +125,10 @@ class SingleStageDetector(BaseDetector):
         self.train_cfg, self.test_cfg = train_cfg, test_cfg
         self._fused = PlanCache(max_plans=4)
         self.use_cuda_graph = True
-        self.passes = 3
+        # tensor-core scheme of the convs (engine.Engine): None = 2 (fp16 pass + e4m3 correction pass, the fastest
+        # fp32-grade scheme) where every op of the model is built for that format, else 3 (bf16 hi|lo x3);
+        # 1 (plain bf16) is an explicit opt-in only
+        self.passes = None
         self.init_weights(pretrained=pretrained)
 
     def init_weights(self, pretrained=None):
@@ -148,11 +151,19 @@ class SingleStageDetector(BaseDetector):
     def forward_train(self, img, img_metas, gt_bboxes, gt_labels, gt_bboxes_ignore=None):
         raise NotImplementedError("training is outside the accelerated inference path")
 
+    def resolved_passes(self):
+        if self.passes is not None:
+            return self.passes
+        # GroupNorm towers (norm_cfg heads) and the FPN's fused-ReLU phase split only exist for the bf16 hi|lo format
+        gn = getattr(self.bbox_head, "norm_cfg", None) is not None
+        relu_split = bool(getattr(getattr(self, "neck", None), "relu_before_extra_convs", False))
+        return 3 if (gn or relu_split) else 2
+
     def fused_plan(self, shape, device, rescale, slot=0):
         """`slot` distinguishes independent plans (own buffers, own CUDA graph) of the same shape."""
-        key = (tuple(shape), str(device), bool(rescale), param_stamp(self), self.use_cuda_graph, self.passes, slot)
-        return self._fused.get(key, lambda: FusedPlan(self, shape, device, rescale, self.use_cuda_graph,
-                                                      self.passes))
+        passes = self.resolved_passes()
+        key = (tuple(shape), str(device), bool(rescale), param_stamp(self), self.use_cuda_graph, passes, slot)
+        return self._fused.get(key, lambda: FusedPlan(self, shape, device, rescale, self.use_cuda_graph, passes))
 
     def detect_device(self, img, img_metas, rescale=False, device=None):
         """Batched, asynchronous: (dets [n,K,5], labels [n,K] int64, counts [n] int32) on the device.

@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
             for (int q = 0; q < 8; ++q) x8[q] = P.relu ? fmaxf(f[j * 8 + q], 0.f) : f[j * 8 + q];
             // packed conversions (F2FP): bf16 hi | lo, or fp16 hi | e4m3 pairs (split_fmt.cuh); border rows are zero
             uint4 hi, lo;
-            encode8<kFmt>(x8, hi, lo);
+            encode8<kFmt, false>(x8, hi, lo);
             if (!interior) { hi = make_uint4(0, 0, 0, 0); lo = hi; }
             const uint32_t sw = (uint32_t)((j ^ swz) << 4);
             sts128(ob + sw, hi);

@@ -30,8 +30,9 @@ __device__ __forceinline__ float2 e4m3x2_to_float2(uint32_t v) {
   return __half22float2(*reinterpret_cast<const __half2*>(&h));
 }
 
-// 8 consecutive channels -> the group's hi and lo vectors
-template <int kFmt>
+// 8 consecutive channels -> the group's hi and lo vectors.  kClamp: saturate at the fp16 range (the layout kernels,
+// which see arbitrary user data); the conv epilogue skips it -- an activation beyond 65504 becomes inf and shows.
+template <int kFmt, bool kClamp = true>
 __device__ __forceinline__ void encode8(const float (&v)[8], uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
   if constexpr (kFmt == kFmtBf16x2) {
@@ -48,7 +49,8 @@ __device__ __forceinline__ void encode8(const float (&v)[8], uint4& hi, uint4& l
     uint32_t x8[4], l8[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float a = fminf(fmaxf(v[2 * q], -65504.f), 65504.f), b = fminf(fmaxf(v[2 * q + 1], -65504.f), 65504.f);
+      const float a = kClamp ? fminf(fmaxf(v[2 * q], -65504.f), 65504.f) : v[2 * q];
+      const float b = kClamp ? fminf(fmaxf(v[2 * q + 1], -65504.f), 65504.f) : v[2 * q + 1];
       const __half2 h2 = __floats2half2_rn(a, b);
       const float2 hf = __half22float2(h2);
       h[q] = *reinterpret_cast<const uint32_t*>(&h2);

@@ -246,7 +246,7 @@ class Engine(object):
 
     def conv(self, name, srcs, taps, weight, cin, cout, out=None, scale=None, shift=None, relu=False,
              residual=None, res_mode=L.RES_NONE, dense_out=None, dense_out2=None, dense_split=0,
-             segs_from=None, diag_k=False, true_flops_scale=1.0, two_cta=None):
+             segs_from=None, diag_k=False, true_flops_scale=1.0, two_cta=None, force_bn=None):
         """srcs: list[FlatMap] (same geometry); out: FlatMap or None (dense).  Returns out."""
         geo = segs_from or srcs[0]
         m_tiles = sum(_round_up(n * (h + 2) * (w + 2), TILE_M) // TILE_M for (_, n, h, w) in geo.segs)
@@ -262,9 +262,12 @@ class Engine(object):
         # tile i no longer overlaps the MMAs of tile i+1.  Convs with a short K loop (1x1 convs, where the epilogue IS
         # the work) keep two accumulator stages with N = 128 instead; deep K loops (3x3 towers) amortise it
         if (self.passes == 2 and block_n > 128 and cout % 128 == 0 and not diag_k and
-                len(taps) * (cin // 64) <= int(os.environ.get("IOU_F8_SHALLOW", "8"))):
+                len(taps) * (cin // 64) <= int(os.environ.get("IOU_F8_SHALLOW", "1000"))):
             block_n, cout_pad = 128, cout
         retry_bn = 128 if (res_wide and block_n == 256) else None
+        if force_bn is not None:                 # (block_n, cout_pad) chosen by the caller (weight packed to match)
+            block_n, cout_pad = force_bn
+            retry_bn = None
         if diag_k:
             block_n, cout_pad = 64, cout
         d = L.ConvDesc()
@@ -502,8 +505,13 @@ class Engine(object):
         reg_out = [torch.empty(n, h, w, nreg, dtype=torch.float32, device=self.device) for (_, n, h, w) in F.segs]
         iou_out = [torch.empty(n, h, w, niou, dtype=torch.float32, device=self.device) for (_, n, h, w) in F.segs]
         bn_c, pad_c = pick_block_n(ncls)
+        force = None
+        cls_bn = int(os.environ.get("IOU_F8_CLS_BN", "128"))
+        if self.passes == 2 and cls_bn:          # two accumulator stages (N <= 128) at the price of padded columns
+            pad_c = _round_up(ncls, cls_bn)
+            force = (cls_bn, pad_c)
         self.conv(prefix + "retina_cls", [c], TAPS_3X3, pack_weight(sd[prefix + "retina_cls.weight"], pad_c),
-                  fc, ncls, shift=sd[prefix + "retina_cls.bias"], dense_out=cls_out)
+                  fc, ncls, shift=sd[prefix + "retina_cls.bias"], dense_out=cls_out, force_bn=force)
         if with_iou:
             # retina_reg and retina_iou read the same feature (shared_conv=4, :198-204): one GEMM, split store
             w_ri = torch.cat([sd[prefix + "retina_reg.weight"], sd[prefix + "retina_iou.weight"]], dim=0)

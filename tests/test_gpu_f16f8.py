@@ -140,6 +140,30 @@ def test_multi_segment_head_style_dense_outputs(pair):
         assert rel_err(reg_out[s].cpu(), ref[..., :36]) < TOL and rel_err(iou_out[s].cpu(), ref[..., 36:]) < TOL
 
 
+@pytest.mark.parametrize("pair", [False, True])
+@pytest.mark.parametrize("width,groups,stride,hw", [(256, 64, 1, (9, 13)), (256, 32, 2, (20, 28))])
+def test_grouped_conv_block_diagonal_vs_torch(width, groups, stride, hw, pair):
+    """ResNeXt 3x3 grouped conv (resnext.py:47-56) as a block-diagonal tap-GEMM, passes = 2."""
+    g = torch.Generator().manual_seed(width + groups + stride)
+    cg = width // groups
+    x = torch.randn(2, width, *hw, generator=g)
+    w = torch.randn(width, cg, 3, 3, generator=g) * (2.0 / (cg * 9)) ** 0.5
+    b = torch.randn(width, generator=g)
+    ref = F.conv2d(x, w, b, stride=stride, padding=1, groups=groups)
+    eng = E.Engine(DEV, passes=2)
+    m = eng.pack_input(x.to(DEV).contiguous())
+    wp = E.pack_weight_grouped(w, groups)
+    if stride == 1:
+        out = eng.conv("g", [m], E.TAPS_3X3, wp, width, width, shift=b, diag_k=True, two_cta=pair)
+    else:
+        out = eng.conv("g", eng.phase_split("p", m), E.TAPS_3X3_S2, wp, width, width, shift=b, diag_k=True,
+                       two_cta=pair)
+    y = eng.unpack_output(out)
+    eng.run()
+    torch.cuda.synchronize()
+    assert y.shape == ref.shape and rel_err(y.cpu(), ref) < TOL, rel_err(y.cpu(), ref)
+
+
 def test_fpn_upsample_residual_and_stem():
     g = torch.Generator().manual_seed(5)
     # lateral 1x1 + nearest-2x top-down add (fpn.py:108-110)

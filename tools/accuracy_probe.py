@@ -64,7 +64,7 @@ def main():
     sd_gpu = {k: v.to(dev) for k, v in sd.items()}
     cud = om.detector_forward(sd_gpu, img.to(dev))
     print("cuDNN fp32 (GPU) vs CPU oracle  :", stats(cud, ref))
-    for passes in (3, 4, 1):
+    for passes in (3, 2, 4, 1):
         det.passes, det.use_cuda_graph = passes, False
         res = det.simple_test_batch(img.to(dev), metas, rescale=False)
         plan = det.fused_plan(img.shape, dev, False)
