@@ -67,6 +67,7 @@ struct ConvParams {
   int a_rows, a_entry_bytes, b_entry_bytes, num_a_stages, num_b_stages, ring_bytes, taps_per_tile;
   int b_tile_bytes;
   int staged, res_staged, staging_per_warp;
+  int res_prefetch;          // residual slabs are prefetched into L2 this many tiles ahead (0 = off)
   const float* scale;
   const float* shift;
   int relu, res_mode;
@@ -219,6 +220,9 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
                ::"l"(tmap), "r"(c0), "r"(c1), "r"(src) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -488,8 +492,24 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
       tma_load_2d(&P.tmap_res, bar, dst, col, row);
       tma_load_2d(&P.tmap_res, bar, dst + 2048, P.cout + col, row);
     };
+    // the 2-deep shared-memory ring covers one slab of latency; the slabs of the tiles further ahead are pulled
+    // into L2 (no shared memory needed) so that the ring's loads hit L2 instead of HBM
+    auto prefetch_res = [&](int tile_) {                   // one elected lane only
+      if (tile_ >= w_total) return;
+      int mt, nt, s_;
+      decode_tile(tile_, mt, nt, s_);
+      const int row = P.seg[s_].row_start + (mt - P.seg_tile_off[s_]) * kBlockM + lane_group * 32;
+      for (int g_ = half; g_ < (P.block_n >> 5); g_ += 2) {
+        const int col = nt * P.block_n + g_ * 32;
+        tma_prefetch_l2_2d(&P.tmap_res, col, row);
+        tma_prefetch_l2_2d(&P.tmap_res, P.cout + col, row);
+      }
+    };
     int rq = 0;                                            // running slab counter of the residual ring
-    if (P.res_staged && w_first < w_total && elect_one()) issue_res(w_first, half, 0);
+    if (P.res_staged && w_first < w_total && elect_one()) {
+      issue_res(w_first, half, 0);
+      for (int a = 1; a <= P.res_prefetch; ++a) prefetch_res(w_first + a * w_stride);
+    }
     int it = 0;
     const bool two_acc = P.num_acc == 2;
     for (int tile = w_first; tile < w_total; tile += w_stride, ++it) {
@@ -497,6 +517,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
       const uint32_t acc_phase = (uint32_t)(two_acc ? (it >> 1) : it) & 1u;
       int m_tile, n_tile, s;
       decode_tile(tile, m_tile, n_tile, s);
+      if (P.res_staged && P.res_prefetch > 0 && elect_one()) prefetch_res(tile + (P.res_prefetch + 1) * w_stride);
+      __syncwarp();
       const bool tile_valid = m_tile < P.num_m_tiles;        // pair mode: the odd CTA of the last pair may idle
       const SegDev sg = P.seg[s];
       const int grow = sg.row_start + (m_tile - P.seg_tile_off[s]) * kBlockM + m_local;
@@ -816,7 +838,11 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
     P.seg[s] = SegDev{g.row_start, g.n_img, g.h, g.w};
     P.res_seg[s] = SegDev{d->res_seg[s].row_start, d->res_seg[s].n_img, d->res_seg[s].h, d->res_seg[s].w};
     P.seg_tile_off[s] = toff;
-    const long long rows = (long long)g.n_img * (g.h + 2) * (g.w + 2);
+    // tiles cover the rows up to the last interior pixel; the (w+2)+1 border rows behind it are never written and
+    // stay zero from the allocation (padded-rows buffers must be zero-initialised, include/iou_b200.h).  At
+    // 800x1344 this turns the 25x42 maps from 75 into 74 tiles = exactly 2 waves of 148 for N = 128 x 4
+    long long rows = (long long)g.n_img * (g.h + 2) * (g.w + 2);
+    rows -= (g.w + 2) + 1;
     toff += (int)((rows + kBlockM - 1) / kBlockM);
     real_rows += (double)g.n_img * g.h * g.w;
     P.out_dense[s] = (float*)d->out_dense[s];
@@ -838,6 +864,8 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   P.staged = (d->out_mode == IOU_OUT_PADDED_BF16X2) && (d->block_n % 64 == 0);
   P.res_staged = P.staged && d->res_mode == IOU_RES_SAME;
   P.staging_per_warp = P.staged ? (4096 + (P.res_staged ? 8192 : 0)) : 0;      // x 8 epilogue warps
+  P.res_prefetch = getenv("IOU_RES_PREFETCH") ? atoi(getenv("IOU_RES_PREFETCH")) : 0;   // measured: no gain
+  if (P.res_prefetch < 0 || P.res_prefetch > 8) P.res_prefetch = 0;
   const int nsplit = d->passes >= 2 ? 2 : 1;
   P.b_entry_bytes = nsplit * P.b_tile_bytes;
   if (P.b_tile_bytes % 1024 != 0) { delete plan; return fail(IOU_ERR_INVALID, "block_n %d: B tile is not a whole number of swizzle atoms", d->block_n); }

@@ -242,31 +242,35 @@ __global__ void __launch_bounds__(256) stem_pack_v_kernel(const float* __restric
         (y >= 0 && y < h && x >= 0 && x < w) ? __ldg(img + (((size_t)im * 3 + ch) * h + y) * w + x) : 0.f;
   }
   __syncthreads();
-  const int nx = xp1 - xp0;
-  for (int i = threadIdx.x; i < kStemRows * nx * 8; i += blockDim.x) {
-    const int rr = i / (nx * 8), rem = i - rr * nx * 8;
-    const int xl = rem >> 3, v = rem & 7;         // vector v holds kk = 8v .. 8v+7
+  // one thread per (row, pixel, vertical neighbour j): the 16 channels kk = 16j .. 16j+15 (12 real + 4 zero) are two
+  // adjacent vectors of each plane, every shared-memory index is a compile-time offset from one base pointer
+  constexpr int kItems = kStemRows * kStemChunk * 4;
+  for (int i = threadIdx.x; i < kItems; i += blockDim.x) {
+    const int rr = i / (kStemChunk * 4), rem = i - rr * (kStemChunk * 4);
+    const int xl = rem >> 2, j = rem & 3;         // j: vertical neighbour y' - 2 + j
     const int yp = yp0 + rr, xp = xp0 + xl;
-    if (yp > ho + 1) continue;
-    uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
+    if (xp >= xp1 || yp > ho + 1) continue;
+    uint4 hi0 = make_uint4(0, 0, 0, 0), hi1 = hi0, lo0 = hi0, lo1 = hi0;
     if (yp >= 1 && yp <= ho && xp >= 1 && xp <= wo) {
-      const int j = v >> 1, q0 = (v & 1) * 8;     // j: vertical neighbour y' - 2 + j
-      float val[8];
+      const float* base = rows + 2 * (rr + j) * kStemRowStride + 2 * xl;
+      float va[8], vb[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int q = q0 + e;
+      for (int q = 0; q < 16; ++q) {
         float t = 0.f;
         if (q < 12) {
           const int pp = q / 3, ch = q - pp * 3, py = pp >> 1, px = pp & 1;
-          t = rows[(ch * kIn + 2 * (rr + j) + py) * kStemRowStride + 2 * xl + px];
+          t = base[(ch * kIn + py) * kStemRowStride + px];
         }
-        val[e] = t;
+        if (q < 8) va[q] = t; else vb[q - 8] = t;
       }
-      encode8<kFmt>(val, hi, lo);
+      encode8<kFmt>(va, hi0, lo0);
+      encode8<kFmt>(vb, hi1, lo1);
     }
-    uint4* drow = reinterpret_cast<uint4*>(dst + ((size_t)im * (ho + 2) + yp) * wop * 128);
-    drow[(size_t)xp * 16 + v] = hi;
-    drow[(size_t)xp * 16 + 8 + v] = lo;
+    uint4* drow = reinterpret_cast<uint4*>(dst + ((size_t)im * (ho + 2) + yp) * wop * 128) + (size_t)xp * 16;
+    drow[2 * j] = hi0;
+    drow[2 * j + 1] = hi1;
+    drow[8 + 2 * j] = lo0;
+    drow[8 + 2 * j + 1] = lo1;
   }
 }
 

@@ -34,6 +34,12 @@ def _round_up(x, m):
     return (x + m - 1) // m * m
 
 
+def seg_tiles(n, h, w):
+    """128-row tiles iou_conv_run computes for one segment: up to the last interior pixel (the trailing border rows
+    stay zero from the allocation)."""
+    return max(1, -(-(n * (h + 2) * (w + 2) - (w + 2) - 1) // TILE_M))
+
+
 class FlatMap(object):
     """A bf16 [rows][2*c] padded-rows buffer holding one or more (n, h, w) segments."""
 
@@ -45,7 +51,8 @@ class FlatMap(object):
             self.segs.append((off, n, h, w))
             off += _round_up(n * (h + 2) * (w + 2), TILE_M)
         if tensor is None and ptr is None:
-            tensor = torch.empty(off, 2 * c, dtype=torch.bfloat16, device=device)
+            # zeros, not empty: the conv engine never writes the border rows behind a segment's last interior pixel
+            tensor = torch.zeros(off, 2 * c, dtype=torch.bfloat16, device=device)
         self.tensor = tensor
         self.ptr = tensor.data_ptr() if ptr is None else ptr
         self.rows = off if rows is None else rows
@@ -249,7 +256,7 @@ class Engine(object):
              segs_from=None, diag_k=False, true_flops_scale=1.0, two_cta=None, force_bn=None):
         """srcs: list[FlatMap] (same geometry); out: FlatMap or None (dense).  Returns out."""
         geo = segs_from or srcs[0]
-        m_tiles = sum(_round_up(n * (h + 2) * (w + 2), TILE_M) // TILE_M for (_, n, h, w) in geo.segs)
+        m_tiles = sum(seg_tiles(n, h, w) for (_, n, h, w) in geo.segs)
         # a same-geometry residual needs its TMA staging ring in shared memory: N tile <= 128, or 256 when the conv
         # runs as a CTA pair (half a B tile per CTA); plan_create decides, so 256 is tried first and 128 is the retry
         pair_aware = self.pair_min_tiles if (self.two_cta and two_cta is None and
