@@ -17,9 +17,11 @@
 // same fp32 accumulator; `passes = 1` runs plain bf16.  Two TMEM accumulator stages let the
 // epilogue of tile i overlap the MMAs of tile i+1.
 // `passes = 2` (template kF8) is the fp16 + e4m3 scheme of split_fmt.cuh: per K step one kind::f16 MMA
-// (fp16 hi x fp16 Whi) into the main accumulator and one kind::f8f6f4 MMA ([x8|l8] x [Wl8;W8], K = 32) into a
-// second accumulator that the epilogue folds in with a per-channel power-of-two scale: two bf16-pass
-// equivalents of tensor-pipe time instead of three.
+// (fp16 hi x fp16 Wh') and one kind::f8f6f4 MMA ([x8|l8] x [Wl8;W8], K = 32).  All three weight copies carry the
+// same per-output-channel power-of-two scale S_n, so both MMAs add into ONE fp32 accumulator (= S_n x result) and
+// the epilogue multiplies by 1/S_n (`scale`): two bf16-pass equivalents of tensor-pipe time instead of three, the
+// same TMEM footprint.  Narrow tiles (N <= 64) keep two column blocks so that consecutive MMAs do not serialise
+// on one accumulator.
 //
 // Replaces the F.conv2d / cuDNN calls of mmdet/models/backbones/resnet.py:224-267,
 // mmdet/models/necks/fpn.py:97-136, mmdet/models/anchor_heads/iou_aware_retina_head.py:171-219.
@@ -80,9 +82,9 @@ struct ConvParams {
   int dense_split;
   unsigned int idesc, idesc2;
   int combine;               // narrow N: A_hi x [B_hi|B_lo] as ONE MMA of N = 2*block_n, A_lo x B_hi into a third column block
-  int f8;                    // passes == 2: fp16 main pass + e4m3 correction pass (split_fmt.cuh); `scale` = 2^-11 / s_n
-  int num_acc;               // TMEM accumulator stages (2, or 1 when main + correction fill all 512 columns)
-  int corr_off;              // f8: TMEM column offset of the correction accumulator inside a stage
+  int f8;                    // passes == 2: fp16 main pass + e4m3 correction pass (split_fmt.cuh); `scale` = 1 / S_n
+  int num_acc;               // TMEM accumulator stages (2)
+  int corr_off;              // f8, narrow tiles: the e4m3 MMAs accumulate into a second column block at this offset (0: same block)
 };
 
 // ------------------------------------------------------------------------------------ PTX
@@ -417,13 +419,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
               const uint32_t dal = da + a_lo_d, dbl = db + b_lo_d;
               const uint32_t first = done > 0 ? 1u : 0u;
               if constexpr (kF8) {
-                // fp16 hi x Whi -> main accumulator; [x8|l8] x [Wl8;W8] (e4m3, K = 32 per 32 bytes) -> correction
-                // accumulator.  Both instruction descriptors have the same bits (formats 0 = F16 / E4M3).
+                // fp16 hi x Wh' and [x8|l8] x [Wl8;W8] (e4m3, K = 32 per 32 bytes), both at scale S_n, into the same
+                // accumulator (narrow tiles: two column blocks).  Both instruction descriptors have the same bits
+                // (formats 0 = F16 / E4M3).
 #pragma unroll
+                const uint32_t cfirst = corr_off ? first : 1u;     // same column block: the fp16 MMA initialised it
                 for (uint32_t kk = 0; kk < kBlockK / 16; ++kk) {
                   mma_i(d_tmem, umma_desc(da + 2 * kk), umma_desc(db + 2 * kk), idesc, kk ? 1u : first);
-                  if constexpr (kTwoCta) tc_mma_f8_pair(d_tmem + corr_off, umma_desc(dal + 2 * kk), umma_desc(dbl + 2 * kk), idesc, kk ? 1u : first);
-                  else tc_mma_f8(d_tmem + corr_off, umma_desc(dal + 2 * kk), umma_desc(dbl + 2 * kk), idesc, kk ? 1u : first);
+                  if constexpr (kTwoCta) tc_mma_f8_pair(d_tmem + corr_off, umma_desc(dal + 2 * kk), umma_desc(dbl + 2 * kk), idesc, kk ? 1u : cfirst);
+                  else tc_mma_f8(d_tmem + corr_off, umma_desc(dal + 2 * kk), umma_desc(dbl + 2 * kk), idesc, kk ? 1u : cfirst);
                 }
               } else if (mode == 5) {
                 // back-to-back MMAs into the SAME accumulator serialise on its read-modify-write latency
@@ -546,13 +550,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
         tc_ld16(t_row + ch * 16, v);
         tc_wait_ld();
         const int c0 = n_tile * P.block_n + ch * 16;      // first output channel of this chunk
-        if constexpr (kF8) {                               // + correction accumulator x per-channel 2^-11 / s_n
-          uint32_t w1[16];
-          tc_ld16(t_row + P.corr_off + ch * 16, w1);
-          tc_wait_ld();
+        if constexpr (kF8) {                               // (+ second column block) x per-channel 1 / S_n
+          if (P.corr_off) {
+            uint32_t w1[16];
+            tc_ld16(t_row + P.corr_off + ch * 16, w1);
+            tc_wait_ld();
 #pragma unroll
-          for (int q = 0; q < 16; ++q)
-            v[q] = __float_as_uint(fmaf(__uint_as_float(w1[q]), __ldg(P.scale + c0 + q), __uint_as_float(v[q])));
+            for (int q = 0; q < 16; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(w1[q]));
+          }
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) * __ldg(P.scale + c0 + q));
         } else if (P.combine) {                            // sum the hi*hi, hi*lo and lo*hi column blocks
           uint32_t w1[16], w2[16];
           tc_ld16(t_row + P.block_n + ch * 16, w1);
@@ -624,7 +631,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
           uint32_t v[32];
           tc_ld32(t_row + g * 32, v);
           uint32_t wc[kF8 ? 32 : 1];
-          if constexpr (kF8) tc_ld32(t_row + P.corr_off + g * 32, wc);
+          if constexpr (kF8) {
+            if (P.corr_off) tc_ld32(t_row + P.corr_off + g * 32, wc);
+          }
           // per-channel shift (and optional scale) of the slab's 32 channels: 8 broadcast 16-byte loads (every lane
           // reads the same address) instead of one load + 32 shuffles
           float shv[32];
@@ -641,16 +650,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
           }
           const float sc_l = (!kF8 && P.scale) ? __ldg(P.scale + c0 + lane) : 1.f;
           tc_wait_ld();
-          if constexpr (kF8) {                             // + correction accumulator x per-channel 2^-11 / s_n
-            const float4* cp = reinterpret_cast<const float4*>(P.scale + c0);
+          if constexpr (kF8) {                             // (+ second column block); x 1 / S_n happens with the shift
+            if (P.corr_off) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 t4 = __ldg(cp + q);
-              const int qq = kF8 ? 4 * q : 0;
-              v[4 * q] = __float_as_uint(fmaf(__uint_as_float(wc[qq]), t4.x, __uint_as_float(v[4 * q])));
-              v[4 * q + 1] = __float_as_uint(fmaf(__uint_as_float(wc[kF8 ? qq + 1 : 0]), t4.y, __uint_as_float(v[4 * q + 1])));
-              v[4 * q + 2] = __float_as_uint(fmaf(__uint_as_float(wc[kF8 ? qq + 2 : 0]), t4.z, __uint_as_float(v[4 * q + 2])));
-              v[4 * q + 3] = __float_as_uint(fmaf(__uint_as_float(wc[kF8 ? qq + 3 : 0]), t4.w, __uint_as_float(v[4 * q + 3])));
+              for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(wc[kF8 ? q : 0]));
             }
           } else if (P.combine) {                          // sum the hi*hi, hi*lo and lo*hi column blocks
             uint32_t w1[32];
@@ -664,7 +667,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
             for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(w1[q]));
           }
           float f[32];
-          if (!kF8 && P.scale) {
+          if constexpr (kF8) {                             // acc / S_n + shift: 8 broadcast 16-byte loads of 1 / S_n
+            const float4* cp = reinterpret_cast<const float4*>(P.scale + c0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 t4 = __ldg(cp + q);
+              f[4 * q] = fmaf(__uint_as_float(v[4 * q]), t4.x, shv[4 * q]);
+              f[4 * q + 1] = fmaf(__uint_as_float(v[4 * q + 1]), t4.y, shv[4 * q + 1]);
+              f[4 * q + 2] = fmaf(__uint_as_float(v[4 * q + 2]), t4.z, shv[4 * q + 2]);
+              f[4 * q + 3] = fmaf(__uint_as_float(v[4 * q + 3]), t4.w, shv[4 * q + 3]);
+            }
+          } else if (P.scale) {
 #pragma unroll
             for (int q = 0; q < 32; ++q)
               f[q] = fmaf(__uint_as_float(v[q]), __shfl_sync(0xffffffffu, sc_l, q), shv[q]);
@@ -791,7 +804,7 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   IOU_REQUIRE(d->num_src >= 1 && d->num_src <= IOU_CONV_MAX_SRC, "num_src out of range");
   IOU_REQUIRE(d->num_seg >= 1 && d->num_seg <= IOU_CONV_MAX_SEG, "num_seg out of range");
   IOU_REQUIRE(d->passes >= 1 && d->passes <= 4, "passes must be 1, 2 (fp16 + e4m3), 3 or 4");
-  IOU_REQUIRE(d->passes != 2 || d->scale != nullptr, "passes == 2 needs `scale` = the per-channel correction scale 2^-11 / s_n");
+  IOU_REQUIRE(d->passes != 2 || d->scale != nullptr, "passes == 2 needs `scale` = 1 / S_n, the inverse of the weights' per-channel scale");
   IOU_REQUIRE(d->weight != nullptr, "weight is NULL");
   IOU_REQUIRE(!d->diag_k || (d->block_n == 64 && d->cin == d->cout), "diag_k (grouped conv) needs block_n == 64 and cin == cout");
   IOU_REQUIRE(d->src_rows > 0 && d->src_rows < (1ll << 31), "src_rows out of range");
@@ -819,9 +832,10 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   P.passes = d->passes == 1 ? 1 : 3;   // 3 = hi/lo operands staged; lolo adds the fourth product
   P.lolo = d->passes == 4;
   P.f8 = d->passes == 2;
-  // f8: main + correction accumulators per stage; wide tiles fill all 512 TMEM columns -> one stage
-  P.num_acc = (P.f8 && d->block_n > 128) ? 1 : 2;
-  P.corr_off = d->block_n > 128 ? 256 : 128;
+  // f8: one accumulator per stage (all weight copies share the scale S_n); narrow tiles split the two MMA kinds
+  // over two column blocks, which the epilogue adds
+  P.num_acc = 2;
+  P.corr_off = (P.f8 && d->block_n <= 64 && !getenv("IOU_F8_ONE_BLOCK")) ? 128 : 0;
   for (int t = 0; t < d->num_taps; ++t) {
     if (d->tap_src[t] < 0 || d->tap_src[t] >= d->num_src) { delete plan; return fail(IOU_ERR_INVALID, "tap_src out of range"); }
     P.tap_src[t] = d->tap_src[t]; P.tap_dy[t] = d->tap_dy[t]; P.tap_dx[t] = d->tap_dx[t];

@@ -85,24 +85,26 @@ F8_LO_SCALE = 2048.0      # 2^11, csrc/split_fmt.cuh
 
 
 def pack_f16f8(t):
-    """fp32 [taps, cout_pad, K] -> (weight matrix for passes == 2, per-channel correction scale).
+    """fp32 [taps, cout_pad, K] -> (weight matrix for passes == 2, per-channel 1 / S_n).
 
-    Row layout mirrors the activations (csrc/split_fmt.cuh): [Wh: K x fp16][per 8 channels: Wl8 x 8 | W8 x 8] with
-    Wh = fp16(w), Wl8 = e4m3((w - Wh) * 2^11 * s_n), W8 = e4m3(w * s_n); s_n is a power of two per OUTPUT channel
-    that puts the row maximum in (64, 128].  The activation bytes [x8 x 8 | l8 x 8] meet [Wl8 x 8 | W8 x 8] in one
-    e4m3 MMA, so the correction accumulator holds 2^11 * s_n * (x*Wl + xl*W); the epilogue multiplies it by the
-    returned 2^-11 / s_n.  Returned as a bf16-typed [taps*cout_pad][2*K] tensor (same bytes per row as hi | lo)."""
+    Row layout mirrors the activations (csrc/split_fmt.cuh): [Wh': K x fp16][per 8 channels: Wl8 x 8 | W8 x 8].
+    With s_n the power of two per OUTPUT channel that puts the row maximum of |w| * s_n in (8, 16] and
+    S_n = 2^11 * s_n:  Wh' = fp16(w * S_n) (<= 32768),  Wl8 = e4m3(w * S_n - Wh'),  W8 = e4m3(w * s_n).
+    The activation's fp16 hi meets Wh' in the fp16 MMA and its bytes [x8 x 8 | l8 x 8] (l8 = (x - hi) * 2^11) meet
+    [Wl8 x 8 | W8 x 8] in the e4m3 MMA: all three products carry the factor S_n, so they add up in ONE fp32
+    accumulator = S_n * (hi*w + x*wl + xl*w), which the epilogue multiplies by the returned 1 / S_n.
+    Returned as a bf16-typed [taps*cout_pad][2*K] tensor (same bytes per row as hi | lo)."""
     taps, co, k = t.shape
     assert k % 8 == 0, k
     t = t.float()
-    wh = t.clamp(-65504.0, 65504.0).to(torch.float16)
-    wl = t - wh.float()
     m = t.abs().amax(dim=(0, 2))
-    s = torch.where(m > 0, torch.exp2(torch.floor(torch.log2(64.0 / m.clamp_min(1e-38))) + 1.0), torch.ones_like(m))
+    s = torch.where(m > 0, torch.exp2(torch.floor(torch.log2(8.0 / m.clamp_min(1e-38))) + 1.0), torch.ones_like(m))
     s = s.clamp(2.0 ** -60, 2.0 ** 60)
     sv = s.view(1, co, 1)
+    ts = t * (F8_LO_SCALE * sv)                                    # exact: powers of two
+    wh = ts.clamp(-65504.0, 65504.0).to(torch.float16)
+    wl8 = (ts - wh.float()).clamp(-448.0, 448.0).to(torch.float8_e4m3fn).view(torch.uint8)
     w8 = (t * sv).clamp(-448.0, 448.0).to(torch.float8_e4m3fn).view(torch.uint8)
-    wl8 = (wl * (F8_LO_SCALE * sv)).clamp(-448.0, 448.0).to(torch.float8_e4m3fn).view(torch.uint8)
     lo = torch.stack([wl8.view(taps, co, k // 8, 8), w8.view(taps, co, k // 8, 8)], dim=3).reshape(taps, co, 2 * k)
     hi = wh.contiguous().view(torch.uint8).view(taps, co, 2 * k)
     rows = torch.cat([hi, lo], dim=2).contiguous().view(torch.bfloat16).reshape(taps * co, 2 * k)
@@ -110,7 +112,7 @@ def pack_f16f8(t):
 
 
 def unpack_f16f8_rows(rows, k):
-    """Inverse view of pack_f16f8 for tests: -> (Wh fp32, Wl8 fp32, W8 fp32), each [rows, K]."""
+    """Inverse view of pack_f16f8 for tests: -> (Wh' fp32, Wl8 fp32, W8 fp32), each [rows, K]."""
     b = rows.contiguous().view(torch.uint8).view(rows.shape[0], 4 * k)
     wh = b[:, :2 * k].contiguous().view(torch.float16).float()
     lo = b[:, 2 * k:].reshape(rows.shape[0], k // 8, 2, 8)
@@ -269,7 +271,7 @@ class Engine(object):
         # tile i no longer overlaps the MMAs of tile i+1.  Convs with a short K loop (1x1 convs, where the epilogue IS
         # the work) keep two accumulator stages with N = 128 instead; deep K loops (3x3 towers) amortise it
         if (self.passes == 2 and block_n > 128 and cout % 128 == 0 and not diag_k and
-                len(taps) * (cin // 64) <= int(os.environ.get("IOU_F8_SHALLOW", "1000"))):
+                len(taps) * (cin // 64) <= int(os.environ.get("IOU_F8_SHALLOW", "0"))):
             block_n, cout_pad = 128, cout
         retry_bn = 128 if (res_wide and block_n == 256) else None
         if force_bn is not None:                 # (block_n, cout_pad) chosen by the caller (weight packed to match)
@@ -294,7 +296,7 @@ class Engine(object):
             src32 = getattr(weight, "src32", None)
             if src32 is None:
                 src32 = (weight[:, :kdim].float() + weight[:, kdim:].float())
-            assert scale is None, "passes == 2 uses `scale` for the correction accumulator"
+            assert scale is None, "passes == 2 uses `scale` for 1 / S_n (fold a BN scale into the weights)"
             weight, corr_scale = pack_f16f8(src32.reshape(len(taps), cout_pad, kdim))
         elif hasattr(weight, "src32"):
             del weight.src32
@@ -513,7 +515,7 @@ class Engine(object):
         iou_out = [torch.empty(n, h, w, niou, dtype=torch.float32, device=self.device) for (_, n, h, w) in F.segs]
         bn_c, pad_c = pick_block_n(ncls)
         force = None
-        cls_bn = int(os.environ.get("IOU_F8_CLS_BN", "128"))
+        cls_bn = int(os.environ.get("IOU_F8_CLS_BN", "0"))
         if self.passes == 2 and cls_bn:          # two accumulator stages (N <= 128) at the price of padded columns
             pad_c = _round_up(ncls, cls_bn)
             force = (cls_bn, pad_c)

@@ -32,15 +32,15 @@ def decode_rows(b):
     return h + l8.reshape(rows, c) / LO_SCALE
 
 
-def emulate_gemm(a_bytes, w_rows, corr_scale):
+def emulate_gemm(a_bytes, w_rows, inv_scale):
     """What the tensor core sums for one tap: a_bytes uint8 [rows, 4K] (encode_rows), w_rows the bf16-typed
-    [cout, 2K] matrix of engine.pack_f16f8, corr_scale [cout].  Main pass: fp16 x fp16 over K; correction pass:
-    e4m3 x e4m3 over the 2K lo BYTES in storage order (this is what pins the [x8|l8] vs [Wl8|W8] pairing).
-    Products and sums in float64."""
+    [cout, 2K] matrix of engine.pack_f16f8, inv_scale [cout] = 1 / S_n.  fp16 pass: hi x Wh' over K; e4m3 pass: the
+    2K lo BYTES in storage order (this is what pins the [x8|l8] vs [Wl8|W8] pairing).  Both land in one accumulator
+    (= S_n x result); products and sums in float64."""
     k = a_bytes.shape[1] // 4
     wb = w_rows.contiguous().view(torch.uint8).view(w_rows.shape[0], 4 * k)
     ah = a_bytes[:, :2 * k].contiguous().view(torch.float16).double()
     wh = wb[:, :2 * k].contiguous().view(torch.float16).double()
     al = a_bytes[:, 2 * k:].contiguous().view(torch.float8_e4m3fn).double()
     wl = wb[:, 2 * k:].contiguous().view(torch.float8_e4m3fn).double()
-    return ah @ wh.t() + (al @ wl.t()) * corr_scale.double().view(1, -1)
+    return (ah @ wh.t() + al @ wl.t()) * inv_scale.double().view(1, -1)
