@@ -198,6 +198,12 @@ typedef struct iou_conv_desc {
   int32_t diag_k;                           /* grouped conv (cin == cout, block_n == 64): output tile j contracts
                                                only input channels [64j, 64j+64); weight is [taps*cout][2*64]   */
   int32_t two_cta;                          /* 1: run as CTA pairs (tcgen05 cta_group::2, cluster of 2)      */
+  /* Fused stride-2 phase split (ABI version 4; PADDED output, one segment, block_n % 64 == 0): the epilogue also
+   * writes every output row (img, yp, xp) to phase_out[(yp&1)*2 + (xp&1)] (where non-NULL) in the layout of
+   * iou_phase_split, i.e. at (u, v) = ((yp>>1)+1, (xp>>1)+1) of a zero-initialised [n][(h+1)/2+2][(w+1)/2+2][2*cout]
+   * map.  phase_only != 0: `out` is not written at all (may be NULL) -- for maps only a stride-2 conv reads.     */
+  void* phase_out[4];
+  int32_t phase_only;
 } iou_conv_desc;
 
 typedef struct iou_conv_plan iou_conv_plan;

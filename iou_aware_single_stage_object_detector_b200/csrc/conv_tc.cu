@@ -70,6 +70,10 @@ struct ConvParams {
   int b_tile_bytes;
   int staged, res_staged, staging_per_warp;
   int res_prefetch;          // residual slabs are prefetched into L2 this many tiles ahead (0 = off)
+  // fused stride-2 phase split (iou_phase_split's layout, written by the epilogue): row (img, yp, xp) also goes to
+  // phase (yp&1, xp&1) at (u, v) = ((yp>>1)+1, (xp>>1)+1) of a [n][ph_h+2][ph_w+2] map; phase_only skips the normal output
+  __nv_bfloat16* phase_out[4];
+  int phase_any, phase_only, ph_h, ph_w;
   const float* scale;
   const float* shift;
   int relu, res_mode;
@@ -540,6 +544,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
         const size_t rrow = (size_t)rs.row_start + ((size_t)img * (rs.h + 2) + ry) * (rs.w + 2) + rx;
         res_row = P.residual + rrow * (2 * P.cout);
       }
+      __nv_bfloat16* ph_row = nullptr;                       // this row's place in a stride-2 phase map, if any
+      if (P.phase_any && tile_valid && img < sg.n_img) {
+        __nv_bfloat16* pb = P.phase_out[((yp & 1) << 1) | (xp & 1)];
+        if (pb != nullptr)
+          ph_row = pb + ((size_t)(img * (P.ph_h + 2) + (yp >> 1) + 1) * (P.ph_w + 2) + (xp >> 1) + 1) * (size_t)(2 * P.cout);
+      }
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(acc * kAccStride);
@@ -706,8 +716,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
               for (int q = 0; q < 8; ++q) f[j * 8 + q] += t8[q];
             }
           }
-          if (lane == 0) tma_store_wait_read();            // previous slab has left the staging tile
-          __syncwarp();
+          if (!P.phase_only) {
+            if (lane == 0) tma_store_wait_read();          // previous slab has left the staging tile
+            __syncwarp();
+          }
           const uint32_t ob = st_out + lane * 64;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -718,10 +730,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
             uint4 hi, lo;
             encode8<kFmt, false>(x8, hi, lo);
             if (!interior) { hi = make_uint4(0, 0, 0, 0); lo = hi; }
-            const uint32_t sw = (uint32_t)((j ^ swz) << 4);
-            sts128(ob + sw, hi);
-            sts128(ob + 2048 + sw, lo);
+            if (ph_row != nullptr) {                       // 64 contiguous bytes per plane and row over the four chunks
+              *reinterpret_cast<uint4*>(ph_row + c0 + 8 * j) = hi;
+              *reinterpret_cast<uint4*>(ph_row + P.cout + c0 + 8 * j) = lo;
+            }
+            if (!P.phase_only) {
+              const uint32_t sw = (uint32_t)((j ^ swz) << 4);
+              sts128(ob + sw, hi);
+              sts128(ob + 2048 + sw, lo);
+            }
           }
+          if (P.phase_only) continue;
           fence_async_smem();
           __syncwarp();
           if (tile_valid && elect_one()) {
@@ -808,8 +827,15 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   IOU_REQUIRE(d->weight != nullptr, "weight is NULL");
   IOU_REQUIRE(!d->diag_k || (d->block_n == 64 && d->cin == d->cout), "diag_k (grouped conv) needs block_n == 64 and cin == cout");
   IOU_REQUIRE(d->src_rows > 0 && d->src_rows < (1ll << 31), "src_rows out of range");
+  const bool phase_any = d->phase_out[0] || d->phase_out[1] || d->phase_out[2] || d->phase_out[3];
+  IOU_REQUIRE(!d->phase_only || phase_any, "phase_only without any phase_out");
+  if (phase_any) {
+    IOU_REQUIRE(d->out_mode == IOU_OUT_PADDED_BF16X2 && d->num_seg == 1 && d->block_n % 64 == 0,
+                "phase_out needs a single-segment padded-rows output and block_n %% 64 == 0");
+    for (int i = 0; i < 4; ++i) IOU_REQUIRE(((uintptr_t)d->phase_out[i] & 15) == 0, "phase_out[%d] must be 16-byte aligned", i);
+  }
   if (d->out_mode == IOU_OUT_PADDED_BF16X2) {
-    IOU_REQUIRE(d->out != nullptr, "out is NULL");
+    IOU_REQUIRE(d->out != nullptr || d->phase_only, "out is NULL");
     IOU_REQUIRE(d->cout == d->cout_pad, "padded output needs cout == cout_pad");
     IOU_REQUIRE(((uintptr_t)d->out & 15) == 0, "out must be 16-byte aligned");
   } else {
@@ -878,6 +904,11 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   P.staged = (d->out_mode == IOU_OUT_PADDED_BF16X2) && (d->block_n % 64 == 0);
   P.res_staged = P.staged && d->res_mode == IOU_RES_SAME;
   P.staging_per_warp = P.staged ? (4096 + (P.res_staged ? 8192 : 0)) : 0;      // x 8 epilogue warps
+  for (int i = 0; i < 4; ++i) P.phase_out[i] = (__nv_bfloat16*)d->phase_out[i];
+  P.phase_any = phase_any ? 1 : 0;
+  P.phase_only = d->phase_only ? 1 : 0;
+  P.ph_h = (d->seg[0].h + 1) / 2;
+  P.ph_w = (d->seg[0].w + 1) / 2;
   P.res_prefetch = getenv("IOU_RES_PREFETCH") ? atoi(getenv("IOU_RES_PREFETCH")) : 0;   // measured: no gain
   if (P.res_prefetch < 0 || P.res_prefetch > 8) P.res_prefetch = 0;
   const int nsplit = d->passes >= 2 ? 2 : 1;
@@ -945,7 +976,7 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   }
   for (int i = d->num_src; i < IOU_CONV_MAX_SRC; ++i) P.tmap_src[i] = P.tmap_src[0];
   P.tmap_out = P.tmap_w; P.tmap_res = P.tmap_w;
-  if (P.staged) {
+  if (P.staged && !P.phase_only) {
     const uint64_t orow = d->out_rows > 0 ? (uint64_t)d->out_rows : (uint64_t)d->src_rows;
     if (int e = encode_2d(&P.tmap_out, d->out, orow, (uint64_t)2 * d->cout, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) { delete plan; return e; }
   }

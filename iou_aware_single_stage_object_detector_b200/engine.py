@@ -255,8 +255,11 @@ class Engine(object):
 
     def conv(self, name, srcs, taps, weight, cin, cout, out=None, scale=None, shift=None, relu=False,
              residual=None, res_mode=L.RES_NONE, dense_out=None, dense_out2=None, dense_split=0,
-             segs_from=None, diag_k=False, true_flops_scale=1.0, two_cta=None, force_bn=None):
-        """srcs: list[FlatMap] (same geometry); out: FlatMap or None (dense).  Returns out."""
+             segs_from=None, diag_k=False, true_flops_scale=1.0, two_cta=None, force_bn=None,
+             phase_outs=None, phase_only=False):
+        """srcs: list[FlatMap] (same geometry); out: FlatMap or None (dense).  Returns out.
+        phase_outs: 4 FlatMaps / None from new_phase_maps(): the epilogue also writes the stride-2 phase split of the
+        output (what iou_phase_split would produce from it); phase_only: nothing else is written (returns None)."""
         geo = segs_from or srcs[0]
         m_tiles = sum(seg_tiles(n, h, w) for (_, n, h, w) in geo.segs)
         # a same-geometry residual needs its TMA staging ring in shared memory: N tile <= 128, or 256 when the conv
@@ -330,7 +333,15 @@ class Engine(object):
         d.num_seg = len(geo.segs)
         for i, (rs, n, h, w) in enumerate(geo.segs):
             d.seg[i] = L.ConvSegment(rs, n, h, w)
-        if dense_out is None:
+        if phase_outs is not None:
+            for i, m in enumerate(phase_outs):
+                if m is not None:
+                    assert m.c == cout
+                    d.phase_out[i] = m.ptr
+            d.phase_only = int(phase_only)
+        if dense_out is None and phase_only:
+            d.out_mode = L.OUT_PADDED
+        elif dense_out is None:
             if out is None:
                 out = self.new_map([(n, h, w) for (_, n, h, w) in geo.segs], cout)
             assert out.c == cout
@@ -358,6 +369,11 @@ class Engine(object):
         lib = self.lib
         self.ops.append((name, lambda st, p=plan: L.check(lib.iou_conv_run(p, st))))
         return out
+
+    def new_phase_maps(self, n, h, w, c, mask=15):
+        """Zero-initialised stride-2 phase maps of an (n, h, w) map with c channels, for conv(phase_outs=...)."""
+        ho, wo = (h + 1) // 2, (w + 1) // 2
+        return [self.new_map([(n, ho, wo)], c) if (mask >> i) & 1 else None for i in range(4)]
 
     def phase_split(self, name, src, mask=15, relu=False):
         """-> list of 4 FlatMaps (None where masked out) in the stride-2 output geometry; relu=True clamps the
@@ -408,6 +424,8 @@ class Engine(object):
         block's stride in the 3x3 conv2, 'caffe' in the 1x1 conv1 (resnet.py:129-134)."""
         x = self.add_stem(sd, img, prefix)
         outs = []
+        fuse = os.environ.get("IOU_FUSE_PHASE", "1") != "0"     # producers write the stride-2 phase maps themselves
+        x_ph3 = None                                            # phase (1,1) of x, if its producer wrote it
         for s, nblocks in enumerate(STAGE_BLOCKS[depth]):
             planes = 64 * 2 ** s
             for b in range(nblocks):
@@ -417,10 +435,19 @@ class Engine(object):
                 width = sd[p + "conv1.weight"].shape[0]          # == planes for ResNet (resnext.py:21-24)
                 sc1, sh1 = bn_fold(sd, p + "bn1")
                 w1 = pack_weight(fold_scale(sd[p + "conv1.weight"], sc1), width)
-                xs = None
+                xs = [None, None, None, x_ph3] if (stride == 2 and x_ph3 is not None) else None
+                x_ph3 = None
+                t1_ph = None
                 if stride == 2 and style == "caffe":        # 1x1 stride 2 reads phase (1,1) of x; conv2 has stride 1
-                    xs = self.phase_split(p + "conv1.phase", x, mask=8)
+                    if xs is None:
+                        xs = self.phase_split(p + "conv1.phase", x, mask=8)
                     t1 = self.conv(p + "conv1", [xs[3]] * 4, TAPS_1X1_S2, w1, cin, width, shift=sh1, relu=True)
+                elif stride == 2 and fuse and width % 64 == 0:
+                    # t1 is only read by the stride-2 conv2: conv1's epilogue writes its four phase maps directly
+                    _, n_, h_, w_ = x.segs[0]
+                    t1_ph = self.new_phase_maps(n_, h_, w_, width)
+                    t1 = self.conv(p + "conv1", [x], TAPS_1X1, w1, cin, width, shift=sh1, relu=True,
+                                   phase_outs=t1_ph, phase_only=True)
                 else:
                     t1 = self.conv(p + "conv1", [x], TAPS_1X1, w1, cin, width, shift=sh1, relu=True)
                 sc2, sh2 = bn_fold(sd, p + "bn2")
@@ -431,7 +458,7 @@ class Engine(object):
                     w2 = pack_weight_grouped(fold_scale(sd[p + "conv2.weight"], sc2), groups)
                     kw = dict(diag_k=True, true_flops_scale=cg / 64.0)
                 if stride == 2 and style != "caffe":
-                    ph = self.phase_split(p + "conv2.phase", t1)
+                    ph = t1_ph if t1_ph is not None else self.phase_split(p + "conv2.phase", t1)
                     t2 = self.conv(p + "conv2", ph, TAPS_3X3_S2, w2, width, width, shift=sh2,
                                    relu=True, **kw)
                 else:
@@ -451,9 +478,15 @@ class Engine(object):
                         idt = self.conv(p + "downsample", [x], TAPS_1X1, wd, cin, planes * 4,
                                         shift=shd)
                 sc3, sh3 = bn_fold(sd, p + "bn3")
+                ph3 = None
+                if fuse and b == nblocks - 1 and s + 1 < len(STAGE_BLOCKS[depth]):
+                    # the next stage's first block reads phase (1,1) of this block's output (stride-2 1x1 convs)
+                    _, n_, h_, w_ = t2.segs[0]
+                    ph3 = self.new_phase_maps(n_, h_, w_, planes * 4, mask=8)
                 x = self.conv(p + "conv3", [t2], TAPS_1X1, pack_weight(fold_scale(sd[p + "conv3.weight"], sc3), planes * 4),
                               width, planes * 4, shift=sh3, relu=True, residual=idt,
-                              res_mode=L.RES_SAME)
+                              res_mode=L.RES_SAME, phase_outs=ph3)
+                x_ph3 = ph3[3] if ph3 is not None else None
             outs.append(x)
         return outs
 

@@ -94,7 +94,8 @@ class ConvDesc(ctypes.Structure):
                 ("dense_split", ctypes.c_int32), ("out_dense2", ctypes.c_void_p * CONV_MAX_SEG),
                 ("num_seg", ctypes.c_int32), ("seg", ConvSegment * CONV_MAX_SEG),
                 ("passes", ctypes.c_int32), ("out_rows", ctypes.c_int64), ("res_rows", ctypes.c_int64),
-                ("diag_k", ctypes.c_int32), ("two_cta", ctypes.c_int32)]
+                ("diag_k", ctypes.c_int32), ("two_cta", ctypes.c_int32),
+                ("phase_out", ctypes.c_void_p * 4), ("phase_only", ctypes.c_int32)]
 
 
 _SIGS = {

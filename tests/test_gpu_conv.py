@@ -270,3 +270,35 @@ def test_cta_pair_mode_dense_head_outputs():
     for s, x in enumerate(xs):
         ref = F.conv2d(x, w_cls, b_cls, padding=1).permute(0, 2, 3, 1)
         assert rel_err(cls_out[s].cpu(), ref) < TOL
+
+
+@pytest.mark.parametrize("passes", [3, 2])
+@pytest.mark.parametrize("cin,cout,hw,res,pair", [(256, 128, (25, 42), False, None), (64, 256, (12, 20), True, None),
+                                                  (128, 512, (13, 21), True, True), (256, 64, (50, 70), False, True)])
+def test_fused_phase_outputs_equal_the_phase_split_kernel(cin, cout, hw, res, pair, passes):
+    """conv(phase_outs=...) writes, from its epilogue, exactly the bytes iou_phase_split produces from the conv's
+    ordinary output (odd and even sizes, with / without the ordinary output, residual ring, CTA pairs)."""
+    g = torch.Generator().manual_seed(cin + cout + hw[0])
+    n = 2
+    x = torch.randn(n, cin, *hw, generator=g)
+    w = torch.randn(cout, cin, 1, 1, generator=g) * (2.0 / cin) ** 0.5
+    b = torch.randn(cout, generator=g)
+    r = torch.randn(n, cout, *hw, generator=g) if res else None
+    eng = E.Engine(DEV, passes=passes)
+    m = eng.pack_input(x.to(DEV).contiguous())
+    rm = eng.pack_input(r.to(DEV).contiguous()) if res else None
+    kw = dict(shift=b, relu=True, residual=rm, res_mode=L.RES_SAME if res else L.RES_NONE, two_cta=pair)
+    plain = eng.conv("plain", [m], E.TAPS_1X1, E.pack_weight(w, cout), cin, cout, **kw)
+    want = eng.phase_split("split", plain)
+    both = eng.new_phase_maps(n, hw[0], hw[1], cout, mask=8 if res else 15)
+    out2 = eng.conv("both", [m], E.TAPS_1X1, E.pack_weight(w, cout), cin, cout, phase_outs=both, **kw)
+    only = eng.new_phase_maps(n, hw[0], hw[1], cout)
+    none = eng.conv("only", [m], E.TAPS_1X1, E.pack_weight(w, cout), cin, cout, phase_outs=only, phase_only=True, **kw)
+    eng.run()
+    torch.cuda.synchronize()
+    assert none is None
+    assert torch.equal(out2.tensor.view(torch.int16), plain.tensor.view(torch.int16))
+    for i in range(4):
+        if both[i] is not None:
+            assert torch.equal(both[i].tensor.view(torch.int16), want[i].tensor.view(torch.int16)), i
+        assert torch.equal(only[i].tensor.view(torch.int16), want[i].tensor.view(torch.int16)), i
