@@ -11,7 +11,9 @@ over ranks; consecutive steps alternate between two launch plans on two streams,
 `e2e` = the same through the public API (detect_stream) with pinned HOST images copied in and detections read
 back every step; `roofline` = per-launch CUDA-event timing of the tcgen05 conv kernel (eager pass, rescaled to
 the forward's CUDA-graph replay time, `graph_over_eager`) against the measured bf16 peak (algorithmic 2*MAC
-flops: the 3-pass split means tensor-pipe time is ~3x `frac`); `cpu_baseline` = the oracle (a port of the
+flops: the default split scheme -- one fp16 pass + one e4m3 pass of doubled K, `--passes 2` -- costs two bf16-pass
+equivalents of tensor-pipe time, so its ceiling is `frac` = 0.5; `--passes 3`, bf16 hi|lo x3: 0.33);
+`cpu_baseline` = the oracle (a port of the
 reference's CPU algorithm) on this box's host cores.
 """
 import argparse
@@ -301,8 +303,9 @@ def run_ours(args):
                 "peak": peaks["tf_sustained"], "peak_source": peaks["source"] + " bf16 sustained (cuBLAS)",
                 "unit": "TFLOP/s", "frac": round(achieved / peaks["tf_sustained"], 4),
                 # dram__bytes_read+write summed over the 71 conv launches of one step / 71, from the ncu pass
-                # committed as profiles/r01_v11_launches_ncu_dram.csv (22.01 GB per step)
-                "traffic": 310.0e6, "traffic_source": "ncu, profiles/r01_v11_launches_ncu_dram.csv",
+                # committed as profiles/r01_v13_launches_ncu_dram.csv (22.22 GB per step, R50 bs=8)
+                "traffic": 312.9e6 if MODEL == "r50" else None,
+                "traffic_source": "ncu, profiles/r01_v13_launches_ncu_dram.csv",
                 "launches_per_step": n_conv,
                 "avg_launch_ms": round(conv_ms / max(n_conv, 1), 4),
                 "algorithmic_gflop_per_step": round(conv_flops / 1e9, 1),
