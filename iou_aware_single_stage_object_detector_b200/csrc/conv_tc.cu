@@ -41,6 +41,7 @@ constexpr int kATileBytes = kBlockM * kBlockK * 2;   // 16 KiB
 constexpr int kNumThreads = 320;             // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
 constexpr int kNumEpiWarps = 8;
 constexpr int kMaxStages = 8;
+constexpr int kMaxBStages = 16;              // B ring entries (resident weights: one entry per (tap, K slab) of a tile)
 constexpr int kAccStride = 256;              // TMEM columns between the two accumulator stages
 constexpr int kTmemCols = 512;
 constexpr int kSmemBudget = 227 * 1024;
@@ -68,6 +69,7 @@ struct ConvParams {
   int grp_tap[IOU_CONV_MAX_TAPS][4], grp_shift[IOU_CONV_MAX_TAPS][4];   // up to 4 taps per window (shift 0..3 rows)
   int a_rows, a_entry_bytes, b_entry_bytes, num_a_stages, num_b_stages, ring_bytes, taps_per_tile;
   int b_tile_bytes;
+  int b_resident;            // one N tile and few (tap, slab) weight tiles: loaded once per CTA, kept for every tile
   int staged, res_staged, staging_per_warp;
   int res_prefetch;          // residual slabs are prefetched into L2 this many tiles ahead (0 = off)
   // fused stride-2 phase split (iou_phase_split's layout, written by the epilogue): row (img, yp, xp) also goes to
@@ -278,9 +280,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
   unsigned char* ctrl = smem_dyn + (base - raw);
   const uint32_t ctrl_addr = base;
   const uint32_t tiles_addr = base + kCtrlBytes;
-  // control block: B full[8] @0, B empty[8] @64, tfull[2] @128, tempty[2] @144, tmem ptr @160,
-  // residual ring @192..320, A full[8] @320, A empty[8] @384
-  const uint32_t bar_full = ctrl_addr, bar_empty = ctrl_addr + 64, bar_tfull = ctrl_addr + 128,
+  // control block: tfull[2] @128, tempty[2] @144, tmem ptr @160, residual ring @192..320, A full[8] @320,
+  // A empty[8] @384, B full[16] @448, B empty[16] @576
+  const uint32_t bar_full = ctrl_addr + 448, bar_empty = ctrl_addr + 576, bar_tfull = ctrl_addr + 128,
                  bar_tempty = ctrl_addr + 144, bar_afull = ctrl_addr + 320, bar_aempty = ctrl_addr + 384;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(ctrl + 160);
 
@@ -365,17 +367,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
             if (++as == P.num_a_stages) { as = 0; aph ^= 1u; }
             // ---- one B tile (hi, lo) per tap
             for (int j = 0; j < nt; ++j) {
-              const int wrow = P.grp_tap[g][j] * P.cout_pad + n_tile * P.block_n + rank * b_rows;
-              mbar_wait(bar_empty + 8 * bs, bph ^ 1u);
-              const uint32_t fb = bar_full + 8 * bs;
-              const uint32_t sb = b_ring_addr + bs * P.b_entry_bytes;
-              if (!kTwoCta || rank == 0) mbar_expect_tx(fb, mult * (uint32_t)P.b_entry_bytes);
-              if constexpr (kTwoCta) {
-                tma_load_2d_pair(&P.tmap_w, fb, sb, ks * kBlockK, wrow);
-                if (P.passes == 3) tma_load_2d_pair(&P.tmap_w, fb, sb + b_lo_off, P.b_cin + ks * kBlockK, wrow);
-              } else {
-                tma_load_2d(&P.tmap_w, fb, sb, ks * kBlockK, wrow);
-                if (P.passes == 3) tma_load_2d(&P.tmap_w, fb, sb + b_lo_off, P.b_cin + ks * kBlockK, wrow);
+              // resident weights: the ring has one entry per (tap, slab) of a tile and is filled once, with the first tile
+              if (!P.b_resident || tile == w_first) {
+                const int wrow = P.grp_tap[g][j] * P.cout_pad + n_tile * P.block_n + rank * b_rows;
+                mbar_wait(bar_empty + 8 * bs, bph ^ 1u);
+                const uint32_t fb = bar_full + 8 * bs;
+                const uint32_t sb = b_ring_addr + bs * P.b_entry_bytes;
+                if (!kTwoCta || rank == 0) mbar_expect_tx(fb, mult * (uint32_t)P.b_entry_bytes);
+                if constexpr (kTwoCta) {
+                  tma_load_2d_pair(&P.tmap_w, fb, sb, ks * kBlockK, wrow);
+                  if (P.passes == 3) tma_load_2d_pair(&P.tmap_w, fb, sb + b_lo_off, P.b_cin + ks * kBlockK, wrow);
+                } else {
+                  tma_load_2d(&P.tmap_w, fb, sb, ks * kBlockK, wrow);
+                  if (P.passes == 3) tma_load_2d(&P.tmap_w, fb, sb + b_lo_off, P.b_cin + ks * kBlockK, wrow);
+                }
               }
               if (++bs == P.num_b_stages) { bs = 0; bph ^= 1u; }
             }
@@ -412,7 +417,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
           mbar_wait(bar_afull + 8 * as, aph);
           const uint32_t sa = tiles_addr + as * P.a_entry_bytes;
           for (int j = 0; j < nt; ++j, ++done) {
-            mbar_wait(bar_full + 8 * bs, bph);
+            if (!P.b_resident || it == 0) mbar_wait(bar_full + 8 * bs, bph);
             tc_fence_after();
             if (elect_one()) {
               // descriptor low words: (addr >> 4) | LBO; every operand lives below 256 KiB, so advancing an
@@ -465,11 +470,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
               }
               // commits fire when the MMAs issued so far retire (pair mode: multicast to BOTH CTAs)
               if constexpr (kTwoCta) {
-                tc_commit_pair(bar_empty + 8 * bs);
+                if (!P.b_resident) tc_commit_pair(bar_empty + 8 * bs);
                 if (j == nt - 1) tc_commit_pair(bar_aempty + 8 * as);
                 if (done == todo - 1) tc_commit_pair(bar_tfull + 8 * acc);
               } else {
-                tc_commit(bar_empty + 8 * bs);                     // frees the B tile
+                if (!P.b_resident) tc_commit(bar_empty + 8 * bs);  // frees the B tile
                 if (j == nt - 1) tc_commit(bar_aempty + 8 * as);   // frees the A window
                 if (done == todo - 1) tc_commit(bar_tfull + 8 * acc);   // accumulator complete
               }
@@ -940,7 +945,16 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
     // ring depths: the A ring is worth (taps per group) B tiles per entry; maximise the shallower of the two
     const int budget = kSmemBudget - kCtrlBytes - 1024 - kNumEpiWarps * P.staging_per_warp;
     int best_na = 0, best_nb = 0, best_score = 0;
-    for (int na = 2; na <= kMaxStages; ++na) {
+    // resident weights: with ONE N tile every tile of a CTA multiplies by the same few weight tiles -- load them once
+    // (entry e = the e-th (tap, slab) of a tile) and spend the rest of shared memory on the A ring
+    const int b_entries = d->num_taps * P.k_slabs;
+    P.b_resident = 0;
+    if (P.num_n_tiles == 1 && b_entries <= kMaxBStages && !getenv("IOU_NO_B_RESIDENT")) {
+      int na = (budget - b_entries * P.b_entry_bytes) / P.a_entry_bytes;
+      if (na > kMaxStages) na = kMaxStages;
+      if (na >= 2) { P.b_resident = 1; best_na = na; best_nb = b_entries; best_score = 1; }
+    }
+    for (int na = 2; na <= kMaxStages && !P.b_resident; ++na) {
       int nb = (budget - na * P.a_entry_bytes) / P.b_entry_bytes;
       if (nb > kMaxStages) nb = kMaxStages;
       if (nb < 2) break;
@@ -957,9 +971,9 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   }
   if (!fits) { delete plan; return fail(IOU_ERR_INVALID, "tile does not fit shared memory (block_n %d, residual %d): use a smaller block_n", d->block_n, d->res_mode); }
   if (getenv("IOU_CONV_DEBUG"))
-    fprintf(stderr, "[iou_conv] cin %d cout %d taps %d block_n %d pair %d res %d staged %d | groups %d a_rows %d nA %d nB %d ring %d KB\n",
+    fprintf(stderr, "[iou_conv] cin %d cout %d taps %d block_n %d pair %d res %d staged %d | groups %d a_rows %d nA %d nB %d%s ring %d KB\n",
             d->cin, d->cout, d->num_taps, d->block_n, P.two_cta, d->res_mode, P.staged, P.num_groups, P.a_rows,
-            P.num_a_stages, P.num_b_stages, P.ring_bytes / 1024);
+            P.num_a_stages, P.num_b_stages, P.b_resident ? " (resident)" : "", P.ring_bytes / 1024);
   P.scale = d->scale; P.shift = d->shift; P.relu = d->relu; P.res_mode = d->res_mode;
   P.residual = (const __nv_bfloat16*)d->residual;
   P.out_mode = d->out_mode; P.out = (__nv_bfloat16*)d->out; P.dense_split = d->dense_split;
