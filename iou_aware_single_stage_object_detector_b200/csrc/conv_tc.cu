@@ -705,20 +705,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint32_t sw = (uint32_t)((j ^ swz) << 4);
-              float t8[8];
-              decode8<kFmt>(lds128(rb + sw), lds128(rb + 2048 + sw), t8);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) f[j * 8 + q] += t8[q];
+              decode8_add<kFmt>(lds128(rb + sw), lds128(rb + 2048 + sw), f + j * 8);
             }
           } else if (res_row != nullptr && interior) {     // nearest-2x upsampled residual (FPN laterals)
             const uint4* rh = reinterpret_cast<const uint4*>(res_row + c0);
             const uint4* rl = reinterpret_cast<const uint4*>(res_row + P.cout + c0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              float t8[8];
-              decode8<kFmt>(__ldg(rh + j), __ldg(rl + j), t8);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) f[j * 8 + q] += t8[q];
+              decode8_add<kFmt>(__ldg(rh + j), __ldg(rl + j), f + j * 8);
             }
           }
           if (!P.phase_only) {

@@ -30,6 +30,20 @@ __device__ __forceinline__ float2 e4m3x2_to_float2(uint32_t v) {
   return __half22float2(*reinterpret_cast<const __half2*>(&h));
 }
 
+// mixed-precision ALU ops of sm_100 (SASS FHADD / FHFMA): an fp16 operand is widened inside the instruction
+__device__ __forceinline__ float fhadd(uint16_t h, float f) {           // f + float(h)
+  float d;
+  asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(d) : "h"(h), "f"(f));
+  return d;
+}
+__device__ __forceinline__ float fhfma(uint16_t a, uint16_t b, float c) {   // float(a) * float(b) + c
+  float d;
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(c));
+  return d;
+}
+constexpr uint16_t kF16LoInv = 0x1000;       // 2^-11 as fp16
+constexpr uint16_t kF16NegLoScale = 0xE800;  // -2048 as fp16
+
 // 8 consecutive channels -> the group's hi and lo vectors.  kClamp: saturate at the fp16 range (the layout kernels,
 // which see arbitrary user data); the conv epilogue skips it -- an activation beyond 65504 becomes inf and shows.
 template <int kFmt, bool kClamp = true>
@@ -52,10 +66,11 @@ __device__ __forceinline__ void encode8(const float (&v)[8], uint4& hi, uint4& l
       const float a = kClamp ? fminf(fmaxf(v[2 * q], -65504.f), 65504.f) : v[2 * q];
       const float b = kClamp ? fminf(fmaxf(v[2 * q + 1], -65504.f), 65504.f) : v[2 * q + 1];
       const __half2 h2 = __floats2half2_rn(a, b);
-      const float2 hf = __half22float2(h2);
       h[q] = *reinterpret_cast<const uint32_t*>(&h2);
       x8[q] = e4m3x2(a, b);
-      l8[q] = e4m3x2((a - hf.x) * kF8LoScale, (b - hf.y) * kF8LoScale);
+      // (v - hi) * 2^11 = fma(hi, -2^11, v * 2^11): exact (the difference has <= 13 significant bits)
+      l8[q] = e4m3x2(fhfma((uint16_t)(h[q] & 0xffffu), kF16NegLoScale, a * kF8LoScale),
+                     fhfma((uint16_t)(h[q] >> 16), kF16NegLoScale, b * kF8LoScale));
     }
     l[0] = x8[0] | (x8[1] << 16); l[1] = x8[2] | (x8[3] << 16);
     l[2] = l8[0] | (l8[1] << 16); l[3] = l8[2] | (l8[3] << 16);
@@ -82,6 +97,27 @@ __device__ __forceinline__ void decode8(const uint4 hi, const uint4 lo, float (&
       const float2 lf = e4m3x2_to_float2(l8[q]);
       v[2 * q] = fmaf(lf.x, kF8LoInv, hf.x);
       v[2 * q + 1] = fmaf(lf.y, kF8LoInv, hf.y);
+    }
+  }
+}
+
+// f[i] += value of channel i (residual adds).  fp16 + e4m3 format: two mixed-precision ops per element
+// (f + hi, then + l8 * 2^-11) instead of convert / convert / fma / add.
+template <int kFmt>
+__device__ __forceinline__ void decode8_add(const uint4 hi, const uint4 lo, float* f) {
+  if constexpr (kFmt == kFmtBf16x2) {
+    float t8[8];
+    decode8<kFmt>(hi, lo, t8);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) f[q] += t8[q];
+  } else {
+    const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w};
+    const uint32_t l8[4] = {lo.z & 0xffffu, lo.z >> 16, lo.w & 0xffffu, lo.w >> 16};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const __half2_raw lr = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)l8[q], __NV_E4M3);
+      f[2 * q] = fhfma(lr.x, kF16LoInv, fhadd((uint16_t)(h[q] & 0xffffu), f[2 * q]));
+      f[2 * q + 1] = fhfma(lr.y, kF16LoInv, fhadd((uint16_t)(h[q] >> 16), f[2 * q + 1]));
     }
   }
 }
