@@ -555,6 +555,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
         if (pb != nullptr)
           ph_row = pb + ((size_t)(img * (P.ph_h + 2) + (yp >> 1) + 1) * (P.ph_w + 2) + (xp >> 1) + 1) * (size_t)(2 * P.cout);
       }
+      // phase rows leave through the staging tile: lane l stores chunk (l & 3) of rows 8*i + (l >> 2), i = 0..3, so one
+      // store instruction writes 8 rows x 64 contiguous bytes (not 32 rows x 16 bytes)
+      unsigned long long ph_dst[4] = {0ull, 0ull, 0ull, 0ull};
+      if (P.phase_any) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          ph_dst[i] = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)ph_row, 8 * i + (lane >> 2));
+      }
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(acc * kAccStride);
@@ -729,19 +737,26 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
             uint4 hi, lo;
             encode8<kFmt, false>(x8, hi, lo);
             if (!interior) { hi = make_uint4(0, 0, 0, 0); lo = hi; }
-            if (ph_row != nullptr) {                       // 64 contiguous bytes per plane and row over the four chunks
-              *reinterpret_cast<uint4*>(ph_row + c0 + 8 * j) = hi;
-              *reinterpret_cast<uint4*>(ph_row + P.cout + c0 + 8 * j) = lo;
-            }
-            if (!P.phase_only) {
-              const uint32_t sw = (uint32_t)((j ^ swz) << 4);
-              sts128(ob + sw, hi);
-              sts128(ob + 2048 + sw, lo);
-            }
+            const uint32_t sw = (uint32_t)((j ^ swz) << 4);
+            sts128(ob + sw, hi);
+            sts128(ob + 2048 + sw, lo);
           }
-          if (P.phase_only) continue;
-          fence_async_smem();
+          if (!P.phase_only) fence_async_smem();
           __syncwarp();
+          if (P.phase_any) {                               // staged rows -> phase maps, 64 contiguous bytes per 4 lanes
+            const uint32_t cch = (uint32_t)(lane & 3);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t r = (uint32_t)(8 * i + (lane >> 2));
+              const uint32_t sa = st_out + r * 64 + ((cch ^ ((r >> 1) & 3u)) << 4);
+              if (ph_dst[i] != 0ull) {
+                __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>((uintptr_t)ph_dst[i]) + c0 + 8 * cch;
+                *reinterpret_cast<uint4*>(dp) = lds128(sa);
+                *reinterpret_cast<uint4*>(dp + P.cout) = lds128(sa + 2048);
+              }
+            }
+            if (P.phase_only) { __syncwarp(); continue; }  // the next slab overwrites the staging tile
+          }
           if (tile_valid && elect_one()) {
             tma_store_2d(&P.tmap_out, st_out, c0, row_tile0);
             tma_store_2d(&P.tmap_out, st_out + 2048, P.cout + c0, row_tile0);
