@@ -495,15 +495,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
     const uint32_t st_out = tiles_addr + P.ring_bytes + ew * P.staging_per_warp;
     const uint32_t st_res = st_out + 4096;
     const uint32_t bar_res = ctrl_addr + 192 + ew * 16;
-    auto issue_res = [&](int tile_, int g_, int q_) {      // one elected lane only
-      int mt, nt, s_;
-      decode_tile(tile_, mt, nt, s_);
-      const int row = P.seg[s_].row_start + (mt - P.seg_tile_off[s_]) * kBlockM + lane_group * 32;
-      const int col = nt * P.block_n + g_ * 32;
+    auto issue_res_at = [&](int row, int col, int q_) {    // one elected lane only
       const uint32_t bar = bar_res + 8 * (q_ & 1), dst = st_res + (q_ & 1) * 4096;
       mbar_expect_tx(bar, 4096u);
       tma_load_2d(&P.tmap_res, bar, dst, col, row);
       tma_load_2d(&P.tmap_res, bar, dst + 2048, P.cout + col, row);
+    };
+    auto issue_res = [&](int tile_, int g_, int q_) {      // one elected lane only; decodes the tile (divisions)
+      int mt, nt, s_;
+      decode_tile(tile_, mt, nt, s_);
+      issue_res_at(P.seg[s_].row_start + (mt - P.seg_tile_off[s_]) * kBlockM + lane_group * 32,
+                   nt * P.block_n + g_ * 32, q_);
     };
     // the 2-deep shared-memory ring covers one slab of latency; the slabs of the tiles further ahead are pulled
     // into L2 (no shared memory needed) so that the ring's loads hit L2 instead of HBM
@@ -645,9 +647,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
           const int c0 = n_tile * P.block_n + g * 32;
           if (P.res_staged) {
             if (elect_one()) {                             // prefetch this warp's next slab
-              int nt = tile, ng = g + 2;
-              if (ng >= n_groups) { nt = tile + w_stride; ng = half; }
-              if (nt < w_total) issue_res(nt, ng, rq + 1);
+              if (g + 2 < n_groups) issue_res_at(row_tile0, n_tile * P.block_n + (g + 2) * 32, rq + 1);
+              else if (tile + w_stride < w_total) issue_res(tile + w_stride, half, rq + 1);
             }
             mbar_wait(bar_res + 8 * (rq & 1), (uint32_t)(rq >> 1) & 1u);
           }
