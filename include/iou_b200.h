@@ -244,7 +244,7 @@ int iou_phase_split(const void* src, int n, int c, int h, int w, void* const* ds
  *   IOU_FMT_BF16X2: hi = bf16(v), lo = bf16(v - hi)                          (conv passes = 3; the *_fmt-less calls)
  *   IOU_FMT_F16F8 : hi = fp16(v), lo vector = [x8 x 8 | l8 x 8], x8 = e4m3(v), l8 = e4m3((v - hi) * 2^11)
  *                                                                            (conv passes = 2; needs c % 8 == 0)
- * iou_phase_split copies bytes and serves both (its fused ReLU only IOU_FMT_BF16X2). */
+ * iou_phase_split copies bytes and serves both (its fused ReLU needs the format: iou_phase_split_fmt). */
 enum { IOU_FMT_BF16X2 = 0, IOU_FMT_F16F8 = 1 };
 int iou_pack_nchw_fmt(const float* src, int n, int c, int h, int w, void* dst, int64_t dst_row_start, int fmt,
                       void* stream);
@@ -252,6 +252,8 @@ int iou_unpack_nchw_fmt(const void* src, int64_t src_row_start, int n, int c, in
                         void* stream);
 int iou_stem_pack_v_fmt(const float* img, int n, int h, int w, void* dst, int fmt, void* stream);
 int iou_maxpool3x3s2_fmt(const void* src, int n, int c, int h, int w, void* dst, int fmt, void* stream);
+int iou_phase_split_fmt(const void* src, int n, int c, int h, int w, void* const* dst4, int phase_mask, int fmt,
+                        void* stream);       /* fmt only matters for the fused ReLU (bit 4 of phase_mask) */
 
 /* ------------------------------------------------------------------ GroupNorm towers (IoUawareFCOSHead, "next" row rank 4)
  * In-place GroupNorm (+ReLU) of a padded-rows map holding num_seg segments (FPN levels): the norm layer of
@@ -262,6 +264,9 @@ size_t iou_group_norm_workspace_bytes(int total_images, int groups);
 int iou_group_norm_relu(void* map, int c, int num_seg, const iou_conv_segment* seg, int groups,
                         const float* gamma, const float* beta, float eps, int relu, void* workspace,
                         size_t workspace_bytes, void* stream);
+int iou_group_norm_relu_fmt(void* map, int c, int num_seg, const iou_conv_segment* seg, int groups,
+                            const float* gamma, const float* beta, float eps, int relu, void* workspace,
+                            size_t workspace_bytes, int fmt, void* stream);   /* either element format (IOU_FMT_*) */
 /* x[i] = exp(x[i] * scale) on n dense fp32 values: bbox_pred = scale(fcos_reg(feat)).exp()
  * (mmdet/models/anchor_heads/iou_aware_fcos_head.py:108). */
 int iou_scale_exp(float* x, size_t n, float scale, void* stream);

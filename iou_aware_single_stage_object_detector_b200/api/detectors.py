@@ -126,8 +126,7 @@ class SingleStageDetector(BaseDetector):
         self._fused = PlanCache(max_plans=4)
         self.use_cuda_graph = True
         # tensor-core scheme of the convs (engine.Engine): None = 2 (fp16 pass + e4m3 correction pass, the fastest
-        # fp32-grade scheme) where every op of the model is built for that format, else 3 (bf16 hi|lo x3);
-        # 1 (plain bf16) is an explicit opt-in only
+        # fp32-grade scheme); 3 = bf16 hi|lo x3; 1 (plain bf16) is an explicit opt-in only
         self.passes = None
         self.init_weights(pretrained=pretrained)
 
@@ -152,12 +151,7 @@ class SingleStageDetector(BaseDetector):
         raise NotImplementedError("training is outside the accelerated inference path")
 
     def resolved_passes(self):
-        if self.passes is not None:
-            return self.passes
-        # GroupNorm towers (norm_cfg heads) and the FPN's fused-ReLU phase split only exist for the bf16 hi|lo format
-        gn = getattr(self.bbox_head, "norm_cfg", None) is not None
-        relu_split = bool(getattr(getattr(self, "neck", None), "relu_before_extra_convs", False))
-        return 3 if (gn or relu_split) else 2
+        return 2 if self.passes is None else self.passes
 
     def fused_plan(self, shape, device, rescale, slot=0):
         """`slot` distinguishes independent plans (own buffers, own CUDA graph) of the same shape."""

@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* __res
 // for u,v >= 1 and in-range sources, else 0.  16-byte vectors along the 2*c channel axis.
 struct PhasePtrs { uint4* p[4]; };
 __global__ void __launch_bounds__(256) phase_split_kernel(const uint4* __restrict__ src, int n, int c, int h, int w,
-                                                          int ho, int wo, PhasePtrs dst, int phase_mask) {
+                                                          int ho, int wo, PhasePtrs dst, int phase_mask, int fmt) {
   const int vec = (2 * c) >> 3;                    // uint4 per pixel
   const int hop = ho + 2, wop = wo + 2, hp = h + 2, wp = w + 2;
   const size_t total = (size_t)n * hop * wop * vec;
@@ -346,10 +346,20 @@ __global__ void __launch_bounds__(256) phase_split_kernel(const uint4* __restric
           const uint4 hv = q < half ? val : __ldg(px + (q - half));
           const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
           uint32_t* vw = reinterpret_cast<uint32_t*>(&val);
+          if (fmt == kFmtBf16x2 || q < half) {               // 16 bits per channel: the hi plane of both formats, bf16 lo
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const uint32_t neg = ((hw[e] & 0x8000u) ? 0xffffu : 0u) | ((hw[e] & 0x80000000u) ? 0xffff0000u : 0u);
-            vw[e] &= ~neg;
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t neg = ((hw[e] & 0x8000u) ? 0xffffu : 0u) | ((hw[e] & 0x80000000u) ? 0xffff0000u : 0u);
+              vw[e] &= ~neg;
+            }
+          } else {                                           // fp16 | e4m3 lo vector: bytes [x8 x 8 | l8 x 8]
+            uint32_t bm[2] = {0u, 0u};                       // byte masks of channels 0..3 and 4..7
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (hw[e] & 0x8000u) bm[e >> 1] |= 0xffu << (16 * (e & 1));
+              if (hw[e] & 0x80000000u) bm[e >> 1] |= 0xff00u << (16 * (e & 1));
+            }
+            vw[0] &= ~bm[0]; vw[1] &= ~bm[1]; vw[2] &= ~bm[0]; vw[3] &= ~bm[1];
           }
         }
       }
@@ -400,17 +410,12 @@ __device__ __forceinline__ void gn_locate(const GnSegs& G, int blk, int& s, int&
   img = r / G.h[s];
   y = r - img * G.h[s];
 }
+template <int kFmt>
 __device__ __forceinline__ void load8(const __nv_bfloat16* px, int c, int ch8, float (&v)[8]) {
-  const uint4 hv = __ldg(reinterpret_cast<const uint4*>(px) + ch8);
-  const uint4 lv = __ldg(reinterpret_cast<const uint4*>(px + c) + ch8);
-  const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    v[2 * q] = __uint_as_float(hw[q] << 16) + __uint_as_float(lw[q] << 16);
-    v[2 * q + 1] = __uint_as_float(hw[q] & 0xffff0000u) + __uint_as_float(lw[q] & 0xffff0000u);
-  }
+  decode8<kFmt>(__ldg(reinterpret_cast<const uint4*>(px) + ch8), __ldg(reinterpret_cast<const uint4*>(px + c) + ch8), v);
 }
 
+template <int kFmt>
 __global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __restrict__ map, const GnSegs G, int c,
                                                        int groups, double* __restrict__ stats) {
   __shared__ double acc[2 * 256];                          // [group][sum, sumsq], groups <= 256
@@ -425,7 +430,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __re
   double sum = 0.0, sq = 0.0;
   for (int x = px0; x < G.w[s]; x += pstride) {
     float v[8];
-    load8(row + (size_t)x * 2 * c, c, ch8, v);
+    load8<kFmt>(row + (size_t)x * 2 * c, c, ch8, v);
 #pragma unroll
     for (int q = 0; q < 8; ++q) { sum += (double)v[q]; sq += (double)v[q] * (double)v[q]; }
   }
@@ -437,6 +442,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __re
   for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) atomicAdd(out + i, acc[i]);
 }
 
+template <int kFmt>
 __global__ void __launch_bounds__(256) gn_apply_kernel(__nv_bfloat16* __restrict__ map, const GnSegs G, int c, int groups,
                                                        const double* __restrict__ stats, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, float eps, int relu) {
@@ -461,20 +467,16 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(__nv_bfloat16* __restrict
   for (int x = px0; x < G.w[s]; x += pstride) {
     __nv_bfloat16* px = row + (size_t)x * 2 * c;
     float v[8];
-    load8(px, c, ch8, v);
-    uint32_t hi[4], lo[4];
+    load8<kFmt>(px, c, ch8, v);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float a = fmaf(v[2 * q], sc[2 * q], bi[2 * q]), b = fmaf(v[2 * q + 1], sc[2 * q + 1], bi[2 * q + 1]);
-      if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(a, h0, l0);
-      split_bf16(b, h1, l1);
-      hi[q] = pack2_bf16(h0, h1);
-      lo[q] = pack2_bf16(l0, l1);
+    for (int q = 0; q < 8; ++q) {
+      v[q] = fmaf(v[q], sc[q], bi[q]);
+      if (relu) v[q] = fmaxf(v[q], 0.f);
     }
-    reinterpret_cast<uint4*>(px)[ch8] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    reinterpret_cast<uint4*>(px + c)[ch8] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    uint4 hi, lo;
+    encode8<kFmt>(v, hi, lo);
+    reinterpret_cast<uint4*>(px)[ch8] = hi;
+    reinterpret_cast<uint4*>(px + c)[ch8] = lo;
   }
 }
 
@@ -559,10 +561,13 @@ extern "C" size_t iou_group_norm_workspace_bytes(int total_images, int groups) {
   return (size_t)total_images * groups * 2 * sizeof(double);
 }
 
-extern "C" int iou_group_norm_relu(void* map, int c, int num_seg, const iou_conv_segment* seg, int groups,
-                                   const float* gamma, const float* beta, float eps, int relu, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
+#define IOU_REQUIRE_FMT(fmt) IOU_REQUIRE((fmt) == kFmtBf16x2 || (fmt) == kFmtF16F8, "fmt must be 0 (bf16 hi|lo) or 1 (fp16 | e4m3 pairs)")
+
+extern "C" int iou_group_norm_relu_fmt(void* map, int c, int num_seg, const iou_conv_segment* seg, int groups,
+                                       const float* gamma, const float* beta, float eps, int relu, void* workspace,
+                                       size_t workspace_bytes, int fmt, void* stream) {
   IOU_REQUIRE(map && seg && gamma && beta && workspace, "NULL argument");
+  IOU_REQUIRE_FMT(fmt);
   IOU_REQUIRE(num_seg >= 1 && num_seg <= IOU_CONV_MAX_SEG, "num_seg out of range");
   IOU_REQUIRE(c >= 8 && c % 8 == 0 && groups >= 1 && groups <= 256 && c % groups == 0 && (c / groups) % 8 == 0,
               "GroupNorm needs channels per group to be a multiple of 8 (c %d, groups %d)", c, groups);
@@ -582,10 +587,20 @@ extern "C" int iou_group_norm_relu(void* map, int c, int num_seg, const iou_conv
   if (workspace_bytes < need) return fail(IOU_ERR_WORKSPACE, "workspace too small: need %zu bytes", need);
   cudaStream_t st = (cudaStream_t)stream;
   IOU_CHECK_CUDA(cudaMemsetAsync(workspace, 0, need, st));
-  gn_stats_kernel<<<boff, 256, 0, st>>>((const __nv_bfloat16*)map, G, c, groups, (double*)workspace);
+  if (fmt == kFmtBf16x2) gn_stats_kernel<kFmtBf16x2><<<boff, 256, 0, st>>>((const __nv_bfloat16*)map, G, c, groups, (double*)workspace);
+  else gn_stats_kernel<kFmtF16F8><<<boff, 256, 0, st>>>((const __nv_bfloat16*)map, G, c, groups, (double*)workspace);
   if (int e = launch_status("gn_stats_kernel")) return e;
-  gn_apply_kernel<<<boff, 256, 0, st>>>((__nv_bfloat16*)map, G, c, groups, (const double*)workspace, gamma, beta, eps, relu);
+  if (fmt == kFmtBf16x2)
+    gn_apply_kernel<kFmtBf16x2><<<boff, 256, 0, st>>>((__nv_bfloat16*)map, G, c, groups, (const double*)workspace, gamma, beta, eps, relu);
+  else
+    gn_apply_kernel<kFmtF16F8><<<boff, 256, 0, st>>>((__nv_bfloat16*)map, G, c, groups, (const double*)workspace, gamma, beta, eps, relu);
   return launch_status("gn_apply_kernel");
+}
+extern "C" int iou_group_norm_relu(void* map, int c, int num_seg, const iou_conv_segment* seg, int groups,
+                                   const float* gamma, const float* beta, float eps, int relu, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  return iou_group_norm_relu_fmt(map, c, num_seg, seg, groups, gamma, beta, eps, relu, workspace, workspace_bytes,
+                                 kFmtBf16x2, stream);
 }
 
 extern "C" int iou_scale_exp(float* x, size_t n, float scale, void* stream) {
@@ -609,8 +624,6 @@ extern "C" int iou_preprocess_u8(const unsigned char* src, int n, int h, int w, 
   return launch_status("preprocess_u8_kernel");
 }
 
-
-#define IOU_REQUIRE_FMT(fmt) IOU_REQUIRE((fmt) == kFmtBf16x2 || (fmt) == kFmtF16F8, "fmt must be 0 (bf16 hi|lo) or 1 (fp16 | e4m3 pairs)")
 
 extern "C" int iou_pack_nchw_fmt(const float* src, int n, int c, int h, int w, void* dst, int64_t dst_row_start,
                                  int fmt, void* stream) {
@@ -704,9 +717,16 @@ extern "C" int iou_maxpool3x3s2(const void* src, int n, int c, int h, int w, voi
   return iou_maxpool3x3s2_fmt(src, n, c, h, w, dst, kFmtBf16x2, stream);
 }
 
+extern "C" int iou_phase_split_fmt(const void* src, int n, int c, int h, int w, void* const* dst4, int phase_mask,
+                                   int fmt, void* stream);
 extern "C" int iou_phase_split(const void* src, int n, int c, int h, int w, void* const* dst4, int phase_mask,
                                void* stream) {
+  return iou_phase_split_fmt(src, n, c, h, w, dst4, phase_mask, kFmtBf16x2, stream);
+}
+extern "C" int iou_phase_split_fmt(const void* src, int n, int c, int h, int w, void* const* dst4, int phase_mask,
+                                   int fmt, void* stream) {
   IOU_REQUIRE(src && dst4 && n > 0 && c > 0 && (c % 4) == 0 && h > 0 && w > 0, "bad argument");
+  IOU_REQUIRE_FMT(fmt);
   IOU_REQUIRE((phase_mask & 15) != 0 && phase_mask < 32, "phase_mask out of range (bits 0..3: phases, bit 4: ReLU)");
   IOU_REQUIRE(!(phase_mask & 16) || (c % 8) == 0, "the fused ReLU needs c %% 8 == 0");
   PhasePtrs P;
@@ -717,6 +737,6 @@ extern "C" int iou_phase_split(const void* src, int n, int c, int h, int w, void
   const int ho = (h + 1) / 2, wo = (w + 1) / 2;
   const size_t total = (size_t)n * (ho + 2) * (wo + 2) * ((2 * c) / 8);
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  phase_split_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)src, n, c, h, w, ho, wo, P, phase_mask);
+  phase_split_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)src, n, c, h, w, ho, wo, P, phase_mask, fmt);
   return launch_status("phase_split_kernel");
 }

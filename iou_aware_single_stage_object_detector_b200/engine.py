@@ -379,16 +379,14 @@ class Engine(object):
         """-> list of 4 FlatMaps (None where masked out) in the stride-2 output geometry; relu=True clamps the
         copied values at zero (FPN relu_before_extra_convs)."""
         assert len(src.segs) == 1
-        if relu and self.fmt != 0:
-            raise RuntimeError("the fused-ReLU phase split is only built for the bf16 hi|lo format (passes == 3)")
         _, n, h, w = src.segs[0]
         ho, wo = (h + 1) // 2, (w + 1) // 2
         outs = [self.new_map([(n, ho, wo)], src.c) if (mask >> i) & 1 else None for i in range(4)]
         arr = (ctypes.c_void_p * 4)(*[(o.ptr if o is not None else None) for o in outs])
         self.keep.append(arr)
-        lib, c, sp = self.lib, src.c, src.ptr
+        lib, c, sp, fmt = self.lib, src.c, src.ptr, self.fmt
         kmask = mask | (16 if relu else 0)
-        self.ops.append((name, lambda st: L.check(lib.iou_phase_split(sp, n, c, h, w, arr, kmask, st))))
+        self.ops.append((name, lambda st: L.check(lib.iou_phase_split_fmt(sp, n, c, h, w, arr, kmask, fmt, st))))
         return outs
 
     # ------------------------------------------------------------------ network builders
@@ -571,8 +569,6 @@ class Engine(object):
 
     def group_norm(self, name, m, gamma, beta, groups, eps=1e-5, relu=True):
         """In-place GroupNorm(+ReLU) of every segment of FlatMap m (ConvModule with norm_cfg type 'GN')."""
-        if self.fmt != 0:
-            raise RuntimeError("GroupNorm is only built for the bf16 hi|lo format (passes == 3)")
         g, b = self._dev(gamma), self._dev(beta)
         segs = (L.ConvSegment * len(m.segs))()
         for i, (rs, n, h, w) in enumerate(m.segs):
@@ -581,8 +577,9 @@ class Engine(object):
         ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=self.device)
         self.keep += [ws, segs]
         lib, mp, c, ns, gp, bp, wp = self.lib, m.ptr, m.c, len(m.segs), g.data_ptr(), b.data_ptr(), ws.data_ptr()
-        self.ops.append((name, lambda st: L.check(lib.iou_group_norm_relu(mp, c, ns, segs, groups, gp, bp, float(eps),
-                                                                          int(relu), wp, nbytes, st))))
+        fmt = self.fmt
+        self.ops.append((name, lambda st: L.check(lib.iou_group_norm_relu_fmt(mp, c, ns, segs, groups, gp, bp, float(eps),
+                                                                              int(relu), wp, nbytes, fmt, st))))
         self.extra_launches = getattr(self, "extra_launches", 0) + 2      # memset + 2 kernels behind one op
         return m
 

@@ -166,9 +166,14 @@ _SIGS = {
     "iou_group_norm_relu": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_int,
                                            ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "iou_group_norm_relu_fmt": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_int,
+                                               ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
     "iou_scale_exp": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_float, ctypes.c_void_p]),
     "iou_phase_split": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "iou_phase_split_fmt": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
 }
 EXPORTED_SYMBOLS = sorted(_SIGS)
 

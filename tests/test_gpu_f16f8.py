@@ -199,10 +199,36 @@ def test_whole_detector_small_passes2():
     assert worst <= 2e-4
 
 
-def test_unsupported_ops_raise_in_f16f8_format():
+@pytest.mark.parametrize("relu", [True, False])
+def test_group_norm_and_relu_phase_split(relu):
+    """The FCOS pieces in the fp16 + e4m3 format: in-place GroupNorm(+ReLU) over two segments against torch, and the
+    phase split with the fused ReLU against relu() of the plain phase split."""
+    g = torch.Generator().manual_seed(9)
+    sizes = [(2, 9, 14), (2, 5, 7)]
+    xs = [torch.randn(n, 256, h, w, generator=g) * 3 + 0.5 for (n, h, w) in sizes]
+    gamma, beta = torch.rand(256, generator=g) + 0.5, torch.randn(256, generator=g) * 0.2
     eng = E.Engine(DEV, passes=2)
-    m = eng.pack_input(torch.randn(1, 64, 4, 4, device=DEV))
-    with pytest.raises(RuntimeError):
-        eng.phase_split("p", m, relu=True)
-    with pytest.raises(RuntimeError):
-        eng.group_norm("gn", m, torch.ones(64), torch.zeros(64), 32)
+    Fm = eng.new_map(sizes, 256)
+    for s_, x in enumerate(xs):
+        n, c, h, w = x.shape
+        xd = x.to(DEV)
+        eng.keep.append(xd)
+        L.check(eng.lib.iou_pack_nchw_fmt(xd.data_ptr(), n, c, h, w, Fm.ptr, Fm.segs[s_][0], 1, L.stream_ptr()))
+    eng.group_norm("gn", Fm, gamma, beta, 32, relu=relu)
+    outs = [eng.unpack_output(Fm, s_) for s_ in range(2)]
+    m = eng.pack_input((xs[0] - 0.5).to(DEV))                 # mixed signs
+    ph_relu = eng.phase_split("pr", m, relu=True)
+    ph_plain = eng.phase_split("pp", m)
+    pr = [eng.unpack_output(p) for p in ph_relu]
+    pp = [eng.unpack_output(p) for p in ph_plain]
+    eng.run()
+    torch.cuda.synchronize()
+    for x, y in zip(xs, outs):
+        ref = F.group_norm(x, 32, gamma, beta, 1e-5)
+        ref = F.relu(ref) if relu else ref
+        assert rel_err(y.cpu(), ref) < TOL, rel_err(y.cpu(), ref)
+    for a, b, ra, rb in zip(pr, pp, ph_relu, ph_plain):
+        assert torch.equal(a.cpu(), F.relu(b.cpu()))
+        # the clamped entries are all-zero bytes (what a conv epilogue would have written for relu(x) = 0)
+        neg = (b.cpu() < 0)
+        assert bool(neg.any())
