@@ -204,6 +204,10 @@ typedef struct iou_conv_desc {
    * map.  phase_only != 0: `out` is not written at all (may be NULL) -- for maps only a stride-2 conv reads.     */
   void* phase_out[4];
   int32_t phase_only;
+  /* Sources with fewer channels than `cin` (ABI version 5): src[i] is [src_rows][2*src_cin[i]] (0 = cin) and the taps
+   * reading it contract only its src_cin[i] channels (the first src_cin[i] K columns of their weight rows, in both
+   * planes) -- K-concatenated GEMMs in one accumulator, e.g. conv3(t2) + downsample(x) of a bottleneck's first block. */
+  int32_t src_cin[IOU_CONV_MAX_SRC];
 } iou_conv_desc;
 
 typedef struct iou_conv_plan iou_conv_plan;

@@ -68,6 +68,9 @@ struct ConvParams {
   int grp_src[IOU_CONV_MAX_TAPS], grp_dy[IOU_CONV_MAX_TAPS], grp_dx0[IOU_CONV_MAX_TAPS], grp_nt[IOU_CONV_MAX_TAPS];
   int grp_tap[IOU_CONV_MAX_TAPS][4], grp_shift[IOU_CONV_MAX_TAPS][4];   // up to 4 taps per window (shift 0..3 rows)
   int a_rows, a_entry_bytes, b_entry_bytes, num_a_stages, num_b_stages, ring_bytes, taps_per_tile;
+  // sources may differ in channel count (K-concatenated GEMMs, e.g. conv3(t2) + downsample(x) of a bottleneck's first
+  // block in one accumulator): K slabs per tap group and the lo-plane offset follow the group's source
+  int src_cin[IOU_CONV_MAX_SRC], grp_ks[IOU_CONV_MAX_TAPS], tap_slabs_per_tile;
   int b_tile_bytes;
   int b_resident;            // one N tile and few (tap, slab) weight tiles: loaded once per CTA, kept for every tile
   int staged, res_staged, staging_per_warp;
@@ -350,7 +353,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
           const int arow = row0 + P.grp_dy[g] * wp + P.grp_dx0[g];
           const CUtensorMap* tm = &P.tmap_src[P.grp_src[g]];
           const int nt = P.grp_nt[g];
-          for (int ks = 0; ks < P.k_slabs; ++ks) {
+          const int g_cin = P.src_cin[P.grp_src[g]];
+          for (int ks = 0; ks < P.grp_ks[g]; ++ks) {
             // ---- one A window (hi, lo) serves all dx taps of the group
             mbar_wait(bar_aempty + 8 * as, aph ^ 1u);
             const uint32_t fa = bar_afull + 8 * as;
@@ -359,10 +363,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
             if (!kTwoCta || rank == 0) mbar_expect_tx(fa, mult * (uint32_t)P.a_entry_bytes);
             if constexpr (kTwoCta) {
               tma_load_2d_pair(tm, fa, sa, a_col, arow);
-              if (P.passes == 3) tma_load_2d_pair(tm, fa, sa + a_lo_off, P.cin + a_col, arow);
+              if (P.passes == 3) tma_load_2d_pair(tm, fa, sa + a_lo_off, g_cin + a_col, arow);
             } else {
               tma_load_2d(tm, fa, sa, a_col, arow);
-              if (P.passes == 3) tma_load_2d(tm, fa, sa + a_lo_off, P.cin + a_col, arow);
+              if (P.passes == 3) tma_load_2d(tm, fa, sa + a_lo_off, g_cin + a_col, arow);
             }
             if (++as == P.num_a_stages) { as = 0; aph ^= 1u; }
             // ---- one B tile (hi, lo) per tap
@@ -410,10 +414,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
       int done = 0;                                    // taps x slabs issued for this tile
-      const int todo = P.taps_per_tile * P.k_slabs;
+      const int todo = P.tap_slabs_per_tile;
       for (int g = 0; g < P.num_groups; ++g) {
         const int nt = P.grp_nt[g];
-        for (int ks = 0; ks < P.k_slabs; ++ks) {
+        for (int ks = 0; ks < P.grp_ks[g]; ++ks) {
           mbar_wait(bar_afull + 8 * as, aph);
           const uint32_t sa = tiles_addr + as * P.a_entry_bytes;
           for (int j = 0; j < nt; ++j, ++done) {
@@ -870,6 +874,11 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   P.diag_k = d->diag_k ? 1 : 0;
   P.b_cin = P.diag_k ? kBlockK : d->cin;
   P.k_slabs = P.diag_k ? 1 : d->cin / kBlockK;
+  for (int i = 0; i < IOU_CONV_MAX_SRC; ++i) {
+    P.src_cin[i] = (i < d->num_src && d->src_cin[i] > 0) ? d->src_cin[i] : d->cin;
+    if (P.src_cin[i] % kBlockK != 0 || P.src_cin[i] > d->cin) { delete plan; return fail(IOU_ERR_INVALID, "src_cin[%d] must be a multiple of %d and <= cin", i, kBlockK); }
+    if (P.diag_k && P.src_cin[i] != d->cin) { delete plan; return fail(IOU_ERR_INVALID, "diag_k needs equal source channel counts"); }
+  }
   P.passes = d->passes == 1 ? 1 : 3;   // 3 = hi/lo operands staged; lolo adds the fourth product
   P.lolo = d->passes == 4;
   P.f8 = d->passes == 2;
@@ -957,7 +966,12 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
     int best_na = 0, best_nb = 0, best_score = 0;
     // resident weights: with ONE N tile every tile of a CTA multiplies by the same few weight tiles -- load them once
     // (entry e = the e-th (tap, slab) of a tile) and spend the rest of shared memory on the A ring
-    const int b_entries = d->num_taps * P.k_slabs;
+    int b_entries = 0;
+    for (int g = 0; g < P.num_groups; ++g) {
+      P.grp_ks[g] = P.diag_k ? 1 : P.src_cin[P.grp_src[g]] / kBlockK;
+      b_entries += P.grp_nt[g] * P.grp_ks[g];
+    }
+    P.tap_slabs_per_tile = b_entries;
     P.b_resident = 0;
     if (P.num_n_tiles == 1 && b_entries <= kMaxBStages && !getenv("IOU_NO_B_RESIDENT")) {
       int na = (budget - b_entries * P.b_entry_bytes) / P.a_entry_bytes;
@@ -996,7 +1010,7 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
             ((uint32_t)((P.two_cta ? 2 * kBlockM : kBlockM) >> 4) << 24);
   for (int i = 0; i < d->num_src; ++i) {
     if (!d->src[i] || ((uintptr_t)d->src[i] & 15)) { delete plan; return fail(IOU_ERR_INVALID, "src[%d] NULL or misaligned", i); }
-    if (int e = encode_2d(&P.tmap_src[i], d->src[i], (uint64_t)d->src_rows, (uint64_t)2 * d->cin, (uint32_t)P.a_rows)) { delete plan; return e; }
+    if (int e = encode_2d(&P.tmap_src[i], d->src[i], (uint64_t)d->src_rows, (uint64_t)2 * P.src_cin[i], (uint32_t)P.a_rows)) { delete plan; return e; }
   }
   for (int i = d->num_src; i < IOU_CONV_MAX_SRC; ++i) P.tmap_src[i] = P.tmap_src[0];
   P.tmap_out = P.tmap_w; P.tmap_res = P.tmap_w;
@@ -1019,7 +1033,9 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
     plan->grid = P.total_tiles < sms ? P.total_tiles : sms;
   }
   plan->smem_bytes = (size_t)kCtrlBytes + 1024 + (size_t)P.ring_bytes + (size_t)kNumEpiWarps * P.staging_per_warp;
-  plan->flops = 2.0 * real_rows * d->cout * (double)(P.diag_k ? kBlockK : d->cin) * d->num_taps;
+  double k_total = 0;
+  for (int t = 0; t < d->num_taps; ++t) k_total += P.diag_k ? kBlockK : P.src_cin[d->tap_src[t]];
+  plan->flops = 2.0 * real_rows * d->cout * k_total;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tap_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);

@@ -289,8 +289,10 @@ class Engine(object):
             d.tap_src[i], d.tap_dy[i], d.tap_dx[i] = s, dy, dx
         d.num_src = len(srcs)
         for i, m in enumerate(srcs):
-            assert m.c == cin, (name, m.c, cin)
+            # sources may have fewer channels than cin (= the K of the weight rows): their taps contract m.c channels
+            assert m.c <= cin and (m.c == cin or not diag_k), (name, m.c, cin)     # % 64: checked by plan_create
             d.src[i] = m.ptr
+            d.src_cin[i] = m.c
         d.src_rows = min(m.rows for m in srcs)
         kdim = 64 if diag_k else cin
         assert weight.shape == (len(taps) * cout_pad, 2 * kdim), (name, weight.shape, len(taps), cout_pad, cin)
@@ -423,6 +425,7 @@ class Engine(object):
         x = self.add_stem(sd, img, prefix)
         outs = []
         fuse = os.environ.get("IOU_FUSE_PHASE", "1") != "0"     # producers write the stride-2 phase maps themselves
+        fuse_ds = os.environ.get("IOU_FUSE_DS", "1") != "0"     # conv3 + downsample of a stage's first block in one GEMM
         x_ph3 = None                                            # phase (1,1) of x, if its producer wrote it
         for s, nblocks in enumerate(STAGE_BLOCKS[depth]):
             planes = 64 * 2 ** s
@@ -463,6 +466,29 @@ class Engine(object):
                     t2 = self.conv(p + "conv2", [t1], TAPS_3X3, w2, width, width, shift=sh2,
                                    relu=True, **kw)
                 idt = x
+                sc3, sh3 = bn_fold(sd, p + "bn3")
+                ph3 = None
+                if fuse and b == nblocks - 1 and s + 1 < len(STAGE_BLOCKS[depth]):
+                    # the next stage's first block reads phase (1,1) of this block's output (stride-2 1x1 convs)
+                    _, n_, h_, w_ = t2.segs[0]
+                    ph3 = self.new_phase_maps(n_, h_, w_, planes * 4, mask=8)
+                if (p + "downsample.0.weight") in sd and fuse_ds:
+                    # relu(bn3(conv3(t2)) + bn_d(downsample(x))) as ONE K-concatenated GEMM: tap 0 contracts t2's `width`
+                    # channels, tap 1 the `cin` channels of x (stride 2: its phase (1,1) map) into the same accumulator --
+                    # the identity branch is never written to or read back from HBM
+                    scd, shd = bn_fold(sd, p + "downsample.1")
+                    if stride == 2 and xs is None:
+                        xs = self.phase_split(p + "downsample.phase", x, mask=8)
+                    w3 = fold_scale(sd[p + "conv3.weight"], sc3)
+                    wdn = fold_scale(sd[p + "downsample.0.weight"], scd)
+                    kmax = max(width, cin)
+                    wt = torch.zeros(2, planes * 4, kmax, dtype=torch.float32, device=w3.device)
+                    wt[0, :, :width] = w3[:, :, 0, 0]
+                    wt[1, :, :cin] = wdn[:, :, 0, 0]
+                    x = self.conv(p + "conv3+downsample", [t2, xs[3] if stride == 2 else x], [(0, 0, 0), (1, 0, 0)],
+                                  _hi_lo_rows(wt), kmax, planes * 4, shift=sh3 + shd, relu=True, phase_outs=ph3)
+                    x_ph3 = ph3[3] if ph3 is not None else None
+                    continue
                 if (p + "downsample.0.weight") in sd:
                     scd, shd = bn_fold(sd, p + "downsample.1")
                     wd = pack_weight(fold_scale(sd[p + "downsample.0.weight"], scd), planes * 4)
@@ -475,12 +501,6 @@ class Engine(object):
                     else:
                         idt = self.conv(p + "downsample", [x], TAPS_1X1, wd, cin, planes * 4,
                                         shift=shd)
-                sc3, sh3 = bn_fold(sd, p + "bn3")
-                ph3 = None
-                if fuse and b == nblocks - 1 and s + 1 < len(STAGE_BLOCKS[depth]):
-                    # the next stage's first block reads phase (1,1) of this block's output (stride-2 1x1 convs)
-                    _, n_, h_, w_ = t2.segs[0]
-                    ph3 = self.new_phase_maps(n_, h_, w_, planes * 4, mask=8)
                 x = self.conv(p + "conv3", [t2], TAPS_1X1, pack_weight(fold_scale(sd[p + "conv3.weight"], sc3), planes * 4),
                               width, planes * 4, shift=sh3, relu=True, residual=idt,
                               res_mode=L.RES_SAME, phase_outs=ph3)

@@ -302,3 +302,30 @@ def test_fused_phase_outputs_equal_the_phase_split_kernel(cin, cout, hw, res, pa
         if both[i] is not None:
             assert torch.equal(both[i].tensor.view(torch.int16), want[i].tensor.view(torch.int16)), i
         assert torch.equal(only[i].tensor.view(torch.int16), want[i].tensor.view(torch.int16)), i
+
+
+@pytest.mark.parametrize("passes", [3, 2])
+@pytest.mark.parametrize("width,cin,cout,stride,hw", [(64, 64, 256, 1, (12, 20)), (128, 256, 512, 2, (20, 28)),
+                                                      (256, 512, 1024, 2, (13, 21))])
+def test_k_concatenated_conv3_plus_downsample(width, cin, cout, stride, hw, passes):
+    """relu(conv3(t2) + downsample(x)) of a bottleneck's first block as ONE GEMM over two sources with different channel
+    counts (iou_conv_desc.src_cin), against torch fp32."""
+    g = torch.Generator().manual_seed(width + cin + stride)
+    x = torch.randn(2, cin, *hw, generator=g)
+    ho, wo = (hw[0] + stride - 1) // stride, (hw[1] + stride - 1) // stride
+    t2 = torch.randn(2, width, ho, wo, generator=g)
+    w3 = torch.randn(cout, width, 1, 1, generator=g) * (1.0 / width) ** 0.5
+    wd = torch.randn(cout, cin, 1, 1, generator=g) * (1.0 / cin) ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = F.relu(F.conv2d(t2, w3) + F.conv2d(x, wd, stride=stride) + b.view(1, -1, 1, 1))
+    eng = E.Engine(DEV, passes=passes)
+    mt, mx = eng.pack_input(t2.to(DEV).contiguous()), eng.pack_input(x.to(DEV).contiguous())
+    src_b = eng.phase_split("p", mx, mask=8)[3] if stride == 2 else mx
+    kmax = max(width, cin)
+    wt = torch.zeros(2, cout, kmax)
+    wt[0, :, :width], wt[1, :, :cin] = w3[:, :, 0, 0], wd[:, :, 0, 0]
+    out = eng.conv("c3+ds", [mt, src_b], [(0, 0, 0), (1, 0, 0)], E._hi_lo_rows(wt), kmax, cout, shift=b, relu=True)
+    y = eng.unpack_output(out)
+    eng.run()
+    torch.cuda.synchronize()
+    assert y.shape == ref.shape and rel_err(y.cpu(), ref) < TOL, rel_err(y.cpu(), ref)
