@@ -303,9 +303,9 @@ def run_ours(args):
                 "peak": peaks["tf_sustained"], "peak_source": peaks["source"] + " bf16 sustained (cuBLAS)",
                 "unit": "TFLOP/s", "frac": round(achieved / peaks["tf_sustained"], 4),
                 # dram__bytes_read+write summed over the 71 conv launches of one step / 71, from the ncu pass
-                # committed as profiles/r01_v14_launches_ncu_dram.csv (22.27 GB per step, R50 bs=8)
-                "traffic": 313.7e6 if MODEL == "r50" else None,
-                "traffic_source": "ncu, profiles/r01_v14_launches_ncu_dram.csv",
+                # committed as profiles/r01_v15_launches_ncu_dram.csv (20.31 GB per step over 67 launches, R50 bs=8)
+                "traffic": 303.1e6 if MODEL == "r50" else None,
+                "traffic_source": "ncu, profiles/r01_v15_launches_ncu_dram.csv",
                 "launches_per_step": n_conv,
                 "avg_launch_ms": round(conv_ms / max(n_conv, 1), 4),
                 "algorithmic_gflop_per_step": round(conv_flops / 1e9, 1),
