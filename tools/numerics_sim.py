@@ -123,6 +123,31 @@ class F16F8:
         return acc / wr[3]
 
 
+class F16F16F8(F16F8):
+    """3-byte element (round-2 candidate): x = h (fp16) + l8 * 2^-11, x8 is NOT stored.  conv = h*Wh' + h*Wl' + l8*W8 with
+    Wl' = fp16(w S - Wh') (a second fp16 pass) and the e4m3 pass only over l8 (K = 64 per slab): 2.25 bf16-pass equivalents,
+    25 % less activation traffic."""
+    name = "f16+f16+f8 (3 B)"
+
+    def act(self, x):
+        x = x.to(torch.float32).to(D)
+        h = rnd(x, torch.float16)
+        return h, e4m3((x - h) * self.LS)
+
+    def wt(self, w):
+        w = w.to(torch.float32).to(D)
+        m = w.abs().flatten(1).max(1).values.clamp_min(1e-30)
+        s = torch.exp2(torch.floor(torch.log2(8.0 / m)) + 1.0).view(-1, 1, 1, 1)
+        S = s * self.LS
+        h = rnd(w * S, torch.float16)
+        return h, rnd(w * S - h, torch.float16), e4m3(w * s), S.view(1, -1, 1, 1)
+
+    def conv(self, r, wr, **kw):
+        acc = (F.conv2d(r[0], wr[0], None, **kw) + F.conv2d(r[0], wr[1], None, **kw) +
+               F.conv2d(r[1], wr[2], None, **kw))
+        return acc / wr[3]
+
+
 def fold_bn(sd, conv, bn, eps=1e-5):
     w = sd[conv + ".weight"].to(D)
     g, b = sd[bn + ".weight"].to(D), sd[bn + ".bias"].to(D)
@@ -201,7 +226,8 @@ def main():
     ref, amax = forward(sd, img, Exact())
     print("image %dx%d; max |activation| %.1f; logit range cls [%.2f, %.2f]" %
           (hh, ww, amax, min(float(l[0].min()) for l in ref), max(float(l[0].max()) for l in ref)))
-    for S in (F32(), Bf16x3(), F16F8(), F16x3(), Single(torch.float16, "fp16x1"), Single(torch.bfloat16, "bf16x1")):
+    for S in (F32(), Bf16x3(), F16F8(), F16F16F8(), F16x3(), Single(torch.float16, "fp16x1"),
+              Single(torch.bfloat16, "bf16x1")):
         out, _ = forward(sd, img, S)
         line = []
         for j, nm in enumerate(("cls", "reg", "iou")):
