@@ -215,6 +215,36 @@ def test_f16f8_weight_packing_pairs_with_the_activation_bytes():
     assert float((SF.decode_rows(SF.encode_rows(x)) - x).abs().max() / x.abs().max()) < 2.0 ** -15
 
 
+def test_k_concatenated_weights_share_one_scale():
+    """conv3(t2) + downsample(x) as one GEMM (engine.add_backbone): both taps' weights are packed under ONE per-channel
+    scale, the narrower tap is zero-padded to the wider K, and the byte-level emulation of the two passes over each
+    source's own channels adds up to the fp64 sum of both products."""
+    from oracle import split_fmt as SF
+    g = torch.Generator().manual_seed(4)
+    width, cin, cout = 64, 128, 32
+    t2 = torch.randn(200, width, generator=g).relu() * 2
+    x = torch.randn(200, cin, generator=g).relu() * 3
+    w3 = torch.randn(cout, width, generator=g) * 0.05
+    wd = torch.randn(cout, cin, generator=g) * 0.3 * torch.exp(torch.randn(cout, 1, generator=g))
+    wt = torch.zeros(2, cout, cin)
+    wt[0, :, :width], wt[1] = w3, wd
+    rows, inv_s = E.pack_f16f8(wt)
+    assert rows.shape == (2 * cout, 2 * cin)
+    wh, wl8, w8 = E.unpack_f16f8_rows(rows, cin)
+    assert float(wh[:cout, width:].abs().max()) == 0 and float(w8[:cout, width:].abs().max()) == 0     # padding
+    # tap 0 contracts only t2's `width` channels: the first `width` K columns of both planes of its weight rows
+    def tap(a, rows_t, k):
+        b = rows_t.contiguous().view(torch.uint8).view(cout, 4 * cin)
+        hi, lo = b[:, :2 * k], b[:, 2 * cin:2 * cin + 2 * k]
+        sub = torch.cat([hi, lo], dim=1).contiguous().view(torch.bfloat16)
+        return SF.emulate_gemm(SF.encode_rows(a), sub, torch.ones(cout))
+    acc = tap(t2, rows[:cout], width) + tap(x, rows[cout:], cin)          # ONE accumulator at scale S_n
+    y = acc * inv_s.double().view(1, -1)
+    ref = t2.double() @ w3.double().t() + x.double() @ wd.double().t()
+    bound = t2.double().abs() @ w3.double().abs().t() + x.double().abs() @ wd.double().abs().t()
+    assert float(((y - ref).abs() / bound).max()) < 6e-5
+
+
 def test_tile_counts_and_default_scheme():
     # tiles stop at the last interior pixel: the 25x42 maps of 8 images are 74 tiles (75 with the trailing border rows)
     assert E.seg_tiles(8, 25, 42) == 74 and E.seg_tiles(8, 100, 168) == 1083 and E.seg_tiles(1, 1, 2) == 1
