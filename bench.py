@@ -336,8 +336,9 @@ def run_ours(args):
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": {3: "fp32 (bf16x3 split on tcgen05, fp32 accumulate)",
-                          2: "fp32 (fp16 + 2x e4m3 split on tcgen05, fp32 accumulate)"}.get(args.passes, "bf16"),
+                "dtype": {3: "bf16 hi|lo split operands x3 on tcgen05, fp32 accumulate (fp32-grade: within 1e-4 of the fp32 oracle)",
+                          2: "fp16 + e4m3 split operands (1 fp16 + 1 e4m3 MMA pass) on tcgen05, fp32 accumulate "
+                             "(fp32-grade: within 1e-4 of the fp32 oracle)"}.get(args.passes, "bf16"),
                 "data": "synthetic",
                 "config": {"workload": "IoU-aware RetinaNet %s-FPN inference bs=%d/GPU, synthetic 800x1344 "
                                        "(img_shape 800x1333), backbone+FPN+head+get_bboxes" % (MODEL.upper(), BATCH),
