@@ -25,7 +25,7 @@ extern "C" {
 #define IOU_MAX_LEVELS 8
 #define IOU_MAX_ANCHORS 16
 #define IOU_MAX_CANDIDATES 6144   /* per image (sum over levels of min(n_l, nms_pre)) */
-#define IOU_MAX_NMS_BOXES 6144    /* iou_nms: boxes per call */
+#define IOU_MAX_NMS_BOXES 6144    /* iou_nms: boxes per call of the shared-memory path; iou_soft_nms: hard limit */
 
 #define IOU_OK 0
 #define IOU_ERR_INVALID (-1)
@@ -105,7 +105,11 @@ int iou_get_bboxes(const iou_postproc_cfg* cfg, int n_img,
  * Drop-in for mmdet.ops.nms.nms_cuda.nms (ops/nms/src/nms_cuda.cpp:8-13,
  * nms_kernel.cu:70-131): dets [n][5] fp32 (x1,y1,x2,y2,score); suppress at
  * IoU > thr; keep_idx receives the ORIGINAL indices of kept boxes in ascending
- * order (int64, capacity n), keep_count the number kept.  n <= IOU_MAX_NMS_BOXES. */
+ * order (int64, capacity n), keep_count the number kept.  Any n, like the reference:
+ * up to IOU_MAX_NMS_BOXES boxes run in one block's shared memory (workspace may be
+ * NULL); above that, n x ceil(n/64) mask words live in `workspace`
+ * (iou_nms_workspace_bytes(n) bytes: ~n*n/8), with the sort and the greedy scan that
+ * the reference runs on the host (nms_kernel.cu:99-123) on the device. */
 size_t iou_nms_workspace_bytes(int n);
 int iou_nms(const float* dets, int n, float iou_thr, int64_t* keep_idx, int32_t* keep_count,
             void* workspace, size_t workspace_bytes, void* stream);
@@ -130,13 +134,23 @@ int iou_batched_soft_nms(const iou_postproc_cfg* cfg, int n_img, const float* bo
 /* ------------------------------------------------------------------ focal loss
  * Drop-in for sigmoid_focal_loss_cuda.forward / .backward
  * (ops/sigmoid_focal_loss/src/sigmoid_focal_loss.cpp:17-43,
- *  sigmoid_focal_loss_cuda.cu:24-105).  logits [n][c] fp32, targets [n] int64
- * (0 = background, class d <-> d+1).                                          */
+ *  sigmoid_focal_loss_cuda.cu:24-105).  logits [n][c], targets [n] int64
+ * (0 = background, class d <-> d+1).  The reference dispatches fp16 / fp32 / fp64
+ * (AT_DISPATCH_FLOATING_TYPES_AND_HALF, .cu:128,167): `dtype` selects the element
+ * type of logits / losses / d_losses / d_logits; the un-suffixed entry points are fp32. */
+#define IOU_DTYPE_F32 0
+#define IOU_DTYPE_F16 1
+#define IOU_DTYPE_F64 2
 int iou_sigmoid_focal_loss_forward(const float* logits, const int64_t* targets, int n, int c,
                                    float gamma, float alpha, float* losses, void* stream);
 int iou_sigmoid_focal_loss_backward(const float* logits, const int64_t* targets,
                                     const float* d_losses, int n, int c, float gamma, float alpha,
                                     float* d_logits, void* stream);
+int iou_sigmoid_focal_loss_forward_dtype(const void* logits, int dtype, const int64_t* targets, int n, int c,
+                                         float gamma, float alpha, void* losses, void* stream);
+int iou_sigmoid_focal_loss_backward_dtype(const void* logits, int dtype, const int64_t* targets,
+                                          const void* d_losses, int n, int c, float gamma, float alpha,
+                                          void* d_logits, void* stream);
 
 /* ------------------------------------------------------------------ conv engine
  * Replaces the F.conv2d (+BatchNorm eval, +bias, +ReLU, +residual add) calls of

@@ -64,6 +64,11 @@ class FusedPlan(object):
         self.rescale = rescale
         eng = E.Engine(self.device, passes=passes)
         sd = cuda_state_dict(det, self.device)
+        if not det.with_neck:
+            raise NotImplementedError("the fused plan needs a neck (FPN): the heads on this path read 5 FPN levels")
+        if tuple(getattr(det.backbone, "out_indices", (0, 1, 2, 3))) != (0, 1, 2, 3):
+            raise NotImplementedError("the fused plan feeds all four backbone stages to the neck: "
+                                      "backbone.out_indices must be (0, 1, 2, 3), got %r" % (det.backbone.out_indices,))
         feats = det.backbone.plan_into(eng, sd, self.img, prefix="backbone.")
         F = det.neck.plan_into(eng, sd, feats, prefix="neck.")
         self.outs = det.bbox_head.plan_into(eng, sd, F, prefix="bbox_head.")
@@ -75,11 +80,11 @@ class FusedPlan(object):
         to_post = getattr(det.bbox_head, "postproc_inputs", None)
         self.post_in = to_post(self.outs) if to_post is not None else (self.outs[0], self.outs[1], self.outs[2])
         sizes = [tuple(t.shape[-2:]) for t in self.outs[0]]
-        shared = det.bbox_head.postproc_workspace(sizes, n, det.test_cfg, self.device)
-        # the head caches ONE workspace per configuration; a plan owns its scratch and outputs so that two plans
-        # (detect_stream's pipeline slots) can be in flight at once
-        self.wsp = PP.PostprocWorkspace(shared.cfg, n, self.device)
-        self.wsp.soft = getattr(shared, 'soft', None)
+        # a plan owns its post-processing scratch and outputs, so that two plans (detect_stream's pipeline slots)
+        # can be in flight at once
+        pcfg, soft = det.bbox_head.postproc_cfg(sizes, det.test_cfg)
+        self.wsp = PP.PostprocWorkspace(pcfg, n, self.device)
+        self.wsp.soft = soft
         self.graph = None
         self.use_graph = use_graph
         self.conv_flops = eng.flops
@@ -159,10 +164,12 @@ class SingleStageDetector(BaseDetector):
         key = (tuple(shape), str(device), bool(rescale), param_stamp(self), self.use_cuda_graph, passes, slot)
         return self._fused.get(key, lambda: FusedPlan(self, shape, device, rescale, self.use_cuda_graph, passes))
 
-    def detect_device(self, img, img_metas, rescale=False, device=None):
+    def detect_device(self, img, img_metas, rescale=False, device=None, clone=True):
         """Batched, asynchronous: (dets [n,K,5], labels [n,K] int64, counts [n] int32) on the device.
         `img` may live on the GPU or in (pinned) host memory; a host batch is copied to `device`
-        (default: the parameters' device) inside this call -- all arithmetic runs on the GPU."""
+        (default: the parameters' device) inside this call -- all arithmetic runs on the GPU.
+        The results are fresh tensors; clone=False hands out the plan's own output buffers instead, which the next
+        call with the same input shape overwrites (what detect_stream / simple_test_batch use internally)."""
         if device is None:
             device = img.device if img.is_cuda else next(self.parameters()).device
         device = torch.device(device)
@@ -173,7 +180,8 @@ class SingleStageDetector(BaseDetector):
         with torch.cuda.device(device):
             plan.img.copy_(img, non_blocking=True)
             plan.img_info.copy_(PP.make_img_info(img_metas, "cpu"), non_blocking=True)
-        return plan.run()
+            out = plan.run()
+            return tuple(t.clone() for t in out) if clone else out
 
     def detect_stream(self, batches, rescale=False, device=None, gather=None, img_transform=None, depth=2):
         """Pipelined batched inference over an iterable of (img, img_metas) with HOST (ideally pinned) images;
@@ -278,7 +286,7 @@ class SingleStageDetector(BaseDetector):
 
     def simple_test_batch(self, img, img_metas, gt_bboxes=None, gt_labels=None, rescale=False):
         """Batched simple_test: list (per image) of per-class ndarray lists."""
-        dets, labels, counts = self.detect_device(img, img_metas, rescale)
+        dets, labels, counts = self.detect_device(img, img_metas, rescale, clone=False)
         return [bbox2result(d, l, self.bbox_head.num_classes)
                 for d, l in PP.split_results(dets, labels, counts)]
 

@@ -82,4 +82,4 @@ class FPN(nn.Module):
             a.copy_(b)
         with torch.cuda.device(dev):
             eng.run()
-        return tuple(outs)
+        return tuple(o.clone() for o in outs)      # fresh tensors (the plan's buffers are reused by the next call)

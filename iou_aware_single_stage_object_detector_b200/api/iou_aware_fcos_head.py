@@ -111,7 +111,8 @@ class IoUawareFCOSHead(nn.Module):
             a_.copy_(b_)
         with torch.cuda.device(dev):
             eng.run()
-        return outs
+        # fresh tensors (the plan's own maps are overwritten by the next call)
+        return tuple([t.clone(memory_format=torch.preserve_format) for t in ts] for ts in outs)
 
     @staticmethod
     def postproc_inputs(outs):
@@ -126,16 +127,21 @@ class IoUawareFCOSHead(nn.Module):
         return c[0], r[0], q[0], u[0]
 
     # ---- get_bboxes --------------------------------------------------------------------------
-    def postproc_workspace(self, featmap_sizes, n_img, cfg, device):
+    def postproc_cfg(self, featmap_sizes, cfg):
+        """(iou_postproc_cfg, None) for a test_cfg, without allocating a workspace."""
         nms_cfg = dict(cfg['nms'])
+        if nms_cfg.pop('type', 'nms') != 'nms':
+            raise NotImplementedError("IoUawareFCOSHead: only nms type 'nms' is wired")
+        pcfg = PP.make_cfg(featmap_sizes, self.strides, [torch.zeros(1, 4)] * len(featmap_sizes),
+                           self.cls_out_channels, cfg.get('nms_pre', -1), cfg['max_per_img'], cfg['score_thr'],
+                           nms_cfg.get('iou_thr', 0.5), alpha=self.alpha, decode_mode=L.DECODE_DISTANCE)
+        return pcfg, None
+
+    def postproc_workspace(self, featmap_sizes, n_img, cfg, device):
         key = (tuple(featmap_sizes), n_img, cfg.get('nms_pre', -1), cfg['score_thr'],
-               tuple(sorted(nms_cfg.items())), cfg['max_per_img'], str(device))
+               tuple(sorted(dict(cfg['nms']).items())), cfg['max_per_img'], str(device))
         if key not in self._post:
-            if nms_cfg.pop('type', 'nms') != 'nms':
-                raise NotImplementedError("IoUawareFCOSHead: only nms type 'nms' is wired")
-            pcfg = PP.make_cfg(featmap_sizes, self.strides, [torch.zeros(1, 4)] * len(featmap_sizes),
-                               self.cls_out_channels, cfg.get('nms_pre', -1), cfg['max_per_img'], cfg['score_thr'],
-                               nms_cfg.get('iou_thr', 0.5), alpha=self.alpha, decode_mode=L.DECODE_DISTANCE)
+            pcfg, _ = self.postproc_cfg(featmap_sizes, cfg)
             self._post.clear()
             self._post[key] = PP.PostprocWorkspace(pcfg, n_img, device)
         return self._post[key]

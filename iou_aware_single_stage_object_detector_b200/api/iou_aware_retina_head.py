@@ -93,7 +93,9 @@ class IoUawareRetinaHead(AnchorHead):
             a.copy_(b)
         with torch.cuda.device(dev):
             eng.run()
-        return outs
+        # fresh tensors, like the reference's forward (the plan's own maps are overwritten by the next call);
+        # FusedPlan uses plan_into() directly and keeps the zero-copy buffers
+        return tuple(None if ts is None else [t.clone(memory_format=torch.preserve_format) for t in ts] for ts in outs)
 
     def forward_single(self, x):
         c, r, q = self.forward((x,))
@@ -104,25 +106,30 @@ class IoUawareRetinaHead(AnchorHead):
         key = (tuple(featmap_sizes), n_img, cfg.get('nms_pre', -1), cfg['score_thr'],
                tuple(sorted(dict(cfg['nms']).items())), cfg['max_per_img'], str(device))
         if key not in self._post:
-            nms_cfg = dict(cfg['nms'])
-            nms_type = nms_cfg.pop('type', 'nms')
-            if nms_type not in ('nms', 'soft_nms'):
-                raise NotImplementedError("nms type '%s' is not on the accelerated path" % nms_type)
-            soft = None
-            if nms_type == 'soft_nms':             # keyword defaults of nms_wrapper.soft_nms (nms_wrapper.py:52)
-                method = nms_cfg.get('method', 'linear')
-                if method not in PP.SOFT_NMS_METHODS:
-                    raise ValueError('Invalid method for SoftNMS: {}'.format(method))
-                soft = (PP.SOFT_NMS_METHODS[method], float(nms_cfg.get('sigma', 0.5)),
-                        float(nms_cfg.get('min_score', 1e-3)))
-            pcfg = PP.make_cfg(featmap_sizes, self.anchor_strides,
-                               [g.base_anchors for g in self.anchor_generators], self.cls_out_channels,
-                               cfg.get('nms_pre', -1), cfg['max_per_img'], cfg['score_thr'],
-                               nms_cfg.get('iou_thr', 0.5), self.target_means, self.target_stds, self.alpha)
+            pcfg, soft = self.postproc_cfg(featmap_sizes, cfg)
             self._post.clear()
             self._post[key] = PP.PostprocWorkspace(pcfg, n_img, device)
             self._post[key].soft = soft
         return self._post[key]
+
+    def postproc_cfg(self, featmap_sizes, cfg):
+        """(iou_postproc_cfg, soft-NMS arguments or None) for a test_cfg, without allocating a workspace."""
+        nms_cfg = dict(cfg['nms'])
+        nms_type = nms_cfg.pop('type', 'nms')
+        if nms_type not in ('nms', 'soft_nms'):
+            raise NotImplementedError("nms type '%s' is not on the accelerated path" % nms_type)
+        soft = None
+        if nms_type == 'soft_nms':             # keyword defaults of nms_wrapper.soft_nms (nms_wrapper.py:52)
+            method = nms_cfg.get('method', 'linear')
+            if method not in PP.SOFT_NMS_METHODS:
+                raise ValueError('Invalid method for SoftNMS: {}'.format(method))
+            soft = (PP.SOFT_NMS_METHODS[method], float(nms_cfg.get('sigma', 0.5)),
+                    float(nms_cfg.get('min_score', 1e-3)))
+        pcfg = PP.make_cfg(featmap_sizes, self.anchor_strides,
+                           [g.base_anchors for g in self.anchor_generators], self.cls_out_channels,
+                           cfg.get('nms_pre', -1), cfg['max_per_img'], cfg['score_thr'],
+                           nms_cfg.get('iou_thr', 0.5), self.target_means, self.target_stds, self.alpha)
+        return pcfg, soft
 
     def get_bboxes_device(self, cls_scores, bbox_preds, iou_preds, img_metas, cfg, rescale=False,
                           img_info=None):

@@ -84,33 +84,51 @@ def soft_nms(dets, iou_thr, method='linear', sigma=0.5, min_score=1e-3):
     return new_dets.astype(np.float32), inds.astype(np.int64)
 
 
+_FOCAL_DTYPES = {torch.float32: L.DTYPE_F32, torch.float16: L.DTYPE_F16, torch.float64: L.DTYPE_F64}
+
+
+def _focal_dtype(logits):
+    if not logits.is_cuda:
+        raise RuntimeError("sigmoid_focal_loss_cuda: logits must be a CUDA tensor")      # sigmoid_focal_loss.cpp:21-25
+    if logits.dim() != 2:
+        raise RuntimeError("sigmoid_focal_loss_cuda: logits should be NxClass")          # .cu:113
+    if logits.dtype not in _FOCAL_DTYPES:                 # AT_DISPATCH_FLOATING_TYPES_AND_HALF (.cu:128)
+        raise RuntimeError("sigmoid_focal_loss_cuda: not implemented for %s" % logits.dtype)
+    return _FOCAL_DTYPES[logits.dtype]
+
+
 class _FocalLossCuda(object):
-    """Stands where the reference's pybind module sigmoid_focal_loss_cuda stood."""
+    """Stands where the reference's pybind module sigmoid_focal_loss_cuda stood: fp16 / fp32 / fp64 logits in,
+    losses / gradients of the same dtype out."""
 
     @staticmethod
     def forward(logits, targets, num_classes, gamma, alpha):
-        if not logits.is_cuda:
-            raise RuntimeError("sigmoid_focal_loss_cuda: logits must be a CUDA tensor")
-        x = logits.detach().float().contiguous()
+        dt = _focal_dtype(logits)
+        x = logits.detach().contiguous()
         t = targets.detach().long().contiguous()
         out = torch.empty_like(x)
         with torch.cuda.device(x.device):
-            L.check(L.load().iou_sigmoid_focal_loss_forward(x.data_ptr(), t.data_ptr(), x.shape[0],
-                                                            num_classes, gamma, alpha, out.data_ptr(),
-                                                            L.stream_ptr()))
+            L.check(L.load().iou_sigmoid_focal_loss_forward_dtype(x.data_ptr(), dt, t.data_ptr(), x.shape[0],
+                                                                  x.shape[1], gamma, alpha, out.data_ptr(),
+                                                                  L.stream_ptr()))
         L.launch_count += 1
         return out
 
     @staticmethod
     def backward(logits, targets, d_losses, num_classes, gamma, alpha):
-        x = logits.detach().float().contiguous()
+        dt = _focal_dtype(logits)
+        if logits.shape[1] != num_classes:
+            raise RuntimeError("logits.size(1) should be num_classes")                   # .cu:151-152
+        x = logits.detach().contiguous()
         t = targets.detach().long().contiguous()
-        g = d_losses.detach().float().contiguous()
+        g = d_losses.detach().to(x.dtype).contiguous()
+        if g.numel() != x.numel():
+            raise RuntimeError("sigmoid_focal_loss_cuda.backward: d_losses must have one element per logit")
         out = torch.empty_like(x)
         with torch.cuda.device(x.device):
-            L.check(L.load().iou_sigmoid_focal_loss_backward(x.data_ptr(), t.data_ptr(), g.data_ptr(),
-                                                             x.shape[0], num_classes, gamma, alpha,
-                                                             out.data_ptr(), L.stream_ptr()))
+            L.check(L.load().iou_sigmoid_focal_loss_backward_dtype(x.data_ptr(), dt, t.data_ptr(), g.data_ptr(),
+                                                                   x.shape[0], num_classes, gamma, alpha,
+                                                                   out.data_ptr(), L.stream_ptr()))
         L.launch_count += 1
         return out
 
@@ -119,6 +137,11 @@ sigmoid_focal_loss_cuda = _FocalLossCuda
 
 
 class SigmoidFocalLossFunction(Function):
+    """ops/sigmoid_focal_loss/functions/sigmoid_focal_loss.py:8-42.  One deviation, on purpose: for the 'mean' and
+    'sum' reductions the reference hands its kernel the 0-dim upstream gradient, which the kernel then indexes per
+    element (sigmoid_focal_loss_cuda.cu:103, an out-of-bounds read); here that scalar is broadcast -- and divided by
+    numel for 'mean' -- so the gradient is the derivative of what forward returned."""
+
     @staticmethod
     def forward(ctx, input, target, gamma=2.0, alpha=0.25, reduction='mean'):
         ctx.save_for_backward(input, target)
@@ -130,7 +153,7 @@ class SigmoidFocalLossFunction(Function):
             return loss.mean()
         if reduction == 'sum':
             return loss.sum()
-        raise ValueError(reduction)
+        raise ValueError("{} is not a valid value for reduction".format(reduction))     # F._Reduction.get_enum
 
     @staticmethod
     @once_differentiable
@@ -155,7 +178,10 @@ class SigmoidFocalLoss(nn.Module):
 
     def forward(self, logits, targets):
         assert logits.is_cuda
-        return sigmoid_focal_loss(logits, targets, self.gamma, self.alpha, 'none').sum()
+        # modules/sigmoid_focal_loss.py:13-16: the function's default reduction ('mean') and then .sum() of that
+        # 0-dim result, i.e. the MEAN over the N*C elements
+        loss = sigmoid_focal_loss(logits, targets, self.gamma, self.alpha)
+        return loss.sum()
 
     def __repr__(self):
         return "{}(gamma={}, alpha={})".format(self.__class__.__name__, self.gamma, self.alpha)

@@ -154,7 +154,8 @@ class ResNet(nn.Module):
         inp.copy_(x)
         with torch.cuda.device(x.device):
             eng.run()
-        return tuple(outs[i] for i in self.out_indices)
+        # fresh tensors, like the reference's modules: the plan's own output buffers are overwritten by the next call
+        return tuple(outs[i].clone() for i in self.out_indices)
 
     def train(self, mode=True):
         super(ResNet, self).train(mode)

@@ -972,6 +972,139 @@ __global__ void __launch_bounds__(512) single_nms_kernel(const float* __restrict
 }
 
 
+// ---------------------------------------------------------------------------------------- single NMS, any n
+// n > IOU_MAX_NMS_BOXES does not fit one block's shared memory: the reference's own structure instead
+// (nms_kernel.cu:23-67: 64 x 64 suppression-mask tiles over the score-sorted boxes), with the sort and the greedy
+// scan (which the reference runs on the HOST after a D2H copy of the mask, :99-123) kept on the device.
+__global__ void nms_large_keys_kernel(const float* __restrict__ dets, const int n, const int P,
+                                      unsigned long long* __restrict__ keys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P)
+    keys[i] = (i < n) ? (((unsigned long long)float_to_ordered(dets[(size_t)i * 5 + 4]) << 32) |
+                         (unsigned long long)(0xffffffffu - (unsigned int)i))
+                      : 0ull;                       // padding sorts behind every real key
+}
+// one compare-exchange pass of a bitonic network over global memory (descending)
+__global__ void nms_large_bitonic_kernel(unsigned long long* __restrict__ a, const int P, const int j, const int k) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const int l = i ^ j;
+  if (l > i) {
+    const unsigned long long x = a[i], y = a[l];
+    const bool desc = (i & k) == 0;
+    if (desc ? (x < y) : (x > y)) { a[i] = y; a[l] = x; }
+  }
+}
+__global__ void nms_large_gather_kernel(const float* __restrict__ dets, const int n,
+                                        const unsigned long long* __restrict__ keys, float4* __restrict__ sbox,
+                                        float* __restrict__ sarea) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const unsigned int j = 0xffffffffu - (unsigned int)(keys[r] & 0xffffffffull);
+  const float4 b = make_float4(dets[(size_t)j * 5], dets[(size_t)j * 5 + 1], dets[(size_t)j * 5 + 2],
+                               dets[(size_t)j * 5 + 3]);
+  sbox[r] = b;
+  sarea[r] = box_area(b);
+}
+// mask[r][cb] bit c: sorted box cb*64+c is suppressed by sorted box r (only pairs with a higher position, :51-57)
+__global__ void __launch_bounds__(64) nms_large_mask_kernel(const float4* __restrict__ sbox, const float* __restrict__ sarea,
+                                                            const int n, const int cb, const float thr,
+                                                            unsigned long long* __restrict__ mask) {
+  const int rb = blockIdx.y, cbk = blockIdx.x;
+  if (cbk < rb) return;
+  __shared__ float4 cbox[64];
+  __shared__ float carea[64];
+  const int cn = min(n - cbk * 64, 64), rn = min(n - rb * 64, 64);
+  if ((int)threadIdx.x < cn) { cbox[threadIdx.x] = sbox[cbk * 64 + threadIdx.x]; carea[threadIdx.x] = sarea[cbk * 64 + threadIdx.x]; }
+  __syncthreads();
+  if ((int)threadIdx.x < rn) {
+    const int r = rb * 64 + threadIdx.x;
+    const float4 a = sbox[r];
+    const float sa = sarea[r];
+    unsigned long long t = 0ull;
+    for (int c = (rb == cbk) ? (int)threadIdx.x + 1 : 0; c < cn; ++c)
+      if (iou_gt(a, sa, cbox[c], carea[c], thr)) t |= 1ull << c;
+    mask[(size_t)r * cb + cbk] = t;
+  }
+}
+// greedy scan over the mask (the reference's host loop, :105-123) + ascending original indices (:127-130)
+__global__ void __launch_bounds__(1024) nms_large_scan_kernel(const unsigned long long* __restrict__ mask, const int n,
+                                                              const int cb, const unsigned long long* __restrict__ keys,
+                                                              unsigned int* __restrict__ keepbits,
+                                                              long long* __restrict__ keep_idx,
+                                                              int32_t* __restrict__ keep_count) {
+  extern __shared__ unsigned long long remv[];
+  __shared__ unsigned long long s_kept;
+  __shared__ unsigned int s_run, warp_cnt[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int w = tid; w < cb; w += 1024) remv[w] = 0ull;
+  for (int w = tid; w < (n + 31) / 32; w += 1024) keepbits[w] = 0u;
+  __syncthreads();
+  for (int blk = 0; blk < cb; ++blk) {
+    if (tid == 0) {
+      unsigned long long r = remv[blk], kept = 0ull;
+      const int rn = min(n - blk * 64, 64);
+      for (int b = 0; b < rn; ++b) {
+        if (!((r >> b) & 1ull)) {
+          kept |= 1ull << b;
+          r |= mask[(size_t)(blk * 64 + b) * cb + blk];
+          const unsigned int j = 0xffffffffu - (unsigned int)(keys[blk * 64 + b] & 0xffffffffull);
+          keepbits[j >> 5] |= 1u << (j & 31);
+        }
+      }
+      s_kept = kept;
+    }
+    __syncthreads();
+    const unsigned long long kept = s_kept;
+    for (int w = blk + 1 + tid; w < cb; w += 1024) {
+      unsigned long long acc = remv[w], kk = kept;
+      while (kk) {
+        const int b = __ffsll((long long)kk) - 1;
+        kk &= kk - 1;
+        acc |= mask[(size_t)(blk * 64 + b) * cb + w];
+      }
+      remv[w] = acc;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) s_run = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int j = base + tid;
+    const bool kp = (j < n) && ((keepbits[j >> 5] >> (j & 31)) & 1u);
+    const unsigned int b = __ballot_sync(0xffffffffu, kp);
+    if (lane == 0) warp_cnt[warp] = __popc(b);
+    __syncthreads();
+    unsigned int off = s_run;
+    for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+    if (kp) keep_idx[off + __popc(b & ((1u << lane) - 1u))] = (long long)j;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int t = 0;
+      for (int w = 0; w < 32; ++w) t += warp_cnt[w];
+      s_run += t;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) *keep_count = (int32_t)s_run;
+}
+
+struct NmsLargeWs { size_t keys, sbox, sarea, mask, keepbits, total; int P, cb; };
+static NmsLargeWs nms_large_carve(int n) {
+  NmsLargeWs W;
+  W.P = next_pow2_host(n) < 2 ? 2 : next_pow2_host(n);
+  W.cb = (n + 63) / 64;
+  size_t off = 0;
+  W.keys = off; off = align_up(off + (size_t)W.P * 8, 256);
+  W.sbox = off; off = align_up(off + (size_t)n * 16, 256);
+  W.sarea = off; off = align_up(off + (size_t)n * 4, 256);
+  W.mask = off; off = align_up(off + (size_t)n * W.cb * 8, 256);
+  W.keepbits = off; off = align_up(off + (size_t)((n + 31) / 32) * 4, 256);
+  W.total = off;
+  return W;
+}
+
+
 // ---------------------------------------------------------------------------------------- soft NMS
 // Drop-in for soft_nms_cpu (mmdet/ops/nms/src/soft_nms_cpu.pyx:22-127), SURVEY 8(f) rank 3.  The reference is
 // a sequential in-place loop; what is kept here is its exact OUTPUT, including the order that its swap /
@@ -1280,6 +1413,8 @@ static int run_decode(PostParams& P, const float* const* cls, const float* const
   if (groups > 0) {
     const int blocks = (int)((groups + 7) / 8 < 148 * 8 ? (groups + 7) / 8 : 148 * 8);
     const size_t sm = (size_t)8 * 32 * (P.C / 4) * sizeof(float);
+    if (sm > 48 * 1024)     // more than 192 classes: above the default dynamic shared-memory limit
+      IOU_CHECK_CUDA(cudaFuncSetAttribute(max_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     max_score_kernel<<<blocks, 256, sm, st>>>(P, maxscore);
     if (int e = launch_status("max_score_kernel")) return e;
     int max_n = 0;
@@ -1377,11 +1512,13 @@ extern "C" int iou_get_bboxes(const iou_postproc_cfg* cfg, int n_img, const floa
                  (cudaStream_t)stream);
 }
 
-extern "C" size_t iou_nms_workspace_bytes(int n) { (void)n; return 256; }
+extern "C" size_t iou_nms_workspace_bytes(int n) {
+  if (n <= IOU_MAX_NMS_BOXES) return 256;          // one block, everything in shared memory
+  return nms_large_carve(n).total;                 // keys + sorted boxes + n x ceil(n/64) mask words
+}
 
 extern "C" int iou_nms(const float* dets, int n, float iou_thr, int64_t* keep_idx, int32_t* keep_count,
                        void* workspace, size_t workspace_bytes, void* stream) {
-  (void)workspace; (void)workspace_bytes;
   IOU_REQUIRE(n >= 0, "n must be >= 0");
   IOU_REQUIRE(keep_count != nullptr, "keep_count is NULL");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1390,9 +1527,30 @@ extern "C" int iou_nms(const float* dets, int n, float iou_thr, int64_t* keep_id
     return IOU_OK;
   }
   IOU_REQUIRE(dets && keep_idx, "NULL argument");
-  if (n > IOU_MAX_NMS_BOXES)
-    return fail(IOU_ERR_UNSUPPORTED, "iou_nms supports at most %d boxes per call (got %d)",
-                IOU_MAX_NMS_BOXES, n);
+  if (n > IOU_MAX_NMS_BOXES) {
+    // the reference has no size limit (nms_kernel.cu:70-131): mask tiles in global memory, sort and scan on the device
+    const NmsLargeWs W = nms_large_carve(n);
+    IOU_REQUIRE(W.cb * 8 <= 200 * 1024, "iou_nms: more than 1 638 400 boxes");
+    if (!workspace || workspace_bytes < W.total)
+      return fail(IOU_ERR_WORKSPACE, "iou_nms with %d boxes needs a workspace of %zu bytes (iou_nms_workspace_bytes)", n, W.total);
+    unsigned char* base = reinterpret_cast<unsigned char*>(workspace);
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(base + W.keys);
+    float4* sbox = reinterpret_cast<float4*>(base + W.sbox);
+    float* sarea = reinterpret_cast<float*>(base + W.sarea);
+    unsigned long long* mask = reinterpret_cast<unsigned long long*>(base + W.mask);
+    unsigned int* keepbits = reinterpret_cast<unsigned int*>(base + W.keepbits);
+    const int pb = (W.P + 255) / 256;
+    nms_large_keys_kernel<<<pb, 256, 0, st>>>(dets, n, W.P, keys);
+    for (int k = 2; k <= W.P; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) nms_large_bitonic_kernel<<<pb, 256, 0, st>>>(keys, W.P, j, k);
+    nms_large_gather_kernel<<<(n + 255) / 256, 256, 0, st>>>(dets, n, keys, sbox, sarea);
+    nms_large_mask_kernel<<<dim3(W.cb, W.cb), 64, 0, st>>>(sbox, sarea, n, W.cb, iou_thr, mask);
+    const size_t sm = (size_t)W.cb * 8;
+    if (sm > 48 * 1024)
+      IOU_CHECK_CUDA(cudaFuncSetAttribute(nms_large_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    nms_large_scan_kernel<<<1, 1024, sm, st>>>(mask, n, W.cb, keys, keepbits, reinterpret_cast<long long*>(keep_idx), keep_count);
+    return launch_status("nms_large_scan_kernel");
+  }
   const int Pmax = next_pow2_host(n) < 2 ? 2 : next_pow2_host(n);
   const size_t sm = (size_t)Pmax * 8 + (size_t)n * 24 + (size_t)((n + 31) / 32) * 4 + 16;
   IOU_CHECK_CUDA(cudaFuncSetAttribute(single_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));

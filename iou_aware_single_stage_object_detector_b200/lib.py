@@ -62,6 +62,7 @@ def build(force=False, verbose=False):
 
 
 DECODE_DELTA, DECODE_DISTANCE = 0, 1      # iou_postproc_cfg.decode_mode
+DTYPE_F32, DTYPE_F16, DTYPE_F64 = 0, 1, 2   # iou_sigmoid_focal_loss_*_dtype
 
 
 class PostprocCfg(ctypes.Structure):
@@ -132,6 +133,12 @@ _SIGS = {
     "iou_sigmoid_focal_loss_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                        ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                                        ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
+    "iou_sigmoid_focal_loss_forward_dtype": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                                            ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                                            ctypes.c_void_p, ctypes.c_void_p]),
+    "iou_sigmoid_focal_loss_backward_dtype": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                                             ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                                             ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
     "iou_conv_plan_create": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(ctypes.c_void_p)]),
     "iou_conv_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "iou_conv_plan_destroy": (None, [ctypes.c_void_p]),

@@ -182,8 +182,10 @@ def nms_cuda(dets, iou_thr):
     n = d.shape[0]
     keep = torch.empty(n, dtype=torch.int64, device=d.device)
     cnt = torch.zeros(1, dtype=torch.int32, device=d.device)
+    ws_bytes = lib.iou_nms_workspace_bytes(n)          # 256 B up to 6144 boxes; ~n*n/8 B of mask words above
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=d.device)
     with torch.cuda.device(d.device):
-        L.check(lib.iou_nms(d.data_ptr(), n, float(iou_thr), keep.data_ptr(), cnt.data_ptr(), None, 0,
-                            L.stream_ptr()))
+        L.check(lib.iou_nms(d.data_ptr(), n, float(iou_thr), keep.data_ptr(), cnt.data_ptr(), ws.data_ptr(),
+                            ws_bytes, L.stream_ptr()))
     L.launch_count += 1
     return keep[:int(cnt.item())]

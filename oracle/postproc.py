@@ -342,3 +342,49 @@ def sigmoid_focal_loss_backward(logits, targets, d_losses, gamma, alpha):
     term2 = torch.pow(p, gamma) * (
         (-1.0 * x * pos - torch.log(1.0 + torch.exp(x - 2.0 * x * pos))) * (1.0 - p) * gamma - p)
     return (-c1 * term1 * alpha - c2 * term2 * (1.0 - alpha)) * d_losses
+
+
+def _focal_terms_typed(logits, targets, gamma, alpha, dtype, backward):
+    """The reference kernel for scalar_t = at::Half / double (sigmoid_focal_loss_cuda.cu:24-105, dispatched at
+    :128,167): locals are scalar_t (a Half local is rounded at every assignment and computes in float), every
+    transcendental is the FLOAT function (expf / logf / powf) and the literals are double."""
+    A = torch.float32 if dtype == torch.float16 else dtype          # arithmetic type of scalar_t
+    rnd = lambda v: v.to(dtype).to(A)
+    f32 = lambda v: v.to(torch.float32)
+    f64 = lambda v: v.to(torch.float64)
+    x = logits.to(dtype).to(A)
+    n, c = x.shape
+    t = targets.reshape(-1, 1)
+    d1 = torch.arange(1, c + 1).reshape(1, -1)
+    c1 = (t == d1).to(A)
+    c2 = ((t >= 0) & (t != d1)).to(A)
+    a32 = torch.tensor(alpha, dtype=torch.float32)
+    zn, zp = rnd((1.0 - f64(a32)).to(A)), rnd(a32.to(A))
+    tiny = torch.finfo(torch.float32).tiny
+    p = rnd((1.0 / (1.0 + f64(torch.exp(-f32(x))))).to(A))
+    pos = f64(x >= 0)
+    soft = f64(torch.log(f32(1.0 + f64(torch.exp(f32(f64(x) - 2.0 * f64(x) * pos))))))
+    if not backward:
+        term1 = rnd((torch.pow(f32(1.0 - f64(p)), gamma) * torch.log(f32(p).clamp(min=tiny))).to(A))
+        term2 = rnd((f64(torch.pow(f32(p), gamma)) * (-1.0 * f64(x) * pos - soft)).to(A))
+    else:
+        term1 = rnd((f64(torch.pow(f32(1.0 - f64(p)), gamma)) *
+                     (1.0 - f64(p) - f64(f32(p) * gamma * torch.log(f32(p).clamp(min=tiny))))).to(A))
+        term2 = rnd((f64(torch.pow(f32(p), gamma)) *
+                     ((-1.0 * f64(x) * pos - soft) * (1.0 - f64(p)) * float(torch.tensor(gamma, dtype=torch.float32))
+                      - f64(p))).to(A))
+    out = rnd(rnd(rnd(-c1 * term1) * zp))
+    out = rnd(out + rnd(rnd(-c2 * term2) * zn))
+    return out, rnd
+
+
+def sigmoid_focal_loss_forward_typed(logits, targets, gamma, alpha, dtype):
+    """fp16 / fp64 flavours of sigmoid_focal_loss_cuda.forward; returns a tensor of `dtype`."""
+    out, _ = _focal_terms_typed(logits, targets, gamma, alpha, dtype, False)
+    return out.to(dtype)
+
+
+def sigmoid_focal_loss_backward_typed(logits, targets, d_losses, gamma, alpha, dtype):
+    out, rnd = _focal_terms_typed(logits, targets, gamma, alpha, dtype, True)
+    return rnd(out * d_losses.to(dtype).to(out.dtype)).to(dtype)
+

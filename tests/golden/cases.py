@@ -184,3 +184,34 @@ def fcos_case():
              dict(ori_shape=(238, 313, 3), img_shape=(190, 250, 3), pad_shape=(224, 288, 3), scale_factor=0.8,
                   flip=False)]
     return dict(cls=cls, reg=reg, cen=cen, iou=iou, img_metas=metas, cfg=cfg, rescale=True, sizes=sizes)
+
+
+def nms_large_inputs():
+    """More boxes than one block's shared memory holds (IOU_MAX_NMS_BOXES = 6144): the mask-tile path of iou_nms.
+    The reference has no size limit (nms_kernel.cu:70-131)."""
+    rs = np.random.RandomState(77)
+    return {"n6145": random_dets(rs, 6145, 900, 150), "n9000_dense": random_dets(rs, 9000, 400, 200),
+            "n20000": random_dets(rs, 20000, 2000, 120)}
+
+
+NMS_LARGE_THR = 0.45      # no pair of the inputs above has IoU == 0.45 exactly (asserted by the generator)
+
+
+def multiclass_inputs():
+    """multiclass_nms calls outside the batched kernels' envelope (bbox_nms.py:6-11 defaults and options):
+    name -> (multi_bboxes, multi_scores, score_thr, nms_cfg, max_num, score_factors)."""
+    rs = np.random.RandomState(31)
+    n, C = 400, 7
+    d = random_dets(rs, n, 300, 90)
+    boxes = d[:, :4]
+    scores = np.concatenate([np.zeros((n, 1), np.float32), rs.rand(n, C).astype(np.float32) ** 3], axis=1)
+    per_class = np.concatenate([boxes + rs.rand(n, 4).astype(np.float32) * 3.0 * c for c in range(C + 1)], axis=1)
+    factors = (rs.rand(n).astype(np.float32) * 0.5 + 0.5)
+    nms = dict(type='nms', iou_thr=0.5)
+    return {
+        "keep_all_default": (boxes, scores, 0.05, nms, -1, None),          # the reference default max_num = -1
+        "keep_all_zero": (boxes, scores, 0.3, nms, 0, None),
+        "score_factors": (boxes, scores, 0.05, nms, 50, factors),
+        "per_class_boxes": (per_class, scores, 0.05, nms, 60, None),
+        "soft_keep_all": (boxes, scores, 0.2, dict(SOFT_MULTICLASS), -1, None),
+    }

@@ -118,10 +118,30 @@ def main():
         np.savez_compressed(os.path.join(HERE, "postproc_%s.npz" % name), **out)
         print(name, {k: v.shape for k, v in out.items() if k.startswith("dets")})
     gen_plain_retina()
+    gen_boundary()
     gen_soft_nms()
     gen_results_json()
     gen_fcos()
     gen_resize()
+
+
+def gen_boundary():
+    """Drop-in ops beyond the batched kernels' envelope: nms on more than 6144 boxes (the reference's nms_cpu;
+    no IoU == thr ties, so '>' and '>=' agree) and multiclass_nms with max_num <= 0 / score_factors / per-class
+    boxes / soft_nms (the reference's own multiclass_nms, bbox_nms.py:6-67)."""
+    ref_shim.load_reference()
+    from mmdet.core import multiclass_nms
+    ref_nms_cpu = sys.modules["mmdet.ops.nms.nms_cpu"]
+    out = {}
+    for name, dets in cases.nms_large_inputs().items():
+        cases.assert_no_threshold_ties(dets, cases.NMS_LARGE_THR)
+        out["nms_" + name] = ref_nms_cpu.nms(torch.from_numpy(dets), cases.NMS_LARGE_THR).numpy()
+    for name, (b, sc, thr, nms_cfg, max_num, fac) in cases.multiclass_inputs().items():
+        d, l = multiclass_nms(torch.from_numpy(b), torch.from_numpy(sc), thr, ref_shim._to_attr(dict(nms_cfg)), max_num,
+                              None if fac is None else torch.from_numpy(fac))
+        out["mc_%s_dets" % name], out["mc_%s_labels" % name] = d.numpy(), l.numpy()
+    np.savez_compressed(os.path.join(HERE, "boundary_ops.npz"), **out)
+    print("boundary", {k: v.shape for k, v in out.items()})
 
 
 def gen_soft_nms():
@@ -261,6 +281,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--results-only" in sys.argv:
         gen_results_json()
+        sys.exit(0)
+    if "--boundary-only" in sys.argv:
+        gen_boundary()
         sys.exit(0)
     if "--soft-nms-only" in sys.argv:
         gen_soft_nms()

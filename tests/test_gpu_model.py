@@ -50,6 +50,33 @@ def test_backbone_fpn_head_modules_standalone():
         assert _rel(a.cpu(), b) < 5e-4
 
 
+def test_public_forwards_return_fresh_tensors():
+    """The reference's modules return independent tensors: a second call with the same input shape must not
+    overwrite what the first call returned (the plans' own buffers stay internal)."""
+    det, cfg = U.small_detector(seed=2)
+    det = det.to(DEV)
+    g = torch.Generator().manual_seed(4)
+    x1, x2 = torch.randn(1, 3, 96, 128, generator=g).to(DEV), torch.randn(1, 3, 96, 128, generator=g).to(DEV)
+    f1 = det.backbone(x1)
+    keep = [t.clone() for t in f1]
+    f2 = det.backbone(x2)
+    assert all(torch.equal(a, b) for a, b in zip(f1, keep)) and not torch.equal(f1[0], f2[0])
+    p1 = det.neck(f1)
+    keep = [t.clone() for t in p1]
+    p2 = det.neck(f2)
+    assert all(torch.equal(a, b) for a, b in zip(p1, keep)) and not torch.equal(p1[0], p2[0])
+    h1 = det.bbox_head(p1)
+    keep = [[t.clone() for t in ts] for ts in h1]
+    h2 = det.bbox_head(p2)
+    assert all(torch.equal(a, b) for ts, ks in zip(h1, keep) for a, b in zip(ts, ks))
+    assert not torch.equal(h1[0][0], h2[0][0])
+    metas = [dict(ori_shape=(96, 128, 3), img_shape=(96, 128, 3), pad_shape=(96, 128, 3), scale_factor=1.0, flip=False)]
+    d1 = det.detect_device(x1, metas)
+    keep = [t.clone() for t in d1]
+    det.detect_device(x2, metas)
+    assert all(torch.equal(a, b) for a, b in zip(d1, keep))
+
+
 def test_detector_end_to_end_small():
     worst = U.check_detector_small(use_graph=False)
     print("worst relative head error", worst)

@@ -45,9 +45,28 @@ def test_nms_edge_cases():
     with pytest.raises(TypeError):
         P.nms([1, 2, 3], 0.5)
     with pytest.raises(RuntimeError):
-        P.nms(torch.zeros(7000, 5, device="cuda"), 0.5)     # > IOU_MAX_NMS_BOXES: loud, not silent
-    with pytest.raises(RuntimeError):
         P.nms(torch.zeros(3, 5), 0.5)                        # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("name", list(cases.nms_large_inputs().keys()))
+def test_nms_beyond_one_block_bit_exact(name):
+    """n > IOU_MAX_NMS_BOXES (6144): the mask-tile path of iou_nms (sort + 64x64 mask tiles + greedy scan, all on the
+    device) == the reference's nms_cpu golden; the reference has no size limit (nms_kernel.cu:70-131)."""
+    gold = np.load(os.path.join(U.GOLD, "boundary_ops.npz"))["nms_" + name]
+    dets = torch.from_numpy(cases.nms_large_inputs()[name]).cuda()
+    kept, inds = P.nms(dets, cases.NMS_LARGE_THR)
+    assert inds.dtype == torch.int64 and inds.is_cuda
+    assert np.array_equal(inds.cpu().numpy(), gold)
+    assert torch.equal(kept, dets[inds])
+
+
+def test_nms_both_paths_agree_across_the_size_limit():
+    rs = np.random.RandomState(9)
+    big = cases.random_dets(rs, 6500, 700, 140)
+    for n in (6143, 6144, 6145, 6208, 6500):
+        want = op.nms(big[:n], 0.45, "cuda").numpy()
+        got = P.nms(torch.from_numpy(big[:n]).cuda(), 0.45)[1].cpu().numpy()
+        assert np.array_equal(got, want), n
 
 
 def test_nms_random_vs_oracle_many_sizes():
@@ -77,11 +96,7 @@ def test_multiclass_nms_api_vs_oracle():
     scores[:, 0] = 0
     for max_num in (100, 3000):
         d_ref, l_ref = op.multiclass_nms(torch.from_numpy(boxes), torch.from_numpy(scores), 0.05, 0.5, max_num)
-        if max_num * 80 > 8000:
-            with pytest.raises(RuntimeError):
-                P.multiclass_nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), 0.05,
-                                 dict(type='nms', iou_thr=0.5), max_num)
-            continue
+        # max_num = 3000: 80 x 3001 kept-row slots exceed the batched kernels -> the class-by-class path
         d, l = P.multiclass_nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), 0.05,
                                 dict(type='nms', iou_thr=0.5), max_num)
         assert np.array_equal(l.cpu().numpy(), l_ref.numpy())
@@ -90,6 +105,21 @@ def test_multiclass_nms_api_vs_oracle():
     d, l = P.multiclass_nms(torch.from_numpy(boxes).cuda(), torch.zeros(n, C + 1).cuda(), 0.05,
                             dict(type='nms', iou_thr=0.5), 100)
     assert d.shape == (0, 5) and l.shape == (0,) and l.dtype == torch.int64
+
+
+@pytest.mark.parametrize("name", list(cases.multiclass_inputs().keys()))
+def test_multiclass_nms_options_vs_reference_golden(name):
+    """max_num = -1 (the reference default, bbox_nms.py:6-11; :57-59 then sorts and drops the last row), max_num = 0,
+    score_factors (threshold on the unscaled score, :37,46-47), per-class boxes (:43-44) and soft_nms: outputs of
+    the reference's own multiclass_nms."""
+    gold = np.load(os.path.join(U.GOLD, "boundary_ops.npz"))
+    b, sc, thr, nms_cfg, max_num, fac = cases.multiclass_inputs()[name]
+    d, l = P.multiclass_nms(torch.from_numpy(b).cuda(), torch.from_numpy(sc).cuda(), thr, dict(nms_cfg), max_num,
+                            None if fac is None else torch.from_numpy(fac).cuda())
+    gd, gl = gold["mc_%s_dets" % name], gold["mc_%s_labels" % name]
+    assert d.shape == gd.shape and l.dtype == torch.int64
+    assert np.array_equal(l.cpu().numpy(), gl)
+    assert np.array_equal(d.cpu().numpy(), gd)
 
 
 def test_topk_with_exact_ties_is_deterministic():
@@ -156,8 +186,38 @@ def test_focal_loss_forward_backward_vs_oracle():
     assert torch.allclose(loss.detach().cpu(), op.sigmoid_focal_loss_forward(x, t, 2.0, 0.25).mean(), rtol=1e-4)
     assert torch.allclose(xg.grad.cpu(), op.sigmoid_focal_loss_backward(
         x, t, torch.full_like(x, 1.0 / x.numel()), 2.0, 0.25), rtol=1e-4, atol=1e-9)
+    # the module returns what modules/sigmoid_focal_loss.py:13-16 returns: sigmoid_focal_loss(...) with its default
+    # reduction ('mean') and .sum() of that 0-dim tensor = the MEAN over the N*C elements
     assert P.SigmoidFocalLoss(2.0, 0.25)(x.cuda(), t.cuda()).item() == pytest.approx(
-        op.sigmoid_focal_loss_forward(x, t, 2.0, 0.25).sum().item(), rel=1e-4)
+        op.sigmoid_focal_loss_forward(x, t, 2.0, 0.25).mean().item(), rel=1e-4)
+    for red, f in (('none', lambda v: v), ('sum', lambda v: v.sum())):
+        got = P.sigmoid_focal_loss(x.cuda(), t.cuda(), 2.0, 0.25, red)
+        assert torch.allclose(got.cpu(), f(op.sigmoid_focal_loss_forward(x, t, 2.0, 0.25)), rtol=1e-4, atol=1e-6)
+    with pytest.raises(ValueError):
+        P.sigmoid_focal_loss(x.cuda(), t.cuda(), 2.0, 0.25, 'bogus')
+
+
+@pytest.mark.parametrize("dtype,rtol,atol", [(torch.float16, 2e-3, 2e-4), (torch.float64, 1e-5, 1e-7)])
+def test_focal_loss_fp16_fp64_dispatch_vs_oracle(dtype, rtol, atol):
+    """AT_DISPATCH_FLOATING_TYPES_AND_HALF (sigmoid_focal_loss_cuda.cu:128,167): fp16 and fp64 logits keep their
+    dtype; the oracle restates the templated kernel per scalar_t (float transcendentals, scalar_t locals)."""
+    torch.manual_seed(1)
+    x = (torch.randn(257, 80) * 3).to(dtype)
+    t = torch.randint(0, 81, (257,))
+    g = torch.rand(257, 80).to(dtype)
+    for gamma, alpha in ((2.0, 0.25), (1.5, 0.4)):
+        f = P.sigmoid_focal_loss_cuda.forward(x.cuda(), t.cuda(), 80, gamma, alpha)
+        b = P.sigmoid_focal_loss_cuda.backward(x.cuda(), t.cuda(), g.cuda(), 80, gamma, alpha)
+        assert f.dtype == dtype and b.dtype == dtype
+        ref_f = op.sigmoid_focal_loss_forward_typed(x, t, gamma, alpha, dtype)
+        ref_b = op.sigmoid_focal_loss_backward_typed(x, t, g, gamma, alpha, dtype)
+        assert torch.allclose(f.cpu().double(), ref_f.double(), rtol=rtol, atol=atol), (f.cpu().double() - ref_f.double()).abs().max()
+        assert torch.allclose(b.cpu().double(), ref_b.double(), rtol=rtol, atol=atol), (b.cpu().double() - ref_b.double()).abs().max()
+        # and both agree with the fp32 formula to the dtype's own precision
+        f32 = op.sigmoid_focal_loss_forward(x.float(), t, gamma, alpha)
+        assert torch.allclose(f.cpu().float(), f32, rtol=5e-3 if dtype == torch.float16 else 1e-5, atol=1e-3 if dtype == torch.float16 else 1e-6)
+    with pytest.raises(RuntimeError):
+        P.sigmoid_focal_loss_cuda.forward(x.cuda().to(torch.bfloat16), t.cuda(), 80, 2.0, 0.25)
 
 
 def test_plain_retina_head_get_bboxes_vs_reference_golden():
