@@ -285,6 +285,12 @@ int iou_group_norm_relu(void* map, int c, int num_seg, const iou_conv_segment* s
 int iou_group_norm_relu_fmt(void* map, int c, int num_seg, const iou_conv_segment* seg, int groups,
                             const float* gamma, const float* beta, float eps, int relu, void* workspace,
                             size_t workspace_bytes, int fmt, void* stream);   /* either element format (IOU_FMT_*) */
+/* Range statistics of a padded-rows map [rows][c] in either element format: out4[0] = max |v| (fp32 bits in the low
+ * word), out4[1] = elements at or beyond the fp16 limit 65504 (the IOU_FMT_F16F8 encode SATURATES there -- the
+ * reference's fp32 would not; inf / NaN count too), out4[2] = elements with |v| > 448 (their e4m3 parts are saturated:
+ * fp16 precision only), out4[3] = non-zero elements.  The detector runs it over every activation map after the first
+ * batch of a plan (api/detectors.py) -- the guard for activation ranges outside what the fp16 + e4m3 scheme holds. */
+int iou_range_stats(const void* map, int64_t rows, int c, int fmt, uint64_t* out4, void* stream);
 /* x[i] = exp(x[i] * scale) on n dense fp32 values: bbox_pred = scale(fcos_reg(feat)).exp()
  * (mmdet/models/anchor_heads/iou_aware_fcos_head.py:108). */
 int iou_scale_exp(float* x, size_t n, float scale, void* stream);

@@ -87,6 +87,8 @@ class FusedPlan(object):
         self.wsp.soft = soft
         self.graph = None
         self.use_graph = use_graph
+        self.range_check = getattr(det, "range_check", True) and passes == 2
+        self.range = None                     # range_report() of the first batch
         self.conv_flops = eng.flops
         self.launches = eng.num_launches() + 5
 
@@ -100,9 +102,28 @@ class FusedPlan(object):
             PP.get_bboxes_device(self.wsp, self.post_in[0], self.post_in[1], self.post_in[2], self.img_info,
                                  self.rescale)
 
+    def check_range(self):
+        """The fp16 + e4m3 scheme holds |v| < 65504 (and full precision up to 448): look at every activation map the
+        last run produced and raise when values were clamped at the fp16 limit -- the reference's fp32 would not have
+        clamped them, so the detections would silently differ."""
+        self.range = self.eng.range_report()
+        bad = [r for r in self.range if r["saturated"] > 0]
+        if bad:
+            raise RuntimeError(
+                "activation range beyond the fp16 + e4m3 conv scheme (passes = 2): %d map(s) hold values at or above "
+                "65504, e.g. '%s' (%d of %d elements).  Use detector.passes = 3 (bf16 hi|lo, fp32 exponent range) for "
+                "this checkpoint / input scaling, or set detector.range_check = False to accept the clamping."
+                % (len(bad), bad[0]["label"], bad[0]["saturated"], bad[0]["elements"]))
+        return self.range
+
     def run(self):
         """Enqueue one pass on the current stream (inputs: self.img, self.img_info)."""
         with torch.cuda.device(self.device):
+            if self.range_check and self.range is None:
+                self._launch()                       # first batch of this plan, eager: activation ranges are checked
+                out = self.wsp.dets, self.wsp.labels, self.wsp.counts
+                self.check_range()
+                return out
             if not self.use_graph:
                 self._launch()
             elif self.graph is None:
@@ -133,6 +154,9 @@ class SingleStageDetector(BaseDetector):
         # tensor-core scheme of the convs (engine.Engine): None = 2 (fp16 pass + e4m3 correction pass, the fastest
         # fp32-grade scheme); 3 = bf16 hi|lo x3; 1 (plain bf16) is an explicit opt-in only
         self.passes = None
+        # passes == 2 only: the first batch of every plan runs eagerly and its activation ranges are checked
+        # (FusedPlan.check_range): values at or beyond the fp16 limit raise instead of being clamped silently
+        self.range_check = True
         self.init_weights(pretrained=pretrained)
 
     def init_weights(self, pretrained=None):

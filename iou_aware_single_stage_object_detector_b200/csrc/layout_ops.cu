@@ -481,6 +481,47 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(__nv_bfloat16* __restrict
 }
 
 // y = exp(x * scale) on a dense fp32 tensor (FCOS: bbox_pred = scale(fcos_reg(x)).exp(), iou_aware_fcos_head.py:108)
+// ---- range statistics of a padded-rows map (both element formats): out[0] = max |v| (float bits), out[1] = number of
+// elements at or beyond the fp16 limit (saturated by the fp16 + e4m3 encode; inf / NaN count as well), out[2] = number
+// of elements with 448 < |v| (e4m3 parts saturated: fp16 precision only), out[3] = number of non-zero elements.
+template <int kFmt>
+__global__ void __launch_bounds__(256) range_stats_kernel(const uint4* __restrict__ map, long long rows, int c,
+                                                          unsigned long long* __restrict__ out) {
+  const long long vec_per_row = c / 8;                       // one hi + one lo vector per 8 channels
+  const long long total = rows * vec_per_row;
+  float mx = 0.f;
+  unsigned long long sat = 0, big = 0, nz = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vec_per_row, g = i - r * vec_per_row;
+    const uint4 hi = map[r * (2 * vec_per_row) + g], lo = map[r * (2 * vec_per_row) + vec_per_row + g];
+    float v[8];
+    decode8<kFmt>(hi, lo, v);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float a = fabsf(v[q]);
+      if (!(a < 65504.f)) ++sat;                             // also true for NaN
+      else mx = fmaxf(mx, a);
+      if (a > 448.f) ++big;
+      if (a != 0.f) ++nz;
+    }
+  }
+  __shared__ float s_mx[256];
+  __shared__ unsigned long long s_cnt[3][256];
+  s_mx[threadIdx.x] = mx; s_cnt[0][threadIdx.x] = sat; s_cnt[1][threadIdx.x] = big; s_cnt[2][threadIdx.x] = nz;
+  __syncthreads();
+  for (int s_ = 128; s_ > 0; s_ >>= 1) {
+    if ((int)threadIdx.x < s_) {
+      s_mx[threadIdx.x] = fmaxf(s_mx[threadIdx.x], s_mx[threadIdx.x + s_]);
+      for (int k = 0; k < 3; ++k) s_cnt[k][threadIdx.x] += s_cnt[k][threadIdx.x + s_];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(s_mx[0]));     // non-negative floats order like uints
+    for (int k = 0; k < 3; ++k) atomicAdd(out + 1 + k, s_cnt[k][0]);
+  }
+}
+
 __global__ void __launch_bounds__(256) scale_exp_kernel(float* __restrict__ x, size_t n, float scale) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     x[i] = expf(__fmul_rn(x[i], scale));
@@ -601,6 +642,23 @@ extern "C" int iou_group_norm_relu(void* map, int c, int num_seg, const iou_conv
                                    size_t workspace_bytes, void* stream) {
   return iou_group_norm_relu_fmt(map, c, num_seg, seg, groups, gamma, beta, eps, relu, workspace, workspace_bytes,
                                  kFmtBf16x2, stream);
+}
+
+extern "C" int iou_range_stats(const void* map, int64_t rows, int c, int fmt, uint64_t* out4, void* stream) {
+  IOU_REQUIRE(map && out4, "NULL argument");
+  IOU_REQUIRE(rows >= 0 && c > 0 && c % 8 == 0, "rows must be >= 0 and c a positive multiple of 8");
+  IOU_REQUIRE(fmt == IOU_FMT_BF16X2 || fmt == IOU_FMT_F16F8, "bad element format");
+  IOU_REQUIRE(((uintptr_t)map & 15) == 0 && ((uintptr_t)out4 & 7) == 0, "map must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  IOU_CHECK_CUDA(cudaMemsetAsync(out4, 0, 4 * sizeof(uint64_t), st));
+  if (rows == 0) return IOU_OK;
+  const long long total = (long long)rows * (c / 8);
+  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  if (fmt == IOU_FMT_F16F8)
+    range_stats_kernel<kFmtF16F8><<<blocks, 256, 0, st>>>((const uint4*)map, rows, c, (unsigned long long*)out4);
+  else
+    range_stats_kernel<kFmtBf16x2><<<blocks, 256, 0, st>>>((const uint4*)map, rows, c, (unsigned long long*)out4);
+  return launch_status("range_stats_kernel");
 }
 
 extern "C" int iou_scale_exp(float* x, size_t n, float scale, void* stream) {

@@ -44,8 +44,17 @@ __device__ __forceinline__ float fhfma(uint16_t a, uint16_t b, float c) {   // f
 constexpr uint16_t kF16LoInv = 0x1000;       // 2^-11 as fp16
 constexpr uint16_t kF16NegLoScale = 0xE800;  // -2048 as fp16
 
-// 8 consecutive channels -> the group's hi and lo vectors.  kClamp: saturate at the fp16 range (the layout kernels,
-// which see arbitrary user data); the conv epilogue skips it -- an activation beyond 65504 becomes inf and shows.
+// fp32 pair -> packed fp16 pair, saturating at +-65504 inside the conversion (SASS F2FP.SATFINITE.F16.F32.PACK_AB: one
+// instruction, like the non-saturating form)
+__device__ __forceinline__ uint32_t f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// 8 consecutive channels -> the group's hi and lo vectors.  Values beyond the fp16 range SATURATE at +-65504 (never inf,
+// so nothing downstream turns into NaN); iou_range_stats counts them, and the detector checks that count on the first
+// batch of every plan.  kClamp is kept for source compatibility: the conversion itself saturates in both cases.
 template <int kFmt, bool kClamp = true>
 __device__ __forceinline__ void encode8(const float (&v)[8], uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
@@ -63,10 +72,8 @@ __device__ __forceinline__ void encode8(const float (&v)[8], uint4& hi, uint4& l
     uint32_t x8[4], l8[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float a = kClamp ? fminf(fmaxf(v[2 * q], -65504.f), 65504.f) : v[2 * q];
-      const float b = kClamp ? fminf(fmaxf(v[2 * q + 1], -65504.f), 65504.f) : v[2 * q + 1];
-      const __half2 h2 = __floats2half2_rn(a, b);
-      h[q] = *reinterpret_cast<const uint32_t*>(&h2);
+      const float a = v[2 * q], b = v[2 * q + 1];
+      h[q] = f16x2_sat(a, b);
       x8[q] = e4m3x2(a, b);
       // (v - hi) * 2^11 = fma(hi, -2^11, v * 2^11): exact (the difference has <= 13 significant bits)
       l8[q] = e4m3x2(fhfma((uint16_t)(h[q] & 0xffffu), kF16NegLoScale, a * kF8LoScale),

@@ -230,6 +230,7 @@ class Engine(object):
         self.ops = []            # (name, callable(stream_ptr))
         self.plans = []
         self.keep = []           # tensors that must outlive the plan
+        self.maps = []           # every padded-rows buffer of this engine (range_report)
         self.flops = 0.0
         self.op_flops = {}
         import os
@@ -246,6 +247,7 @@ class Engine(object):
         """Allocates a padded-rows buffer owned by this engine (plans only hold raw pointers)."""
         m = FlatMap(segs, c, self.device)
         self.keep.append(m.tensor)
+        self.maps.append(m)
         return m
 
     def _dev(self, t):
@@ -365,6 +367,9 @@ class Engine(object):
             rc = self.lib.iou_conv_plan_create(ctypes.byref(d), ctypes.byref(plan))
         L.check(rc)
         self.plans.append(plan)
+        for m in ([out] if out is not None else []) + [m for m in (phase_outs or []) if m is not None]:
+            if getattr(m, "label", None) is None:
+                m.label = name
         f = self.lib.iou_conv_plan_flops(plan) * true_flops_scale
         self.flops += f
         self.op_flops[name] = self.op_flops.get(name, 0.0) + f
@@ -689,6 +694,22 @@ class Engine(object):
 
     def num_launches(self):
         return len(self.ops)
+
+    def range_report(self):
+        """Range statistics of every activation map as the LAST run left them (iou_range_stats): list of dicts
+        (label, max_abs, saturated, above_448, nonzero, elements).  `saturated` counts values at or beyond the fp16
+        limit: with passes == 2 the encode clamps there, i.e. the value the reference's fp32 holds was lost."""
+        out = torch.zeros(len(self.maps), 4, dtype=torch.int64, device=self.device)
+        st = L.stream_ptr()
+        for i, m in enumerate(self.maps):
+            L.check(self.lib.iou_range_stats(m.ptr, m.rows, m.c, self.fmt, out[i].data_ptr(), st))
+        rows = out.cpu()
+        rep = []
+        for i, m in enumerate(self.maps):
+            mx = torch.tensor([int(rows[i, 0]) & 0xffffffff], dtype=torch.int64).to(torch.int32).view(torch.float32).item()
+            rep.append(dict(label=getattr(m, "label", None) or "map%d" % i, max_abs=mx, saturated=int(rows[i, 1]),
+                            above_448=int(rows[i, 2]), nonzero=int(rows[i, 3]), elements=m.rows * m.c))
+        return rep
 
     def __del__(self):
         try:

@@ -232,3 +232,97 @@ def test_group_norm_and_relu_phase_split(relu):
         # the clamped entries are all-zero bytes (what a conv epilogue would have written for relu(x) = 0)
         neg = (b.cpu() < 0)
         assert bool(neg.any())
+
+
+# ------------------------------------------------------------------------------------------------
+# Dynamic range of the fp16 + e4m3 format outside synthetic weights (trained-checkpoint-like activation ranges)
+def _conv_chain(scale, n_layers=2, cin=64, hw=(20, 28)):
+    """x -> conv3x3 -> relu -> conv3x3, activations scaled by `scale`; returns (gpu maps, torch-CPU fp32 maps, engine)."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, cin, *hw, generator=g) * scale
+    ws = [torch.randn(cin, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5 for _ in range(n_layers)]
+    eng = E.Engine(DEV, passes=2)
+    m = eng.pack_input(x.to(DEV))
+    outs, refs, r = [], [], x
+    for i, w in enumerate(ws):
+        m = eng.conv("c%d" % i, [m], E.TAPS_3X3, E.pack_weight(w, cin), cin, cin, relu=(i + 1 < n_layers))
+        outs.append(eng.unpack_output(m))
+        r = F.conv2d(r, w, padding=1)
+        if i + 1 < n_layers:
+            r = F.relu(r)
+        refs.append(r)
+    eng.run()
+    torch.cuda.synchronize()
+    return [o.cpu() for o in outs], refs, eng
+
+
+def test_range_above_448_degrades_to_fp16_precision_and_stays_finite():
+    """|v| > 448: the e4m3 parts saturate (split_fmt.cuh) and the element keeps fp16 precision -- never worse."""
+    outs, refs, eng = _conv_chain(scale=300.0)
+    assert refs[0].abs().max() > 448 and refs[0].abs().max() < 65504
+    for o, r in zip(outs, refs):
+        assert torch.isfinite(o).all()
+        assert rel_err(o, r) < 2.0 ** -9, rel_err(o, r)          # fp16-grade (2^-11 per element), summed over K
+    rep = {r["label"]: r for r in eng.range_report()}
+    assert rep["c0"]["above_448"] > 0 and rep["c0"]["saturated"] == 0
+    assert abs(rep["c0"]["max_abs"] - refs[0].clamp_min(0).max().item()) < 1e-2 * refs[0].max().item()
+
+
+def test_range_beyond_fp16_saturates_finite_and_is_counted():
+    """|v| > 65504: the encode clamps at the fp16 limit (no inf, so no NaN downstream) and iou_range_stats counts it."""
+    outs, refs, eng = _conv_chain(scale=3.0e4)
+    assert refs[0].abs().max() > 65504
+    for o in outs:
+        assert torch.isfinite(o).all()
+    assert outs[0].max().item() <= 65505.0
+    rep = {r["label"]: r for r in eng.range_report()}
+    assert rep["c0"]["saturated"] == int((F.relu(refs[0]) >= 65504).sum())
+
+
+def test_range_tiny_activations_keep_absolute_precision():
+    """|v| < 2^-5: the e4m3 residual goes subnormal, absolute error 2^-21 per stored element."""
+    outs, refs, _ = _conv_chain(scale=2.0e-3)
+    assert refs[-1].abs().max() < 2.0 ** -5
+    for o, r in zip(outs, refs):
+        assert (o - r).abs().max().item() < 2e-6, (o - r).abs().max().item()
+
+
+def test_detector_unnormalised_input_range_guard():
+    """Un-normalised input (pixel scale, as a caffe-style checkpoint sees it) pushes activations past 448; a wild input
+    scale pushes them past the fp16 limit: the first batch of the plan raises instead of clamping silently, and
+    detector.passes = 3 (fp32 exponent range) still matches the oracle."""
+    from oracle import model as om
+    det, cfg = U.small_detector()
+    sd = {k: v.clone() for k, v in det.state_dict().items()}
+    det = det.to(DEV)
+    g = torch.Generator().manual_seed(3)
+    base = torch.randn(1, 3, 128, 160, generator=g)
+    metas = [dict(ori_shape=(128, 157, 3), img_shape=(128, 157, 3), pad_shape=(128, 160, 3), scale_factor=1.0, flip=False)]
+    # (a) pixel-scale input: some maps exceed 448, none the fp16 limit -> runs, the report says so, logits stay close
+    img = base * 58.0
+    det.use_cuda_graph = False
+    det.detect_device(img.to(DEV), metas, rescale=False)
+    plan = det.fused_plan(img.shape, DEV, False)
+    assert plan.range is not None and sum(r["above_448"] for r in plan.range) > 0
+    assert sum(r["saturated"] for r in plan.range) == 0
+    ref_cls, ref_reg, ref_iou = om.detector_forward(sd, img)
+    for mine, ref in ((plan.outs[0], ref_cls), (plan.outs[1], ref_reg), (plan.outs[2], ref_iou)):
+        for a, b in zip(mine, ref):
+            assert torch.isfinite(a).all()
+            assert rel_err(a.cpu(), b) < 2e-3, rel_err(a.cpu(), b)          # fp16-grade on the saturated elements
+    # (b) a wild scale: beyond the fp16 limit -> loud
+    wild = base * 3.0e5
+    with pytest.raises(RuntimeError, match="65504"):
+        det.detect_device(wild.to(DEV), metas, rescale=False)
+    # ... unless the caller accepts the clamping: finite, no NaN
+    det.range_check = False
+    det._fused.clear()
+    d, l, c = det.detect_device(wild.to(DEV), metas, rescale=False)
+    assert torch.isfinite(d).all()
+    # (c) passes = 3 holds the fp32 exponent range
+    det.passes = 3
+    det.detect_device(wild.to(DEV), metas, rescale=False)
+    plan3 = det.fused_plan(wild.shape, DEV, False)
+    ref_cls, _, _ = om.detector_forward(sd, wild)
+    for a, b in zip(plan3.outs[0], ref_cls):
+        assert rel_err(a.cpu(), b) < 5e-4, rel_err(a.cpu(), b)
