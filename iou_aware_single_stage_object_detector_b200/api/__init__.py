@@ -18,4 +18,5 @@ from .iou_aware_fcos_head import IoUawareFCOSHead
 from .detectors import BaseDetector, SingleStageDetector, RetinaNet, FCOS, FusedPlan
 from .ops import (nms, soft_nms, sigmoid_focal_loss, SigmoidFocalLoss, nms_cuda, nms_cpu, soft_nms_cpu,
                   sigmoid_focal_loss_cuda)
+from .datasets import BboxTransform, DataContainer, bbox_flip, prepare_test_img, to_tensor
 from .engine_cache import invalidate_plans

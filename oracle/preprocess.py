@@ -9,8 +9,11 @@ which is absent from /root/reference; its published algorithm is restated here:
   imflip(img): horizontal flip;  impad_to_multiple(img, d): zero-pad bottom/right to multiples of d
 The resize is OpenCV's: ``resize_linear_u8`` restates the 8-bit fixed-point bilinear path of imgproc/resize.cpp
 and IS PINNED -- bit-identical to ``cv2.resize`` (opencv 4.13 in this image) on the goldens of
-tests/golden/resize_cv2.npz and on random sizes (tests/test_oracle_golden.py).  The normalise / flip / pad steps
-are float32 numpy one-liners of mmcv; mmcv itself cannot be run here, so those stay "parity unpinned".
+tests/golden/resize_cv2.npz and on random sizes (tests/test_oracle_golden.py).  The normalise / flip / pad steps and
+the whole call sequence are pinned by tests/golden/test_items.npz: the reference's OWN ImageTransform.__call__ and
+CustomDataset.prepare_test_img run in the build container on mmcv 0.2.8's image functions restated on cv2 / numpy
+(oracle/ref_shim._install_mmcv_image -- mmcv itself is absent), and image_transform_rescaled equals those items bit
+for bit.
 """
 import numpy as np
 

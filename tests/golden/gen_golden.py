@@ -119,6 +119,7 @@ def main():
         print(name, {k: v.shape for k, v in out.items() if k.startswith("dets")})
     gen_plain_retina()
     gen_boundary()
+    gen_test_items()
     gen_soft_nms()
     gen_results_json()
     gen_fcos()
@@ -142,6 +143,41 @@ def gen_boundary():
         out["mc_%s_dets" % name], out["mc_%s_labels" % name] = d.numpy(), l.numpy()
     np.savez_compressed(os.path.join(HERE, "boundary_ops.npz"), **out)
     print("boundary", {k: v.shape for k, v in out.items()})
+
+
+def gen_test_items():
+    """the reference's OWN ImageTransform.__call__ (datasets/transforms.py:31-50), BboxTransform
+    (:68-104) and CustomDataset.prepare_test_img (custom.py:283-359, incl. the fork's gt_bboxes / gt_labels) on
+    synthetic frames.  mmcv is absent from the reference tree: the shim restates its 0.2.8 image functions on cv2 /
+    numpy (oracle/ref_shim._install_mmcv_image), the call sequence and the item layout are the reference's code."""
+    ref_shim.load_reference()
+    from mmdet.datasets.custom import CustomDataset
+    from mmdet.datasets.transforms import ImageTransform, BboxTransform
+    from gen_golden_fixtures import test_item_cases, IMG_NORM
+    out = {}
+    for name, c in test_item_cases().items():
+        ds = object.__new__(CustomDataset)          # no annotation file: fill in what prepare_test_img reads
+        ds.img_infos, ds.img_prefix, ds.proposals = [c["img_info"]], "/synthetic", None
+        ds.img_scales, ds.flip_ratio, ds.resize_keep_ratio = c["img_scales"], c["flip_ratio"], c["resize_keep_ratio"]
+        ds.img_transform = ImageTransform(size_divisor=32, **IMG_NORM)
+        ds.bbox_transform = BboxTransform()
+        ds.get_ann_info = lambda idx, a=c["ann"]: a
+        ref_shim.IMREAD_REGISTRY["/synthetic/" + c["img_info"]["filename"]] = c["frame"]
+        item = ds.prepare_test_img(0)
+        assert sorted(item.keys()) == ["gt_bboxes", "gt_labels", "img", "img_meta"]
+        out[name + "_n_img"] = np.int64(len(item["img"]))
+        out[name + "_n_gt"] = np.int64(len(item["gt_bboxes"]))
+        for i, (im, meta) in enumerate(zip(item["img"], item["img_meta"])):
+            m = meta.data
+            assert meta.cpu_only and not meta.stack
+            out["%s_img_%d" % (name, i)] = im.numpy()
+            out["%s_meta_%d" % (name, i)] = np.array(list(m["ori_shape"]) + list(m["img_shape"]) + list(m["pad_shape"]) +
+                                                     [int(m["flip"])], dtype=np.int64)
+            out["%s_sf_%d" % (name, i)] = np.asarray(m["scale_factor"], dtype=np.float64).reshape(-1)
+        for i, (gb, gl) in enumerate(zip(item["gt_bboxes"], item["gt_labels"])):
+            out["%s_gtb_%d" % (name, i)], out["%s_gtl_%d" % (name, i)] = gb.data.numpy(), gl.data.numpy()
+    np.savez_compressed(os.path.join(HERE, "test_items.npz"), **out)
+    print("test items", {k: v.shape for k, v in out.items() if "_img_" in k})
 
 
 def gen_soft_nms():
@@ -281,6 +317,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--results-only" in sys.argv:
         gen_results_json()
+        sys.exit(0)
+    if "--items-only" in sys.argv:
+        gen_test_items()
         sys.exit(0)
     if "--boundary-only" in sys.argv:
         gen_boundary()

@@ -239,7 +239,7 @@ def test_group_norm_and_relu_phase_split(relu):
 def _conv_chain(scale, n_layers=2, cin=64, hw=(20, 28)):
     """x -> conv3x3 -> relu -> conv3x3, activations scaled by `scale`; returns (gpu maps, torch-CPU fp32 maps, engine)."""
     g = torch.Generator().manual_seed(5)
-    x = torch.randn(2, cin, *hw, generator=g) * scale
+    x = (torch.randn(2, cin, *hw, generator=g) * scale).clamp(-65504.0, 65504.0)     # the input pack clamps too
     ws = [torch.randn(cin, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5 for _ in range(n_layers)]
     eng = E.Engine(DEV, passes=2)
     m = eng.pack_input(x.to(DEV))
@@ -276,7 +276,8 @@ def test_range_beyond_fp16_saturates_finite_and_is_counted():
         assert torch.isfinite(o).all()
     assert outs[0].max().item() <= 65505.0
     rep = {r["label"]: r for r in eng.range_report()}
-    assert rep["c0"]["saturated"] == int((F.relu(refs[0]) >= 65504).sum())
+    lo, hi = int((refs[0] >= 65504 * 1.001).sum()), int((refs[0] >= 65504 * 0.999).sum())
+    assert lo > 0 and lo <= rep["c0"]["saturated"] <= hi, (lo, rep["c0"]["saturated"], hi)
 
 
 def test_range_tiny_activations_keep_absolute_precision():

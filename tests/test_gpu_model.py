@@ -389,3 +389,37 @@ def test_fcos_detector_end_to_end_small():
         assert abs(len(d_my) - d_ref.shape[0]) <= 3 and d_ref.shape[0] > 0
         U.match_as_sets(d_my, l_my, d_ref.numpy(), l_ref.numpy(), min_frac=0.97, score_tol=1e-4,
                         box_tol=1e-4 * max(h, w))
+
+
+def test_prepare_test_img_item_layout_vs_reference_golden():
+    """prepare_test_img == the reference's CustomDataset.prepare_test_img (custom.py:283-359) on the same frames:
+    entry order (scale-major, flipped twin second), the fork's gt_bboxes / gt_labels lists, img_meta fields, and every
+    image bit for bit (rescale + normalise + flip + pad + CHW in one device kernel)."""
+    from gen_golden_fixtures import test_item_cases, IMG_NORM
+    gold = np.load(os.path.join(U.GOLD, "test_items.npz"))
+    tf = P.ImageTransform(size_divisor=32, **IMG_NORM)
+    for name, c in test_item_cases().items():
+        item = P.prepare_test_img(c["frame"], c["img_info"], c["ann"], tf, P.BboxTransform(), c["img_scales"],
+                                  c["flip_ratio"], c["resize_keep_ratio"], device=DEV)
+        assert sorted(item.keys()) == ["gt_bboxes", "gt_labels", "img", "img_meta"]
+        assert len(item["img"]) == len(item["img_meta"]) == int(gold[name + "_n_img"])
+        assert len(item["gt_bboxes"]) == len(item["gt_labels"]) == int(gold[name + "_n_gt"])
+        for i, (im, meta) in enumerate(zip(item["img"], item["img_meta"])):
+            assert meta.cpu_only and not meta.stack
+            m = meta.data
+            assert np.array_equal(im.cpu().numpy(), gold["%s_img_%d" % (name, i)]), (name, i)
+            want = gold["%s_meta_%d" % (name, i)]
+            assert list(m["ori_shape"]) + list(m["img_shape"]) + list(m["pad_shape"]) + [int(m["flip"])] == want.tolist()
+            assert np.array_equal(np.asarray(m["scale_factor"], dtype=np.float64).reshape(-1), gold["%s_sf_%d" % (name, i)])
+        for i, (gb, gl) in enumerate(zip(item["gt_bboxes"], item["gt_labels"])):
+            assert np.array_equal(gb.data.numpy(), gold["%s_gtb_%d" % (name, i)])
+            assert np.array_equal(gl.data.numpy(), gold["%s_gtl_%d" % (name, i)])
+    # the item feeds forward_test unchanged (base.py:62-103): one image per call, gt lists forwarded
+    det, cfg = U.small_detector()
+    det = det.to(DEV)
+    c = test_item_cases()["single_scale"]
+    item = P.prepare_test_img(c["frame"], c["img_info"], c["ann"], tf, None, c["img_scales"], 0, True, device=DEV)
+    res = det(return_loss=False, rescale=True, img=[t.unsqueeze(0) for t in item["img"]],
+              img_meta=[[m.data] for m in item["img_meta"]], gt_bboxes=[[g.data] for g in item["gt_bboxes"]],
+              gt_labels=[[g.data] for g in item["gt_labels"]])
+    assert len(res) == 80 and all(r.shape[1] == 5 for r in res)

@@ -232,3 +232,32 @@ def test_resize_oracle_matches_cv2_golden():
     assert OP.rescale_size(100, 200, 0.5)[:2] == (50, 100)
     nh, nw, f = OP.rescale_size(100, 200, (300, 150), keep_ratio=False)
     assert (nh, nw) == (150, 300) and np.allclose(f, [1.5, 1.5, 1.5, 1.5])
+
+
+# ------------------------------------------------------------------ test items
+def test_image_transform_oracle_and_bbox_transform_vs_reference_items():
+    """tests/golden/test_items.npz was written by the reference's own ImageTransform / BboxTransform /
+    CustomDataset.prepare_test_img (mmcv 0.2.8's image functions restated in the shim on cv2 / numpy): the oracle's
+    image_transform_rescaled reproduces every image bit for bit (normalise / flip / pad are thereby pinned), and the
+    host-side BboxTransform of this repo reproduces the gt boxes."""
+    from oracle import preprocess as OP
+    from gen_golden_fixtures import test_item_cases, IMG_NORM
+    import iou_aware_single_stage_object_detector_b200 as P
+    gold = np.load(os.path.join(G, "test_items.npz"))
+    for name, c in test_item_cases().items():
+        i = 0
+        boxes = c["ann"]["bboxes"]
+        for s_i, scale in enumerate(c["img_scales"]):
+            for flip in ([False, True] if c["flip_ratio"] > 0 else [False]):
+                chw, img_shape, pad_shape, factor = OP.image_transform_rescaled(
+                    c["frame"], scale, IMG_NORM["mean"], IMG_NORM["std"], IMG_NORM["to_rgb"], 32, flip,
+                    c["resize_keep_ratio"])
+                assert np.array_equal(chw, gold["%s_img_%d" % (name, i)]), (name, i)
+                meta = gold["%s_meta_%d" % (name, i)]
+                assert tuple(meta[3:6]) == tuple(img_shape) and tuple(meta[6:9]) == tuple(pad_shape) and bool(meta[9]) == flip
+                assert np.allclose(np.asarray(factor, dtype=np.float64).reshape(-1), gold["%s_sf_%d" % (name, i)], rtol=0, atol=0)
+                if not flip:
+                    boxes = P.BboxTransform()(boxes, img_shape, factor, flip=False)
+                    assert np.array_equal(boxes, gold["%s_gtb_%d" % (name, s_i)]), (name, s_i)
+                i += 1
+        assert i == int(gold[name + "_n_img"]) and len(c["img_scales"]) == int(gold[name + "_n_gt"])
