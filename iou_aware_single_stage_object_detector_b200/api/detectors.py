@@ -10,6 +10,7 @@ import torch
 import torch.nn as nn
 
 from .. import engine as E
+from .. import dist as D
 from .. import postproc as PP
 from . import builder
 from .engine_cache import PlanCache, cuda_state_dict, param_stamp, require_cuda
@@ -232,6 +233,7 @@ class SingleStageDetector(BaseDetector):
             compute = [main, torch.cuda.Stream(device) if depth == 2 else main]
             stage, ready, consumed = [None, None], [None, None], [None, None]
             host, pending = [None, None], None      # pinned result buffers per slot; (slot, event) not yet yielded
+            busy = [None, None]                     # event behind the side-stream work that still reads a plan's outputs
             if depth == 2:
                 start = torch.cuda.Event()
                 start.record(main)
@@ -249,21 +251,21 @@ class SingleStageDetector(BaseDetector):
                     ev.record(copy_stream)
                 ready[slot] = (ev, metas)
 
-            def read_back(slot, tensors, stream):
-                """Async device->host copy of this batch's results into the slot's pinned buffers (enqueued on
-                the slot's stream BEFORE its next launches overwrite the plan's output tensors)."""
-                if host[slot] is None or any(hb.shape != t.shape for hb, t in zip(host[slot], tensors)):
-                    host[slot] = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in tensors]
-                for hb, t in zip(host[slot], tensors):
-                    hb.copy_(t, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(stream)
-                return ev
+            def read_back(slot, packed, stream, ranks):
+                """Async device->host copy of this batch's PACKED results (dets | labels | counts of every rank in one
+                buffer) into the slot's pinned buffer, enqueued on `stream` before anything overwrites the source."""
+                if host[slot] is None or host[slot].numel() != packed.numel():
+                    host[slot] = torch.empty(packed.numel(), dtype=torch.uint8, pin_memory=True)
+                with torch.cuda.stream(stream):
+                    host[slot].copy_(packed, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(stream)
+                return ev, ranks
 
             def hand_out(p):
-                pslot, pev = p
+                pslot, (pev, ranks), (b_, k_) = p
                 pev.synchronize()
-                return tuple(hb.clone() for hb in host[pslot])
+                return tuple(t.clone() for t in D.unpack_gathered(host[pslot], ranks, b_, k_))
 
             nxt = next(it, None)
             if nxt is None:
@@ -291,14 +293,32 @@ class SingleStageDetector(BaseDetector):
                     done.record(cs)
                     consumed[slot] = done
                     plan.img_info.copy_(PP.make_img_info(metas, "cpu"), non_blocking=True)
+                    if busy[slot] is not None:
+                        cs.wait_event(busy[slot])            # the gather / read-back of this plan's previous batch
                     dets, labels, counts = plan.run()
-                    if gather is not None:
-                        dets, labels, counts = gather(dets, labels, counts)
-                    rb_ev = read_back(slot, (dets, labels, counts), cs)
+                    shape = (dets.shape[0], dets.shape[1])
+                    if isinstance(gather, D.PackedGather):
+                        # one all-gather of the packed results on the gather's SIDE stream, read-back behind it; this
+                        # compute stream goes straight on to the next batch
+                        buf, gdone = gather(plan.wsp.packed)
+                        rb = read_back(slot, buf, gather.stream, gather.world)
+                        busy[slot] = rb[0]
+                    elif gather is not None:                 # legacy callable on (dets, labels, counts)
+                        gd, gl, gc = gather(dets, labels, counts)
+                        ranks = gd.shape[0] // dets.shape[0]
+                        tmp = torch.empty(ranks * plan.wsp.packed.numel(), dtype=torch.uint8, device=device)
+                        for r in range(ranks):
+                            pv = D.packed_views(tmp[r * plan.wsp.packed.numel():], *shape)
+                            b0 = r * shape[0]
+                            pv[0].copy_(gd[b0:b0 + shape[0]]); pv[1].copy_(gl[b0:b0 + shape[0]]); pv[2].copy_(gc[b0:b0 + shape[0]])
+                        rb = read_back(slot, tmp, cs, ranks)
+                    else:
+                        rb = read_back(slot, plan.wsp.packed, cs, 1)
+                    rb_ev = (rb, shape)
                 # the previous batch is handed out only now, after this batch's launches are queued
                 if pending is not None:
                     yield hand_out(pending)
-                pending = (slot, rb_ev)
+                pending = (slot, rb_ev[0], rb_ev[1])
                 if nxt is None:
                     yield hand_out(pending)
                     if depth == 2:                                   # later work on the caller's stream comes after

@@ -80,9 +80,11 @@ class PostprocWorkspace(object):
             L.check(-1)
         self.ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
         self.ws_bytes = nbytes
-        self.dets = torch.zeros(n_img, cfg.max_per_img, 5, dtype=torch.float32, device=device)
-        self.labels = torch.zeros(n_img, cfg.max_per_img, dtype=torch.int64, device=device)
-        self.counts = torch.zeros(n_img, dtype=torch.int32, device=device)
+        # dets | labels | counts live in ONE byte buffer: a step's results leave the GPU as one all-gather / one
+        # device->host copy with no pack or cast kernels (dist.PackedGather, detect_stream)
+        from .dist import packed_layout, packed_views
+        self.packed = torch.zeros(packed_layout(n_img, cfg.max_per_img)[3], dtype=torch.uint8, device=device)
+        self.dets, self.labels, self.counts = packed_views(self.packed, n_img, cfg.max_per_img)
 
 
 def get_bboxes_device(wsp, cls_list, reg_list, iou_list, img_info, rescale):
