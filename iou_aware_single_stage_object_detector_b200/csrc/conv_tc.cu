@@ -94,6 +94,7 @@ struct ConvParams {
   int f8;                    // passes == 2: fp16 main pass + e4m3 correction pass (split_fmt.cuh); `scale` = 1 / S_n
   int num_acc;               // TMEM accumulator stages (2)
   int corr_off;              // f8, narrow tiles: the e4m3 MMAs accumulate into a second column block at this offset (0: same block)
+  int pdl;                   // programmatic dependent launch: prologue overlaps the previous kernel's tail (griddepcontrol)
 };
 
 // ------------------------------------------------------------------------------------ PTX
@@ -246,6 +247,10 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// Programmatic dependent launch (PDL): `launch_dependents` lets the NEXT kernel of the stream start its prologue on SMs
+// this grid has already left; `wait` blocks until the PREVIOUS grid has completed and its writes are visible.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
@@ -332,6 +337,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (P.pdl) griddep_launch_dependents();      // every CTA of this (persistent) grid is resident: dependents fill freed SMs
 
   const uint32_t a_lo_off = (uint32_t)P.a_rows * 128u;       // A entry: hi window | lo window
   const uint32_t b_lo_off = (uint32_t)P.b_tile_bytes;        // B entry: hi tile | lo tile
@@ -340,6 +346,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (elect_one()) {
+      if (P.pdl) griddep_wait();                 // the activations are the previous kernel's output
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       const uint32_t mult = kTwoCta ? 2u : 1u;   // pair: both CTAs' loads complete on the LEADER's barrier
@@ -492,6 +499,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
     }
   } else {
     // =============================== epilogue ===============================
+    if (P.pdl) griddep_wait();                   // residual reads (and, conservatively, every store) follow the previous grid
     const int lane_group = warp & 3;                      // TMEM lanes 32*lane_group .. +31
     const int m_local = lane_group * 32 + lane;
     const int ew = warp - 2;                               // 0..7
@@ -933,6 +941,7 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   P.phase_only = d->phase_only ? 1 : 0;
   P.ph_h = (d->seg[0].h + 1) / 2;
   P.ph_w = (d->seg[0].w + 1) / 2;
+  P.pdl = (getenv("IOU_PDL") && atoi(getenv("IOU_PDL")) != 0) ? 1 : 0;
   P.res_prefetch = getenv("IOU_RES_PREFETCH") ? atoi(getenv("IOU_RES_PREFETCH")) : 0;   // measured: no gain
   if (P.res_prefetch < 0 || P.res_prefetch > 8) P.res_prefetch = 0;
   const int nsplit = d->passes >= 2 ? 2 : 1;
@@ -1054,26 +1063,33 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
 
 extern "C" int iou_conv_run(const iou_conv_plan* plan, void* stream) {
   IOU_REQUIRE(plan != nullptr, "plan is NULL");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(plan->grid);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = plan->smem_bytes;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
   if (plan->params.two_cta) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(plan->grid);
-    cfg.blockDim = dim3(kNumThreads);
-    cfg.dynamicSmemBytes = plan->smem_bytes;
-    cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = plan->params.f8 ? cudaLaunchKernelEx(&cfg, conv_tap_gemm_kernel<true, true>, plan->params)
-                                    : cudaLaunchKernelEx(&cfg, conv_tap_gemm_kernel<true, false>, plan->params);
-    if (e != cudaSuccess) return fail(IOU_ERR_CUDA, "conv_tap_gemm_kernel<pair> launch failed: %s", cudaGetErrorString(e));
-    return IOU_OK;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
   }
-  if (plan->params.f8)
-    conv_tap_gemm_kernel<false, true><<<plan->grid, kNumThreads, plan->smem_bytes, (cudaStream_t)stream>>>(plan->params);
+  if (plan->params.pdl) {        // may start while the previous kernel of the stream drains (it waits in griddepcontrol.wait)
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  cudaError_t e;
+  if (plan->params.two_cta)
+    e = plan->params.f8 ? cudaLaunchKernelEx(&cfg, conv_tap_gemm_kernel<true, true>, plan->params)
+                        : cudaLaunchKernelEx(&cfg, conv_tap_gemm_kernel<true, false>, plan->params);
   else
-    conv_tap_gemm_kernel<false, false><<<plan->grid, kNumThreads, plan->smem_bytes, (cudaStream_t)stream>>>(plan->params);
-  return launch_status("conv_tap_gemm_kernel");
+    e = plan->params.f8 ? cudaLaunchKernelEx(&cfg, conv_tap_gemm_kernel<false, true>, plan->params)
+                        : cudaLaunchKernelEx(&cfg, conv_tap_gemm_kernel<false, false>, plan->params);
+  if (e != cudaSuccess) return fail(IOU_ERR_CUDA, "conv_tap_gemm_kernel launch failed: %s", cudaGetErrorString(e));
+  return IOU_OK;
 }
 
 extern "C" void iou_conv_plan_destroy(iou_conv_plan* plan) { delete plan; }

@@ -118,8 +118,16 @@ def test_multiclass_nms_options_vs_reference_golden(name):
                             None if fac is None else torch.from_numpy(fac).cuda())
     gd, gl = gold["mc_%s_dets" % name], gold["mc_%s_labels" % name]
     assert d.shape == gd.shape and l.dtype == torch.int64
-    assert np.array_equal(l.cpu().numpy(), gl)
-    assert np.array_equal(d.cpu().numpy(), gd)
+    d, l = d.cpu().numpy(), l.cpu().numpy()
+    assert np.array_equal(d[:, 4], gd[:, 4])                  # the score order itself is exact
+    # rows with EQUAL scores come out of torch.sort (not stable, :58) in an unspecified order: compare those as sets
+
+    def canon(dd, ll):
+        o = np.lexsort((dd[:, 0], dd[:, 1], ll, -dd[:, 4].astype(np.float64)))
+        return dd[o], ll[o]
+    (d, l), (gd, gl) = canon(d, l), canon(gd, gl)
+    assert np.array_equal(l, gl)
+    assert np.array_equal(d, gd)
 
 
 def test_topk_with_exact_ties_is_deterministic():
