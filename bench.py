@@ -158,11 +158,12 @@ def run_ours(args):
     plans, main_stream = [plan], torch.cuda.current_stream()
     streams = [main_stream]
     if pipelined:
-        plan_b = det.fused_plan(img_dev.shape, dev, rescale=True, slot=1)
-        plan_b.img.copy_(img_dev)
-        plan_b.img_info.copy_(PP.make_img_info(metas, "cpu"))
-        plans.append(plan_b)
-        streams.append(torch.cuda.Stream(dev))
+        for slot in range(1, args.plans):
+            plan_b = det.fused_plan(img_dev.shape, dev, rescale=True, slot=slot)
+            plan_b.img.copy_(img_dev)
+            plan_b.img_info.copy_(PP.make_img_info(metas, "cpu"))
+            plans.append(plan_b)
+            streams.append(torch.cuda.Stream(dev))
     step_no = [0]
     # N > 1: ONE all-gather of the packed detections per step, on a side stream (dist.PackedGather): the compute
     # streams never wait for the collective, only a plan's NEXT run waits for the gather of its previous results
@@ -180,17 +181,17 @@ def run_ours(args):
                 out, busy[k] = pg(plans[k].wsp.packed)
             return out
 
-    def fork():                                   # the side stream starts after everything queued on the main one
+    def fork():                                   # the side streams start after everything queued on the main one
         if pipelined:
             ev = torch.cuda.Event()
             ev.record(main_stream)
-            streams[1].wait_event(ev)
+            for st_ in streams[1:]:
+                st_.wait_event(ev)
 
     def join():                                   # ... and the main stream ends after the side streams
         if pipelined:
-            ev = torch.cuda.Event()
-            ev.record(streams[1])
-            main_stream.wait_event(ev)
+            for st_ in streams[1:]:
+                main_stream.wait_stream(st_)
         if pg is not None:
             main_stream.wait_stream(pg.stream)
 
@@ -379,7 +380,7 @@ def run_ours(args):
                            "parallelism": "dp%d (image batch sharded, one all-gather of detections)" % world,
                            "l2": "per-step working set (~10 GB of activations) exceeds the 126 MB L2; no flush",
                            "cuda_graph": not args.no_graph,
-                           "pipeline": "2 launch plans alternating on 2 streams" if pipelined else "none"},
+                           "pipeline": "%d launch plans alternating on %d streams" % (len(plans), len(plans)) if pipelined else "none"},
                 "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h},
                 "e2e_uint8_frames": {"value": round(e2e_u8_value, 2), "unit": UNIT,
@@ -492,6 +493,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu launch lists)")
     ap.add_argument("--no-pipeline", action="store_true", help="one launch plan on one stream (no step overlap)")
+    ap.add_argument("--plans", type=int, default=2, help="launch plans alternating on as many streams (device-timed loop)")
     ap.add_argument("--ncu-range", action="store_true",
                     help="bracket the timed steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     ap.add_argument("--dump-ops", default=None, help="write the per-launch CUDA-event table to this JSON file")

@@ -148,12 +148,57 @@ class IoUawareRetinaHead(AnchorHead):
                 return PP.batched_soft_nms(wsp, boxes, scores_cm, *wsp.soft)
             return PP.get_bboxes_device(wsp, cls_scores, bbox_preds, iou_preds, img_info, rescale)
 
+    def in_kernel_envelope(self, featmap_sizes, cfg):
+        """True when the five batched kernels cover this test_cfg (the limits iou_get_bboxes checks, csrc/postproc.cu):
+        per-level top-k <= 2048, <= 6144 candidates per image, classes a multiple of 4 and <= 256,
+        classes x (max_per_img + 1) <= 8192 kept-row slots."""
+        nms_pre, k = cfg.get('nms_pre', -1), cfg['max_per_img']
+        per_level = [h * w * self.num_anchors for (h, w) in featmap_sizes]
+        m = sum(min(n, nms_pre) if nms_pre > 0 else n for n in per_level)
+        c = self.cls_out_channels
+        return (k >= 1 and (nms_pre <= 2048 or max(per_level) <= 2048) and m <= 6144 and c % 4 == 0 and c <= 256
+                and c * (k + 1) <= 8192)
+
+    def _get_bboxes_level_by_level(self, cls_scores, bbox_preds, iou_preds, img_metas, cfg, rescale):
+        """test_cfg outside the batched kernels' envelope (nms_pre <= 0 or > 2048, max_per_img in the thousands, an
+        odd class count ...): the reference's own schedule (:434-564) image by image and level by level on the device
+        -- elementwise / top-k in torch, then mmdet.ops through multiclass_nms's class-by-class path.  Same outputs;
+        none of the launch fusion."""
+        from .bbox_nms import multiclass_nms
+        from .transforms import delta2bbox
+        nms_pre = cfg.get('nms_pre', -1)
+        sizes = [tuple(t.shape[-2:]) for t in cls_scores]
+        dev = cls_scores[0].device
+        anchors = [g.grid_anchors(sz, st, device=dev) for g, sz, st in zip(self.anchor_generators, sizes, self.anchor_strides)]
+        out = []
+        for i, meta in enumerate(img_metas):
+            boxes, scores = [], []
+            for l, a in enumerate(anchors):
+                s = cls_scores[l][i].permute(1, 2, 0).reshape(-1, self.cls_out_channels).sigmoid()
+                d = bbox_preds[l][i].permute(1, 2, 0).reshape(-1, 4)
+                if iou_preds is not None:
+                    q = iou_preds[l][i].permute(1, 2, 0).reshape(-1, 1).sigmoid()
+                    s = s.pow(self.alpha) * q.pow(1 - self.alpha)
+                if nms_pre > 0 and s.shape[0] > nms_pre:
+                    top = s.max(dim=1)[0].topk(nms_pre)[1]
+                    a, d, s = a[top], d[top], s[top]
+                boxes.append(delta2bbox(a, d, self.target_means, self.target_stds, meta['img_shape']))
+                scores.append(s)
+            boxes, scores = torch.cat(boxes), torch.cat(scores)
+            if rescale:
+                boxes = boxes / boxes.new_tensor(meta['scale_factor'])
+            scores = torch.cat([scores.new_zeros(scores.shape[0], 1), scores], dim=1)     # background column
+            out.append(multiclass_nms(boxes, scores, cfg['score_thr'], cfg['nms'], cfg['max_per_img']))
+        return out
+
     def get_bboxes(self, cls_scores, bbox_preds, iou_preds, gt_bboxes, gt_labels, img_metas, cfg,
                    rescale=False):
         """Same signature/return as the reference (:390-461).  gt_* are accepted and ignored (the
         reference only feeds them to a discarded diagnostic, :517-524)."""
         for t in cls_scores:
             require_cuda(t, "IoUawareRetinaHead.get_bboxes")
+        if not self.in_kernel_envelope([tuple(t.shape[-2:]) for t in cls_scores], cfg):
+            return self._get_bboxes_level_by_level(cls_scores, bbox_preds, iou_preds, img_metas, cfg, rescale)
         dets, labels, counts = self.get_bboxes_device(cls_scores, bbox_preds, iou_preds, img_metas, cfg,
                                                       rescale)
         return [(d.clone(), l.clone()) for d, l in PP.split_results(dets, labels, counts)]

@@ -55,5 +55,7 @@ class RetinaHead(IoUawareRetinaHead):
         """Signature of this fork's AnchorHead.get_bboxes (anchor_head.py:325-362, gt_* added by WSK)."""
         for t in cls_scores:
             require_cuda(t, "RetinaHead.get_bboxes")
+        if not self.in_kernel_envelope([tuple(t.shape[-2:]) for t in cls_scores], cfg):
+            return self._get_bboxes_level_by_level(cls_scores, bbox_preds, None, img_metas, cfg, rescale)
         dets, labels, counts = self.get_bboxes_device(cls_scores, bbox_preds, img_metas, cfg, rescale)
         return [(d.clone(), l.clone()) for d, l in PP.split_results(dets, labels, counts)]

@@ -235,7 +235,7 @@ class Engine(object):
         self.op_flops = {}
         import os
         self.two_cta = os.environ.get("IOU_TWO_CTA", "1") != "0"
-        self.pair_min_bn = int(os.environ.get("IOU_PAIR_MIN_BN", "64"))
+        self.pair_min_bn = int(os.environ.get("IOU_PAIR_MIN_BN", "48"))   # 48: the reg+iou output conv as a CTA pair (-28 %)
         self.pair_min_tiles = int(os.environ.get("IOU_PAIR_MIN_TILES", "32"))
         self.stem_vertical = os.environ.get("IOU_STEM_VERTICAL", "1") != "0"
         self.res_bn256 = os.environ.get("IOU_RES_BN256", "1") != "0"        # N = 256 tiles for residual convs in pair mode
@@ -431,6 +431,7 @@ class Engine(object):
         outs = []
         fuse = os.environ.get("IOU_FUSE_PHASE", "1") != "0"     # producers write the stride-2 phase maps themselves
         fuse_ds = os.environ.get("IOU_FUSE_DS", "1") != "0"     # conv3 + downsample of a stage's first block in one GEMM
+        fuse_ph3 = os.environ.get("IOU_FUSE_PH3", "1") != "0"   # a stage's last conv3 also writes phase (1,1) of its output
         x_ph3 = None                                            # phase (1,1) of x, if its producer wrote it
         for s, nblocks in enumerate(STAGE_BLOCKS[depth]):
             planes = 64 * 2 ** s
@@ -473,7 +474,7 @@ class Engine(object):
                 idt = x
                 sc3, sh3 = bn_fold(sd, p + "bn3")
                 ph3 = None
-                if fuse and b == nblocks - 1 and s + 1 < len(STAGE_BLOCKS[depth]):
+                if fuse and fuse_ph3 and b == nblocks - 1 and s + 1 < len(STAGE_BLOCKS[depth]):
                     # the next stage's first block reads phase (1,1) of this block's output (stride-2 1x1 convs)
                     _, n_, h_, w_ = t2.segs[0]
                     ph3 = self.new_phase_maps(n_, h_, w_, planes * 4, mask=8)

@@ -130,6 +130,32 @@ def test_multiclass_nms_options_vs_reference_golden(name):
     assert np.array_equal(d, gd)
 
 
+def test_get_bboxes_outside_the_kernel_envelope_vs_oracle():
+    """test_cfg beyond the batched kernels (nms_pre > 2048, classes x (max_per_img + 1) > 8192): get_bboxes still
+    answers, through the reference's own level-by-level / class-by-class schedule on the device."""
+    case = cases.postproc_case("small")
+    head = U.get_head()
+    cfgd = dict(case["cfg"])
+    cfgd.update(nms_pre=2500, max_per_img=150)
+    cfg = P.ConfigDict(cfgd)
+    sizes = [tuple(t.shape[-2:]) for t in case["cls"]]
+    assert head.in_kernel_envelope(sizes, P.ConfigDict(case["cfg"])) and not head.in_kernel_envelope(sizes, cfg)
+    dev = torch.device("cuda:0")
+    cls, reg, iou = [[t.to(dev) for t in ts] for ts in (case["cls"], case["reg"], case["iou"])]
+    n_img = cls[0].shape[0]
+    res = head.get_bboxes(cls, reg, iou, [None] * n_img, [None] * n_img, case["img_metas"], cfg, rescale=True)
+    bases = U.oracle_bases()
+    for i, (d, l) in enumerate(res):
+        m = case["img_metas"][i]
+        d_ref, l_ref = op.get_bboxes_single([c[i] for c in case["cls"]], [r[i] for r in case["reg"]],
+                                            [q[i] for q in case["iou"]], cases.STRIDES, bases, m["img_shape"],
+                                            m["scale_factor"], cfgd, rescale=True)
+        assert d.shape[0] == d_ref.shape[0] == 150 and l.dtype == torch.int64
+        frac, ms, mb = U.match_as_sets(d.cpu().numpy(), l.cpu().numpy(), d_ref.numpy(), l_ref.numpy(), min_frac=1.0,
+                                       score_tol=1e-5, box_tol=1e-3)
+        assert frac == 1.0
+
+
 def test_topk_with_exact_ties_is_deterministic():
     """Many identical max scores at the top-k boundary: lowest anchor indices win (documented rule)."""
     case = cases.postproc_case("small")
