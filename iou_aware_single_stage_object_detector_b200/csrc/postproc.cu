@@ -29,6 +29,7 @@ struct PostParams {
   long long group_off[IOU_MAX_LEVELS + 1];  // K1 work prefix (only top-k levels have width)
   int num_topk_levels;
   int topk_level[IOU_MAX_LEVELS];
+  int topk_slot[IOU_MAX_LEVELS];     // inverse of topk_level (-1: the level keeps all its anchors)
   const float* cls[IOU_MAX_LEVELS];
   const float* reg[IOU_MAX_LEVELS];
   const float* iou[IOU_MAX_LEVELS];
@@ -56,11 +57,20 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   return r;
 }
 
+// Monotone bucket of a fused score (scores live in [0, 1]): b(s1) > b(s2) implies s1 > s2, so the per-level top-k is
+// "every anchor in a bucket above the boundary bucket + the best of the boundary bucket" (topk_hist_kernel).
+#define TOPK_BINS 4096
+__device__ __forceinline__ int score_bucket(float s) {
+  return (int)fminf(fmaxf(s * (float)TOPK_BINS, 0.0f), (float)(TOPK_BINS - 1));
+}
+
 // ---------------------------------------------------------------------------------------- K1
 // One warp per group of 32 consecutive anchors (32*C contiguous floats): coalesced 16-byte
-// streaming loads, per-slot max staged in shared memory, then lane a reduces anchor a.
+// streaming loads, per-slot max staged in shared memory, then lane a reduces anchor a.  The same pass builds the
+// per-(image, level) histogram of score buckets that the top-k selection starts from (warp-aggregated atomics).
 __global__ void __launch_bounds__(256) max_score_kernel(const __grid_constant__ PostParams P,
-                                                        float* __restrict__ maxscore) {
+                                                        float* __restrict__ maxscore,
+                                                        unsigned int* __restrict__ hist) {
   extern __shared__ float smem_f[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Q = P.C >> 2;
@@ -83,12 +93,18 @@ __global__ void __launch_bounds__(256) max_score_kernel(const __grid_constant__ 
       sm[f] = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
     }
     __syncwarp();
+    int bucket = TOPK_BINS + lane;                       // idle lanes: a bucket of their own
     if (lane < v) {
       float m = -INFINITY;
       for (int t = 0; t < Q; ++t) m = fmaxf(m, sm[lane * Q + t]);
       const float q = P.iou[l] ? __ldg(P.iou[l] + (size_t)img * n_l + a0 + lane) : 0.f;
-      maxscore[(size_t)img * P.A_total + P.anchor_off[l] + a0 + lane] = fuse_score(m, q, P.alpha);
+      const float sc = fuse_score(m, q, P.alpha);
+      maxscore[(size_t)img * P.A_total + P.anchor_off[l] + a0 + lane] = sc;
+      bucket = score_bucket(sc);
     }
+    const unsigned int peers = __match_any_sync(0xffffffffu, bucket);
+    if (lane < v && (__ffs(peers) - 1) == lane)
+      atomicAdd(hist + ((size_t)img * P.num_topk_levels + P.topk_slot[l]) * TOPK_BINS + bucket, (unsigned int)__popc(peers));
     __syncwarp();
   }
 }
@@ -118,21 +134,17 @@ __device__ __forceinline__ int next_pow2(int x) {
   return p;
 }
 
-// ---------------------------------------------------------------------------------------- K2
-// torch.topk(max_scores, nms_pre) (iou_aware_retina_head.py:544): exact k-th key by 4x8-bit
-// radix select, then the selected set is ordered by (score desc, index asc).
+// torch.topk(max_scores, nms_pre) (iou_aware_retina_head.py:544): the selected set is ordered by (score desc, index asc).
 #define TOPK_MAX 2048
-__global__ void __launch_bounds__(1024) topk_kernel(const __grid_constant__ PostParams P,
-                                                    const float* __restrict__ maxscore,
-                                                    int32_t* __restrict__ cand_idx) {
-  __shared__ unsigned long long sortbuf[TOPK_MAX];
+// Exact radix select over all n keys of one (image, level), one CTA of 1024 threads: the path for score distributions
+// the bucket histogram cannot split (e.g. the reference init, where every score is 0.07098 +- 2e-5).
+__device__ void topk_radix_select(const float* __restrict__ keys, const int n, const int k,
+                                  unsigned long long* sortbuf /* [TOPK_MAX] shared */, int32_t* __restrict__ out) {
   __shared__ unsigned int hist[256];
   __shared__ unsigned int s_prefix, s_mask, s_kleft, s_cnt, s_eq_total, s_eq_run;
   __shared__ unsigned int warp_eq[32];
-  const int l = P.topk_level[blockIdx.x], img = blockIdx.y;
-  const int n = P.n_anchor[l], k = P.keep[l];
-  const float* keys = maxscore + (size_t)img * P.A_total + P.anchor_off[l];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __syncthreads();
   if (tid == 0) { s_prefix = 0; s_mask = 0; s_kleft = k; s_cnt = 0; s_eq_run = 0; }
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = 24 - 8 * pass;
@@ -211,141 +223,85 @@ __global__ void __launch_bounds__(1024) topk_kernel(const __grid_constant__ Post
   const int Psort = next_pow2(k);
   for (int i = k + tid; i < Psort; i += 1024) sortbuf[i] = 0ull;
   bitonic_sort_desc(sortbuf, Psort);
-  int32_t* out = cand_idx + (size_t)img * P.M + P.cand_off[l];
   for (int r = tid; r < k; r += 1024)
     out[r] = (int32_t)(0xffffffffu - (unsigned int)(sortbuf[r] & 0xffffffffull));
 }
 
-// ---------------------------------------------------------------------------------------- K2'
-// Cluster version of the top-k: 8 CTAs (one thread-block cluster) per (image, level).  Every CTA
-// loads its eighth of the keys into shared memory ONCE; the four radix-select passes then run out
-// of shared memory, with the 256-bin histograms merged across the cluster through distributed
-// shared memory.  Same result as topk_kernel (exact k-th key, ties by lowest index, output ordered
-// by score desc / index asc); topk_kernel stays as the fallback for slices that do not fit.
-#define TOPK_CLUSTER 8
-__global__ void __cluster_dims__(TOPK_CLUSTER, 1, 1) __launch_bounds__(1024)
-topk_cluster_kernel(const __grid_constant__ PostParams P, const float* __restrict__ maxscore,
-                    int32_t* __restrict__ cand_idx, unsigned long long* __restrict__ scratch) {
-  extern __shared__ __align__(16) unsigned char tk_smem[];
-  unsigned int* skeys = reinterpret_cast<unsigned int*>(tk_smem);
-  __shared__ unsigned int hist[256], tot[256];
-  __shared__ unsigned int s_prefix, s_kleft, s_eq_total, s_cnt[2], s_slot, s_eq_run, warp_eq[32];
-  cg::cluster_group cluster = cg::this_cluster();
-  const unsigned int rank = cluster.block_rank();
-  const int lslot = blockIdx.x / TOPK_CLUSTER, l = P.topk_level[lslot], img = blockIdx.y;
+// ---------------------------------------------------------------------------------------- K2
+// Per (image, level), one CTA: the bucket histogram written by max_score_kernel gives the boundary bucket tb (the
+// bucket holding the k-th best score) and the number of anchors above it; ONE pass over the level's keys collects
+// every anchor with bucket >= tb (k + a bucket's worth of keys, not n), a bitonic sort orders them by
+// (score desc, index asc) and the first k are the level's candidates -- the same set and order as an exact select.
+#define TOPK_LIST 4096
+__global__ void __launch_bounds__(1024) topk_hist_kernel(const __grid_constant__ PostParams P,
+                                                         const float* __restrict__ maxscore,
+                                                         const unsigned int* __restrict__ hist,
+                                                         int32_t* __restrict__ cand_idx) {
+  __shared__ unsigned long long list[TOPK_LIST];
+  __shared__ unsigned int warp_sum[32];
+  __shared__ int s_tb;
+  __shared__ unsigned int s_total, s_cnt;
+  const int slot = blockIdx.x, l = P.topk_level[slot], img = blockIdx.y;
   const int n = P.n_anchor[l], k = P.keep[l];
   const float* keys = maxscore + (size_t)img * P.A_total + P.anchor_off[l];
+  int32_t* out = cand_idx + (size_t)img * P.M + P.cand_off[l];
+  const unsigned int* h = hist + ((size_t)img * P.num_topk_levels + slot) * TOPK_BINS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int slice = (n + TOPK_CLUSTER - 1) / TOPK_CLUSTER;
-  const int lo = min(n, (int)rank * slice), m = min(n, lo + slice) - lo;
-  for (int i = tid; i < m; i += 1024) skeys[i] = float_to_ordered(__ldg(keys + lo + i));
-  if (tid == 0) { s_prefix = 0; s_kleft = k; s_slot = 0; s_eq_run = 0; }
-  unsigned int mask = 0;
-  for (int pass = 0; pass < 4; ++pass) {
-    const int shift = 24 - 8 * pass;
-    if (tid < 256) hist[tid] = 0;
-    __syncthreads();
-    const unsigned int prefix = s_prefix;
-    for (int base = 0; base < m; base += 1024) {
-      const int i = base + tid;
-      const unsigned int u = (i < m) ? skeys[i] : 0u;
-      const bool valid = (i < m) && ((u & mask) == prefix);
-      const unsigned int d = valid ? ((u >> shift) & 255u) : (256u + lane);
-      const unsigned int peers = __match_any_sync(0xffffffffu, d);
-      if (valid && (__ffs(peers) - 1) == lane) atomicAdd(&hist[d], __popc(peers));
-    }
-    cluster.sync();
-    if (tid < 256) {
-      unsigned int t = 0;
-      for (unsigned int r = 0; r < TOPK_CLUSTER; ++r) t += cluster.map_shared_rank(hist, r)[tid];
-      tot[tid] = t;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      unsigned int c = 0, kl = s_kleft;
-      int d = 255;
-      for (; d > 0; --d) {
-        if (c + tot[d] >= kl) break;
-        c += tot[d];
-      }
-      s_kleft = kl - c;
-      s_prefix = prefix | ((unsigned int)d << shift);
-      s_eq_total = tot[d];
-    }
-    mask |= 255u << shift;
-    cluster.sync();                       // nobody still reads my histogram when the next pass clears it
+  // thread t owns buckets [4t, 4t+4); suffix sums from the top bucket down
+  const uint4 h4 = *reinterpret_cast<const uint4*>(h + 4 * tid);
+  const unsigned int mine = h4.x + h4.y + h4.z + h4.w;
+  unsigned int incl = mine;                                  // inclusive suffix sum inside the warp (higher lanes first)
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int t = __shfl_down_sync(0xffffffffu, incl, o);
+    if (lane + o < 32) incl += t;
   }
-  const unsigned int T = s_prefix, need_eq = s_kleft;
-  const bool ties = (s_eq_total != need_eq);
-  // counts of (> T) and (== T) in my slice
-  if (tid < 2) s_cnt[tid] = 0;
+  if (lane == 0) warp_sum[warp] = incl;
+  if (tid == 0) { s_tb = -1; s_cnt = 0; }
   __syncthreads();
-  {
-    unsigned int g = 0, e = 0;
-    for (int i = tid; i < m; i += 1024) { const unsigned int u = skeys[i]; g += (u > T); e += (u == T); }
-    for (int o = 16; o > 0; o >>= 1) { g += __shfl_xor_sync(0xffffffffu, g, o); e += __shfl_xor_sync(0xffffffffu, e, o); }
-    if (lane == 0) { atomicAdd(&s_cnt[0], g); atomicAdd(&s_cnt[1], e); }
-  }
-  cluster.sync();
-  unsigned int base_slot = 0, eq_before = 0;
-  {
-    unsigned int eqb = 0;
-    for (unsigned int r = 0; r < TOPK_CLUSTER; ++r) {
-      const unsigned int* rc = cluster.map_shared_rank(s_cnt, r);
-      const unsigned int gr = rc[0], er = rc[1];
-      const unsigned int left = need_eq > eqb ? need_eq - eqb : 0u;
-      const unsigned int take = gr + (er < left ? er : left);
-      if (r < rank) base_slot += take;
-      if (r == rank) eq_before = eqb;
-      eqb += er;
+  unsigned int above = 0;                                    // keys in buckets owned by higher threads
+  for (int w = warp + 1; w < 32; ++w) above += warp_sum[w];
+  above += incl - mine;
+  if (above < (unsigned int)k && above + mine >= (unsigned int)k) {       // the k-th best key sits in one of my buckets
+    unsigned int c = above;
+    const unsigned int hv[4] = {h4.x, h4.y, h4.z, h4.w};
+    int b = 3;
+    for (; b > 0; --b) {
+      if (c + hv[b] >= (unsigned int)k) break;
+      c += hv[b];
     }
+    s_tb = 4 * tid + b;
+    s_total = c + hv[b];                                      // anchors with bucket >= tb
   }
-  const unsigned int my_eq_quota = need_eq > eq_before ? need_eq - eq_before : 0u;   // ties: lowest index first
-  unsigned long long* out = scratch + ((size_t)img * IOU_MAX_LEVELS + lslot) * TOPK_MAX;
-  for (int base = 0; base < m; base += 1024) {
+  __syncthreads();
+  const int tb = s_tb;
+  if (tb < 0 || s_total > TOPK_LIST) {                        // histogram cannot split this level: exact radix select
+    topk_radix_select(keys, n, k, list, out);
+    return;
+  }
+  for (int base = 0; base < n; base += 1024) {
     const int i = base + tid;
-    const unsigned int u = (i < m) ? skeys[i] : 0u;
-    const bool gt = (i < m) && (u > T), eq = (i < m) && (u == T);
-    bool take = gt;
-    if (!ties) {
-      take = gt || eq;
-    } else {
-      const unsigned int be = __ballot_sync(0xffffffffu, eq);
-      if (lane == 0) warp_eq[warp] = __popc(be);
-      __syncthreads();
-      unsigned int before = s_eq_run;
-      for (int w = 0; w < warp; ++w) before += warp_eq[w];
-      if (eq && before + __popc(be & ((1u << lane) - 1u)) < my_eq_quota) take = true;
-      __syncthreads();
-      if (tid == 0) {
-        unsigned int t = 0;
-        for (int w = 0; w < 32; ++w) t += warp_eq[w];
-        s_eq_run += t;
-      }
-      __syncthreads();
-    }
+    const float sc = (i < n) ? __ldg(keys + i) : 0.f;
+    const bool take = (i < n) && score_bucket(sc) >= tb;
     const unsigned int bt = __ballot_sync(0xffffffffu, take);
     unsigned int slot0 = 0;
-    if (lane == 0 && bt) slot0 = atomicAdd(&s_slot, __popc(bt));
+    if (lane == 0 && bt) slot0 = atomicAdd(&s_cnt, __popc(bt));
     slot0 = __shfl_sync(0xffffffffu, slot0, 0);
     if (take) {
-      const unsigned int slot = base_slot + slot0 + __popc(bt & ((1u << lane) - 1u));
-      if (slot < TOPK_MAX)
-        out[slot] = ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (unsigned int)(lo + i));
+      const unsigned int pos = slot0 + __popc(bt & ((1u << lane) - 1u));
+      if (pos < TOPK_LIST)
+        list[pos] = ((unsigned long long)float_to_ordered(sc) << 32) | (unsigned long long)(0xffffffffu - (unsigned int)i);
     }
   }
-  __threadfence();
-  cluster.sync();
-  if (rank == 0) {
-    unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(tk_smem);
-    const int Psort = next_pow2(k);
-    for (int i = tid; i < Psort; i += 1024) sortbuf[i] = (i < k) ? __ldcg(out + i) : 0ull;
-    bitonic_sort_desc(sortbuf, Psort);
-    int32_t* dst = cand_idx + (size_t)img * P.M + P.cand_off[l];
-    for (int r = tid; r < k; r += 1024)
-      dst[r] = (int32_t)(0xffffffffu - (unsigned int)(sortbuf[r] & 0xffffffffull));
-  }
+  __syncthreads();
+  const int total = min((int)s_cnt, TOPK_LIST);
+  const int Psort = next_pow2(max(total, 2));
+  for (int i = total + tid; i < Psort; i += 1024) list[i] = 0ull;
+  bitonic_sort_desc(list, Psort);
+  for (int r = tid; r < k; r += 1024)
+    out[r] = (int32_t)(0xffffffffu - (unsigned int)(list[r] & 0xffffffffull));
 }
+
 
 // ---------------------------------------------------------------------------------------- K3
 // 32 candidates per CTA: every warp computes the C class scores of 4 candidates (coalesced
@@ -1352,8 +1308,10 @@ static int fill_params(const iou_postproc_cfg* cfg, int n_img, PostParams& P) {
     P.keep[l] = P.is_topk[l] ? P.nms_pre : P.n_anchor[l];
     P.cand_off[l] = coff; coff += P.keep[l];
     P.group_off[l] = goff;
+    P.topk_slot[l] = -1;
     if (P.is_topk[l]) {
       goff += (long long)n_img * ((P.n_anchor[l] + 31) / 32);
+      P.topk_slot[l] = P.num_topk_levels;
       P.topk_level[P.num_topk_levels++] = l;
     }
     for (int a = 0; a < P.A; ++a)
@@ -1378,7 +1336,7 @@ static int fill_params(const iou_postproc_cfg* cfg, int n_img, PostParams& P) {
 struct PostWorkspace {
   float* maxscore; unsigned long long* kept_keys; int32_t* kept_cnt;
   float* boxes; float* scores_cm; int32_t* cand_idx;
-  unsigned long long* topk_scratch;
+  unsigned int* topk_hist;           // [n_img][num_topk_levels][TOPK_BINS] score-bucket histograms (K1 -> K2)
   size_t total;
 };
 static PostWorkspace carve(const PostParams& P, void* base) {
@@ -1392,14 +1350,14 @@ static PostWorkspace carve(const PostParams& P, void* base) {
   W.boxes = (float*)take((size_t)P.n_img * P.M * 16);
   W.scores_cm = (float*)take((size_t)P.n_img * P.C * P.M * 4);
   W.cand_idx = (int32_t*)take((size_t)P.n_img * P.M * 4);
-  W.topk_scratch = (unsigned long long*)take((size_t)P.n_img * IOU_MAX_LEVELS * TOPK_MAX * 8);
+  W.topk_hist = (unsigned int*)take((size_t)P.n_img * (P.num_topk_levels > 0 ? P.num_topk_levels : 1) * TOPK_BINS * 4);
   W.total = off;
   return W;
 }
 
 static int run_decode(PostParams& P, const float* const* cls, const float* const* reg,
                       const float* const* iou, const float* img_info, int rescale, float* boxes,
-                      float* scores_cm, int32_t* cand_idx, float* maxscore, unsigned long long* topk_scratch,
+                      float* scores_cm, int32_t* cand_idx, float* maxscore, unsigned int* topk_hist,
                       cudaStream_t st) {
   for (int l = 0; l < P.num_levels; ++l) {
     IOU_REQUIRE(cls[l] && reg[l], "NULL level pointer at level %d", l);
@@ -1415,21 +1373,11 @@ static int run_decode(PostParams& P, const float* const* cls, const float* const
     const size_t sm = (size_t)8 * 32 * (P.C / 4) * sizeof(float);
     if (sm > 48 * 1024)     // more than 192 classes: above the default dynamic shared-memory limit
       IOU_CHECK_CUDA(cudaFuncSetAttribute(max_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    max_score_kernel<<<blocks, 256, sm, st>>>(P, maxscore);
+    IOU_CHECK_CUDA(cudaMemsetAsync(topk_hist, 0, (size_t)P.n_img * P.num_topk_levels * TOPK_BINS * 4, st));
+    max_score_kernel<<<blocks, 256, sm, st>>>(P, maxscore, topk_hist);
     if (int e = launch_status("max_score_kernel")) return e;
-    int max_n = 0;
-    for (int t = 0; t < P.num_topk_levels; ++t) max_n = max_n > P.n_anchor[P.topk_level[t]] ? max_n : P.n_anchor[P.topk_level[t]];
-    size_t tk_sm = (size_t)((max_n + TOPK_CLUSTER - 1) / TOPK_CLUSTER) * 4;
-    if (tk_sm < (size_t)TOPK_MAX * 8) tk_sm = (size_t)TOPK_MAX * 8;
-    if (tk_sm <= 200 * 1024) {
-      IOU_CHECK_CUDA(cudaFuncSetAttribute(topk_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      topk_cluster_kernel<<<dim3(P.num_topk_levels * TOPK_CLUSTER, P.n_img), 1024, tk_sm, st>>>(P, maxscore, cand_idx,
-                                                                                              topk_scratch);
-      if (int e = launch_status("topk_cluster_kernel")) return e;
-    } else {
-      topk_kernel<<<dim3(P.num_topk_levels, P.n_img), 1024, 0, st>>>(P, maxscore, cand_idx);
-      if (int e = launch_status("topk_kernel")) return e;
-    }
+    topk_hist_kernel<<<dim3(P.num_topk_levels, P.n_img), 1024, 0, st>>>(P, maxscore, topk_hist, cand_idx);
+    if (int e = launch_status("topk_hist_kernel")) return e;
   }
   const size_t sm3 = (size_t)P.C * 33 * sizeof(float);
   gather_decode_kernel<<<dim3((P.M + 31) / 32, P.n_img), 256, sm3, st>>>(P, img_info, cand_idx, boxes,
@@ -1480,7 +1428,7 @@ extern "C" int iou_decode_candidates(const iou_postproc_cfg* cfg, int n_img, con
   if (!workspace || workspace_bytes < W.total)
     return fail(IOU_ERR_WORKSPACE, "workspace too small: need %zu bytes", W.total);
   return run_decode(P, cls, reg, iou, img_info, rescale, boxes, scores_cm, cand_idx, W.maxscore,
-                    W.topk_scratch, (cudaStream_t)stream);
+                    W.topk_hist, (cudaStream_t)stream);
 }
 
 extern "C" int iou_batched_nms(const iou_postproc_cfg* cfg, int n_img, const float* boxes,
@@ -1506,7 +1454,7 @@ extern "C" int iou_get_bboxes(const iou_postproc_cfg* cfg, int n_img, const floa
   if (!workspace || workspace_bytes < W.total)
     return fail(IOU_ERR_WORKSPACE, "workspace too small: need %zu bytes", W.total);
   if (int e = run_decode(P, cls, reg, iou, img_info, rescale, W.boxes, W.scores_cm, W.cand_idx,
-                         W.maxscore, W.topk_scratch, (cudaStream_t)stream))
+                         W.maxscore, W.topk_hist, (cudaStream_t)stream))
     return e;
   return run_nms(P, W.boxes, W.scores_cm, dets, labels, counts, W.kept_keys, W.kept_cnt,
                  (cudaStream_t)stream);

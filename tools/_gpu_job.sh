@@ -1,15 +1,12 @@
 set -x
-O=gpurun_out/r2j; mkdir -p $O
-run() { name=$1; shift; env "$@" python bench.py --steps 30 --warmup 5 --no-cpu-baseline $EXTRA --dump-ops $O/ops_$name.json > $O/bench_$name.json 2> $O/$name.err; python - <<PY
-import json
-try:
-    d=json.load(open('$O/bench_$name.json')); print('$name', d['value'], d['ms_per_step'], d['e2e']['value'], d['conv_ms_per_step'])
-except Exception as e: print('$name ERR', e)
-PY
-}
-EXTRA="" run base A=1
-EXTRA="" run pair48 IOU_PAIR_MIN_BN=48
-EXTRA="" run noph3 IOU_FUSE_PH3=0
-EXTRA="" run respf1 IOU_RES_PREFETCH=1
-EXTRA="--plans 3" run plans3 A=1
-EXTRA="" run base2 A=1
+O=gpurun_out/r2k; mkdir -p $O
+( time python -m pytest tests -q -m gpu ) > $O/gpu_tests.log 2>&1
+tail -4 $O/gpu_tests.log | cut -c1-200
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 60 -c 40 --csv --log-file $O/config5_launches.csv python tools/bench_postproc.py > $O/c5.out 2>&1
+grep -v "^==" $O/config5_launches.csv | python -c "
+import csv,sys,collections
+r=csv.DictReader(sys.stdin); agg=collections.OrderedDict()
+for row in r:
+    k=row['Kernel Name'][:50]; agg.setdefault(k,collections.defaultdict(list))[row['Metric Name']].append(float(row['Metric Value'].replace(',','')))
+for k,v in agg.items(): print(k, {m:(round(sum(x)/len(x)/1e3,1) if 'time' in m else round(sum(x)/len(x)/1e6,1)) for m,x in v.items()}, len(list(v.values())[0]))
+"
