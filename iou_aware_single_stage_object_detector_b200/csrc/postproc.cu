@@ -233,56 +233,107 @@ __device__ void topk_radix_select(const float* __restrict__ keys, const int n, c
 // every anchor with bucket >= tb (k + a bucket's worth of keys, not n), a bitonic sort orders them by
 // (score desc, index asc) and the first k are the level's candidates -- the same set and order as an exact select.
 #define TOPK_LIST 4096
-__global__ void __launch_bounds__(1024) topk_hist_kernel(const __grid_constant__ PostParams P,
-                                                         const float* __restrict__ maxscore,
-                                                         const unsigned int* __restrict__ hist,
-                                                         int32_t* __restrict__ cand_idx) {
-  __shared__ unsigned long long list[TOPK_LIST];
-  __shared__ unsigned int warp_sum[32];
-  __shared__ int s_tb;
-  __shared__ unsigned int s_total, s_cnt;
-  const int slot = blockIdx.x, l = P.topk_level[slot], img = blockIdx.y;
-  const int n = P.n_anchor[l], k = P.keep[l];
-  const float* keys = maxscore + (size_t)img * P.A_total + P.anchor_off[l];
-  int32_t* out = cand_idx + (size_t)img * P.M + P.cand_off[l];
-  const unsigned int* h = hist + ((size_t)img * P.num_topk_levels + slot) * TOPK_BINS;
+#define TOPK_SUB 2048
+// position of a score inside its bucket, in TOPK_SUB steps (monotone; s * 4096 and the subtraction are exact)
+__device__ __forceinline__ int score_sub_bucket(float s, int bucket) {
+  const float t = s * (float)TOPK_BINS - (float)bucket;
+  return (int)fminf(fmaxf(t * (float)TOPK_SUB, 0.0f), (float)(TOPK_SUB - 1));
+}
+// Block-wide search over a histogram split as NB consecutive bins per thread (thread t owns [NB*t, NB*t + NB), the
+// top bins belong to the top threads): finds the bin holding the need-th key counted from the top.  Returns through
+// shared memory: *s_bin (-1 if the histogram holds fewer than `need` keys) and *s_ge = keys in bins >= that bin.
+template <int NB>
+__device__ __forceinline__ void find_boundary_bin(const unsigned int (&hv)[NB], const unsigned int need,
+                                                  unsigned int* warp_sum, int* s_bin, unsigned int* s_ge) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // thread t owns buckets [4t, 4t+4); suffix sums from the top bucket down
-  const uint4 h4 = *reinterpret_cast<const uint4*>(h + 4 * tid);
-  const unsigned int mine = h4.x + h4.y + h4.z + h4.w;
+  unsigned int mine = 0;
+#pragma unroll
+  for (int q = 0; q < NB; ++q) mine += hv[q];
   unsigned int incl = mine;                                  // inclusive suffix sum inside the warp (higher lanes first)
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const unsigned int t = __shfl_down_sync(0xffffffffu, incl, o);
     if (lane + o < 32) incl += t;
   }
+  __syncthreads();                                            // warp_sum / s_bin may still be read from an earlier call
   if (lane == 0) warp_sum[warp] = incl;
-  if (tid == 0) { s_tb = -1; s_cnt = 0; }
+  if (tid == 0) *s_bin = -1;
   __syncthreads();
-  unsigned int above = 0;                                    // keys in buckets owned by higher threads
+  unsigned int above = incl - mine;                          // keys in bins owned by higher threads
   for (int w = warp + 1; w < 32; ++w) above += warp_sum[w];
-  above += incl - mine;
-  if (above < (unsigned int)k && above + mine >= (unsigned int)k) {       // the k-th best key sits in one of my buckets
+  if (above < need && above + mine >= need) {                 // the need-th key sits in one of my bins
     unsigned int c = above;
-    const unsigned int hv[4] = {h4.x, h4.y, h4.z, h4.w};
-    int b = 3;
+    int b = NB - 1;
     for (; b > 0; --b) {
-      if (c + hv[b] >= (unsigned int)k) break;
+      if (c + hv[b] >= need) break;
       c += hv[b];
     }
-    s_tb = 4 * tid + b;
-    s_total = c + hv[b];                                      // anchors with bucket >= tb
+    *s_bin = NB * tid + b;
+    *s_ge = c + hv[b];
   }
   __syncthreads();
-  const int tb = s_tb;
-  if (tb < 0 || s_total > TOPK_LIST) {                        // histogram cannot split this level: exact radix select
-    topk_radix_select(keys, n, k, list, out);
-    return;
+}
+
+__global__ void __launch_bounds__(1024) topk_hist_kernel(const __grid_constant__ PostParams P,
+                                                         const float* __restrict__ maxscore,
+                                                         const unsigned int* __restrict__ hist,
+                                                         int32_t* __restrict__ cand_idx) {
+  __shared__ unsigned long long list[TOPK_LIST];
+  __shared__ unsigned int sub[TOPK_SUB];
+  __shared__ unsigned int warp_sum[32];
+  __shared__ int s_bin;
+  __shared__ unsigned int s_ge, s_cnt;
+  const int slot = blockIdx.x, l = P.topk_level[slot], img = blockIdx.y;
+  const int n = P.n_anchor[l], k = P.keep[l];
+  const float* keys = maxscore + (size_t)img * P.A_total + P.anchor_off[l];
+  int32_t* out = cand_idx + (size_t)img * P.M + P.cand_off[l];
+  const unsigned int* h = hist + ((size_t)img * P.num_topk_levels + slot) * TOPK_BINS;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint4 h4 = *reinterpret_cast<const uint4*>(h + 4 * tid);
+  const unsigned int hv[4] = {h4.x, h4.y, h4.z, h4.w};
+  find_boundary_bin<4>(hv, (unsigned int)k, warp_sum, &s_bin, &s_ge);
+  const int tb = s_bin;
+  if (tb < 0) { topk_radix_select(keys, n, k, list, out); return; }
+  int tb2 = 0;                                                // keys of bucket tb are taken from sub-bucket tb2 upwards
+  if (s_ge > TOPK_LIST) {
+    // the boundary bucket alone holds too many keys (clustered scores, e.g. the reference init: every score is
+    // 0.07098 +- 2e-5): split it once more, TOPK_SUB sub-buckets of width 2^-23
+    for (int i = tid; i < TOPK_SUB; i += 1024) sub[i] = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+      const int i = base + tid;
+      const float sc = (i < n) ? __ldg(keys + i) : 0.f;
+      const bool hit = (i < n) && score_bucket(sc) == tb;
+      const int d = hit ? score_sub_bucket(sc, tb) : (TOPK_SUB + lane);
+      const unsigned int peers = __match_any_sync(0xffffffffu, d);
+      if (hit && (__ffs(peers) - 1) == lane) atomicAdd(&sub[d], (unsigned int)__popc(peers));
+    }
+    __syncthreads();
+    // keys above bucket tb = s_ge - (keys in tb); keys in tb = sum of sub[]
+    const unsigned int sv[2] = {sub[2 * tid], sub[2 * tid + 1]};
+    unsigned int tot = sv[0] + sv[1];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    __shared__ unsigned int s_intb;
+    if (tid == 0) s_intb = 0;
+    __syncthreads();
+    if (lane == 0) atomicAdd(&s_intb, tot);
+    __syncthreads();
+    const unsigned int gt_tb = s_ge - s_intb;                 // anchors in buckets above tb (< k)
+    find_boundary_bin<2>(sv, (unsigned int)k - gt_tb, warp_sum, &s_bin, &s_ge);
+    if (s_bin < 0 || gt_tb + s_ge > TOPK_LIST) {              // still one lump (exact ties): exact radix select
+      topk_radix_select(keys, n, k, list, out);
+      return;
+    }
+    tb2 = s_bin;
   }
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
   for (int base = 0; base < n; base += 1024) {
     const int i = base + tid;
     const float sc = (i < n) ? __ldg(keys + i) : 0.f;
-    const bool take = (i < n) && score_bucket(sc) >= tb;
+    const int b = score_bucket(sc);
+    const bool take = (i < n) && (b > tb || (b == tb && (tb2 == 0 || score_sub_bucket(sc, tb) >= tb2)));
     const unsigned int bt = __ballot_sync(0xffffffffu, take);
     unsigned int slot0 = 0;
     if (lane == 0 && bt) slot0 = atomicAdd(&s_cnt, __popc(bt));
@@ -301,7 +352,6 @@ __global__ void __launch_bounds__(1024) topk_hist_kernel(const __grid_constant__
   for (int r = tid; r < k; r += 1024)
     out[r] = (int32_t)(0xffffffffu - (unsigned int)(list[r] & 0xffffffffull));
 }
-
 
 // ---------------------------------------------------------------------------------------- K3
 // 32 candidates per CTA: every warp computes the C class scores of 4 candidates (coalesced

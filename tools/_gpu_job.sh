@@ -1,12 +1,17 @@
 set -x
-O=gpurun_out/r2k; mkdir -p $O
-( time python -m pytest tests -q -m gpu ) > $O/gpu_tests.log 2>&1
-tail -4 $O/gpu_tests.log | cut -c1-200
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 60 -c 40 --csv --log-file $O/config5_launches.csv python tools/bench_postproc.py > $O/c5.out 2>&1
+O=gpurun_out/r2l; mkdir -p $O
+( time python -m pytest tests/test_gpu_postproc.py tests/test_gpu_detector_golden.py tests/test_gpu_model.py -q -x ) > $O/gpu_tests.log 2>&1
+tail -25 $O/gpu_tests.log | cut -c1-220
+python tools/bench_postproc.py > $O/config5.json 2> $O/c5.err; cat $O/config5.json
+ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 40 --csv --log-file $O/config5_launches.csv python tools/bench_postproc.py > $O/c5.out 2>&1
 grep -v "^==" $O/config5_launches.csv | python -c "
 import csv,sys,collections
 r=csv.DictReader(sys.stdin); agg=collections.OrderedDict()
 for row in r:
-    k=row['Kernel Name'][:50]; agg.setdefault(k,collections.defaultdict(list))[row['Metric Name']].append(float(row['Metric Value'].replace(',','')))
-for k,v in agg.items(): print(k, {m:(round(sum(x)/len(x)/1e3,1) if 'time' in m else round(sum(x)/len(x)/1e6,1)) for m,x in v.items()}, len(list(v.values())[0]))
+    agg.setdefault(row['Kernel Name'][:40],[]).append(float(row['Metric Value'].replace(',','')))
+for k,v in agg.items(): print(k, round(sum(v)/len(v)/1e3,1), len(v))
 "
+python bench.py --steps 30 --warmup 5 --no-cpu-baseline > $O/bench.json 2> $O/bench.err; python -c "
+import json; d=json.load(open('$O/bench.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['conv_ms_per_step'], d['postproc_ms_per_step'])"
+python bench.py --steps 30 --warmup 5 --no-cpu-baseline --weights reference-init > $O/bench_ri.json 2> $O/bench_ri.err; python -c "
+import json; d=json.load(open('$O/bench_ri.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['conv_ms_per_step'], d['postproc_ms_per_step'])"
