@@ -1,17 +1,8 @@
 set -x
-O=gpurun_out/r2l; mkdir -p $O
-( time python -m pytest tests/test_gpu_postproc.py tests/test_gpu_detector_golden.py tests/test_gpu_model.py -q -x ) > $O/gpu_tests.log 2>&1
-tail -25 $O/gpu_tests.log | cut -c1-220
-python tools/bench_postproc.py > $O/config5.json 2> $O/c5.err; cat $O/config5.json
-ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 40 --csv --log-file $O/config5_launches.csv python tools/bench_postproc.py > $O/c5.out 2>&1
-grep -v "^==" $O/config5_launches.csv | python -c "
-import csv,sys,collections
-r=csv.DictReader(sys.stdin); agg=collections.OrderedDict()
-for row in r:
-    agg.setdefault(row['Kernel Name'][:40],[]).append(float(row['Metric Value'].replace(',','')))
-for k,v in agg.items(): print(k, round(sum(v)/len(v)/1e3,1), len(v))
-"
-python bench.py --steps 30 --warmup 5 --no-cpu-baseline > $O/bench.json 2> $O/bench.err; python -c "
-import json; d=json.load(open('$O/bench.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['conv_ms_per_step'], d['postproc_ms_per_step'])"
-python bench.py --steps 30 --warmup 5 --no-cpu-baseline --weights reference-init > $O/bench_ri.json 2> $O/bench_ri.err; python -c "
-import json; d=json.load(open('$O/bench_ri.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['conv_ms_per_step'], d['postproc_ms_per_step'])"
+O=gpurun_out/r2m; mkdir -p $O
+timeout 600 ncu --profile-from-start off --clock-control none --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv --log-file $O/launches_ncu_dram.csv python bench.py --no-graph --ncu-range --no-cpu-baseline --steps 1 --warmup 3 > $O/ncu_launches.out 2>&1
+timeout 600 ncu --set full --import-source on --clock-control none --profile-from-start off -k "regex:max_score|topk_hist|gather_decode|class_nms|final_select" -c 5 -f -o $O/ncu_postproc python bench.py --no-graph --ncu-range --no-cpu-baseline --steps 1 --warmup 3 > $O/ncu_postproc.out 2>&1
+timeout 600 ncu --set full --import-source on --clock-control none --profile-from-start off --launch-skip 65 --launch-count 1 -f -o $O/ncu_head_tower python bench.py --no-graph --ncu-range --no-cpu-baseline --steps 1 --warmup 3 > $O/ncu_head.out 2>&1
+python bench.py --steps 20 --warmup 5 --dump-ops $O/ops_r50.json > $O/bench_line_r50.json 2> $O/bench.err
+python bench.py --impl reference --steps 20 --warmup 5 > $O/bench_line_reference_arm.json 2> $O/ref.err
+ls -la $O
