@@ -231,6 +231,8 @@ class Engine(object):
         self.plans = []
         self.keep = []           # tensors that must outlive the plan
         self.maps = []           # every padded-rows buffer of this engine (range_report)
+        self.side = []           # (fork_at, first, last): ops[first..last] run on a side stream forked before op fork_at
+        self._side_stream = None
         self.flops = 0.0
         self.op_flops = {}
         import os
@@ -521,6 +523,7 @@ class Engine(object):
         a ReLU (relu_before_extra_convs; fpn.py:117-128)."""
         used = feats[start_level:]
         nl = len(used)
+        fpn_first = len(self.ops)
         lat = [None] * nl
         for i in range(nl - 1, -1, -1):
             kp = "%slateral_convs.%d.conv." % (prefix, i)
@@ -546,6 +549,7 @@ class Engine(object):
             self.conv(kp[:-1], [lat[i]], TAPS_3X3, pack_weight(sd[kp + "weight"], out_channels),
                       out_channels, out_channels, out=F.view(i), shift=sd[kp + "bias"])
         src = feats[-1] if extra_convs_on_inputs else F.view(nl - 1)     # fpn.py:118-122
+        first_extra = len(self.ops)
         for i in range(nl, num_outs):
             kp = "%sfpn_convs.%d.conv." % (prefix, i)
             # fpn.py:123-128: ReLU only in front of the extra convs AFTER the first one
@@ -553,6 +557,10 @@ class Engine(object):
             self.conv(kp[:-1], ph, TAPS_3X3_S2, pack_weight(sd[kp + "weight"], out_channels), src.c,
                       out_channels, out=F.view(i), shift=sd[kp + "bias"])
             src = F.view(i)
+        if extra_convs_on_inputs and num_outs > nl and os.environ.get("IOU_FPN_SIDE", "0") != "0":
+            # P6 / P7 only read C5 (fpn.py:118-128): their launches (few tiles, long K) run on a side stream next to the
+            # laterals and the P3..P5 output convs, joined before the head
+            self.side.append((fpn_first, first_extra, len(self.ops) - 1))
         return F
 
     def add_head(self, sd, F, prefix="bbox_head.", stacked=4, num_anchors=9, num_classes=80, with_iou=True):
@@ -669,8 +677,27 @@ class Engine(object):
     # ------------------------------------------------------------------ execution
     def run(self):
         st = L.stream_ptr()
-        for _, fn in self.ops:
-            fn(st)
+        if not self.side:
+            for _, fn in self.ops:
+                fn(st)
+        else:
+            cur = torch.cuda.current_stream(self.device)
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(self.device)
+            side = self._side_stream
+            sst = ctypes.c_void_p(side.cuda_stream)
+            fork = {f: (a, b) for (f, a, b) in self.side}
+            on_side = set(i for (_, a, b) in self.side for i in range(a, b + 1))
+            join = set(b for (_, a, b) in self.side)
+            for i, (_, fn) in enumerate(self.ops):
+                if i in fork:
+                    side.wait_stream(cur)                 # fork: the side branch sees everything queued so far
+                if i in on_side:
+                    fn(sst)
+                else:
+                    fn(st)
+                if i in join:
+                    cur.wait_stream(side)                 # join (also what ends a CUDA-graph capture cleanly)
         L.launch_count += len(self.ops)
 
     def profile(self, iters=3):

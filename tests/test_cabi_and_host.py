@@ -305,6 +305,78 @@ def test_all_gather_of_detections_world2_gloo():
             assert torch.equal(gc[src * 3:(src + 1) * 3], got[src][6])
 
 
+def _gloo_packed_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    D.init_dist("gloo")
+    b, k = 3, 100
+    g = torch.Generator().manual_seed(200 + rank)
+    packed = torch.zeros(D.packed_layout(b, k)[3], dtype=torch.uint8)
+    dets, labels, counts = D.packed_views(packed, b, k)
+    dets.copy_(torch.rand(b, k, 5, generator=g))
+    labels.copy_(torch.randint(0, 80, (b, k), generator=g))
+    counts.copy_(torch.tensor([rank, 50 + rank, 100], dtype=torch.int32))
+    pg = D.PackedGather(world, "cpu")
+    outs = []
+    for _ in range(3):                                  # buffers rotate between two slots
+        buf, done = pg(packed)
+        assert done is None
+        outs.append(tuple(t.clone() for t in D.unpack_gathered(buf, world, b, k)))
+    q.put((rank, outs, dets.clone(), labels.clone(), counts.clone()))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_packed_gather_world2_gloo():
+    """The N > 1 result path of bench.py / detect_stream: ONE all-gather of the packed dets | labels | counts buffer."""
+    import socket
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    with socket.socket() as sk:
+        sk.bind(('127.0.0.1', 0))
+        port = sk.getsockname()[1]
+    procs = [ctx.Process(target=_gloo_packed_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, outs, *_ in got:
+        for gd, gl, gc in outs:
+            assert gd.shape == (6, 100, 5) and gl.shape == (6, 100) and gl.dtype == torch.int64 and gc.dtype == torch.int32
+            for src in range(2):
+                assert torch.equal(gd[src * 3:(src + 1) * 3], got[src][2])
+                assert torch.equal(gl[src * 3:(src + 1) * 3], got[src][3])
+                assert torch.equal(gc[src * 3:(src + 1) * 3], got[src][4])
+
+
+def test_packed_layout_is_aligned_and_round_trips():
+    for b, k in ((1, 1), (8, 100), (3, 7), (64, 100)):
+        o_d, o_l, o_c, total = D.packed_layout(b, k)
+        assert o_d == 0 and o_l % 16 == 0 and o_c % 16 == 0 and total % 16 == 0
+        assert o_l >= b * k * 20 and o_c >= o_l + b * k * 8 and total >= o_c + b * 4
+        buf = torch.zeros(total, dtype=torch.uint8)
+        d, l, c = D.packed_views(buf, b, k)
+        assert d.shape == (b, k, 5) and l.shape == (b, k) and c.shape == (b,)
+        d.fill_(1.5); l.fill_(7); c.fill_(3)
+        d2, l2, c2 = D.unpack_gathered(buf, 1, b, k)
+        assert float(d2.sum()) == 1.5 * b * k * 5 and int(l2.sum()) == 7 * b * k and int(c2.sum()) == 3 * b
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU arm of the measurement contract) runs here: one JSON line with the keys the
+    driver reads; the bounded sample stops at the time cap."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--reference-budget-s", "1"], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "images/sec" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
+
+
 def test_result_formats_match_reference(tmp_path):
     """det2json / xyxy2xywh / results2json vs the golden written by the reference's own functions
     (tests/golden/gen_golden.py::gen_results_json); batch_bbox2result == per-image bbox2result."""
