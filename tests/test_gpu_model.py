@@ -167,6 +167,13 @@ def test_detect_stream_matches_detect_device():
         for (d, l, c), (d2, l2, c2) in zip(want5, got):
             assert torch.equal(c, c2) and torch.equal(d, d2) and torch.equal(l, l2)
     assert list(det.detect_stream(iter(()), rescale=True)) == []
+    # the side-stream packed gather (what N > 1 ranks use; world 1 = a device copy) and the legacy gather callable
+    from iou_aware_single_stage_object_detector_b200 import dist as D
+    for gather in (D.PackedGather(1, DEV), lambda d, l, c: (d, l, c)):
+        got = list(det.detect_stream(((im, [meta, meta]) for im in imgs5), rescale=True, gather=gather))
+        assert len(got) == 5
+        for (d, l, c), (d2, l2, c2) in zip(want5, got):
+            assert torch.equal(c, c2) and torch.equal(d, d2) and torch.equal(l, l2)
 
 
 def test_unpadded_input_raises_like_the_reference():
