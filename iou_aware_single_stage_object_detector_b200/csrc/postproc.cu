@@ -60,6 +60,8 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
 // Monotone bucket of a fused score (scores live in [0, 1]): b(s1) > b(s2) implies s1 > s2, so the per-level top-k is
 // "every anchor in a bucket above the boundary bucket + the best of the boundary bucket" (topk_hist_kernel).
 #define TOPK_BINS 4096
+#define TOPK_HSTRIDE (TOPK_BINS + 16)   // per (image, level): the histogram, then [0] = collected-list length, [1] = chunk ticket
+#define TOPK_CHUNKS 8                  // CTAs that share one level's collect pass
 __device__ __forceinline__ int score_bucket(float s) {
   return (int)fminf(fmaxf(s * (float)TOPK_BINS, 0.0f), (float)(TOPK_BINS - 1));
 }
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(256) max_score_kernel(const __grid_constant__ 
     }
     const unsigned int peers = __match_any_sync(0xffffffffu, bucket);
     if (lane < v && (__ffs(peers) - 1) == lane)
-      atomicAdd(hist + ((size_t)img * P.num_topk_levels + P.topk_slot[l]) * TOPK_BINS + bucket, (unsigned int)__popc(peers));
+      atomicAdd(hist + ((size_t)img * P.num_topk_levels + P.topk_slot[l]) * TOPK_HSTRIDE + bucket, (unsigned int)__popc(peers));
     __syncwarp();
   }
 }
@@ -276,29 +278,38 @@ __device__ __forceinline__ void find_boundary_bin(const unsigned int (&hv)[NB], 
 
 __global__ void __launch_bounds__(1024) topk_hist_kernel(const __grid_constant__ PostParams P,
                                                          const float* __restrict__ maxscore,
-                                                         const unsigned int* __restrict__ hist,
+                                                         unsigned int* __restrict__ hist,
+                                                         unsigned long long* __restrict__ glist,
                                                          int32_t* __restrict__ cand_idx) {
+  // grid (level slot, image, chunk): the TOPK_CHUNKS CTAs of one (image, level) each scan a slice of its keys into a
+  // shared global list; the CTA that finishes last sorts the list and writes the level's candidates.  Score
+  // distributions the histogram cannot split take the single-CTA paths in chunk 0 (the other chunks leave at once).
   __shared__ unsigned long long list[TOPK_LIST];
   __shared__ unsigned int sub[TOPK_SUB];
   __shared__ unsigned int warp_sum[32];
   __shared__ int s_bin;
-  __shared__ unsigned int s_ge, s_cnt;
-  const int slot = blockIdx.x, l = P.topk_level[slot], img = blockIdx.y;
+  __shared__ unsigned int s_ge, s_cnt, s_intb, s_last;
+  const int slot = blockIdx.x, l = P.topk_level[slot], img = blockIdx.y, chunk = blockIdx.z;
   const int n = P.n_anchor[l], k = P.keep[l];
   const float* keys = maxscore + (size_t)img * P.A_total + P.anchor_off[l];
   int32_t* out = cand_idx + (size_t)img * P.M + P.cand_off[l];
-  const unsigned int* h = hist + ((size_t)img * P.num_topk_levels + slot) * TOPK_BINS;
+  unsigned int* h = hist + ((size_t)img * P.num_topk_levels + slot) * TOPK_HSTRIDE;
+  unsigned int* ctr = h + TOPK_BINS;
+  unsigned long long* gl = glist + ((size_t)img * P.num_topk_levels + slot) * TOPK_LIST;
   const int tid = threadIdx.x, lane = tid & 31;
   const uint4 h4 = *reinterpret_cast<const uint4*>(h + 4 * tid);
   const unsigned int hv[4] = {h4.x, h4.y, h4.z, h4.w};
   find_boundary_bin<4>(hv, (unsigned int)k, warp_sum, &s_bin, &s_ge);
   const int tb = s_bin;
+  const bool multi = (tb >= 0) && (s_ge <= TOPK_LIST);          // the plain case: every chunk collects its slice
+  if (!multi && chunk != 0) return;
   if (tb < 0) { topk_radix_select(keys, n, k, list, out); return; }
   int tb2 = 0;                                                // keys of bucket tb are taken from sub-bucket tb2 upwards
-  if (s_ge > TOPK_LIST) {
+  if (!multi) {
     // the boundary bucket alone holds too many keys (clustered scores, e.g. the reference init: every score is
     // 0.07098 +- 2e-5): split it once more, TOPK_SUB sub-buckets of width 2^-23
     for (int i = tid; i < TOPK_SUB; i += 1024) sub[i] = 0;
+    if (tid == 0) s_intb = 0;
     __syncthreads();
     for (int base = 0; base < n; base += 1024) {
       const int i = base + tid;
@@ -309,14 +320,10 @@ __global__ void __launch_bounds__(1024) topk_hist_kernel(const __grid_constant__
       if (hit && (__ffs(peers) - 1) == lane) atomicAdd(&sub[d], (unsigned int)__popc(peers));
     }
     __syncthreads();
-    // keys above bucket tb = s_ge - (keys in tb); keys in tb = sum of sub[]
     const unsigned int sv[2] = {sub[2 * tid], sub[2 * tid + 1]};
     unsigned int tot = sv[0] + sv[1];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    __shared__ unsigned int s_intb;
-    if (tid == 0) s_intb = 0;
-    __syncthreads();
     if (lane == 0) atomicAdd(&s_intb, tot);
     __syncthreads();
     const unsigned int gt_tb = s_ge - s_intb;                 // anchors in buckets above tb (< k)
@@ -327,22 +334,35 @@ __global__ void __launch_bounds__(1024) topk_hist_kernel(const __grid_constant__
     }
     tb2 = s_bin;
   }
+  const int slice = multi ? (n + TOPK_CHUNKS - 1) / TOPK_CHUNKS : n;
+  const int lo = multi ? min(n, chunk * slice) : 0, hi = multi ? min(n, lo + slice) : n;
   if (tid == 0) s_cnt = 0;
   __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
+  for (int base = lo; base < hi; base += 1024) {
     const int i = base + tid;
-    const float sc = (i < n) ? __ldg(keys + i) : 0.f;
+    const float sc = (i < hi) ? __ldg(keys + i) : 0.f;
     const int b = score_bucket(sc);
-    const bool take = (i < n) && (b > tb || (b == tb && (tb2 == 0 || score_sub_bucket(sc, tb) >= tb2)));
+    const bool take = (i < hi) && (b > tb || (b == tb && (tb2 == 0 || score_sub_bucket(sc, tb) >= tb2)));
     const unsigned int bt = __ballot_sync(0xffffffffu, take);
     unsigned int slot0 = 0;
-    if (lane == 0 && bt) slot0 = atomicAdd(&s_cnt, __popc(bt));
+    if (lane == 0 && bt) slot0 = multi ? atomicAdd(&ctr[0], (unsigned int)__popc(bt)) : atomicAdd(&s_cnt, (unsigned int)__popc(bt));
     slot0 = __shfl_sync(0xffffffffu, slot0, 0);
     if (take) {
       const unsigned int pos = slot0 + __popc(bt & ((1u << lane) - 1u));
-      if (pos < TOPK_LIST)
-        list[pos] = ((unsigned long long)float_to_ordered(sc) << 32) | (unsigned long long)(0xffffffffu - (unsigned int)i);
+      const unsigned long long key = ((unsigned long long)float_to_ordered(sc) << 32) | (unsigned long long)(0xffffffffu - (unsigned int)i);
+      if (pos < TOPK_LIST) { if (multi) gl[pos] = key; else list[pos] = key; }
     }
+  }
+  if (multi) {
+    __threadfence();                                          // my list entries are visible before my ticket
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&ctr[1], 1u) == (unsigned int)(TOPK_CHUNKS - 1)) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int total_g = min((int)__ldcg(&ctr[0]), TOPK_LIST);
+    for (int i = tid; i < total_g; i += 1024) list[i] = __ldcg(gl + i);
+    if (tid == 0) s_cnt = (unsigned int)total_g;
   }
   __syncthreads();
   const int total = min((int)s_cnt, TOPK_LIST);
@@ -1386,7 +1406,8 @@ static int fill_params(const iou_postproc_cfg* cfg, int n_img, PostParams& P) {
 struct PostWorkspace {
   float* maxscore; unsigned long long* kept_keys; int32_t* kept_cnt;
   float* boxes; float* scores_cm; int32_t* cand_idx;
-  unsigned int* topk_hist;           // [n_img][num_topk_levels][TOPK_BINS] score-bucket histograms (K1 -> K2)
+  unsigned int* topk_hist;           // [n_img][num_topk_levels][TOPK_HSTRIDE] score-bucket histograms + counters (K1 -> K2)
+  unsigned long long* topk_list;     // [n_img][num_topk_levels][TOPK_LIST] keys collected by the chunks of a level
   size_t total;
 };
 static PostWorkspace carve(const PostParams& P, void* base) {
@@ -1400,14 +1421,15 @@ static PostWorkspace carve(const PostParams& P, void* base) {
   W.boxes = (float*)take((size_t)P.n_img * P.M * 16);
   W.scores_cm = (float*)take((size_t)P.n_img * P.C * P.M * 4);
   W.cand_idx = (int32_t*)take((size_t)P.n_img * P.M * 4);
-  W.topk_hist = (unsigned int*)take((size_t)P.n_img * (P.num_topk_levels > 0 ? P.num_topk_levels : 1) * TOPK_BINS * 4);
+  W.topk_hist = (unsigned int*)take((size_t)P.n_img * (P.num_topk_levels > 0 ? P.num_topk_levels : 1) * TOPK_HSTRIDE * 4);
+  W.topk_list = (unsigned long long*)take((size_t)P.n_img * (P.num_topk_levels > 0 ? P.num_topk_levels : 1) * TOPK_LIST * 8);
   W.total = off;
   return W;
 }
 
 static int run_decode(PostParams& P, const float* const* cls, const float* const* reg,
                       const float* const* iou, const float* img_info, int rescale, float* boxes,
-                      float* scores_cm, int32_t* cand_idx, float* maxscore, unsigned int* topk_hist,
+                      float* scores_cm, int32_t* cand_idx, float* maxscore, unsigned int* topk_hist, unsigned long long* topk_list,
                       cudaStream_t st) {
   for (int l = 0; l < P.num_levels; ++l) {
     IOU_REQUIRE(cls[l] && reg[l], "NULL level pointer at level %d", l);
@@ -1423,10 +1445,10 @@ static int run_decode(PostParams& P, const float* const* cls, const float* const
     const size_t sm = (size_t)8 * 32 * (P.C / 4) * sizeof(float);
     if (sm > 48 * 1024)     // more than 192 classes: above the default dynamic shared-memory limit
       IOU_CHECK_CUDA(cudaFuncSetAttribute(max_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    IOU_CHECK_CUDA(cudaMemsetAsync(topk_hist, 0, (size_t)P.n_img * P.num_topk_levels * TOPK_BINS * 4, st));
+    IOU_CHECK_CUDA(cudaMemsetAsync(topk_hist, 0, (size_t)P.n_img * P.num_topk_levels * TOPK_HSTRIDE * 4, st));
     max_score_kernel<<<blocks, 256, sm, st>>>(P, maxscore, topk_hist);
     if (int e = launch_status("max_score_kernel")) return e;
-    topk_hist_kernel<<<dim3(P.num_topk_levels, P.n_img), 1024, 0, st>>>(P, maxscore, topk_hist, cand_idx);
+    topk_hist_kernel<<<dim3(P.num_topk_levels, P.n_img, TOPK_CHUNKS), 1024, 0, st>>>(P, maxscore, topk_hist, topk_list, cand_idx);
     if (int e = launch_status("topk_hist_kernel")) return e;
   }
   const size_t sm3 = (size_t)P.C * 33 * sizeof(float);
@@ -1478,7 +1500,7 @@ extern "C" int iou_decode_candidates(const iou_postproc_cfg* cfg, int n_img, con
   if (!workspace || workspace_bytes < W.total)
     return fail(IOU_ERR_WORKSPACE, "workspace too small: need %zu bytes", W.total);
   return run_decode(P, cls, reg, iou, img_info, rescale, boxes, scores_cm, cand_idx, W.maxscore,
-                    W.topk_hist, (cudaStream_t)stream);
+                    W.topk_hist, W.topk_list, (cudaStream_t)stream);
 }
 
 extern "C" int iou_batched_nms(const iou_postproc_cfg* cfg, int n_img, const float* boxes,
@@ -1504,7 +1526,7 @@ extern "C" int iou_get_bboxes(const iou_postproc_cfg* cfg, int n_img, const floa
   if (!workspace || workspace_bytes < W.total)
     return fail(IOU_ERR_WORKSPACE, "workspace too small: need %zu bytes", W.total);
   if (int e = run_decode(P, cls, reg, iou, img_info, rescale, W.boxes, W.scores_cm, W.cand_idx,
-                         W.maxscore, W.topk_hist, (cudaStream_t)stream))
+                         W.maxscore, W.topk_hist, W.topk_list, (cudaStream_t)stream))
     return e;
   return run_nms(P, W.boxes, W.scores_cm, dets, labels, counts, W.kept_keys, W.kept_cnt,
                  (cudaStream_t)stream);
