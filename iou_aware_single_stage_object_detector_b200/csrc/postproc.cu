@@ -643,11 +643,12 @@ __global__ void __launch_bounds__(512) class_nms_kernel(const __grid_constant__ 
   __shared__ unsigned int s_n, warp_cnt[16];
   const int c = blockIdx.x, img = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T = blockDim.x, nw = T >> 5;            // four CTAs per SM at full width, five at 384 threads
   const float* sc = scores_cm + ((size_t)img * P.C + c) * P.M;
   if (tid == 0) s_n = 0;
   __syncthreads();
   // compaction of rows with score > score_thr (bbox_nms.py:37), ascending row index
-  for (int base = 0; base < P.M; base += 512) {
+  for (int base = 0; base < P.M; base += T) {
     const int j = base + tid;
     const float s = (j < P.M) ? __ldg(sc + j) : 0.f;
     const bool pass = (j < P.M) && (s > P.score_thr);
@@ -664,7 +665,7 @@ __global__ void __launch_bounds__(512) class_nms_kernel(const __grid_constant__ 
     __syncthreads();
     if (tid == 0) {
       unsigned int t = 0;
-      for (int w = 0; w < 16; ++w) t += warp_cnt[w];
+      for (int w = 0; w < nw; ++w) t += warp_cnt[w];
       s_n += t;
     }
     __syncthreads();
@@ -697,19 +698,19 @@ __global__ void __launch_bounds__(512) class_nms_kernel(const __grid_constant__ 
   };
   bool use_buckets = false;
   if (n > NMS_FIRST) {
-    for (int i = tid; i < 1024; i += 512) bh[i] = 0;
+    for (int i = tid; i < 1024; i += T) bh[i] = 0;
     if (tid == 0) s_maxb = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += 512) atomicAdd(&bh[bucket_of(key_at(i))], 1u);
+    for (int i = tid; i < n; i += T) atomicAdd(&bh[bucket_of(key_at(i))], 1u);
     __syncthreads();
-    for (int i = tid; i < 1024; i += 512) if (bh[i] > NMS_FIRST) atomicMax(&s_maxb, bh[i]);
+    for (int i = tid; i < 1024; i += T) if (bh[i] > NMS_FIRST) atomicMax(&s_maxb, bh[i]);
     __syncthreads();
     use_buckets = (s_maxb == 0);               // every bucket fits the first (smallest) round
   }
   if (n <= NMS_FIRST) {
     // small class: sort everything once
     const int Ps = next_pow2(n);
-    for (int i = tid; i < Ps; i += 512) rb[i] = (i < n) ? key_at(i) : 0ull;
+    for (int i = tid; i < Ps; i += T) rb[i] = (i < n) ? key_at(i) : 0ull;
     bitonic_sort_desc(rb, Ps);
     const unsigned long long* sb = rb;
     greedy_nms_bounded(sb, n, bx, P.iou_thr, P.kcap, &s_total, kbox, karea,
@@ -727,7 +728,7 @@ __global__ void __launch_bounds__(512) class_nms_kernel(const __grid_constant__ 
       __syncthreads();
       const int blo = s_blo, teff = s_teff;
       if (teff > 0) {
-        for (int base = 0; base < n; base += 512) {
+        for (int base = 0; base < n; base += T) {
           const int i = base + tid;
           const unsigned long long u = (i < n) ? key_at(i) : 0ull;
           const int bq = (i < n) ? bucket_of(u) : -1;
@@ -740,7 +741,7 @@ __global__ void __launch_bounds__(512) class_nms_kernel(const __grid_constant__ 
         }
         __syncthreads();
         const int Ps = next_pow2(teff);
-        for (int i = teff + tid; i < Ps; i += 512) rb[i] = 0ull;
+        for (int i = teff + tid; i < Ps; i += T) rb[i] = 0ull;
         bitonic_sort_desc(rb, Ps);
         const int total = greedy_nms_bounded(rb, teff, bx, P.iou_thr, P.kcap, &s_total, kbox, karea,
                                              [&](int r, int pos) { keys_out[pos] = rb[r]; });
@@ -767,7 +768,7 @@ __global__ void __launch_bounds__(512) class_nms_kernel(const __grid_constant__ 
         if (tid < 256) hist[tid] = 0;
         __syncthreads();
         const unsigned long long prefix = s_prefix;
-        for (int base = 0; base < n; base += 512) {
+        for (int base = 0; base < n; base += T) {
           const int i = base + tid;
           const unsigned long long u = (i < n) ? key_at(i) : 0ull;
           const bool valid = (i < n) && (u < bound) && ((u & mask) == prefix);
@@ -790,7 +791,7 @@ __global__ void __launch_bounds__(512) class_nms_kernel(const __grid_constant__ 
         __syncthreads();
       }
       const unsigned long long kt = s_prefix;   // the teff-th largest key below `bound`
-      for (int base = 0; base < n; base += 512) {
+      for (int base = 0; base < n; base += T) {
         const int i = base + tid;
         const unsigned long long u = (i < n) ? key_at(i) : 0ull;
         const bool take = (i < n) && (u < bound) && (u >= kt);
@@ -802,7 +803,7 @@ __global__ void __launch_bounds__(512) class_nms_kernel(const __grid_constant__ 
       }
       __syncthreads();
       const int Ps = next_pow2(teff);
-      for (int i = teff + tid; i < Ps; i += 512) rb[i] = 0ull;
+      for (int i = teff + tid; i < Ps; i += T) rb[i] = 0ull;
       bitonic_sort_desc(rb, Ps);
       const int total = greedy_nms_bounded(rb, teff, bx, P.iou_thr, P.kcap, &s_total, kbox, karea,
                                            [&](int r, int pos) { keys_out[pos] = rb[r]; });
@@ -844,20 +845,23 @@ __global__ void __launch_bounds__(1024) final_select_kernel(const __grid_constan
   const bool by_score = total > P.max_per_img;
   const int Ps = next_pow2(max(total, 1));
   for (int i = total + tid; i < Ps; i += 1024) sortbuf[i] = 0ull;
-  for (int c = 0; c < P.C; ++c) {
-    const int n_c = s_off[c + 1] - s_off[c];
-    const unsigned long long* kk = kept_keys + ((size_t)img * P.C + c) * P.kcap;
-    for (int r = tid; r < n_c; r += 1024) {
-      const unsigned long long key = kk[r];
-      const unsigned int sbits = (unsigned int)(key >> 32);
-      const unsigned int j = 0xffffffffu - (unsigned int)(key & 0xffffffffull);
-      const unsigned int pos = rank_order ? (unsigned int)(c * P.kcap + r)
-                                          : (unsigned int)c * (unsigned int)P.M + j;   // class-major, row-minor
-      const int e = s_off[c] + r;
-      // payload (pos) must survive the sort: by_score -> key = (score, ~pos); else key = (~pos, score)
-      sortbuf[e] = by_score ? (((unsigned long long)sbits << 32) | (0xffffffffu - pos))
-                            : (((unsigned long long)(0xffffffffu - pos) << 32) | sbits);
+  // one kept row per thread and trip (all loads of a trip in flight together; a class-by-class loop would wait for
+  // global memory C times in a row): the row's class comes from a binary search in the class offsets
+  for (int e = tid; e < total; e += 1024) {
+    int lo_c = 0, hi_c = P.C;                                  // s_off[lo_c] <= e < s_off[hi_c]
+    while (hi_c - lo_c > 1) {
+      const int mid = (lo_c + hi_c) >> 1;
+      if (s_off[mid] <= e) lo_c = mid; else hi_c = mid;
     }
+    const int c = lo_c, r = e - s_off[c];
+    const unsigned long long key = kept_keys[((size_t)img * P.C + c) * P.kcap + r];
+    const unsigned int sbits = (unsigned int)(key >> 32);
+    const unsigned int j = 0xffffffffu - (unsigned int)(key & 0xffffffffull);
+    const unsigned int pos = rank_order ? (unsigned int)(c * P.kcap + r)
+                                        : (unsigned int)c * (unsigned int)P.M + j;     // class-major, row-minor
+    // payload (pos) must survive the sort: by_score -> key = (score, ~pos); else key = (~pos, score)
+    sortbuf[e] = by_score ? (((unsigned long long)sbits << 32) | (0xffffffffu - pos))
+                          : (((unsigned long long)(0xffffffffu - pos) << 32) | sbits);
   }
   const int k = min(total, P.max_per_img);
   if (by_score && total > 4 * P.max_per_img) {
@@ -1463,7 +1467,10 @@ static int run_nms(const PostParams& P, const float* boxes, const float* scores_
   const int Pmax = (P.M + 7) & ~7;          // multiple of 8 keeps kbox 16-byte aligned behind the 6-byte entries
   const size_t sm4 = (size_t)Pmax * 6 + (size_t)P.kcap * 20 + 16;
   IOU_CHECK_CUDA(cudaFuncSetAttribute(class_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4));
-  class_nms_kernel<<<dim3(P.C, P.n_img), 512, sm4, st>>>(P, boxes, scores_cm, kept_keys, kept_cnt, Pmax);
+  // 640 (class, image) CTAs at bs = 8: with 512 threads 4 fit an SM (592 slots, two waves), with 384 threads 5 (740 slots)
+  static const int nms_threads = getenv("IOU_NMS_THREADS") ? atoi(getenv("IOU_NMS_THREADS")) : 512;
+  const int nt = (nms_threads == 384 || nms_threads == 256) ? nms_threads : 512;
+  class_nms_kernel<<<dim3(P.C, P.n_img), nt, sm4, st>>>(P, boxes, scores_cm, kept_keys, kept_cnt, Pmax);
   if (int e = launch_status("class_nms_kernel")) return e;
   const size_t sm5 = (size_t)next_pow2_host(P.C * P.kcap) * 8 + 64;
   IOU_CHECK_CUDA(cudaFuncSetAttribute(final_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm5));
