@@ -222,6 +222,12 @@ typedef struct iou_conv_desc {
    * reading it contract only its src_cin[i] channels (the first src_cin[i] K columns of their weight rows, in both
    * planes) -- K-concatenated GEMMs in one accumulator, e.g. conv3(t2) + downsample(x) of a bottleneck's first block. */
   int32_t src_cin[IOU_CONV_MAX_SRC];
+  /* Split-K through N-concatenated partial sums (ABI version 7; 0 or 1 = off): the sources hold k_split * cin channels;
+   * output channels [j * cout/k_split, (j+1) * cout/k_split) are the PARTIAL sums of a (cout/k_split)-channel convolution
+   * over input channels [j*cin, (j+1)*cin) (weight: [taps*cout_pad][2*cin], row block j = that channel slice).  A conv
+   * with few output rows and a long K (FPN P6: 22 row tiles, K = 18 432) gets k_split times more work items of
+   * 1/k_split the length; iou_sum_channel_groups adds the partial maps (+ bias).  cout_pad/block_n % k_split == 0. */
+  int32_t k_split;
 } iou_conv_desc;
 
 typedef struct iou_conv_plan iou_conv_plan;
@@ -291,6 +297,11 @@ int iou_group_norm_relu_fmt(void* map, int c, int num_seg, const iou_conv_segmen
  * fp16 precision only), out4[3] = non-zero elements.  The detector runs it over every activation map after the first
  * batch of a plan (api/detectors.py) -- the guard for activation ranges outside what the fp16 + e4m3 scheme holds. */
 int iou_range_stats(const void* map, int64_t rows, int c, int fmt, uint64_t* out4, void* stream);
+/* out[row][c] = bias[c] + sum_j part[row][j*c_out + c] on interior rows of one [n][h+2][w+2] padded-rows segment (border
+ * rows are written as zeros): the reduction behind a k_split convolution.  part: [rows][2*groups*c_out], out:
+ * [rows][2*c_out], both in element format fmt; bias may be NULL; c_out % 8 == 0. */
+int iou_sum_channel_groups(const void* part, int n, int h, int w, int c_out, int groups, const float* bias, void* out,
+                           int fmt, void* stream);
 /* x[i] = exp(x[i] * scale) on n dense fp32 values: bbox_pred = scale(fcos_reg(feat)).exp()
  * (mmdet/models/anchor_heads/iou_aware_fcos_head.py:108). */
 int iou_scale_exp(float* x, size_t n, float scale, void* stream);

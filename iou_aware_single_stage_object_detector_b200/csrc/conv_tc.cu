@@ -94,6 +94,7 @@ struct ConvParams {
   int f8;                    // passes == 2: fp16 main pass + e4m3 correction pass (split_fmt.cuh); `scale` = 1 / S_n
   int num_acc;               // TMEM accumulator stages (2)
   int corr_off;              // f8, narrow tiles: the e4m3 MMAs accumulate into a second column block at this offset (0: same block)
+  int ksplit_ntiles;         // split-K: N tiles per K split (0 = off); split j = n_tile / ksplit_ntiles reads K slabs [j*grp_ks, (j+1)*grp_ks)
   int pdl;                   // programmatic dependent launch: prologue overlaps the previous kernel's tail (griddepcontrol)
 };
 
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
             mbar_wait(bar_aempty + 8 * as, aph ^ 1u);
             const uint32_t fa = bar_afull + 8 * as;
             const uint32_t sa = tiles_addr + as * P.a_entry_bytes;
-            const int a_col = P.diag_k ? n_tile * kBlockK : ks * kBlockK;
+            const int a_col = (P.diag_k ? n_tile : (P.ksplit_ntiles ? (n_tile / P.ksplit_ntiles) * P.grp_ks[g] + ks : ks)) * kBlockK;
             if (!kTwoCta || rank == 0) mbar_expect_tx(fa, mult * (uint32_t)P.a_entry_bytes);
             if constexpr (kTwoCta) {
               tma_load_2d_pair(tm, fa, sa, a_col, arow);
@@ -882,9 +883,15 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   P.diag_k = d->diag_k ? 1 : 0;
   P.b_cin = P.diag_k ? kBlockK : d->cin;
   P.k_slabs = P.diag_k ? 1 : d->cin / kBlockK;
+  const int ksplit = d->k_split > 1 ? d->k_split : 1;
+  if (ksplit > 1 && (P.diag_k || (d->cout_pad / d->block_n) % ksplit != 0 || d->out_mode != IOU_OUT_PADDED_BF16X2)) {
+    delete plan;
+    return fail(IOU_ERR_INVALID, "k_split needs a padded-rows output, no diag_k and cout_pad/block_n a multiple of k_split");
+  }
   for (int i = 0; i < IOU_CONV_MAX_SRC; ++i) {
-    P.src_cin[i] = (i < d->num_src && d->src_cin[i] > 0) ? d->src_cin[i] : d->cin;
-    if (P.src_cin[i] % kBlockK != 0 || P.src_cin[i] > d->cin) { delete plan; return fail(IOU_ERR_INVALID, "src_cin[%d] must be a multiple of %d and <= cin", i, kBlockK); }
+    P.src_cin[i] = (i < d->num_src && d->src_cin[i] > 0) ? d->src_cin[i] : d->cin * ksplit;
+    if (ksplit > 1 && P.src_cin[i] != d->cin * ksplit) { delete plan; return fail(IOU_ERR_INVALID, "k_split: every source must hold k_split * cin channels"); }
+    if (P.src_cin[i] % kBlockK != 0 || (ksplit == 1 && P.src_cin[i] > d->cin)) { delete plan; return fail(IOU_ERR_INVALID, "src_cin[%d] must be a multiple of %d and <= cin", i, kBlockK); }
     if (P.diag_k && P.src_cin[i] != d->cin) { delete plan; return fail(IOU_ERR_INVALID, "diag_k needs equal source channel counts"); }
   }
   P.passes = d->passes == 1 ? 1 : 3;   // 3 = hi/lo operands staged; lolo adds the fourth product
@@ -926,6 +933,7 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   P.num_m_tiles = toff;
   P.num_n_tiles = d->cout_pad / d->block_n;
   P.total_tiles = P.num_m_tiles * P.num_n_tiles;
+  P.ksplit_ntiles = ksplit > 1 ? P.num_n_tiles / ksplit : 0;
   // CTA-pair mode (tcgen05 cta_group::2): two CTAs of a cluster own two consecutive 128-row tiles and share
   // one BLOCK_N-wide B tile, each staging half of its rows -> half the B traffic per CTA and a deeper pipeline
   P.two_cta = (d->two_cta && d->block_n % 16 == 0) ? 1 : 0;   // each CTA stages block_n/2 rows of B (whole 8-row swizzle atoms)
@@ -977,7 +985,7 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
     // (entry e = the e-th (tap, slab) of a tile) and spend the rest of shared memory on the A ring
     int b_entries = 0;
     for (int g = 0; g < P.num_groups; ++g) {
-      P.grp_ks[g] = P.diag_k ? 1 : P.src_cin[P.grp_src[g]] / kBlockK;
+      P.grp_ks[g] = P.diag_k ? 1 : (ksplit > 1 ? d->cin / kBlockK : P.src_cin[P.grp_src[g]] / kBlockK);
       b_entries += P.grp_nt[g] * P.grp_ks[g];
     }
     P.tap_slabs_per_tile = b_entries;
@@ -1043,7 +1051,7 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   }
   plan->smem_bytes = (size_t)kCtrlBytes + 1024 + (size_t)P.ring_bytes + (size_t)kNumEpiWarps * P.staging_per_warp;
   double k_total = 0;
-  for (int t = 0; t < d->num_taps; ++t) k_total += P.diag_k ? kBlockK : P.src_cin[d->tap_src[t]];
+  for (int t = 0; t < d->num_taps; ++t) k_total += P.diag_k ? kBlockK : (ksplit > 1 ? d->cin : P.src_cin[d->tap_src[t]]);
   plan->flops = 2.0 * real_rows * d->cout * k_total;
   static bool attr_set = false;
   if (!attr_set) {

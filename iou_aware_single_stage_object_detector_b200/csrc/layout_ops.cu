@@ -481,6 +481,38 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(__nv_bfloat16* __restrict
 }
 
 // y = exp(x * scale) on a dense fp32 tensor (FCOS: bbox_pred = scale(fcos_reg(x)).exp(), iou_aware_fcos_head.py:108)
+// ---- sum of `groups` channel groups of a padded-rows map (+ bias): the reduction behind a k_split convolution.
+// One thread per (row, 8 channels); border rows are written as zeros.
+template <int kFmt>
+__global__ void __launch_bounds__(256) sum_groups_kernel(const uint4* __restrict__ part, int n, int h, int w, int c_out,
+                                                         int groups, const float* __restrict__ bias,
+                                                         uint4* __restrict__ out) {
+  const int c8 = c_out >> 3, wp = w + 2, plane = (h + 2) * wp;
+  const long long total = (long long)n * plane * c8;
+  const int in_vec = 2 * groups * c8;            // 16-byte vectors per input row: hi plane then lo plane
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c8);
+    const long long row = i / c8;
+    const int rem = (int)(row % plane), yp = rem / wp, xp = rem - yp * wp;
+    uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+    if (yp >= 1 && yp <= h && xp >= 1 && xp <= w) {
+      float acc[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = bias ? __ldg(bias + cg * 8 + q) : 0.f;
+      const uint4* r = part + row * in_vec;
+      for (int j = 0; j < groups; ++j) {
+        float t8[8];
+        decode8<kFmt>(__ldg(r + j * c8 + cg), __ldg(r + groups * c8 + j * c8 + cg), t8);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] += t8[q];
+      }
+      encode8<kFmt>(acc, hi, lo);
+    }
+    out[row * (2 * c8) + cg] = hi;
+    out[row * (2 * c8) + c8 + cg] = lo;
+  }
+}
+
 // ---- range statistics of a padded-rows map (both element formats): out[0] = max |v| (float bits), out[1] = number of
 // elements at or beyond the fp16 limit (saturated by the fp16 + e4m3 encode; inf / NaN count as well), out[2] = number
 // of elements with 448 < |v| (e4m3 parts saturated: fp16 precision only), out[3] = number of non-zero elements.
@@ -642,6 +674,22 @@ extern "C" int iou_group_norm_relu(void* map, int c, int num_seg, const iou_conv
                                    size_t workspace_bytes, void* stream) {
   return iou_group_norm_relu_fmt(map, c, num_seg, seg, groups, gamma, beta, eps, relu, workspace, workspace_bytes,
                                  kFmtBf16x2, stream);
+}
+
+extern "C" int iou_sum_channel_groups(const void* part, int n, int h, int w, int c_out, int groups, const float* bias,
+                                      void* out, int fmt, void* stream) {
+  IOU_REQUIRE(part && out, "NULL argument");
+  IOU_REQUIRE(n >= 1 && h >= 1 && w >= 1 && groups >= 1 && c_out > 0 && c_out % 8 == 0, "bad shape");
+  IOU_REQUIRE(fmt == IOU_FMT_BF16X2 || fmt == IOU_FMT_F16F8, "bad element format");
+  IOU_REQUIRE(((uintptr_t)part & 15) == 0 && ((uintptr_t)out & 15) == 0, "maps must be 16-byte aligned");
+  const long long total = (long long)n * (h + 2) * (w + 2) * (c_out / 8);
+  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (fmt == IOU_FMT_F16F8)
+    sum_groups_kernel<kFmtF16F8><<<blocks, 256, 0, st>>>((const uint4*)part, n, h, w, c_out, groups, bias, (uint4*)out);
+  else
+    sum_groups_kernel<kFmtBf16x2><<<blocks, 256, 0, st>>>((const uint4*)part, n, h, w, c_out, groups, bias, (uint4*)out);
+  return launch_status("sum_groups_kernel");
 }
 
 extern "C" int iou_range_stats(const void* map, int64_t rows, int c, int fmt, uint64_t* out4, void* stream) {

@@ -260,10 +260,12 @@ class Engine(object):
     def conv(self, name, srcs, taps, weight, cin, cout, out=None, scale=None, shift=None, relu=False,
              residual=None, res_mode=L.RES_NONE, dense_out=None, dense_out2=None, dense_split=0,
              segs_from=None, diag_k=False, true_flops_scale=1.0, two_cta=None, force_bn=None,
-             phase_outs=None, phase_only=False):
+             phase_outs=None, phase_only=False, k_split=1):
         """srcs: list[FlatMap] (same geometry); out: FlatMap or None (dense).  Returns out.
         phase_outs: 4 FlatMaps / None from new_phase_maps(): the epilogue also writes the stride-2 phase split of the
-        output (what iou_phase_split would produce from it); phase_only: nothing else is written (returns None)."""
+        output (what iou_phase_split would produce from it); phase_only: nothing else is written (returns None).
+        k_split = S > 1: the sources hold S * cin channels and `cout` = S * (real cout) output channels are the S partial
+        sums over the channel slices (weight rows packed to match, see split_k_weight); sum_groups() adds them."""
         geo = segs_from or srcs[0]
         m_tiles = sum(seg_tiles(n, h, w) for (_, n, h, w) in geo.segs)
         # a same-geometry residual needs its TMA staging ring in shared memory: N tile <= 128, or 256 when the conv
@@ -294,7 +296,7 @@ class Engine(object):
         d.num_src = len(srcs)
         for i, m in enumerate(srcs):
             # sources may have fewer channels than cin (= the K of the weight rows): their taps contract m.c channels
-            assert m.c <= cin and (m.c == cin or not diag_k), (name, m.c, cin)     # % 64: checked by plan_create
+            assert (m.c == cin * k_split) if k_split > 1 else (m.c <= cin and (m.c == cin or not diag_k)), (name, m.c, cin)
             d.src[i] = m.ptr
             d.src_cin[i] = m.c
         d.src_rows = min(m.rows for m in srcs)
@@ -362,6 +364,7 @@ class Engine(object):
                 for i, t in enumerate(dense_out2):
                     d.out_dense2[i] = t.data_ptr()
         d.passes = self.passes
+        d.k_split = int(k_split)
         plan = ctypes.c_void_p()
         rc = self.lib.iou_conv_plan_create(ctypes.byref(d), ctypes.byref(plan))
         if rc != 0 and retry_bn is not None:         # the wide residual tile did not fit next to the staging rings
@@ -377,6 +380,16 @@ class Engine(object):
         self.op_flops[name] = self.op_flops.get(name, 0.0) + f
         lib = self.lib
         self.ops.append((name, lambda st, p=plan: L.check(lib.iou_conv_run(p, st))))
+        return out
+
+    def sum_groups(self, name, part, out, groups, bias=None):
+        """out (FlatMap, one segment, c channels) <- bias + sum of the `groups` channel groups of part (groups * c
+        channels): the reduction behind conv(..., k_split=groups)."""
+        (_, n, h, w), c = out.segs[0], out.c
+        assert part.c == groups * c and part.segs[0][1:] == (n, h, w)
+        b = self._dev(bias) if bias is not None else None
+        lib, pp, op, bp, fmt = self.lib, part.ptr, out.ptr, (b.data_ptr() if b is not None else None), self.fmt
+        self.ops.append((name, lambda st: L.check(lib.iou_sum_channel_groups(pp, n, h, w, c, groups, bp, op, fmt, st))))
         return out
 
     def new_phase_maps(self, n, h, w, c, mask=15):
@@ -554,8 +567,21 @@ class Engine(object):
             kp = "%sfpn_convs.%d.conv." % (prefix, i)
             # fpn.py:123-128: ReLU only in front of the extra convs AFTER the first one
             ph = self.phase_split(kp + "phase", src, relu=(relu_before_extra_convs and i > nl))
-            self.conv(kp[:-1], ph, TAPS_3X3_S2, pack_weight(sd[kp + "weight"], out_channels), src.c,
-                      out_channels, out=F.view(i), shift=sd[kp + "bias"])
+            ks = int(os.environ.get("IOU_P6_KSPLIT", "4"))
+            _, n_, h_, w_ = F.segs[i]
+            if ks > 1 and src.c % (64 * ks) == 0 and src.c >= 1024 and seg_tiles(n_, h_, w_) < NUM_SMS // 2:
+                # few output rows, long K (P6 on C5: 22 row tiles x K = 18 432): S times more work items of 1/S the
+                # length through N-concatenated partial sums, added (+ bias) by one small kernel
+                wk = sd[kp + "weight"]
+                cs = src.c // ks
+                wsp = torch.cat([wk[:, j * cs:(j + 1) * cs] for j in range(ks)], dim=0)     # (S*cout, cin/S, 3, 3)
+                part = self.new_map([(n_, h_, w_)], ks * out_channels)
+                self.conv(kp[:-1], ph, TAPS_3X3_S2, pack_weight(wsp, ks * out_channels), cs, ks * out_channels,
+                          out=part, k_split=ks, two_cta=(True if os.environ.get("IOU_P6_PAIR", "1") != "0" else None))
+                self.sum_groups(kp + "sum", part, F.view(i), ks, bias=sd[kp + "bias"])
+            else:
+                self.conv(kp[:-1], ph, TAPS_3X3_S2, pack_weight(sd[kp + "weight"], out_channels), src.c,
+                          out_channels, out=F.view(i), shift=sd[kp + "bias"])
             src = F.view(i)
         if extra_convs_on_inputs and num_outs > nl and os.environ.get("IOU_FPN_SIDE", "0") != "0":
             # P6 / P7 only read C5 (fpn.py:118-128): their launches (few tiles, long K) run on a side stream next to the

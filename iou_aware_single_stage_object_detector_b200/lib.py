@@ -97,7 +97,7 @@ class ConvDesc(ctypes.Structure):
                 ("passes", ctypes.c_int32), ("out_rows", ctypes.c_int64), ("res_rows", ctypes.c_int64),
                 ("diag_k", ctypes.c_int32), ("two_cta", ctypes.c_int32),
                 ("phase_out", ctypes.c_void_p * 4), ("phase_only", ctypes.c_int32),
-                ("src_cin", ctypes.c_int32 * CONV_MAX_SRC)]
+                ("src_cin", ctypes.c_int32 * CONV_MAX_SRC), ("k_split", ctypes.c_int32)]
 
 
 _SIGS = {
@@ -177,6 +177,9 @@ _SIGS = {
     "iou_group_norm_relu_fmt": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_int,
                                                ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
+    "iou_sum_channel_groups": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                              ctypes.c_void_p]),
     "iou_range_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                        ctypes.c_void_p]),
     "iou_scale_exp": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_float, ctypes.c_void_p]),

@@ -333,3 +333,33 @@ def test_detector_unnormalised_input_range_guard():
     ref_cls, _, _ = om.detector_forward(sd, wild)
     for a, b in zip(plan3.outs[0], ref_cls):
         assert rel_err(a.cpu(), b) < 5e-4, rel_err(a.cpu(), b)
+
+
+@pytest.mark.parametrize("passes", [2, 3])
+@pytest.mark.parametrize("ks,cin,cout,stride", [(4, 512, 64, 1), (8, 1024, 256, 2), (2, 256, 128, 1)])
+def test_split_k_conv_with_channel_group_sum_vs_torch(passes, ks, cin, cout, stride):
+    """k_split: the K loop of a conv with few output rows is cut into `ks` channel slices whose partial sums land in
+    N-concatenated output channels (iou_conv_desc.k_split) and are added, with the bias, by iou_sum_channel_groups
+    (how FPN's P6 conv on C5 runs, fpn.py:126-128)."""
+    g = torch.Generator().manual_seed(ks * 7 + cin)
+    x = torch.randn(2, cin, 13, 21, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = F.conv2d(x, w, b, stride=stride, padding=1)
+    eng = E.Engine(DEV, passes=passes)
+    m = eng.pack_input(x.to(DEV))
+    cs = cin // ks
+    wsp = torch.cat([w[:, j * cs:(j + 1) * cs] for j in range(ks)], dim=0)
+    n, _, ho, wo = ref.shape
+    part = eng.new_map([(n, ho, wo)], ks * cout)
+    srcs, taps = ([m], E.TAPS_3X3) if stride == 1 else (eng.phase_split("p", m), E.TAPS_3X3_S2)
+    eng.conv("c", srcs, taps, E.pack_weight(wsp, ks * cout), cs, ks * cout, out=part, k_split=ks)
+    out = eng.new_map([(n, ho, wo)], cout)
+    eng.sum_groups("s", part, out, ks, bias=b)
+    y = eng.unpack_output(out)
+    eng.run()
+    torch.cuda.synchronize()
+    assert rel_err(y.cpu(), ref) < TOL, rel_err(y.cpu(), ref)
+    # border rows of the summed map stay zero (the next conv's taps read them as padding)
+    rows = out.tensor[: n * (ho + 2) * (wo + 2)].view(torch.uint8).view(n, ho + 2, wo + 2, 4 * cout)
+    assert int(rows[:, 0].max()) == 0 and int(rows[:, -1].max()) == 0 and int(rows[:, :, 0].max()) == 0

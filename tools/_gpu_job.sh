@@ -1,13 +1,16 @@
 set -x
-O=gpurun_out/r2q; mkdir -p $O
-for t in 512 384 256; do
-IOU_NMS_THREADS=$t timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -k "regex:class_nms|final_select" --csv --log-file $O/post_bs8_$t.csv python bench.py --no-graph --ncu-range --no-cpu-baseline --steps 1 --warmup 3 > $O/post_$t.out 2>&1
-python - <<PY
-import csv
-rows=[l for l in open('$O/post_bs8_$t.csv') if l.startswith('"')]
-for r in csv.DictReader(rows): print($t, r['Kernel Name'][:24], r['Block Size'], r['Metric Value'])
+O=gpurun_out/r2s; mkdir -p $O
+run() { name=$1; shift; env "$@" python bench.py --steps 30 --warmup 5 --no-cpu-baseline --dump-ops $O/ops_$name.json > $O/bench_$name.json 2> $O/$name.err; python - <<PY
+import json
+try:
+    d=json.load(open('$O/bench_$name.json')); o={x['op']:x['ms'] for x in json.load(open('$O/ops_$name.json'))}
+    print('$name', d['value'], d['ms_per_step'], d['e2e']['value'], d['conv_ms_per_step'], {k:v for k,v in o.items() if 'fpn_convs.3' in k})
+except Exception as e: print('$name ERR', e); print(open('$O/$name.err').read()[-800:])
 PY
-IOU_NMS_THREADS=$t python tools/bench_postproc.py | cut -c80-220
-done
-IOU_NMS_THREADS=384 python -m pytest tests/test_gpu_postproc.py -q -x 2>&1 | tail -2
-python -m pytest tests/test_gpu_postproc.py -q -x 2>&1 | tail -2
+}
+run ks4_pair IOU_P6_KSPLIT=4 IOU_P6_PAIR=1
+run ks8_pair IOU_P6_KSPLIT=8 IOU_P6_PAIR=1
+run ks4_nopair IOU_P6_KSPLIT=4 IOU_P6_PAIR=0
+run ks2_pair IOU_P6_KSPLIT=2 IOU_P6_PAIR=1
+IOU_P6_KSPLIT=4 python -m pytest tests/test_gpu_detector_golden.py -q -x -k "r50_full_size_default" 2>&1 | tail -2
+IOU_P6_KSPLIT=8 python -m pytest tests/test_gpu_detector_golden.py -q -x -k "r50_full_size_default" 2>&1 | tail -2
