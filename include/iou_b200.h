@@ -235,6 +235,13 @@ typedef struct iou_conv_plan iou_conv_plan;
 int iou_conv_plan_create(const iou_conv_desc* desc, iou_conv_plan** plan_out);
 int iou_conv_run(const iou_conv_plan* plan, void* stream);
 void iou_conv_plan_destroy(iou_conv_plan* plan);
+/* Chains two plans into ONE launch (ABI version 8): `second` must be a plain 1x1 conv whose only source is the padded-rows
+ * output of `first` (also a plain 1x1 conv, optionally with a same-geometry residual), both as CTA pairs with passes == 2,
+ * same segments, one N tile in `second` -- relu(bn3(conv3(t2)) + x) followed by the next bottleneck's conv1
+ * (backbones/resnet.py:224-226,256-265).  Each CTA pair then computes both convs for its rows and reads conv 1's
+ * output back while it is still in L2 instead of from HBM.  On success *plan_out == first (which now owns `second`; run
+ * and destroy it like any plan); on IOU_ERR_INVALID both plans are untouched and can be run one after the other. */
+int iou_conv_chain_plan_create(iou_conv_plan* first, iou_conv_plan* second, iou_conv_plan** plan_out);
 /* 2*MAC flops the plan performs on real (non-padding) outputs, for rooflines. */
 double iou_conv_plan_flops(const iou_conv_plan* plan);
 

@@ -16,7 +16,7 @@ int fail(int code, const char* fmt, ...) {
 }  // namespace iou
 
 extern "C" const char* iou_last_error(void) { return iou::g_last_error.c_str(); }
-extern "C" int iou_abi_version(void) { return 7; }
+extern "C" int iou_abi_version(void) { return 8; }
 extern "C" size_t iou_sizeof(int what) {
   switch (what) {
     case 0: return sizeof(iou_postproc_cfg);

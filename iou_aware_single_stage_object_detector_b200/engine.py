@@ -260,10 +260,12 @@ class Engine(object):
     def conv(self, name, srcs, taps, weight, cin, cout, out=None, scale=None, shift=None, relu=False,
              residual=None, res_mode=L.RES_NONE, dense_out=None, dense_out2=None, dense_split=0,
              segs_from=None, diag_k=False, true_flops_scale=1.0, two_cta=None, force_bn=None,
-             phase_outs=None, phase_only=False, k_split=1):
+             phase_outs=None, phase_only=False, k_split=1, hold=False, chain=False):
         """srcs: list[FlatMap] (same geometry); out: FlatMap or None (dense).  Returns out.
         phase_outs: 4 FlatMaps / None from new_phase_maps(): the epilogue also writes the stride-2 phase split of the
         output (what iou_phase_split would produce from it); phase_only: nothing else is written (returns None).
+        hold=True keeps the launch back so that the NEXT conv(chain=True) -- a plain 1x1 conv reading this conv's output --
+        can be chained into the same launch (iou_conv_chain_plan_create); if the pair does not qualify both run as usual.
         k_split = S > 1: the sources hold S * cin channels and `cout` = S * (real cout) output channels are the S partial
         sums over the channel slices (weight rows packed to match, see split_k_weight); sum_groups() adds them."""
         geo = segs_from or srcs[0]
@@ -377,8 +379,25 @@ class Engine(object):
                 m.label = name
         f = self.lib.iou_conv_plan_flops(plan) * true_flops_scale
         self.flops += f
-        self.op_flops[name] = self.op_flops.get(name, 0.0) + f
         lib = self.lib
+        held, self._held = getattr(self, "_held", None), None
+        if held is not None:
+            h_name, h_plan, h_f = held
+            merged = ctypes.c_void_p()
+            rc = lib.iou_conv_chain_plan_create(h_plan, plan, ctypes.byref(merged)) if chain else -1
+            if rc == 0:                          # one launch computes both convs (the first plan now owns the second)
+                self.plans.remove(plan)
+                name2 = h_name + "+" + name.split(".")[-1]
+                self.op_flops[name2] = self.op_flops.get(name2, 0.0) + h_f + f
+                self.ops.append((name2, lambda st, p=h_plan: L.check(lib.iou_conv_run(p, st))))
+                self.chained = getattr(self, "chained", 0) + 1
+                return out
+            self.op_flops[h_name] = self.op_flops.get(h_name, 0.0) + h_f
+            self.ops.append((h_name, lambda st, p=h_plan: L.check(lib.iou_conv_run(p, st))))
+        if hold:
+            self._held = (name, plan, f)
+            return out
+        self.op_flops[name] = self.op_flops.get(name, 0.0) + f
         self.ops.append((name, lambda st, p=plan: L.check(lib.iou_conv_run(p, st))))
         return out
 
@@ -447,6 +466,10 @@ class Engine(object):
         fuse = os.environ.get("IOU_FUSE_PHASE", "1") != "0"     # producers write the stride-2 phase maps themselves
         fuse_ds = os.environ.get("IOU_FUSE_DS", "1") != "0"     # conv3 + downsample of a stage's first block in one GEMM
         fuse_ph3 = os.environ.get("IOU_FUSE_PH3", "1") != "0"   # a stage's last conv3 also writes phase (1,1) of its output
+        # conv3 of block b and conv1 of block b+1 (same stage) in ONE launch: conv1 reads x back from L2 (conv_chain.cu)
+        chain = os.environ.get("IOU_CHAIN", "0") != "0" and self.passes == 2 and groups == 1 and style == "pytorch"
+        chain_stages = [int(v) for v in os.environ.get("IOU_CHAIN_STAGES", "0,1,2").split(",") if v != ""]
+        chained_in = False                                      # this block's conv1 completes a held conv3
         x_ph3 = None                                            # phase (1,1) of x, if its producer wrote it
         for s, nblocks in enumerate(STAGE_BLOCKS[depth]):
             planes = 64 * 2 ** s
@@ -471,7 +494,9 @@ class Engine(object):
                     t1 = self.conv(p + "conv1", [x], TAPS_1X1, w1, cin, width, shift=sh1, relu=True,
                                    phase_outs=t1_ph, phase_only=True)
                 else:
-                    t1 = self.conv(p + "conv1", [x], TAPS_1X1, w1, cin, width, shift=sh1, relu=True)
+                    t1 = self.conv(p + "conv1", [x], TAPS_1X1, w1, cin, width, shift=sh1, relu=True, chain=chained_in,
+                                   force_bn=((width, width) if (chained_in and width <= 256) else None))
+                chained_in = False
                 sc2, sh2 = bn_fold(sd, p + "bn2")
                 if groups == 1:
                     w2, kw = pack_weight(fold_scale(sd[p + "conv2.weight"], sc2), width), {}
@@ -522,9 +547,11 @@ class Engine(object):
                     else:
                         idt = self.conv(p + "downsample", [x], TAPS_1X1, wd, cin, planes * 4,
                                         shift=shd)
+                hold = chain and s in chain_stages and ph3 is None and b + 1 < nblocks and idt is x
                 x = self.conv(p + "conv3", [t2], TAPS_1X1, pack_weight(fold_scale(sd[p + "conv3.weight"], sc3), planes * 4),
                               width, planes * 4, shift=sh3, relu=True, residual=idt,
-                              res_mode=L.RES_SAME, phase_outs=ph3)
+                              res_mode=L.RES_SAME, phase_outs=ph3, hold=hold)
+                chained_in = hold
                 x_ph3 = ph3[3] if ph3 is not None else None
             outs.append(x)
         return outs

@@ -140,6 +140,7 @@ _SIGS = {
                                                              ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                                              ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
     "iou_conv_plan_create": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(ctypes.c_void_p)]),
+    "iou_conv_chain_plan_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     "iou_conv_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "iou_conv_plan_destroy": (None, [ctypes.c_void_p]),
     "iou_conv_plan_flops": (ctypes.c_double, [ctypes.c_void_p]),

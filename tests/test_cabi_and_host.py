@@ -35,7 +35,7 @@ def test_library_builds_and_exports_header_symbols():
         assert hasattr(lib, n), "symbol %s declared in the header is not exported" % n
     assert set(names) == set(L.EXPORTED_SYMBOLS)
     lib.iou_abi_version.restype = ctypes.c_int
-    assert lib.iou_abi_version() == 7
+    assert lib.iou_abi_version() == 8
 
 
 def test_sass_is_blackwell_native():

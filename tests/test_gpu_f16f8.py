@@ -363,3 +363,39 @@ def test_split_k_conv_with_channel_group_sum_vs_torch(passes, ks, cin, cout, str
     # border rows of the summed map stay zero (the next conv's taps read them as padding)
     rows = out.tensor[: n * (ho + 2) * (wo + 2)].view(torch.uint8).view(n, ho + 2, wo + 2, 4 * cout)
     assert int(rows[:, 0].max()) == 0 and int(rows[:, -1].max()) == 0 and int(rows[:, :, 0].max()) == 0
+
+
+@pytest.mark.parametrize("ca,cb,cc,shape", [(64, 256, 64, (2, 40, 60)),        # layer-1 shape: one N tile, resident weights
+                                            (128, 512, 128, (2, 40, 60)),      # two N tiles of conv A, streamed weights
+                                            (256, 1024, 256, (1, 50, 84)),     # layer-3 shape: four N tiles, K = 1024 for conv B
+                                            (64, 256, 64, (1, 45, 67)),        # odd tile count: the last pair's second CTA idles
+                                            (64, 256, 128, (8, 30, 30))])      # several images
+def test_chained_1x1_convs_one_launch_equal_two_launches(ca, cb, cc, shape):
+    """conv3(+residual, ReLU) of a bottleneck and conv1 of the next one in ONE launch (iou_conv_chain_plan_create,
+    csrc/conv_chain.cu): bit-identical to the two separate launches, and fp32-grade against torch."""
+    n, h, w = shape
+    g = torch.Generator().manual_seed(ca + cb + cc + h)
+    x = torch.randn(n, ca, h, w, generator=g)
+    r = torch.randn(n, cb, h, w, generator=g)
+    wa = torch.randn(cb, ca, 1, 1, generator=g) * (2.0 / ca) ** 0.5
+    wb = torch.randn(cc, cb, 1, 1, generator=g) * (2.0 / cb) ** 0.5
+    ba, bb = torch.randn(cb, generator=g), torch.randn(cc, generator=g)
+    ref_y = F.relu(F.conv2d(x, wa, ba) + r)
+    ref_t = F.relu(F.conv2d(ref_y, wb, bb))
+    outs = []
+    for chained in (True, False):
+        eng = E.Engine(DEV, passes=2)
+        m, rm = eng.pack_input(x.to(DEV)), eng.pack_input(r.to(DEV))
+        y = eng.conv("a", [m], E.TAPS_1X1, E.pack_weight(wa, cb), ca, cb, shift=ba, relu=True, residual=rm,
+                     res_mode=L.RES_SAME, hold=chained, two_cta=True)
+        t = eng.conv("b", [y], E.TAPS_1X1, E.pack_weight(wb, cc), cb, cc, shift=bb, relu=True, chain=chained,
+                     force_bn=(cc, cc), two_cta=True)
+        assert getattr(eng, "chained", 0) == (1 if chained else 0)
+        assert len([o for o in eng.ops if not o[0].startswith("pack")]) == (1 if chained else 2)
+        yo, to = eng.unpack_output(y), eng.unpack_output(t)
+        eng.run()
+        torch.cuda.synchronize()
+        outs.append((yo.cpu(), to.cpu()))
+    (y1, t1), (y2, t2) = outs
+    assert torch.equal(y1, y2) and torch.equal(t1, t2)
+    assert rel_err(y1, ref_y) < TOL and rel_err(t1, ref_t) < TOL, (rel_err(y1, ref_y), rel_err(t1, ref_t))
