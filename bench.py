@@ -95,7 +95,7 @@ class ClockSampler(object):
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
@@ -104,14 +104,21 @@ class ClockSampler(object):
                 sm.append(float(f[0])); mx.append(float(f[1]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[2]))
+            except ValueError:
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
             return None
         busy = sorted(sm)[len(sm) // 2:]          # upper half ~ samples under load
-        return {"sm_mhz": sorted(busy)[len(busy) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        out = {"sm_mhz": sorted(busy)[len(busy) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+               "samples": len(sm), "sm_mhz_min": min(sm)}
+        if pw:
+            out["power_w_median"], out["power_w_max"] = sorted(pw)[len(pw) // 2], max(pw)
+        return out
 
 
 # ------------------------------------------------------------------------------------------------

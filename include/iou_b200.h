@@ -228,6 +228,10 @@ typedef struct iou_conv_desc {
    * with few output rows and a long K (FPN P6: 22 row tiles, K = 18 432) gets k_split times more work items of
    * 1/k_split the length; iou_sum_channel_groups adds the partial maps (+ bias).  cout_pad/block_n % k_split == 0. */
   int32_t k_split;
+  /* Epilogue width (ABI version 8): 0 = library default (12 epilogue warps for the padded-rows convs that add a
+   * same-geometry residual, 8 otherwise; IOU_WIDE overrides), 1 = 12 warps if eligible (passes == 2, padded-rows
+   * output), -1 = 8 warps. */
+  int32_t wide;
 } iou_conv_desc;
 
 typedef struct iou_conv_plan iou_conv_plan;

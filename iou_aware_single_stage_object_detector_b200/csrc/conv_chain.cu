@@ -24,9 +24,12 @@ struct ChainParams {
   int num_a_stages, num_b_stages, a_entry_bytes, b_entry_bytes, ring_bytes, staging_per_warp;
   int b_resident;            // both convs keep all their weight tiles in shared memory (loaded with their first item)
   int b_res_off1;            // byte offset of conv 1's resident entries inside the B area
+  int direct;                // n0 == 1: the epilogue of conv 0 writes y's 64-channel slabs straight into the A ring (UMMA layout) --
+                             // conv 1 never reloads y; item order c3(u0), c1(u0), c3(u1), c1(u1), ...
 };
 
 constexpr uint32_t kBarOutDone = 704;     // control block offsets 704, 712: "y of unit parity 0 / 1 is stored"
+constexpr uint32_t kBarDirect = 720;      // 8 barriers: "A stage s holds a slab written by the epilogue warps of both CTAs"
 
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -41,7 +44,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_chain_kernel(const __grid
   const uint32_t tiles_addr = base + kCtrlBytes;
   const uint32_t bar_full = ctrl_addr + 448, bar_empty = ctrl_addr + 576, bar_tfull = ctrl_addr + 128,
                  bar_tempty = ctrl_addr + 144, bar_afull = ctrl_addr + 320, bar_aempty = ctrl_addr + 384,
-                 bar_outdone = ctrl_addr + kBarOutDone;
+                 bar_outdone = ctrl_addr + kBarOutDone, bar_dfull = ctrl_addr + kBarDirect;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(ctrl + 160);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -52,7 +55,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_chain_kernel(const __grid
   const int total_items = U * (n0 + 1);
   // item s of this pair -> (conv k, unit q, N tile n, unit sequence number j)
   auto item_at = [&](int s, int& k, int& q, int& n, int& j) {
-    if (s < n0) { k = 0; j = 0; n = s; }
+    if (C.direct) { k = s & 1; j = s >> 1; n = 0; }
+    else if (s < n0) { k = 0; j = 0; n = s; }
     else {
       const int s2 = s - n0, blk = s2 / (n0 + 1), r = s2 - blk * (n0 + 1);
       if (blk + 1 < U && r < n0) { k = 0; j = blk + 1; n = r; }
@@ -73,6 +77,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_chain_kernel(const __grid
     for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 2 * kNumEpiWarps * 32); }
     for (int r = 0; r < 2 * kNumEpiWarps; ++r) mbar_init(ctrl_addr + 192 + 8 * r, 1);
     for (int a = 0; a < 2; ++a) mbar_init(bar_outdone + 8 * a, kNumEpiWarps);
+    for (int a = 0; a < kMaxStages; ++a) mbar_init(bar_dfull + 8 * a, 2 * kNumEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     for (int k = 0; k < 2; ++k) {
@@ -110,17 +115,24 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_chain_kernel(const __grid
         const int row0 = P.seg[sidx].row_start + (m_tile - P.seg_tile_off[sidx]) * kBlockM;
         const int b_rows = P.block_n >> 1;
         const int ksl = P.cin / kBlockK;
-        if (k == 1) {                                   // y of this unit must be in global memory
+        const bool direct_item = C.direct && k == 1;    // its A slabs are written by the epilogue warps, not loaded
+        if (k == 1 && !C.direct) {                      // y of this unit must be in global memory
           mbar_wait(bar_outdone + 8 * (j & 1), (uint32_t)(j >> 1) & 1u);
           fence_proxy_async_all();
         }
         for (int ks = 0; ks < ksl; ++ks) {
-          mbar_wait(bar_aempty + 8 * as, aph ^ 1u);
-          const uint32_t fa = bar_afull + 8 * as;
-          const uint32_t sa = tiles_addr + as * C.a_entry_bytes;
-          if (rank == 0) mbar_expect_tx(fa, 2u * (uint32_t)C.a_entry_bytes);
-          tma_load_2d_pair(&P.tmap_src[0], fa, sa, ks * kBlockK, row0);
-          tma_load_2d_pair(&P.tmap_src[0], fa, sa + a_lo_off, P.cin + ks * kBlockK, row0);
+          if (!direct_item) {
+            mbar_wait(bar_aempty + 8 * as, aph ^ 1u);
+            const uint32_t fa = bar_afull + 8 * as;
+            const uint32_t sa = tiles_addr + as * C.a_entry_bytes;
+            if (rank == 0) mbar_expect_tx(fa, 2u * (uint32_t)C.a_entry_bytes);
+            tma_load_2d_pair(&P.tmap_src[0], fa, sa, ks * kBlockK, row0);
+            tma_load_2d_pair(&P.tmap_src[0], fa, sa + a_lo_off, P.cin + ks * kBlockK, row0);
+          } else {
+            // not loaded here, but observed: every use of a stage is waited for in order, so that a parity wait is never
+            // more than one phase behind its barrier
+            mbar_wait(bar_aempty + 8 * as, aph ^ 1u);
+          }
           if (++as == C.num_a_stages) { as = 0; aph ^= 1u; }
           const int wrow = n * P.block_n + rank * b_rows;
           if (C.b_resident) {
@@ -148,7 +160,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_chain_kernel(const __grid
   } else if (warp == 1) {
     // =============================== MMA issuer (leader CTA only) ===============================
     int as = 0, bs = 0;
-    uint32_t aph = 0, bph = 0;
+    uint32_t bph = 0;
+    uint32_t tma_par = 0, dir_par = 0;               // per A stage: parity of its next TMA-filled / epilogue-filled use
     bool b_seen[2] = {false, false};
     const uint32_t a_lo_d = a_lo_off >> 4;
     for (int s = 0; s < total_items && rank == 0; ++s) {
@@ -162,8 +175,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_chain_kernel(const __grid
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
       const int ksl = P.cin / kBlockK;
       const uint32_t corr_off = (uint32_t)P.corr_off, idesc = P.idesc, b_lo_d = (uint32_t)P.b_tile_bytes >> 4;
+      const bool direct_item = C.direct && k == 1;
       for (int ks = 0; ks < ksl; ++ks) {
-        mbar_wait(bar_afull + 8 * as, aph);
+        if (direct_item) { mbar_wait(bar_dfull + 8 * as, (dir_par >> as) & 1u); dir_par ^= 1u << as; }
+        else { mbar_wait(bar_afull + 8 * as, (tma_par >> as) & 1u); tma_par ^= 1u << as; }
         const uint32_t sa = tiles_addr + as * C.a_entry_bytes;
         uint32_t sb;
         if (C.b_resident) {
@@ -191,7 +206,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_chain_kernel(const __grid
         }
         __syncwarp();
         if (!C.b_resident) { if (++bs == C.num_b_stages) { bs = 0; bph ^= 1u; } }
-        if (++as == C.num_a_stages) { as = 0; aph ^= 1u; }
+        if (++as == C.num_a_stages) as = 0;
       }
       b_seen[k] = true;
     }
@@ -227,6 +242,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_chain_kernel(const __grid
       return false;
     };
     int rq = 0;                                            // running slab counter of the residual ring
+    int ring_pos = 0;                                      // A-ring position (in slabs) of the item being processed
+    const int ksl0 = C.p[0].cin / kBlockK, ksl1 = C.p[1].cin / kBlockK;
     if (res && total_items > 0 && elect_one()) issue_res_at(res_row_of(u_first), half * 32, 0);
     for (int s = 0; s < total_items; ++s) {
       int k, q, n, j;
@@ -252,6 +269,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_chain_kernel(const __grid
       const int n_groups = P.block_n >> 5;
       const uint32_t swz = (uint32_t)((lane >> 1) & 3);
       const bool use_res = res && k == 0;
+      const bool feed = C.direct && k == 0;                  // this item's output slabs are conv 1's A operand
+      const int feed_pos = ring_pos + ksl0;                  // ring position of conv 1's first slab (behind this item's own)
+      ring_pos += (k == 0) ? ksl0 : ksl1;
       for (int g = half; g < n_groups; g += 2) {
         const int c0 = n * P.block_n + g * 32;
         if (use_res) {
@@ -306,6 +326,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_chain_kernel(const __grid
         if (lane == 0) tma_store_wait_read();              // the previous slab has left the staging tile
         __syncwarp();
         const uint32_t ob = st_out + lane * 64;
+        uint32_t feed_row = 0, feed_bar = 0;
+        if (feed) {
+          // slab sl = g / 2 of conv 1's K: stage and parity from its ring position; the stage is free once the MMAs of
+          // the slab that used it before have retired
+          const int pos = feed_pos + (g >> 1);
+          const int stage = pos % C.num_a_stages;
+          mbar_wait(bar_aempty + 8 * stage, (((uint32_t)(pos / C.num_a_stages)) & 1u) ^ 1u);
+          feed_row = tiles_addr + stage * C.a_entry_bytes + (uint32_t)m_local * 128u;
+          feed_bar = bar_dfull + 8 * stage;
+        }
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           float x8[8];
@@ -317,9 +347,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_chain_kernel(const __grid
           const uint32_t sw = (uint32_t)((t ^ swz) << 4);
           sts128(ob + sw, hi);
           sts128(ob + 2048 + sw, lo);
+          if (feed) {                                      // K-major 128B-swizzled A tile: 16-byte chunk c of row r sits at c ^ (r & 7)
+            const uint32_t chunk = (uint32_t)((g & 1) * 4 + t);
+            const uint32_t fo = feed_row + ((chunk ^ ((uint32_t)m_local & 7u)) << 4);
+            sts128(fo, hi);
+            sts128(fo + a_lo_off, lo);
+          }
         }
         fence_async_smem();
         __syncwarp();
+        // (a .release.cluster arrive costs MEMBAR.GPU + ERRBAR per slab, a quarter of the kernel's stall samples; the
+        // writes are already ordered for the async proxy of THIS SM -- which is the one that reads them, each CTA's
+        // tensor core fetches its own half of A -- by the proxy fence above)
+        if (feed && lane == 0) mbar_arrive_leader(feed_bar);
         if (tile_valid && lane == 0) {
           tma_store_2d(&P.tmap_out, st_out, c0, row_tile0);
           tma_store_2d(&P.tmap_out, st_out + 2048, P.cout + c0, row_tile0);
@@ -328,7 +368,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_chain_kernel(const __grid
       }
       tc_fence_before();
       mbar_arrive_leader(bar_tempty + 8 * acc);
-      if (k == 0 && n == n0 - 1) {
+      if (k == 0 && n == n0 - 1 && !C.direct) {
         // y of unit j is complete for this warp's rows once its bulk stores have been PERFORMED (not only read)
         if (lane == 0) {
           tma_store_wait_all();
@@ -360,6 +400,7 @@ extern "C" int iou_conv_chain_plan_create(iou_conv_plan* first, iou_conv_plan* s
   IOU_REQUIRE(first && second && plan_out, "NULL argument");
   const ConvParams &A = first->params, &B = second->params;
   IOU_REQUIRE(!first->chained && !second->chained, "plans are already chained");
+  IOU_REQUIRE(!first->params.wide && !second->params.wide, "chain: plans of the wide variant (create them with IOU_WIDE=0)");
   IOU_REQUIRE(A.two_cta && B.two_cta && A.f8 && B.f8, "chain: both convs must run as CTA pairs with passes == 2");
   IOU_REQUIRE(A.num_taps == 1 && B.num_taps == 1 && A.tap_dy[0] == 0 && A.tap_dx[0] == 0 && B.tap_dy[0] == 0 && B.tap_dx[0] == 0 &&
               A.tap_src[0] == 0 && B.tap_src[0] == 0, "chain: both convs must be plain 1x1 convs (one tap, one source)");
@@ -438,6 +479,10 @@ int launch_chain(const iou_conv_plan* plan, void* stream) {
   C.ring_bytes = C.num_a_stages * C.a_entry_bytes +
                  (C.b_resident ? e0 * plan->params.b_entry_bytes + e1 * plan->params2.b_entry_bytes : C.num_b_stages * C.b_entry_bytes);
   C.staging_per_warp = 4096 + (plan->params.res_staged ? 8192 : 0);
+  static const bool no_direct = getenv("IOU_CHAIN_NO_DIRECT") != nullptr;
+  // direct hand-over needs conv 0's whole N in one item (its 64-channel slabs are conv 1's K slabs) and, for the parity
+  // waits of the epilogue warps, no more than two ring wraps inside one conv-1 item
+  C.direct = (!no_direct && C.n0 == 1 && C.b_resident && e1 <= 2 * C.num_a_stages) ? 1 : 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(plan->grid);
   cfg.blockDim = dim3(kNumThreads);

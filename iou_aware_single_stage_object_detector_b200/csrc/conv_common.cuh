@@ -16,6 +16,11 @@ constexpr int kBlockK = 64;                  // bf16 elements = one 128-byte swi
 constexpr int kATileBytes = kBlockM * kBlockK * 2;   // 16 KiB
 constexpr int kNumThreads = 320;             // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
 constexpr int kNumEpiWarps = 8;
+// "wide" variant: 16 warps = warpgroup 0 (warp 0 TMA, warp 1 MMA, warps 2-3 idle) + 12 epilogue warps (three per TMEM lane
+// quadrant); setmaxnreg moves registers from warpgroup 0 to the epilogue warpgroups (56 / 152 per thread)
+constexpr int kNumThreadsWide = 512;
+constexpr int kNumEpiWarpsWide = 12;
+constexpr uint32_t kBarResWide = 704;        // control-block offset of the wide variant's 24 residual barriers
 constexpr int kMaxStages = 8;
 constexpr int kMaxBStages = 16;              // B ring entries (resident weights: one entry per (tap, K slab) of a tile)
 constexpr int kAccStride = 256;              // TMEM columns between the two accumulator stages
@@ -71,6 +76,7 @@ struct ConvParams {
   int num_acc;               // TMEM accumulator stages (2)
   int corr_off;              // f8, narrow tiles: the e4m3 MMAs accumulate into a second column block at this offset (0: same block)
   int ksplit_ntiles;         // split-K: N tiles per K split (0 = off); split j = n_tile / ksplit_ntiles reads K slabs [j*grp_ks, (j+1)*grp_ks)
+  int wide;                  // 12 epilogue warps (kEpiQ == 3): the HBM-bound convs whose epilogue is issue-latency bound
   int pdl;                   // programmatic dependent launch: prologue overlaps the previous kernel's tail (griddepcontrol)
 };
 

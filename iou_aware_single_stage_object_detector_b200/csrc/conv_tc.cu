@@ -30,9 +30,13 @@
 namespace iou {
 
 // ------------------------------------------------------------------------------------ kernel
-template <bool kTwoCta, bool kF8>
-__global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __grid_constant__ ConvParams P) {
+// kEpiQ = epilogue warps per TMEM lane quadrant: 2 (10 warps) or 3 (the "wide" variant, 16 warps with setmaxnreg)
+template <bool kTwoCta, bool kF8, int kEpiQ = 2>
+__global__ void __launch_bounds__(kEpiQ == 3 ? kNumThreadsWide : kNumThreads, 1) conv_tap_gemm_kernel(const __grid_constant__ ConvParams P) {
   constexpr int kFmt = kF8 ? kFmtF16F8 : kFmtBf16x2;
+  constexpr int kEpiWarps = 4 * kEpiQ;
+  constexpr int kFirstEpiWarp = kEpiQ == 3 ? 4 : 2;
+  constexpr uint32_t kBarRes = kEpiQ == 3 ? kBarResWide : 192u;
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte alignment is required by the 128B swizzle atoms
   const uint32_t raw = smem_u32(smem_dyn);
@@ -63,8 +67,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < P.num_b_stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     for (int s = 0; s < P.num_a_stages; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, (kTwoCta ? 2 : 1) * kNumEpiWarps * 32); }
-    for (int r = 0; r < 2 * kNumEpiWarps; ++r) mbar_init(ctrl_addr + 192 + 8 * r, 1);   // residual ring: 8 warps x 2
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, (kTwoCta ? 2 : 1) * kEpiWarps * 32); }
+    for (int r = 0; r < 2 * kEpiWarps; ++r) mbar_init(ctrl_addr + kBarRes + 8 * r, 1);   // residual ring: two per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     for (int i = 0; i < IOU_CONV_MAX_SRC; ++i)
@@ -95,6 +99,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
   const uint32_t b_lo_off = (uint32_t)P.b_tile_bytes;        // B entry: hi tile | lo tile
   const uint32_t b_ring_addr = tiles_addr + (uint32_t)(P.num_a_stages * P.a_entry_bytes);
 
+  // wide: register budget per scheduler partition: 4 warps x 128 at launch -> 56 (warpgroup 0) + 3 x 152 (epilogue).  The
+  // setmaxnreg instructions sit INSIDE the role branches: ptxas sizes the register allocation of the code they dominate
+  if (warp < kFirstEpiWarp) {
+  if constexpr (kEpiQ == 3) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (elect_one()) {
@@ -249,16 +257,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
         }
       }
     }
+  }
   } else {
     // =============================== epilogue ===============================
+    if constexpr (kEpiQ == 3) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
     if (P.pdl) griddep_wait();                   // residual reads (and, conservatively, every store) follow the previous grid
     const int lane_group = warp & 3;                      // TMEM lanes 32*lane_group .. +31
     const int m_local = lane_group * 32 + lane;
-    const int ew = warp - 2;                               // 0..7
-    const int half = ew >> 2;                              // the two warps of a quadrant take alternate column groups
+    const int ew = warp - kFirstEpiWarp;                   // 0..7 (wide: 0..11)
+    const int half = ew >> 2;                              // the kEpiQ warps of a quadrant take alternate column groups
     const uint32_t st_out = tiles_addr + P.ring_bytes + ew * P.staging_per_warp;
-    const uint32_t st_res = st_out + 4096;
-    const uint32_t bar_res = ctrl_addr + 192 + ew * 16;
+    // kEpiQ == 2: staging tile + 2 residual buffers.  kEpiQ == 3: two buffers, used IN PLACE -- the residual slab
+    // arrives in buffer q & 1, every lane reads its own row and writes its results over it, the TMA store leaves from there
+    const uint32_t st_res = kEpiQ == 3 ? st_out : st_out + 4096;
+    const uint32_t bar_res = ctrl_addr + kBarRes + ew * 16;
     auto issue_res_at = [&](int row, int col, int q_) {    // one elected lane only
       const uint32_t bar = bar_res + 8 * (q_ & 1), dst = st_res + (q_ & 1) * 4096;
       mbar_expect_tx(bar, 4096u);
@@ -285,9 +297,29 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
       }
     };
     int rq = 0;                                            // running slab counter of the residual ring
-    if (P.res_staged && w_first < w_total && elect_one()) {
-      issue_res(w_first, half, 0);
-      for (int a = 1; a <= P.res_prefetch; ++a) prefetch_res(w_first + a * w_stride);
+    // wide: the three warps of a quadrant take the column groups round-robin ACROSS tiles (group id = it * n_groups + g,
+    // warp = id % 3), so that 8, 4 or 2 groups per tile still keep all three busy
+    const int n_groups_w = P.block_n >> 5;
+    auto first_group = [&](int it_) { return (half + 3 - (it_ * n_groups_w) % 3) % 3; };
+    // this warp's first slab at or after (tile_, it_, g_): false when there is none
+    auto find_slab = [&](int& tile_, int& it_, int& g_) {
+      for (;;) {
+        if (g_ < n_groups_w) return true;
+        tile_ += w_stride; ++it_;
+        if (tile_ >= w_total) return false;
+        g_ = first_group(it_);
+      }
+    };
+    if constexpr (kEpiQ == 3) {
+      if (P.res_staged && w_first < w_total && elect_one()) {
+        int t0 = w_first, i0 = 0, g0 = first_group(0);
+        if (find_slab(t0, i0, g0)) issue_res(t0, g0, 0);
+      }
+    } else {
+      if (P.res_staged && w_first < w_total && elect_one()) {
+        issue_res(w_first, half, 0);
+        for (int a = 1; a <= P.res_prefetch; ++a) prefetch_res(w_first + a * w_stride);
+      }
     }
     int it = 0;
     const bool two_acc = P.num_acc == 2;
@@ -296,7 +328,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
       const uint32_t acc_phase = (uint32_t)(two_acc ? (it >> 1) : it) & 1u;
       int m_tile, n_tile, s;
       decode_tile(tile, m_tile, n_tile, s);
-      if (P.res_staged && P.res_prefetch > 0 && elect_one()) prefetch_res(tile + (P.res_prefetch + 1) * w_stride);
+      if (kEpiQ == 2 && P.res_staged && P.res_prefetch > 0 && elect_one()) prefetch_res(tile + (P.res_prefetch + 1) * w_stride);
       __syncwarp();
       const bool tile_valid = m_tile < P.num_m_tiles;        // pair mode: the odd CTA of the last pair may idle
       const SegDev sg = P.seg[s];
@@ -334,7 +366,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
       const uint32_t t_row = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(acc * kAccStride);
       const int n_chunks = P.block_n >> 4;
       if (!P.staged) {
-      for (int ch = half; ch < n_chunks; ch += 2) {
+      for (int ch = half; ch < n_chunks; ch += kEpiQ) {
         uint32_t v[16];
         tc_ld16(t_row + ch * 16, v);
         tc_wait_ld();
@@ -407,10 +439,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
         const int row_tile0 = grow - lane;                 // first row of this warp's 32-row slab
         const int n_groups = P.block_n >> 5;
         const uint32_t swz = (uint32_t)((lane >> 1) & 3);  // 64B swizzle: 16B chunk j of row r sits at j ^ ((r>>1)&3)
-        for (int g = half; g < n_groups; g += 2, ++rq) {
+        for (int g = kEpiQ == 3 ? first_group(it) : half; g < n_groups; g += kEpiQ, ++rq) {
           const int c0 = n_tile * P.block_n + g * 32;
+          // where this slab's results are staged (wide + residual: over the residual slab itself)
+          const uint32_t buf_out = (kEpiQ == 3 && P.res_staged) ? st_out + (uint32_t)(rq & 1) * 4096u : st_out;
           if (P.res_staged) {
-            if (elect_one()) {                             // prefetch this warp's next slab
+            if (kEpiQ == 2 && elect_one()) {               // prefetch this warp's next slab
               if (g + 2 < n_groups) issue_res_at(row_tile0, n_tile * P.block_n + (g + 2) * 32, rq + 1);
               else if (tile + w_stride < w_total) issue_res(tile + w_stride, half, rq + 1);
             }
@@ -488,11 +522,22 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
               decode8_add<kFmt>(__ldg(rh + j), __ldg(rl + j), f + j * 8);
             }
           }
-          if (!P.phase_only) {
+          if (kEpiQ == 3 && P.res_staged) {
+            // the other buffer: once the previous slab's store has read it, the NEXT slab's residual may land there.  (This
+            // slab's buffer needs no wait: its last store was waited for one slab ago, before its residual load was issued.)
+            if (lane == 0) {
+              tma_store_wait_read();
+              int t2 = tile, i2 = it, g2 = g + 3;
+              if (find_slab(t2, i2, g2)) {
+                if (t2 == tile) issue_res_at(row_tile0, n_tile * P.block_n + g2 * 32, rq + 1);
+                else issue_res(t2, g2, rq + 1);
+              }
+            }
+          } else if (!P.phase_only) {
             if (lane == 0) tma_store_wait_read();          // previous slab has left the staging tile
             __syncwarp();
           }
-          const uint32_t ob = st_out + lane * 64;
+          const uint32_t ob = buf_out + lane * 64;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float x8[8];
@@ -513,7 +558,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const uint32_t r = (uint32_t)(8 * i + (lane >> 2));
-              const uint32_t sa = st_out + r * 64 + ((cch ^ ((r >> 1) & 3u)) << 4);
+              const uint32_t sa = buf_out + r * 64 + ((cch ^ ((r >> 1) & 3u)) << 4);
               if (ph_dst[i] != 0ull) {
                 __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>((uintptr_t)ph_dst[i]) + c0 + 8 * cch;
                 *reinterpret_cast<uint4*>(dp) = lds128(sa);
@@ -523,8 +568,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tap_gemm_kernel(const __g
             if (P.phase_only) { __syncwarp(); continue; }  // the next slab overwrites the staging tile
           }
           if (tile_valid && elect_one()) {
-            tma_store_2d(&P.tmap_out, st_out, c0, row_tile0);
-            tma_store_2d(&P.tmap_out, st_out + 2048, P.cout + c0, row_tile0);
+            tma_store_2d(&P.tmap_out, buf_out, c0, row_tile0);
+            tma_store_2d(&P.tmap_out, buf_out + 2048, P.cout + c0, row_tile0);
             tma_store_commit();
           }
         }
@@ -687,7 +732,12 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   // and TMA stores; a same-geometry residual arrives through a 2-deep TMA-load ring per warp
   P.staged = (d->out_mode == IOU_OUT_PADDED_BF16X2) && (d->block_n % 64 == 0);
   P.res_staged = P.staged && d->res_mode == IOU_RES_SAME;
-  P.staging_per_warp = P.staged ? (4096 + (P.res_staged ? 8192 : 0)) : 0;      // x 8 epilogue warps
+  // wide variant (12 epilogue warps), decided below once the rings are known: IOU_WIDE = 0 never, 1 (default) the convs
+  // whose epilogue, not their operand stream, is the work -- resident weights, or a residual with a short K loop --,
+  // 2 every padded-rows conv of the fp16 + e4m3 scheme.  iou_conv_desc.wide = 1 / -1 overrides.
+  const int wide_mode = getenv("IOU_WIDE") ? atoi(getenv("IOU_WIDE")) : 1;
+  const bool wide_ok = P.f8 && P.staged && d->wide >= 0 && (d->wide > 0 || wide_mode >= 1);
+  const bool wide_forced = d->wide > 0 || wide_mode >= 2;
   for (int i = 0; i < 4; ++i) P.phase_out[i] = (__nv_bfloat16*)d->phase_out[i];
   P.phase_any = phase_any ? 1 : 0;
   P.phase_only = d->phase_only ? 1 : 0;
@@ -703,6 +753,12 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   // tap groups: taps reading the same source at the same dy with dx within a span of 4 share one A window
   // (tried first; if the rings do not fit shared memory that way, every tap loads its own 128-row window)
   bool fits = false;
+  int epi_warps = kNumEpiWarps;
+  for (int try_wide = wide_ok ? 1 : 0; try_wide >= 0 && !fits; --try_wide) {
+  P.wide = try_wide;
+  epi_warps = P.wide ? kNumEpiWarpsWide : kNumEpiWarps;
+  // per epilogue warp: a 4 KB staging tile (+ two 4 KB residual buffers); wide: the two residual buffers double as staging
+  P.staging_per_warp = P.staged ? (P.wide ? (P.res_staged ? 8192 : 4096) : (4096 + (P.res_staged ? 8192 : 0))) : 0;
   for (int share = getenv("IOU_NO_A_SHARE") ? 0 : 1; share >= 0 && !fits; --share) {
     P.num_groups = 0;
     bool used[IOU_CONV_MAX_TAPS] = {false};
@@ -723,7 +779,7 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
     P.a_rows = (P.num_groups == d->num_taps) ? kBlockM : kBlockM + 8;    // shifted windows need up to 2 extra rows
     P.a_entry_bytes = nsplit * P.a_rows * kBlockK * 2;
     // ring depths: the A ring is worth (taps per group) B tiles per entry; maximise the shallower of the two
-    const int budget = kSmemBudget - kCtrlBytes - 1024 - kNumEpiWarps * P.staging_per_warp;
+    const int budget = kSmemBudget - kCtrlBytes - 1024 - epi_warps * P.staging_per_warp;
     int best_na = 0, best_nb = 0, best_score = 0;
     // resident weights: with ONE N tile every tile of a CTA multiplies by the same few weight tiles -- load them once
     // (entry e = the e-th (tap, slab) of a tile) and spend the rest of shared memory on the A ring
@@ -754,10 +810,15 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
     }
     if (share == 0) break;
   }
+  if (fits && P.wide && !wide_forced &&
+      !(P.b_resident || (P.tap_slabs_per_tile <= 8 && (d->res_mode != IOU_RES_NONE || d->block_n <= 128))))
+    fits = false;                                        // operand-bound: 8 epilogue warps and deeper rings (measured)
+  }
+  if (P.wide) P.res_prefetch = 0;
   if (!fits) { delete plan; return fail(IOU_ERR_INVALID, "tile does not fit shared memory (block_n %d, residual %d): use a smaller block_n", d->block_n, d->res_mode); }
   if (getenv("IOU_CONV_DEBUG"))
-    fprintf(stderr, "[iou_conv] cin %d cout %d taps %d block_n %d pair %d res %d staged %d | groups %d a_rows %d nA %d nB %d%s ring %d KB\n",
-            d->cin, d->cout, d->num_taps, d->block_n, P.two_cta, d->res_mode, P.staged, P.num_groups, P.a_rows,
+    fprintf(stderr, "[iou_conv] cin %d cout %d taps %d block_n %d pair %d res %d staged %d wide %d | groups %d a_rows %d nA %d nB %d%s ring %d KB\n",
+            d->cin, d->cout, d->num_taps, d->block_n, P.two_cta, d->res_mode, P.staged, P.wide, P.num_groups, P.a_rows,
             P.num_a_stages, P.num_b_stages, P.b_resident ? " (resident)" : "", P.ring_bytes / 1024);
   P.scale = d->scale; P.shift = d->shift; P.relu = d->relu; P.res_mode = d->res_mode;
   P.residual = (const __nv_bfloat16*)d->residual;
@@ -793,7 +854,7 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   } else {
     plan->grid = P.total_tiles < sms ? P.total_tiles : sms;
   }
-  plan->smem_bytes = (size_t)kCtrlBytes + 1024 + (size_t)P.ring_bytes + (size_t)kNumEpiWarps * P.staging_per_warp;
+  plan->smem_bytes = (size_t)kCtrlBytes + 1024 + (size_t)P.ring_bytes + (size_t)epi_warps * P.staging_per_warp;
   double k_total = 0;
   for (int t = 0; t < d->num_taps; ++t) k_total += P.diag_k ? kBlockK : (ksplit > 1 ? d->cin : P.src_cin[d->tap_src[t]]);
   plan->flops = 2.0 * real_rows * d->cout * k_total;
@@ -806,6 +867,10 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
       e = cudaFuncSetAttribute(conv_tap_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_tap_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_tap_gemm_kernel<false, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_tap_gemm_kernel<true, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     if (e != cudaSuccess) { delete plan; return fail(IOU_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
     attr_set = true;
   }
@@ -818,7 +883,7 @@ extern "C" int iou_conv_run(const iou_conv_plan* plan, void* stream) {
   if (plan->chained) return iou::launch_chain(plan, stream);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(plan->grid);
-  cfg.blockDim = dim3(kNumThreads);
+  cfg.blockDim = dim3(plan->params.wide ? kNumThreadsWide : kNumThreads);
   cfg.dynamicSmemBytes = plan->smem_bytes;
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[2];
@@ -835,7 +900,10 @@ extern "C" int iou_conv_run(const iou_conv_plan* plan, void* stream) {
   }
   cfg.attrs = attr; cfg.numAttrs = na;
   cudaError_t e;
-  if (plan->params.two_cta)
+  if (plan->params.wide)
+    e = plan->params.two_cta ? cudaLaunchKernelEx(&cfg, conv_tap_gemm_kernel<true, true, 3>, plan->params)
+                             : cudaLaunchKernelEx(&cfg, conv_tap_gemm_kernel<false, true, 3>, plan->params);
+  else if (plan->params.two_cta)
     e = plan->params.f8 ? cudaLaunchKernelEx(&cfg, conv_tap_gemm_kernel<true, true>, plan->params)
                         : cudaLaunchKernelEx(&cfg, conv_tap_gemm_kernel<true, false>, plan->params);
   else

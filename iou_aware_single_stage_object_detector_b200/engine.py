@@ -260,12 +260,13 @@ class Engine(object):
     def conv(self, name, srcs, taps, weight, cin, cout, out=None, scale=None, shift=None, relu=False,
              residual=None, res_mode=L.RES_NONE, dense_out=None, dense_out2=None, dense_split=0,
              segs_from=None, diag_k=False, true_flops_scale=1.0, two_cta=None, force_bn=None,
-             phase_outs=None, phase_only=False, k_split=1, hold=False, chain=False):
+             phase_outs=None, phase_only=False, k_split=1, hold=False, chain=False, wide=0):
         """srcs: list[FlatMap] (same geometry); out: FlatMap or None (dense).  Returns out.
         phase_outs: 4 FlatMaps / None from new_phase_maps(): the epilogue also writes the stride-2 phase split of the
         output (what iou_phase_split would produce from it); phase_only: nothing else is written (returns None).
         hold=True keeps the launch back so that the NEXT conv(chain=True) -- a plain 1x1 conv reading this conv's output --
         can be chained into the same launch (iou_conv_chain_plan_create); if the pair does not qualify both run as usual.
+        wide: iou_conv_desc.wide (0 = library default, 1 = 12 epilogue warps, -1 = 8).
         k_split = S > 1: the sources hold S * cin channels and `cout` = S * (real cout) output channels are the S partial
         sums over the channel slices (weight rows packed to match, see split_k_weight); sum_groups() adds them."""
         geo = segs_from or srcs[0]
@@ -367,6 +368,7 @@ class Engine(object):
                     d.out_dense2[i] = t.data_ptr()
         d.passes = self.passes
         d.k_split = int(k_split)
+        d.wide = -1 if (hold or chain) else int(wide)      # the chained launch has its own (8-warp) epilogue
         plan = ctypes.c_void_p()
         rc = self.lib.iou_conv_plan_create(ctypes.byref(d), ctypes.byref(plan))
         if rc != 0 and retry_bn is not None:         # the wide residual tile did not fit next to the staging rings

@@ -97,7 +97,7 @@ class ConvDesc(ctypes.Structure):
                 ("passes", ctypes.c_int32), ("out_rows", ctypes.c_int64), ("res_rows", ctypes.c_int64),
                 ("diag_k", ctypes.c_int32), ("two_cta", ctypes.c_int32),
                 ("phase_out", ctypes.c_void_p * 4), ("phase_only", ctypes.c_int32),
-                ("src_cin", ctypes.c_int32 * CONV_MAX_SRC), ("k_split", ctypes.c_int32)]
+                ("src_cin", ctypes.c_int32 * CONV_MAX_SRC), ("k_split", ctypes.c_int32), ("wide", ctypes.c_int32)]
 
 
 _SIGS = {

@@ -369,7 +369,8 @@ def test_split_k_conv_with_channel_group_sum_vs_torch(passes, ks, cin, cout, str
                                             (128, 512, 128, (2, 40, 60)),      # two N tiles of conv A, streamed weights
                                             (256, 1024, 256, (1, 50, 84)),     # layer-3 shape: four N tiles, K = 1024 for conv B
                                             (64, 256, 64, (1, 45, 67)),        # odd tile count: the last pair's second CTA idles
-                                            (64, 256, 128, (8, 30, 30))])      # several images
+                                            (64, 256, 128, (8, 30, 30)),       # several images
+                                            (64, 256, 64, (3, 200, 304))])     # ~9 units per CTA pair: the ring wraps, stages change hands
 def test_chained_1x1_convs_one_launch_equal_two_launches(ca, cb, cc, shape):
     """conv3(+residual, ReLU) of a bottleneck and conv1 of the next one in ONE launch (iou_conv_chain_plan_create,
     csrc/conv_chain.cu): bit-identical to the two separate launches, and fp32-grade against torch."""
