@@ -248,6 +248,8 @@ void iou_conv_plan_destroy(iou_conv_plan* plan);
 int iou_conv_chain_plan_create(iou_conv_plan* first, iou_conv_plan* second, iou_conv_plan** plan_out);
 /* 2*MAC flops the plan performs on real (non-padding) outputs, for rooflines. */
 double iou_conv_plan_flops(const iou_conv_plan* plan);
+/* Epilogue warps of the kernel variant the plan launches: 8, or 12 for the wide variant (iou_conv_desc.wide). */
+int iou_conv_plan_epilogue_warps(const iou_conv_plan* plan);
 
 /* ------------------------------------------------------------------ layout kernels
  * (elementwise, HBM-bound helpers around the conv engine)                      */

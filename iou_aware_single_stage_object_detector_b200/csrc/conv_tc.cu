@@ -916,3 +916,7 @@ extern "C" int iou_conv_run(const iou_conv_plan* plan, void* stream) {
 extern "C" void iou_conv_plan_destroy(iou_conv_plan* plan) { delete plan; }
 
 extern "C" double iou_conv_plan_flops(const iou_conv_plan* plan) { return plan ? plan->flops : 0.0; }
+
+extern "C" int iou_conv_plan_epilogue_warps(const iou_conv_plan* plan) {
+  return plan ? (plan->params.wide ? kNumEpiWarpsWide : kNumEpiWarps) : 0;
+}

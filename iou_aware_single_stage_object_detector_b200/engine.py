@@ -235,6 +235,7 @@ class Engine(object):
         self._side_stream = None
         self.flops = 0.0
         self.op_flops = {}
+        self.epi_warps = {}                     # conv name -> 8 / 12 (which kernel variant its plan launches)
         import os
         self.two_cta = os.environ.get("IOU_TWO_CTA", "1") != "0"
         self.pair_min_bn = int(os.environ.get("IOU_PAIR_MIN_BN", "48"))   # 48: the reg+iou output conv as a CTA pair (-28 %)
@@ -379,6 +380,7 @@ class Engine(object):
         for m in ([out] if out is not None else []) + [m for m in (phase_outs or []) if m is not None]:
             if getattr(m, "label", None) is None:
                 m.label = name
+        self.epi_warps[name] = self.lib.iou_conv_plan_epilogue_warps(plan)
         f = self.lib.iou_conv_plan_flops(plan) * true_flops_scale
         self.flops += f
         lib = self.lib

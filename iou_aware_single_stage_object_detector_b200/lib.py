@@ -144,6 +144,7 @@ _SIGS = {
     "iou_conv_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "iou_conv_plan_destroy": (None, [ctypes.c_void_p]),
     "iou_conv_plan_flops": (ctypes.c_double, [ctypes.c_void_p]),
+    "iou_conv_plan_epilogue_warps": (ctypes.c_int, [ctypes.c_void_p]),
     "iou_pack_nchw": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     "iou_unpack_nchw": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,

@@ -400,3 +400,42 @@ def test_chained_1x1_convs_one_launch_equal_two_launches(ca, cb, cc, shape):
     (y1, t1), (y2, t2) = outs
     assert torch.equal(y1, y2) and torch.equal(t1, t2)
     assert rel_err(y1, ref_y) < TOL and rel_err(t1, ref_t) < TOL, (rel_err(y1, ref_y), rel_err(t1, ref_t))
+
+
+@pytest.mark.parametrize("cin,cout,k,shape,res,pair,phase", [
+    (64, 256, 1, (3, 200, 304), True, True, False),     # layer-1 conv3: 8 column groups per tile over 3 warps, ~10 tiles per CTA pair
+    (256, 1024, 1, (2, 50, 84), True, True, False),     # layer-3 conv3: four N tiles per row tile
+    (128, 512, 1, (1, 45, 67), True, None, True),       # odd tile count, phase (1,1) written next to the output
+    (256, 64, 1, (2, 100, 150), False, True, False),    # two column groups per tile: every third tile a warp has nothing to do
+    (256, 128, 1, (2, 60, 90), False, None, True),      # four groups, all four phase maps
+    (64, 64, 3, (2, 60, 90), False, True, False),       # 3x3, resident weights
+    (64, 256, 1, (2, 37, 53), True, False, False)])     # single-CTA kernel (no pairs)
+def test_wide_epilogue_is_bit_identical_to_the_8_warp_kernel(cin, cout, k, shape, res, pair, phase):
+    """iou_conv_desc.wide = 1 (conv_tap_gemm_kernel<., ., 3>: 12 epilogue warps behind setmaxnreg, column groups handed out
+    round-robin across tiles, residual slabs overwritten in place by the results) computes exactly what the 8-warp kernel does."""
+    n, h, w = shape
+    g = torch.Generator().manual_seed(cin + cout + h)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    b = torch.randn(cout, generator=g)
+    r = torch.randn(n, cout, h, w, generator=g) if res else None
+    ref = F.conv2d(x, wt, b, padding=k // 2)
+    ref = F.relu(ref + r) if res else F.relu(ref)
+    outs = []
+    for wide in (1, -1):
+        eng = E.Engine(DEV, passes=2)
+        m = eng.pack_input(x.to(DEV))
+        rm = eng.pack_input(r.to(DEV)) if res else None
+        ph = eng.new_phase_maps(n, h, w, cout, mask=8 if res else 15) if phase else None
+        taps = E.TAPS_1X1 if k == 1 else E.TAPS_3X3
+        y = eng.conv("c", [m], taps, E.pack_weight(wt, cout), cin, cout, shift=b, relu=True, residual=rm,
+                     res_mode=L.RES_SAME if res else L.RES_NONE, two_cta=pair, phase_outs=ph, wide=wide)
+        assert eng.epi_warps["c"] == (12 if wide == 1 else 8)
+        yo = eng.unpack_output(y)
+        eng.run()
+        torch.cuda.synchronize()
+        outs.append((yo.cpu(), y.tensor.view(torch.int16).cpu(), [p.tensor.view(torch.int16).cpu() for p in (ph or []) if p is not None]))
+    assert torch.equal(outs[0][1], outs[1][1])
+    for a, c in zip(outs[0][2], outs[1][2]):
+        assert torch.equal(a, c)
+    assert rel_err(outs[0][0], ref) < TOL, rel_err(outs[0][0], ref)
