@@ -101,6 +101,18 @@ int iou_get_bboxes(const iou_postproc_cfg* cfg, int n_img,
                    float* dets, int64_t* labels, int32_t* counts,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* iou_get_bboxes with the per-anchor maximum class logit already reduced by the producer of the class maps
+ * (iou_conv_desc.group_max_cols = num_classes on retina_cls): cls_max2 is a host array of num_levels device pointers,
+ * level l = fp32 [n_img][H_l*W_l*A][2] whose two entries' max is the anchor's max class logit; a NULL entry (or a NULL
+ * array) makes that level read its class map as iou_get_bboxes does.  Same results as iou_get_bboxes, bit for bit:
+ * the top-k pre-selection (iou_aware_retina_head.py:510-519) only needs the max, the candidates' class rows are
+ * still gathered from `cls`. */
+int iou_get_bboxes_premax(const iou_postproc_cfg* cfg, int n_img,
+                          const float* const* cls, const float* const* reg, const float* const* iou,
+                          const float* const* cls_max2, const float* img_info, int rescale,
+                          float* dets, int64_t* labels, int32_t* counts,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ plain NMS
  * Drop-in for mmdet.ops.nms.nms_cuda.nms (ops/nms/src/nms_cuda.cpp:8-13,
  * nms_kernel.cu:70-131): dets [n][5] fp32 (x1,y1,x2,y2,score); suppress at
@@ -232,6 +244,14 @@ typedef struct iou_conv_desc {
    * same-geometry residual, 8 otherwise; IOU_WIDE overrides), 1 = 12 warps if eligible (passes == 2, padded-rows
    * output), -1 = 8 warps. */
   int32_t wide;
+  /* Column-group maxima (ABI version 8; DENSE output only): with group_max_cols = G > 0 (a multiple of 16, >= 32,
+   * dividing block_n and cout) the epilogue also writes, for every output pixel and every group g of G consecutive
+   * output channels, TWO partial maxima whose max is max_c out[pixel][g*G + c]: group_max_out[seg] is fp32
+   * [n_img*h*w][cout/G][2] (the two epilogue warps of a row quadrant take alternate 16-column chunks; each stores the
+   * max over its own).  For retina_cls (G = num_classes) this is the per-anchor max class logit that
+   * iou_get_bboxes_premax consumes instead of re-reading the class map (iou_aware_retina_head.py:510-519). */
+  void* group_max_out[IOU_CONV_MAX_SEG];
+  int32_t group_max_cols;
 } iou_conv_desc;
 
 typedef struct iou_conv_plan iou_conv_plan;

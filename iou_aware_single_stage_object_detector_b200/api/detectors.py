@@ -77,6 +77,8 @@ class FusedPlan(object):
             raise RuntimeError("SingleStageDetector was built without test_cfg (nms_pre, score_thr, nms, "
                                "max_per_img): pass test_cfg=cfg.test_cfg to build_detector")
         self.eng = eng
+        # anchor heads: the retina_cls epilogue also writes each anchor's max class logit (Engine.add_head)
+        self.cls_max2 = getattr(eng, "cls_max2", None) if hasattr(det.bbox_head, "num_anchors") else None
         # heads return their forward() tuple; get_bboxes' kernels take (cls, reg, iou-or-None)
         to_post = getattr(det.bbox_head, "postproc_inputs", None)
         self.post_in = to_post(self.outs) if to_post is not None else (self.outs[0], self.outs[1], self.outs[2])
@@ -101,7 +103,7 @@ class FusedPlan(object):
             PP.batched_soft_nms(self.wsp, boxes, scores_cm, *self.wsp.soft)
         else:
             PP.get_bboxes_device(self.wsp, self.post_in[0], self.post_in[1], self.post_in[2], self.img_info,
-                                 self.rescale)
+                                 self.rescale, cls_max2=self.cls_max2)
 
     def check_range(self):
         """The fp16 + e4m3 scheme holds |v| < 65504 (and full precision up to 448): look at every activation map the

@@ -76,6 +76,8 @@ struct ConvParams {
   int num_acc;               // TMEM accumulator stages (2)
   int corr_off;              // f8, narrow tiles: the e4m3 MMAs accumulate into a second column block at this offset (0: same block)
   int ksplit_ntiles;         // split-K: N tiles per K split (0 = off); split j = n_tile / ksplit_ntiles reads K slabs [j*grp_ks, (j+1)*grp_ks)
+  float* gmax_out[IOU_CONV_MAX_SEG];   // dense outputs: per pixel and group of gmax_cols columns, two partial maxima
+  int gmax_cols, gmax_groups;          // columns per group (0 = off), groups in cout
   int wide;                  // 12 epilogue warps (kEpiQ == 3): the HBM-bound convs whose epilogue is issue-latency bound
   int pdl;                   // programmatic dependent launch: prologue overlaps the previous kernel's tail (griddepcontrol)
 };

@@ -366,6 +366,17 @@ __global__ void __launch_bounds__(kEpiQ == 3 ? kNumThreadsWide : kNumThreads, 1)
       const uint32_t t_row = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(acc * kAccStride);
       const int n_chunks = P.block_n >> 4;
       if (!P.staged) {
+      // column-group maxima (retina_cls: the per-anchor max class logit): a running max over this warp's chunks of the
+      // current group, flushed when the group changes
+      float gm = -INFINITY;
+      int gcur = -1;
+      const int cpg = P.gmax_cols >> 4;                      // 16-column chunks per group
+      const size_t gpix = ((size_t)img * sg.h + (yp - 1)) * sg.w + (xp - 1);
+      auto gmax_flush = [&]() {
+        const int gidx = n_tile * (P.block_n / (P.gmax_cols > 0 ? P.gmax_cols : 1)) + gcur;
+        if (gcur >= 0 && interior && gidx < P.gmax_groups)
+          P.gmax_out[s][(gpix * P.gmax_groups + gidx) * 2 + half] = gm;
+      };
       for (int ch = half; ch < n_chunks; ch += kEpiQ) {
         uint32_t v[16];
         tc_ld16(t_row + ch * 16, v);
@@ -413,6 +424,12 @@ __global__ void __launch_bounds__(kEpiQ == 3 ? kNumThreadsWide : kNumThreads, 1)
 #pragma unroll
           for (int q = 0; q < 16; ++q) f[q] = fmaxf(f[q], 0.f);
         }
+        if (P.gmax_cols) {
+          const int gi = ch / cpg;
+          if (gi != gcur) { gmax_flush(); gcur = gi; gm = -INFINITY; }
+#pragma unroll
+          for (int q = 0; q < 16; ++q) gm = fmaxf(gm, f[q]);
+        }
         if (interior) {
           const size_t pix = ((size_t)img * sg.h + (yp - 1)) * sg.w + (xp - 1);
           const int split = P.dense_split > 0 ? P.dense_split : P.cout;
@@ -431,6 +448,7 @@ __global__ void __launch_bounds__(kEpiQ == 3 ? kNumThreadsWide : kNumThreads, 1)
           }
         }
       }
+      if (P.gmax_cols) gmax_flush();
       } else {
         // ---- staged path (padded-rows output): 32 output channels per step and warp.  Results go to a
         // 64B-swizzled shared-memory tile (32 rows x 32 ch, hi and lo) and leave through TMA stores
@@ -659,6 +677,12 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
     IOU_REQUIRE(d->out_mode == IOU_OUT_DENSE_F32, "bad out_mode");
     IOU_REQUIRE(d->dense_split >= 0 && d->dense_split < d->cout, "dense_split out of range");
   }
+  if (d->group_max_cols != 0) {
+    IOU_REQUIRE(d->out_mode == IOU_OUT_DENSE_F32 && d->dense_split == 0, "group_max_cols needs a dense, unsplit output");
+    IOU_REQUIRE(d->group_max_cols >= 32 && d->group_max_cols % 16 == 0 && d->block_n % d->group_max_cols == 0 &&
+                d->cout % d->group_max_cols == 0, "group_max_cols must be a multiple of 16, >= 32, and divide block_n and cout");
+    for (int s = 0; s < d->num_seg; ++s) IOU_REQUIRE(d->group_max_out[s] != nullptr, "group_max_out[%d] is NULL", s);
+  }
   if (d->res_mode != IOU_RES_NONE) {
     IOU_REQUIRE(d->residual != nullptr, "residual is NULL");
     IOU_REQUIRE(d->cout == d->cout_pad && d->cout % 16 == 0, "residual needs cout == cout_pad, multiple of 16");
@@ -715,10 +739,13 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
     real_rows += (double)g.n_img * g.h * g.w;
     P.out_dense[s] = (float*)d->out_dense[s];
     P.out_dense2[s] = (float*)d->out_dense2[s];
+    P.gmax_out[s] = (float*)d->group_max_out[s];
     if (d->out_mode == IOU_OUT_DENSE_F32 && !d->out_dense[s]) { delete plan; return fail(IOU_ERR_INVALID, "out_dense[%d] is NULL", s); }
     if (d->out_mode == IOU_OUT_DENSE_F32 && d->dense_split > 0 && !d->out_dense2[s]) { delete plan; return fail(IOU_ERR_INVALID, "out_dense2[%d] is NULL", s); }
   }
   for (int s = d->num_seg; s <= IOU_CONV_MAX_SEG; ++s) P.seg_tile_off[s] = toff;
+  P.gmax_cols = d->group_max_cols;
+  P.gmax_groups = d->group_max_cols > 0 ? d->cout / d->group_max_cols : 0;
   P.num_m_tiles = toff;
   P.num_n_tiles = d->cout_pad / d->block_n;
   P.total_tiles = P.num_m_tiles * P.num_n_tiles;

@@ -33,6 +33,7 @@ struct PostParams {
   const float* cls[IOU_MAX_LEVELS];
   const float* reg[IOU_MAX_LEVELS];
   const float* iou[IOU_MAX_LEVELS];
+  const float* cmax2[IOU_MAX_LEVELS];   // optional: per anchor, two partial maxima of its class logits (iou_get_bboxes_premax)
   float base[IOU_MAX_LEVELS][IOU_MAX_ANCHORS][4];
   float mean[4], stdv[4];
   float alpha, score_thr, iou_thr, max_ratio;
@@ -87,18 +88,26 @@ __global__ void __launch_bounds__(256) max_score_kernel(const __grid_constant__ 
     const int img = gl / gpi, gi = gl - img * gpi;
     const int a0 = gi * 32;
     const int v = min(32, n_l - a0);
-    const float4* src = reinterpret_cast<const float4*>(P.cls[l] + ((size_t)img * n_l + a0) * P.C);
-    const int nslots = v * Q;
+    const bool premax = P.cmax2[l] != nullptr;            // the class-map producer already reduced the classes
+    if (!premax) {
+      const float4* src = reinterpret_cast<const float4*>(P.cls[l] + ((size_t)img * n_l + a0) * P.C);
+      const int nslots = v * Q;
 #pragma unroll 4
-    for (int f = lane; f < nslots; f += 32) {
-      float4 x = ldg_stream(src + f);
-      sm[f] = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
+      for (int f = lane; f < nslots; f += 32) {
+        float4 x = ldg_stream(src + f);
+        sm[f] = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
+      }
+      __syncwarp();
     }
-    __syncwarp();
     int bucket = TOPK_BINS + lane;                       // idle lanes: a bucket of their own
     if (lane < v) {
       float m = -INFINITY;
-      for (int t = 0; t < Q; ++t) m = fmaxf(m, sm[lane * Q + t]);
+      if (premax) {
+        const float2 p2 = __ldg(reinterpret_cast<const float2*>(P.cmax2[l]) + (size_t)img * n_l + a0 + lane);
+        m = fmaxf(p2.x, p2.y);
+      } else {
+        for (int t = 0; t < Q; ++t) m = fmaxf(m, sm[lane * Q + t]);
+      }
       const float q = P.iou[l] ? __ldg(P.iou[l] + (size_t)img * n_l + a0 + lane) : 0.f;
       const float sc = fuse_score(m, q, P.alpha);
       maxscore[(size_t)img * P.A_total + P.anchor_off[l] + a0 + lane] = sc;
@@ -472,7 +481,7 @@ __device__ __forceinline__ float box_area(const float4 a) {
   return __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.0f), __fadd_rn(__fsub_rn(a.w, a.y), 1.0f));
 }
 
-#define NMS_ROUND 1024
+#define NMS_ROUND 512
 #define NMS_FIRST 256
 struct NmsSmem {
   unsigned long long* sortbuf;   // [P]
@@ -495,6 +504,7 @@ __device__ int greedy_nms_range(const NmsSmem& S, const int begin, const int n, 
                                 const int stop_after, int* s_total_p, Emit emit) {
   __shared__ unsigned long long cmask[64];
   __shared__ unsigned int dead[2];
+  __shared__ unsigned long long s_keep;
   int& s_total = *s_total_p;                   // kept count so far (shared memory, persists across ranges)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   __syncthreads();
@@ -564,6 +574,7 @@ __device__ int greedy_nms_bounded(const unsigned long long* keys, const int n, c
   __shared__ float4 cbox[64];
   __shared__ float carea[64];
   __shared__ unsigned int dead[2];
+  __shared__ unsigned long long s_keep;
   int& s_total = *s_total_p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   __syncthreads();
@@ -604,28 +615,39 @@ __device__ int greedy_nms_bounded(const unsigned long long* keys, const int n, c
     }
     __syncthreads();
     if (tid == 0) {
-      unsigned long long R = (unsigned long long)dead[0] | ((unsigned long long)dead[1] << 32);
+      // the sequential part is only the keep / suppress decision (a 64-bit mask walk, branch-free so that the mask loads
+      // pipeline); copying the kept boxes and emitting their keys is done by all threads below
+      unsigned long long R = (unsigned long long)dead[0] | ((unsigned long long)dead[1] << 32), keep = 0ull;
       int total = total0;
+#pragma unroll 8
       for (int i = 0; i < cnt; ++i) {
-        if (!((R >> i) & 1ull)) {
-          R |= cmask[i];
-          kbox[total] = cbox[i];
-          karea[total] = carea[i];
-          emit(cs + i, total);
-          ++total;
-          if (total >= stop_after) break;
-        }
+        const unsigned long long m = cmask[i];
+        const bool take = !((R >> i) & 1ull) && total < stop_after;
+        R |= take ? m : 0ull;
+        keep |= take ? (1ull << i) : 0ull;
+        total += take ? 1 : 0;
       }
       s_total = total;
+      s_keep = keep;
     }
     __syncthreads();
+    if (tid < cnt) {
+      const unsigned long long keep = s_keep;
+      if ((keep >> tid) & 1ull) {
+        const int pos = total0 + __popcll(keep & ((1ull << tid) - 1ull));
+        kbox[pos] = cbox[tid];
+        karea[pos] = carea[tid];
+        emit(cs + tid, pos);
+      }
+    }
+    __syncthreads();                                   // kbox complete, cbox free for the next chunk
     if (s_total >= stop_after) break;
   }
   return s_total;
 }
 
 // ---------------------------------------------------------------------------------------- K4
-__global__ void __launch_bounds__(512) class_nms_kernel(const __grid_constant__ PostParams P,
+__global__ void __launch_bounds__(384, 5) class_nms_kernel(const __grid_constant__ PostParams P,
                                                         const float* __restrict__ boxes,
                                                         const float* __restrict__ scores_cm,
                                                         unsigned long long* __restrict__ kept_keys,
@@ -643,31 +665,34 @@ __global__ void __launch_bounds__(512) class_nms_kernel(const __grid_constant__ 
   __shared__ unsigned int s_n, warp_cnt[16];
   const int c = blockIdx.x, img = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int T = blockDim.x, nw = T >> 5;            // four CTAs per SM at full width, five at 384 threads
+  const int T = blockDim.x, nw = T >> 5;            // 384 threads: five CTAs per SM
   const float* sc = scores_cm + ((size_t)img * P.C + c) * P.M;
-  if (tid == 0) s_n = 0;
-  __syncthreads();
-  // compaction of rows with score > score_thr (bbox_nms.py:37), ascending row index
-  for (int base = 0; base < P.M; base += T) {
-    const int j = base + tid;
-    const float s = (j < P.M) ? __ldg(sc + j) : 0.f;
-    const bool pass = (j < P.M) && (s > P.score_thr);
-    const unsigned int b = __ballot_sync(0xffffffffu, pass);
-    if (lane == 0) warp_cnt[warp] = __popc(b);
-    __syncthreads();
-    unsigned int off = s_n;
-    for (int w = 0; w < warp; ++w) off += warp_cnt[w];
-    if (pass) {
-      const unsigned int slot = off + __popc(b & ((1u << lane) - 1u));
-      c_bits[slot] = float_to_ordered(s);
-      c_row[slot] = (unsigned short)j;
+  // compaction of rows with score > score_thr (bbox_nms.py:37), ascending row index: warp w owns the contiguous rows
+  // [w * per, (w + 1) * per) -- count, one barrier, prefix over the warps, write (the second read hits L1)
+  {
+    const int per = ((P.M + nw - 1) / nw + 31) & ~31;
+    const int lo = warp * per, hi = min(P.M, lo + per);
+    unsigned int mine = 0;
+    for (int j = lo + lane; j < lo + per; j += 32) {
+      const bool pass = (j < hi) && (__ldg(sc + j) > P.score_thr);
+      mine += __popc(__ballot_sync(0xffffffffu, pass));
     }
+    if (lane == 0) warp_cnt[warp] = mine;
     __syncthreads();
-    if (tid == 0) {
-      unsigned int t = 0;
-      for (int w = 0; w < nw; ++w) t += warp_cnt[w];
-      s_n += t;
+    unsigned int off = 0, tot = 0;
+    for (int w = 0; w < nw; ++w) { const unsigned int c_ = warp_cnt[w]; tot += c_; if (w < warp) off += c_; }
+    for (int j = lo + lane; j < lo + per; j += 32) {
+      const float sv = (j < hi) ? __ldg(sc + j) : 0.f;
+      const bool pass = (j < hi) && (sv > P.score_thr);
+      const unsigned int b = __ballot_sync(0xffffffffu, pass);
+      if (pass) {
+        const unsigned int slot = off + __popc(b & ((1u << lane) - 1u));
+        c_bits[slot] = float_to_ordered(sv);
+        c_row[slot] = (unsigned short)j;
+      }
+      off += __popc(b);
     }
+    if (tid == 0) s_n = tot;
     __syncthreads();
   }
   const int n = (int)s_n;
@@ -720,10 +745,32 @@ __global__ void __launch_bounds__(512) class_nms_kernel(const __grid_constant__ 
     int bhi = 1024, cap = NMS_FIRST;
     while (bhi > 0) {
       __syncthreads();
-      if (tid == 0) {
-        int bq = bhi, cum = 0;
-        while (bq > 0 && cum + (int)bh[bq - 1] <= cap) cum += (int)bh[--bq];
-        s_blo = bq; s_teff = cum; s_slot2 = 0;
+      if (warp == 0) {
+        // lowest blo with sum(bh[blo .. bhi)) <= cap, walking down from bhi and stopping at the first bin that would
+        // overflow: lane L owns bins [32L, 32L + 32); suffix sums over the lanes find the lane where the walk stops,
+        // that lane finishes inside its own bins
+        unsigned int mine = 0;
+        for (int k = 0; k < 32; ++k) { const int b_ = 32 * lane + k; if (b_ < bhi) mine += bh[b_]; }
+        unsigned int suf = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned int v_ = __shfl_down_sync(0xffffffffu, suf, o);
+          if (lane + o < 32) suf += v_;
+        }
+        const unsigned int over = __ballot_sync(0xffffffffu, suf > (unsigned int)cap);
+        const unsigned int above_mine = __shfl_down_sync(0xffffffffu, suf, 1);
+        int bq = 0, cum = (int)__shfl_sync(0xffffffffu, suf, 0);
+        if (over != 0u) {
+          const int lc = 31 - __clz(over);
+          if (lane == lc) {
+            bq = min(bhi, 32 * lc + 32);
+            cum = (lc < 31) ? (int)above_mine : 0;
+            while (bq > 32 * lc && cum + (int)bh[bq - 1] <= cap) cum += (int)bh[--bq];
+          }
+          bq = __shfl_sync(0xffffffffu, bq, lc);
+          cum = __shfl_sync(0xffffffffu, cum, lc);
+        }
+        if (lane == 0) { s_blo = bq; s_teff = cum; s_slot2 = 0; }
       }
       __syncthreads();
       const int blo = s_blo, teff = s_teff;
@@ -754,7 +801,7 @@ __global__ void __launch_bounds__(512) class_nms_kernel(const __grid_constant__ 
     // big class: the scan stops after max_per_img+1 kept boxes, so only the head of the score order is
     // ever needed.  Rounds of NMS_ROUND boxes: exact radix select of the round's lowest composite key
     // (keys are unique: score bits | ~index), compaction, a 1024-wide sort, then the lazy greedy scan.
-    __shared__ unsigned int hist[256];
+    unsigned int* hist = bh;                    // [256]: the bucket histogram is not used on this path
     __shared__ unsigned long long s_prefix;
     __shared__ unsigned int s_kleft, s_slot;
     unsigned long long bound = ~0ull;           // keys of this round are < bound
@@ -1432,7 +1479,7 @@ static PostWorkspace carve(const PostParams& P, void* base) {
 }
 
 static int run_decode(PostParams& P, const float* const* cls, const float* const* reg,
-                      const float* const* iou, const float* img_info, int rescale, float* boxes,
+                      const float* const* iou, const float* const* cls_max2, const float* img_info, int rescale, float* boxes,
                       float* scores_cm, int32_t* cand_idx, float* maxscore, unsigned int* topk_hist, unsigned long long* topk_list,
                       cudaStream_t st) {
   for (int l = 0; l < P.num_levels; ++l) {
@@ -1441,6 +1488,8 @@ static int run_decode(PostParams& P, const float* const* cls, const float* const
     IOU_REQUIRE(((uintptr_t)cls[l] & 15) == 0 && ((uintptr_t)reg[l] & 15) == 0,
                 "cls/reg pointers must be 16-byte aligned (level %d)", l);
     P.cls[l] = cls[l]; P.reg[l] = reg[l]; P.iou[l] = iou ? iou[l] : nullptr;
+    P.cmax2[l] = cls_max2 ? cls_max2[l] : nullptr;
+    IOU_REQUIRE(((uintptr_t)P.cmax2[l] & 7) == 0, "cls_max2 pointers must be 8-byte aligned (level %d)", l);
   }
   P.rescale = rescale;
   const long long groups = P.group_off[P.num_levels];
@@ -1467,9 +1516,11 @@ static int run_nms(const PostParams& P, const float* boxes, const float* scores_
   const int Pmax = (P.M + 7) & ~7;          // multiple of 8 keeps kbox 16-byte aligned behind the 6-byte entries
   const size_t sm4 = (size_t)Pmax * 6 + (size_t)P.kcap * 20 + 16;
   IOU_CHECK_CUDA(cudaFuncSetAttribute(class_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4));
-  // 640 (class, image) CTAs at bs = 8: with 512 threads 4 fit an SM (592 slots, two waves), with 384 threads 5 (740 slots)
-  static const int nms_threads = getenv("IOU_NMS_THREADS") ? atoi(getenv("IOU_NMS_THREADS")) : 512;
-  const int nt = (nms_threads == 384 || nms_threads == 256) ? nms_threads : 512;
+  // 640 (class, image) CTAs at bs = 8 must be ONE wave (the kernel is a chain of block-wide latencies, a second wave
+  // doubles its time): 44 KB of shared memory and 384 threads per CTA -> 5 CTAs per SM = 740 slots
+  IOU_CHECK_CUDA(cudaFuncSetAttribute(class_nms_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  static const int nms_threads = getenv("IOU_NMS_THREADS") ? atoi(getenv("IOU_NMS_THREADS")) : 384;
+  const int nt = (nms_threads == 256 || nms_threads == 128) ? nms_threads : 384;
   class_nms_kernel<<<dim3(P.C, P.n_img), nt, sm4, st>>>(P, boxes, scores_cm, kept_keys, kept_cnt, Pmax);
   if (int e = launch_status("class_nms_kernel")) return e;
   const size_t sm5 = (size_t)next_pow2_host(P.C * P.kcap) * 8 + 64;
@@ -1506,7 +1557,7 @@ extern "C" int iou_decode_candidates(const iou_postproc_cfg* cfg, int n_img, con
   PostWorkspace W = carve(P, workspace);
   if (!workspace || workspace_bytes < W.total)
     return fail(IOU_ERR_WORKSPACE, "workspace too small: need %zu bytes", W.total);
-  return run_decode(P, cls, reg, iou, img_info, rescale, boxes, scores_cm, cand_idx, W.maxscore,
+  return run_decode(P, cls, reg, iou, nullptr, img_info, rescale, boxes, scores_cm, cand_idx, W.maxscore,
                     W.topk_hist, W.topk_list, (cudaStream_t)stream);
 }
 
@@ -1526,13 +1577,21 @@ extern "C" int iou_get_bboxes(const iou_postproc_cfg* cfg, int n_img, const floa
                               const float* const* reg, const float* const* iou, const float* img_info,
                               int rescale, float* dets, int64_t* labels, int32_t* counts,
                               void* workspace, size_t workspace_bytes, void* stream) {
+  return iou_get_bboxes_premax(cfg, n_img, cls, reg, iou, nullptr, img_info, rescale, dets, labels, counts, workspace,
+                               workspace_bytes, stream);
+}
+
+extern "C" int iou_get_bboxes_premax(const iou_postproc_cfg* cfg, int n_img, const float* const* cls,
+                                     const float* const* reg, const float* const* iou, const float* const* cls_max2,
+                                     const float* img_info, int rescale, float* dets, int64_t* labels, int32_t* counts,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
   PostParams P;
   if (int e = fill_params(cfg, n_img, P)) return e;
   IOU_REQUIRE(cls && reg && img_info && dets && labels && counts, "NULL argument");
   PostWorkspace W = carve(P, workspace);
   if (!workspace || workspace_bytes < W.total)
     return fail(IOU_ERR_WORKSPACE, "workspace too small: need %zu bytes", W.total);
-  if (int e = run_decode(P, cls, reg, iou, img_info, rescale, W.boxes, W.scores_cm, W.cand_idx,
+  if (int e = run_decode(P, cls, reg, iou, cls_max2, img_info, rescale, W.boxes, W.scores_cm, W.cand_idx,
                          W.maxscore, W.topk_hist, W.topk_list, (cudaStream_t)stream))
     return e;
   return run_nms(P, W.boxes, W.scores_cm, dets, labels, counts, W.kept_keys, W.kept_cnt,

@@ -261,12 +261,15 @@ class Engine(object):
     def conv(self, name, srcs, taps, weight, cin, cout, out=None, scale=None, shift=None, relu=False,
              residual=None, res_mode=L.RES_NONE, dense_out=None, dense_out2=None, dense_split=0,
              segs_from=None, diag_k=False, true_flops_scale=1.0, two_cta=None, force_bn=None,
-             phase_outs=None, phase_only=False, k_split=1, hold=False, chain=False, wide=0):
+             phase_outs=None, phase_only=False, k_split=1, hold=False, chain=False, wide=0,
+             group_max_out=None, group_max_cols=0):
         """srcs: list[FlatMap] (same geometry); out: FlatMap or None (dense).  Returns out.
         phase_outs: 4 FlatMaps / None from new_phase_maps(): the epilogue also writes the stride-2 phase split of the
         output (what iou_phase_split would produce from it); phase_only: nothing else is written (returns None).
         hold=True keeps the launch back so that the NEXT conv(chain=True) -- a plain 1x1 conv reading this conv's output --
         can be chained into the same launch (iou_conv_chain_plan_create); if the pair does not qualify both run as usual.
+        group_max_out / group_max_cols: dense outputs only -- per pixel and group of `group_max_cols` output channels, two
+        partial maxima (fp32 [n*h*w][cout/cols][2] per segment; iou_conv_desc.group_max_cols).
         wide: iou_conv_desc.wide (0 = library default, 1 = 12 epilogue warps, -1 = 8).
         k_split = S > 1: the sources hold S * cin channels and `cout` = S * (real cout) output channels are the S partial
         sums over the channel slices (weight rows packed to match, see split_k_weight); sum_groups() adds them."""
@@ -367,6 +370,10 @@ class Engine(object):
             if dense_out2 is not None:
                 for i, t in enumerate(dense_out2):
                     d.out_dense2[i] = t.data_ptr()
+            if group_max_out is not None:
+                d.group_max_cols = int(group_max_cols)
+                for i, t in enumerate(group_max_out):
+                    d.group_max_out[i] = t.data_ptr()
         d.passes = self.passes
         d.k_split = int(k_split)
         d.wide = -1 if (hold or chain) else int(wide)      # the chained launch has its own (8-warp) epilogue
@@ -641,8 +648,18 @@ class Engine(object):
         if self.passes == 2 and cls_bn:          # two accumulator stages (N <= 128) at the price of padded columns
             pad_c = _round_up(ncls, cls_bn)
             force = (cls_bn, pad_c)
+        # the per-anchor max class logit leaves the retina_cls epilogue (two partial maxima per anchor), so that the top-k
+        # pre-selection of get_bboxes does not re-read the class maps (iou_get_bboxes_premax)
+        bn_used = force[0] if force is not None else bn_c
+        self.cls_max2 = None
+        if (os.environ.get("IOU_FUSE_MAX", "1") != "0" and num_classes >= 32 and num_classes % 16 == 0 and
+                bn_used % num_classes == 0):
+            self.cls_max2 = [torch.empty(n, h, w, num_anchors, 2, dtype=torch.float32, device=self.device)
+                             for (_, n, h, w) in F.segs]
+            self.keep += self.cls_max2
         self.conv(prefix + "retina_cls", [c], TAPS_3X3, pack_weight(sd[prefix + "retina_cls.weight"], pad_c),
-                  fc, ncls, shift=sd[prefix + "retina_cls.bias"], dense_out=cls_out, force_bn=force)
+                  fc, ncls, shift=sd[prefix + "retina_cls.bias"], dense_out=cls_out, force_bn=force,
+                  group_max_out=self.cls_max2, group_max_cols=num_classes if self.cls_max2 is not None else 0)
         if with_iou:
             # retina_reg and retina_iou read the same feature (shared_conv=4, :198-204): one GEMM, split store
             w_ri = torch.cat([sd[prefix + "retina_reg.weight"], sd[prefix + "retina_iou.weight"]], dim=0)

@@ -97,7 +97,8 @@ class ConvDesc(ctypes.Structure):
                 ("passes", ctypes.c_int32), ("out_rows", ctypes.c_int64), ("res_rows", ctypes.c_int64),
                 ("diag_k", ctypes.c_int32), ("two_cta", ctypes.c_int32),
                 ("phase_out", ctypes.c_void_p * 4), ("phase_only", ctypes.c_int32),
-                ("src_cin", ctypes.c_int32 * CONV_MAX_SRC), ("k_split", ctypes.c_int32), ("wide", ctypes.c_int32)]
+                ("src_cin", ctypes.c_int32 * CONV_MAX_SRC), ("k_split", ctypes.c_int32), ("wide", ctypes.c_int32),
+                ("group_max_out", ctypes.c_void_p * CONV_MAX_SEG), ("group_max_cols", ctypes.c_int32)]
 
 
 _SIGS = {
@@ -117,6 +118,10 @@ _SIGS = {
                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                       ctypes.c_size_t, ctypes.c_void_p]),
+    "iou_get_bboxes_premax": (ctypes.c_int, [ctypes.POINTER(PostprocCfg), ctypes.c_int, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_size_t, ctypes.c_void_p]),
     "iou_nms_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int]),
     "iou_nms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_void_p,
                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),

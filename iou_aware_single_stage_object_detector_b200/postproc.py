@@ -87,17 +87,24 @@ class PostprocWorkspace(object):
         self.dets, self.labels, self.counts = packed_views(self.packed, n_img, cfg.max_per_img)
 
 
-def get_bboxes_device(wsp, cls_list, reg_list, iou_list, img_info, rescale):
-    """Launches the whole get_bboxes pipeline; returns device tensors (dets, labels, counts)."""
+def get_bboxes_device(wsp, cls_list, reg_list, iou_list, img_info, rescale, cls_max2=None):
+    """Launches the whole get_bboxes pipeline; returns device tensors (dets, labels, counts).
+    cls_max2: optional per-level fp32 [n][H][W][A][2] tensors (None entries allowed) whose last-axis max is the anchor's
+    max class logit (what the retina_cls conv epilogue writes, Engine.cls_max2): the class maps are then only read for
+    the candidates (iou_get_bboxes_premax)."""
     lib = L.load()
     cls_list = [nhwc_rows(t) for t in cls_list]
     reg_list = [nhwc_rows(t) for t in reg_list]
     iou_list = [nhwc_rows(t) for t in iou_list] if iou_list is not None else None
-    L.check(lib.iou_get_bboxes(ctypes.byref(wsp.cfg), wsp.n_img, _ptr_array(cls_list), _ptr_array(reg_list),
-                               _ptr_array(iou_list) if iou_list is not None else None, img_info.data_ptr(),
-                               int(bool(rescale)),
-                               wsp.dets.data_ptr(), wsp.labels.data_ptr(), wsp.counts.data_ptr(),
-                               wsp.ws.data_ptr(), wsp.ws_bytes, L.stream_ptr()))
+    pm = None
+    if cls_max2 is not None:
+        assert len(cls_max2) == len(cls_list)
+        pm = (ctypes.c_void_p * len(cls_max2))(*[(t.data_ptr() if t is not None else None) for t in cls_max2])
+    L.check(lib.iou_get_bboxes_premax(ctypes.byref(wsp.cfg), wsp.n_img, _ptr_array(cls_list), _ptr_array(reg_list),
+                                      _ptr_array(iou_list) if iou_list is not None else None, pm, img_info.data_ptr(),
+                                      int(bool(rescale)),
+                                      wsp.dets.data_ptr(), wsp.labels.data_ptr(), wsp.counts.data_ptr(),
+                                      wsp.ws.data_ptr(), wsp.ws_bytes, L.stream_ptr()))
     L.launch_count += 5
     return wsp.dets, wsp.labels, wsp.counts
 

@@ -127,13 +127,18 @@ def test_multi_segment_head_style_dense_outputs(pair):
     cls_out = [torch.zeros(n, h, w, 720, device=DEV) for (n, h, w) in sizes]
     reg_out = [torch.zeros(n, h, w, 36, device=DEV) for (n, h, w) in sizes]
     iou_out = [torch.zeros(n, h, w, 9, device=DEV) for (n, h, w) in sizes]
+    # iou_conv_desc.group_max_cols = 80: per pixel and anchor, two partial maxima of the 80 class logits
+    gmax = [torch.full((n, h, w, 9, 2), float("nan"), device=DEV) for (n, h, w) in sizes]
     eng.conv("cls", [Fm], E.TAPS_3X3, E.pack_weight(w_cls, 720), 256, 720, shift=b_cls, dense_out=cls_out,
-             two_cta=pair)
+             two_cta=pair, group_max_out=gmax, group_max_cols=80)
     eng.conv("ri", [Fm], E.TAPS_3X3, E.pack_weight(w_ri, 48), 256, 45, shift=b_ri, dense_out=reg_out,
              dense_out2=iou_out, dense_split=36, two_cta=False)
     eng.run()
     torch.cuda.synchronize()
     for s, x in enumerate(xs):
+        n, _, h, w = x.shape
+        # exactly the maximum of the values the same launch stored (no NaN left: every slot was written)
+        assert torch.equal(gmax[s].max(dim=-1).values, cls_out[s].view(n, h, w, 9, 80).max(dim=-1).values)
         ref = F.conv2d(x, w_cls, b_cls, padding=1).permute(0, 2, 3, 1)
         assert rel_err(cls_out[s].cpu(), ref) < TOL
         ref = F.conv2d(x, w_ri, b_ri, padding=1).permute(0, 2, 3, 1)

@@ -257,6 +257,41 @@ def test_full_size_properties():
     assert torch.equal(solo[0][0], r1[1][0]) and torch.equal(solo[0][1], r1[1][1])
 
 
+@pytest.mark.parametrize("name", ["small", "full"])
+def test_get_bboxes_premax_equals_get_bboxes(name):
+    """iou_get_bboxes_premax (per-anchor max class logit handed in as two partial maxima, the way the retina_cls conv
+    epilogue produces them) returns bit for bit what iou_get_bboxes reduces from the class maps itself; a level without
+    partials (NULL entry) falls back to its class map."""
+    case = cases.postproc_case(name)
+    head = U.get_head()
+    dev = torch.device("cuda:0")
+    cfg = P.ConfigDict(case["cfg"])
+    cls = [t.to(dev) for t in case["cls"]]
+    reg = [t.to(dev) for t in case["reg"]]
+    iou = [t.to(dev) for t in case["iou"]]
+    n_img = cls[0].shape[0]
+    sizes = [tuple(t.shape[-2:]) for t in cls]
+    info = PP.make_img_info(case["img_metas"], dev)
+    outs = []
+    for mode in ("plain", "premax", "mixed"):
+        wsp = head.postproc_workspace(sizes, n_img, cfg, dev)
+        pm = None
+        if mode != "plain":
+            pm = []
+            for l, t in enumerate(cls):                      # (n, A*C, H, W) -> (n, H, W, A, C): even / odd 16-class chunks
+                n, ac, h, w = t.shape
+                v = t.permute(0, 2, 3, 1).reshape(n, h, w, 9, 5, 16)
+                pm.append(torch.stack([v[..., 0::2, :].amax(dim=(-1, -2)), v[..., 1::2, :].amax(dim=(-1, -2))], dim=-1).contiguous())
+            if mode == "mixed":
+                pm[0] = None
+        d, l_, c = PP.get_bboxes_device(wsp, cls, reg, iou, info, case["rescale"], cls_max2=pm)
+        torch.cuda.synchronize()
+        outs.append((d.clone(), l_.clone(), c.clone()))
+    for o in outs[1:]:
+        assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]) and torch.equal(o[2], outs[0][2])
+    assert int(outs[0][2].sum()) > 0
+
+
 def test_focal_loss_forward_backward_vs_oracle():
     torch.manual_seed(0)
     x = (torch.randn(513, 80) * 3)
