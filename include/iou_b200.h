@@ -262,8 +262,10 @@ void iou_conv_plan_destroy(iou_conv_plan* plan);
 /* Chains two plans into ONE launch (ABI version 8): `second` must be a plain 1x1 conv whose only source is the padded-rows
  * output of `first` (also a plain 1x1 conv, optionally with a same-geometry residual), both as CTA pairs with passes == 2,
  * same segments, one N tile in `second` -- relu(bn3(conv3(t2)) + x) followed by the next bottleneck's conv1
- * (backbones/resnet.py:224-226,256-265).  Each CTA pair then computes both convs for its rows and reads conv 1's
- * output back while it is still in L2 instead of from HBM.  On success *plan_out == first (which now owns `second`; run
+ * (backbones/resnet.py:224-226,256-265).  Each CTA pair then computes both convs for its rows: when `first` has ONE N tile
+ * its epilogue writes its output slabs straight into the second conv's A ring in shared memory (next to the TMA store of the
+ * output map, which still happens), otherwise the second conv reads them back while they are still in L2.  Both plans must be
+ * of the 8-warp kind (iou_conv_desc.wide = -1).  On success *plan_out == first (which now owns `second`; run
  * and destroy it like any plan); on IOU_ERR_INVALID both plans are untouched and can be run one after the other. */
 int iou_conv_chain_plan_create(iou_conv_plan* first, iou_conv_plan* second, iou_conv_plan** plan_out);
 /* 2*MAC flops the plan performs on real (non-padding) outputs, for rooflines. */

@@ -13,6 +13,14 @@
 // and an mbarrier per unit parity ("y of unit j is in global memory") orders conv1'(u_j)'s loads behind the TMA stores of
 // conv3(u_j): the epilogue warps wait for their bulk stores to COMPLETE (cp.async.bulk.wait_group 0, not .read), fence
 // the async proxy and arrive; the producer waits, fences and loads.  Every CTA only reads back rows it wrote itself.
+//
+// DIRECT mode (conv3 with ONE N tile, i.e. layer 1; ChainParams.direct): y is not reloaded at all.  The conv3 epilogue also
+// writes each 64-channel slab of y into an A-ring stage in the UMMA K-major 128B-swizzled layout (16-byte chunk c of row r
+// at c ^ (r & 7) -- what TMA would have produced), fences the async proxy and arrives on a per-stage "direct full" barrier
+// of the leader (16 arrivals: the epilogue warps of both CTAs); the MMA warp waits on that barrier for conv1' items and
+// releases the stage through the usual commit.  Item order c3(u0), c1(u0), c3(u1), ...; A-stage parities are tracked per
+// producer kind (TMA / epilogue), and the TMA thread still waits on the stages it does not fill, so that every parity
+// wait stays within one phase of its barrier.
 #include "conv_common.cuh"
 
 namespace iou {
