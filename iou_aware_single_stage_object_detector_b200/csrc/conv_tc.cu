@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(kEpiQ == 3 ? kNumThreadsWide : kNumThreads, 1)
           if (kEpiQ == 3 && P.res_staged) {
             // the other buffer: once the previous slab's store has read it, the NEXT slab's residual may land there.  (This
             // slab's buffer needs no wait: its last store was waited for one slab ago, before its residual load was issued.)
-            if (lane == 0) {
+            if (elect_one()) {                             // the lane that issued the stores: bulk groups are per thread
               tma_store_wait_read();
               int t2 = tile, i2 = it, g2 = g + 3;
               if (find_slab(t2, i2, g2)) {
@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(kEpiQ == 3 ? kNumThreadsWide : kNumThreads, 1)
               }
             }
           } else if (!P.phase_only) {
-            if (lane == 0) tma_store_wait_read();          // previous slab has left the staging tile
+            if (elect_one()) tma_store_wait_read();        // (same elected lane as the stores) previous slab has left the staging tile
             __syncwarp();
           }
           const uint32_t ob = buf_out + lane * 64;
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(kEpiQ == 3 ? kNumThreadsWide : kNumThreads, 1)
       if constexpr (kTwoCta) mbar_arrive_leader(bar_tempty + 8 * acc);   // only the leader's MMA warp waits on it
       else mbar_arrive(bar_tempty + 8 * acc);
     }
-    if (P.staged && lane == 0) tma_store_wait_read();      // staging must outlive the last TMA store
+    if (P.staged && elect_one()) tma_store_wait_read();    // staging must outlive the last TMA store
   }
 
   tc_fence_before();
