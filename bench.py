@@ -174,7 +174,7 @@ def run_ours(args):
     step_no = [0]
     # N > 1: ONE all-gather of the packed detections per step, on a side stream (dist.PackedGather): the compute
     # streams never wait for the collective, only a plan's NEXT run waits for the gather of its previous results
-    pg = D.PackedGather(world, dev) if world > 1 else None
+    pg = D.PackedGather(world, dev) if world > 1 and not os.environ.get("IOU_BENCH_NO_GATHER") else None   # (diagnostic knob)
     busy = [None] * len(plans)
 
     def step_device():
@@ -236,7 +236,11 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     launches = L.launch_count
     t = torch.tensor([ms], device=dev)
+    ms_ranks = None
     if world > 1:
+        every = torch.zeros(world, device=dev)
+        dist.all_gather_into_tensor(every, t)            # which rank set the max: a slow GPU or the collective
+        ms_ranks = [round(float(v) / args.steps, 3) for v in every.tolist()]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = world * BATCH * args.steps / (ms / 1e3)
@@ -401,6 +405,8 @@ def run_ours(args):
                                      "note": "extra: raw 800x1333x3 uint8 frames in, device-side ImageTransform"},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof}
         line.update(extra)
+        if ms_ranks is not None:
+            line["ms_per_step_ranks"] = ms_ranks          # `ms_per_step` is their max
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.weights, images=args.cpu_images)
     if world > 1:
