@@ -202,8 +202,8 @@ __global__ void __launch_bounds__(kEpiQ == 3 ? kNumThreadsWide : kNumThreads, 1)
                 // fp16 hi x Wh' and [x8|l8] x [Wl8;W8] (e4m3, K = 32 per 32 bytes), both at scale S_n, into the same
                 // accumulator (narrow tiles: two column blocks).  Both instruction descriptors have the same bits
                 // (formats 0 = F16 / E4M3).
-#pragma unroll
                 const uint32_t cfirst = corr_off ? first : 1u;     // same column block: the fp16 MMA initialised it
+#pragma unroll
                 for (uint32_t kk = 0; kk < kBlockK / 16; ++kk) {
                   mma_i(d_tmem, umma_desc(da + 2 * kk), umma_desc(db + 2 * kk), idesc, kk ? 1u : first);
                   if constexpr (kTwoCta) tc_mma_f8_pair(d_tmem + corr_off, umma_desc(dal + 2 * kk), umma_desc(dbl + 2 * kk), idesc, kk ? 1u : cfirst);

@@ -504,7 +504,6 @@ __device__ int greedy_nms_range(const NmsSmem& S, const int begin, const int n, 
                                 const int stop_after, int* s_total_p, Emit emit) {
   __shared__ unsigned long long cmask[64];
   __shared__ unsigned int dead[2];
-  __shared__ unsigned long long s_keep;
   int& s_total = *s_total_p;                   // kept count so far (shared memory, persists across ranges)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   __syncthreads();
