@@ -875,6 +875,7 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   if (int e = encode_2d(&P.tmap_w, d->weight, (uint64_t)d->num_taps * d->cout_pad, (uint64_t)2 * P.b_cin, (uint32_t)(P.two_cta ? d->block_n / 2 : d->block_n))) { delete plan; return e; }
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (getenv("IOU_MAX_SMS") && atoi(getenv("IOU_MAX_SMS")) > 1 && atoi(getenv("IOU_MAX_SMS")) < sms) sms = atoi(getenv("IOU_MAX_SMS"));   // (experiments)
   if (P.two_cta) {
     const int pairs = sms / 2;
     plan->grid = 2 * (P.total_pair_tiles < pairs ? P.total_pair_tiles : pairs);
