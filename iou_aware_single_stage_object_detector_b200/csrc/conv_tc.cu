@@ -713,7 +713,8 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
   // f8: one accumulator per stage (all weight copies share the scale S_n); narrow tiles split the two MMA kinds
   // over two column blocks, which the epilogue adds
   P.num_acc = 2;
-  P.corr_off = (P.f8 && d->block_n <= 64 && !getenv("IOU_F8_ONE_BLOCK")) ? 128 : 0;
+  const int corr_max_bn = getenv("IOU_F8_CORR_MAX_BN") ? atoi(getenv("IOU_F8_CORR_MAX_BN")) : 64;
+  P.corr_off = (P.f8 && d->block_n <= corr_max_bn && d->block_n <= 128 && !getenv("IOU_F8_ONE_BLOCK")) ? 128 : 0;
   for (int t = 0; t < d->num_taps; ++t) {
     if (d->tap_src[t] < 0 || d->tap_src[t] >= d->num_src) { delete plan; return fail(IOU_ERR_INVALID, "tap_src out of range"); }
     P.tap_src[t] = d->tap_src[t]; P.tap_dy[t] = d->tap_dy[t]; P.tap_dx[t] = d->tap_dx[t];
@@ -822,7 +823,9 @@ extern "C" int iou_conv_plan_create(const iou_conv_desc* d, iou_conv_plan** plan
       if (na > kMaxStages) na = kMaxStages;
       if (na >= 2) { P.b_resident = 1; best_na = na; best_nb = b_entries; best_score = 1; }
     }
+    const int force_na = (getenv("IOU_FORCE_NA") && d->num_taps == 9 && d->cin <= 128) ? atoi(getenv("IOU_FORCE_NA")) : 0;   // (experiments)
     for (int na = 2; na <= kMaxStages && !P.b_resident; ++na) {
+      if (force_na > 0 && na != force_na) continue;
       int nb = (budget - na * P.a_entry_bytes) / P.b_entry_bytes;
       if (nb > kMaxStages) nb = kMaxStages;
       if (nb < 2) break;
